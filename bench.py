@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — LGTEUN forward throughput (image pairs / s) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference's CPU forward (oracle port) on the host cores
+
+A "step" is one Pansharpening.forward (models/unlg_former.py:50-67, K=2 stages, BOTH priors executed exactly as the
+reference executes them) over one batch of synthetic GF-2-shaped pairs (PAN 256x256 + LrMS 64x64x4, the shape
+BASELINE.json's metric is quoted on; BASELINE configs[2]).  Per-GPU batch is fixed (weak scaling): image pairs are
+independent, every rank runs its own shard, there is no data-path collective.
+
+One JSON line on stdout (rank 0): value = device-resident whole-job pairs/s; e2e = the same metric through the
+public nn.Module API with pinned HOST buffers (H2D and D2H inside the timed region); roofline = the dominant
+kernel (conv-FFN) timed live with CUDA events; cpu_baseline = the CPU oracle port timed on this box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LGTEUN fwd pairs/sec @PAN256/MS64x4"
+UNIT = "pairs/s"
+WORKLOADS = {  # name: (bands, h, default per-GPU batch, description)
+    "gf2": (4, 64, 512, "BASELINE configs[2]: GF-2 shape PAN 256x256 + LrMS 64x64x4, K=2 stages"),
+    "wv3": (8, 64, 64, "BASELINE configs[1]: WV-3 shape PAN 256x256 + LrMS 64x64x8, K=2 stages"),
+}
+FLOPS_PER_PAIR = {"gf2": 10_890_657_792, "wv3": 39_732_936_704}      # BASELINE.md §2 (as executed, 2xMAC)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def golden_weights(bands):
+    import numpy as np
+    import torch
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"weights_b{bands}.npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def synth_inputs(n, bands, h, seed=0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, bands, h, h, generator=g), torch.rand(n, 1, 4 * h, 4 * h, generator=g)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference (oracle port) — used by --impl reference and by the cpu_baseline leg
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        n = os.cpu_count()
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, int(n))
+
+
+def time_cpu_reference(bands, h, batch, reps, warmup, threads):
+    """pairs/s of the reference forward restated in oracle/ (fp32, eval, both priors as the reference executes)."""
+    import torch
+    from oracle import lgteun_oracle as O
+    torch.set_num_threads(threads)
+    sd = golden_weights(bands)
+    ms, pan = synth_inputs(batch, bands, h)
+    for _ in range(warmup):
+        O.forward(sd, ms, pan, skip_dead_priors=False)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.forward(sd, ms, pan, skip_dead_priors=False)
+        times.append(time.perf_counter() - t0)
+    return batch / statistics.median(times), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    bands, h, _, desc = WORKLOADS[args.workload]
+    threads = cpu_threads()
+    batch = 2
+    t0 = time.perf_counter()
+    value, times = time_cpu_reference(bands, h, batch, args.steps, max(1, min(args.warmup, 2)), threads)
+    ms_step = 1e3 * statistics.median(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc + f"; CPU sample: batch {batch} per step", "parallelism": f"cpu x{threads} threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} forwards of {batch} pairs (oracle/lgteun_oracle.py, torch CPU fp32, "
+                                   f"both priors executed), median"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="lgteun_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"warning: WORLD_SIZE={world} but --gpus {args.gpus}")
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import lgteun_b200
+    from lgteun_b200 import _abi
+    from lgteun_b200.sharding import max_over_ranks, sum_over_ranks
+
+    bands, h, default_batch, desc = WORKLOADS[args.workload]
+    batch = args.batch or default_batch               # per GPU (weak scaling)
+    H = 4 * h
+    flags = 0 if args.skip_dead_priors else _abi.RUN_DEAD_PRIORS
+    sd = golden_weights(bands)
+
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=2, skip_dead_priors=args.skip_dead_priors)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+
+    ms_h, pan_h = synth_inputs(batch, bands, h, seed=rank)
+    ms_h, pan_h = ms_h.pin_memory(), pan_h.pin_memory()
+    out_h = torch.empty(batch, bands, H, H).pin_memory()
+    ms_d, pan_d = ms_h.to(dev), pan_h.to(dev)
+    out_d = torch.empty(batch, bands, H, H, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    handle = net._runtime(dev)                          # the C-ABI handle behind the module (weights loaded)
+
+    def step_resident():
+        handle.forward(ms_d.data_ptr(), pan_d.data_ptr(), out_d.data_ptr(), batch, h, h, flags, stream.cuda_stream)
+
+    def step_e2e():
+        with torch.no_grad():
+            a = ms_h.to(dev, non_blocking=True)
+            b = pan_h.to(dev, non_blocking=True)
+            o = net(a, b)
+            out_h.copy_(o, non_blocking=True)
+        return o
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev)        # ms, max over ranks
+
+    # parity spot check before timing (the number is meaningless if the result is wrong)
+    step_resident()
+    torch.cuda.synchronize(dev)
+    if not torch.isfinite(out_d).all():
+        raise RuntimeError("non-finite output")
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    total_pairs = sum_over_ranks(batch, dev) * args.steps
+    value = total_pairs / (ms_total * 1e-3)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = timed(step_e2e, e2e_steps, 3)
+    e2e_value = sum_over_ranks(batch, dev) * e2e_steps / (ms_e2e * 1e-3)
+
+    launches_per_fwd = handle.launches(batch, h, h, flags)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": batch, "global_batch": int(sum_over_ranks(batch, dev)),
+                   "parallelism": f"batch-sharded x{world} (no collective)",
+                   "priors": "live prior only (dead priors skipped, identical output)" if args.skip_dead_priors
+                   else "both priors executed (as the reference does)",
+                   "l2": "inputs + activations per step are far larger than the 126 MB L2 (no flush needed)",
+                   "weights": "reference default init, seed 19971118 (tests/golden)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((ms_h.numel() + pan_h.numel()) * 4),
+                "d2h_bytes_per_step": int(out_h.numel() * 4), "api": "lgteun_b200.Pansharpening.forward, pinned host tensors",
+                "steps": e2e_steps},
+        "gpu_launches": int(launches_per_fwd * args.steps),
+        "clocks": clocks,
+    }
+
+    if rank == 0:
+        peaks = load_peaks()
+        line["roofline"] = roofline_ffn(handle, bands, batch, H, dev, stream, peaks, args)
+        line["gflop_per_pair"] = FLOPS_PER_PAIR[args.workload] / 1e9 * (0.5008 if args.skip_dead_priors else 1.0)
+        line["model_tflops"] = value * line["gflop_per_pair"] / 1e3
+        if world == 1 and not args.no_cpu_baseline:
+            threads = cpu_threads()
+            t0 = time.perf_counter()
+            v, times = time_cpu_reference(bands, h, 2, 3, 1, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"3 forwards of 2 pairs of the same workload shape (oracle port, torch CPU fp32, "
+                                              f"both priors), median; {time.perf_counter() - t0:.1f}s"}
+        if world == 1 and args.other_workloads:
+            line["other_workloads"] = other_workload(args, dev)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline_ffn(handle, bands, batch, H, dev, stream, peaks, args):
+    """The dominant kernel: residual(pre_norm(feed_forward)) of a full-resolution block (c = 4*bands at HxH), timed
+    on its own with CUDA events on the launch stream right after the timed steps (same shapes, same buffers).
+    Algorithmic FLOPs per launch = 48 c^2 + 72 c per pixel x N*H*W pixels."""
+    import torch
+    c = 4 * bands
+    n = min(batch, 64)
+    x = torch.randn(n, H, H, c, device=dev)
+    y = torch.empty_like(x)
+    reps = 10
+    for _ in range(3):
+        handle.op("ffn", 1, 0, 0, x.data_ptr(), y.data_ptr(), n, H, H, stream=stream.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(reps):
+        handle.op("ffn", 1, 0, 0, x.data_ptr(), y.data_ptr(), n, H, H, stream=stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    flops = (48 * c * c + 72 * c) * n * H * H
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    return {"bound": "tensor", "kernel": f"ffn (LN+1x1+GELU+1x1+dw3x3+GELU+1x1+res), c={c}, {n}x{H}x{H} px",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "ms_per_launch": ms, "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json)",
+            "note": "fp32 parity needs 3-way split operands on the tensor pipe: the reachable ceiling is peak/3"}
+
+
+def other_workload(args, dev):
+    import torch
+    import lgteun_b200
+    from lgteun_b200 import _abi
+    name = "wv3" if args.workload == "gf2" else "gf2"
+    bands, h, batch, desc = WORKLOADS[name]
+    batch = min(batch, 64)
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=2)
+    net.load_state_dict(golden_weights(bands))
+    net = net.to(dev).eval()
+    handle = net._runtime(dev)
+    ms, pan = synth_inputs(batch, bands, h)
+    ms, pan = ms.to(dev), pan.to(dev)
+    out = torch.empty(batch, bands, 4 * h, 4 * h, device=dev)
+    flags = 0 if args.skip_dead_priors else _abi.RUN_DEAD_PRIORS
+    s = torch.cuda.current_stream(dev)
+    for _ in range(3):
+        handle.forward(ms.data_ptr(), pan.data_ptr(), out.data_ptr(), batch, h, h, flags, s.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(s)
+    reps = 5
+    for _ in range(reps):
+        handle.forward(ms.data_ptr(), pan.data_ptr(), out.data_ptr(), batch, h, h, flags, s.cuda_stream)
+    e1.record(s)
+    torch.cuda.synchronize(dev)
+    t = e0.elapsed_time(e1) / reps
+    return {name: {"workload": desc, "batch": batch, "pairs_per_s": batch / (t * 1e-3), "ms_per_step": t}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gf2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--skip-dead-priors", action="store_true",
+                    help="skip prior_module[0..K-2] whose output the reference discards (identical result)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--other-workloads", action="store_true", default=True)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

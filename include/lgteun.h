@@ -1,0 +1,129 @@
+/* lgteun.h — C ABI of the B200-native LGTEUN forward hot path.
+ *
+ * Drop-in boundary: the reference calls
+ *     self.module_dict['core_module'](input_lr, input_pan)          models/unlg_former.py:80-85
+ * i.e. Pansharpening.forward(ms, pan)                               models/unlg_former.py:50-67
+ * The reference has no native FFI (it is pure PyTorch); these entry points are what a ctypes/cffi
+ * binding of that call binds (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *  - plain C types only: device pointers are `const float*` / `float*` into CUDA global memory of the
+ *    handle's device, `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *  - all tensors are fp32, contiguous; ms [N,B,h,w], pan [N,1,4h,4w], out [N,B,4h,4w] (NCHW) exactly as
+ *    the reference's forward(LrMS, PAN) receives/returns them;
+ *  - every function returns 0 on success or a negative LGTEUN_E* code; the message is available through
+ *    lgteun_last_error() (thread-local).  Nothing throws across the ABI.  Unsupported shapes are errors,
+ *    never a fallback: 4h and 4w must be powers of two in [16, 1024] (window 8 at two U-Net levels,
+ *    power-of-two FFT passes), B in {4, 8}.
+ *  - a handle is bound to one device and must be used by one host thread at a time (the reference's
+ *    nn.DataParallel path uses one replica, hence one handle, per GPU: models/base/base_model.py:95-97).
+ *  - the caller owns ms/pan/out; inputs are never written (base_model.py:304-305 reuses them).
+ */
+#ifndef LGTEUN_H_
+#define LGTEUN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lgteun_ctx lgteun_t;
+
+enum {
+  LGTEUN_OK = 0,
+  LGTEUN_EINVAL = -1,   /* bad argument / unsupported shape            */
+  LGTEUN_ECUDA = -2,    /* a CUDA runtime call failed                  */
+  LGTEUN_ESTATE = -3,   /* weights not loaded / missing state_dict key */
+  LGTEUN_ENOMEM = -4
+};
+
+/* forward() flags */
+enum {
+  LGTEUN_RUN_DEAD_PRIORS = 1, /* also execute prior_module[0..K-2], whose output the reference discards
+                                 (models/unlg_former.py:63-67); the returned tensor is identical        */
+  LGTEUN_NO_GRAPH = 2         /* launch kernels directly instead of replaying the cached CUDA graph      */
+};
+
+/* ABI version of this header (bumped on any signature change). */
+int lgteun_abi_version(void);
+
+/* Thread-local message of the last failing call ("" if none). */
+const char* lgteun_last_error(void);
+
+/* Pansharpening.__init__(cfg, logger, stage)  — models/unlg_former.py:22-48.
+ * bands = cfg.ms_chans (4: GF-2/WV-2, 8: WV-3), stages = K (config: 2, configs/unlg_former.py:92-94). */
+int lgteun_create(int device, int bands, int stages, lgteun_t** out);
+void lgteun_destroy(lgteun_t* ctx);
+
+/* Number of state_dict tensors the handle expects and the i-th key / element count
+ * (the weight ABI: SURVEY.md Appendix B; nn.Module.state_dict() of the reference class). */
+int lgteun_num_weights(const lgteun_t* ctx);
+const char* lgteun_weight_name(const lgteun_t* ctx, int i);
+int64_t lgteun_weight_numel(const lgteun_t* ctx, int i);
+
+/* load_state_dict: snapshot n fp32 device tensors (names = reference state_dict keys) into the handle's
+ * packed weight arena.  Every expected key must be present with the expected element count.
+ * Mirrors base_model.py:102-114 (module.load_state_dict(ckpt[name].state_dict())). */
+int lgteun_load_weights(lgteun_t* ctx, const char* const* names, const float* const* dev_ptrs,
+                        const int64_t* numels, int n, void* stream);
+
+/* Bytes of device workspace the handle holds for a given problem size (allocated lazily, grown on demand). */
+int64_t lgteun_workspace_bytes(const lgteun_t* ctx, int N, int h, int w);
+
+/* Pansharpening.forward(ms, pan) -> HrMS   — models/unlg_former.py:50-67.
+ * ms [N,B,h,w], pan [N,1,4h,4w], out [N,B,4h,4w]; device pointers; enqueued on `stream`. */
+int lgteun_forward(lgteun_t* ctx, const float* ms, const float* pan, float* out,
+                   int N, int h, int w, int flags, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D of ms/pan, forward, D2H of out, all on `stream`,
+ * returns after the result is in out_host.  This is the end-to-end path of base_model.py:293-305
+ * (set_batch_cuda -> get_model_output -> torch2np). */
+int lgteun_forward_host(lgteun_t* ctx, const float* ms_host, const float* pan_host, float* out_host,
+                        int N, int h, int w, int flags, void* stream);
+
+/* How many kernels one lgteun_forward of this size launches (graph nodes), for the bench's launch count. */
+int lgteun_forward_launches(lgteun_t* ctx, int N, int h, int w, int flags);
+
+/* ---- per-operator entry points (same kernels the forward chains; used by tests and ncu) ----------
+ * `prior` selects prior_module[prior]; `lgb` selects 0 = encoder_layers.0.0, 1 = bottleneck,
+ * 2 = decoder_layers.0.2; `block` the block inside that LGB.  NHWC tensors are [N,H,W,c]. */
+
+/* bmu.sampling_(x, s_factor) for s in {4, 2, 0.5} on NCHW planes  — basic_module_unformer_v2.py:21-23.
+ * scale_num/scale_den = 4/1, 2/1 or 1/2. */
+int lgteun_op_bicubic(lgteun_t* ctx, const float* x, float* y, int planes, int h, int w,
+                      int scale_num, int scale_den, void* stream);
+
+/* One data-module step  Z - eta[stage]*(DT(D(Z)-ms) + RT(R(Z)-pan))  — unlg_former.py:58-61.
+ * z_in/z_out [N,B,4h,4w] (must not alias). */
+int lgteun_op_data_step(lgteun_t* ctx, int stage, const float* z_in, const float* ms, const float* pan,
+                        float* z_out, int N, int h, int w, void* stream);
+
+/* patch_embedding.forward — LGT.py:85-88: NCHW [N,B,H,W] -> NHWC [N,H,W,4B]. */
+int lgteun_op_patch_embed(lgteun_t* ctx, int prior, const float* x_nchw, float* y_nhwc,
+                          int N, int H, int W, void* stream);
+
+/* residual(pre_norm(LGMixer))  — LGT.py:45-61,200-219: y = LGMixer(LN(x)) + x, NHWC [N,H,W,c]. */
+int lgteun_op_mixer(lgteun_t* ctx, int prior, int lgb, int block, const float* x, float* y,
+                    int N, int H, int W, void* stream);
+
+/* the two halves of the mixer on their own, input = LN'd half [N,H,W,c/2] as the reference modules see it:
+ * local_mixer.forward + window merge (LGT.py:130-146,207-208) and global_mixer.forward (LGT.py:162-180). */
+int lgteun_op_local_mixer(lgteun_t* ctx, int prior, int lgb, int block, const float* x_half, float* y_half,
+                          int N, int H, int W, void* stream);
+int lgteun_op_global_mixer(lgteun_t* ctx, int prior, int lgb, int block, const float* x_half, float* y_half,
+                           int N, int H, int W, void* stream);
+
+/* residual(pre_norm(feed_forward))  — LGT.py:95-109: y = FFN(LN(x)) + x, NHWC. */
+int lgteun_op_ffn(lgteun_t* ctx, int prior, int lgb, int block, const float* x, float* y,
+                  int N, int H, int W, void* stream);
+
+/* LGT.forward — LGT.py:314-344: NCHW [N,B,H,W] -> NCHW [N,B,H,W]. */
+int lgteun_op_prior(lgteun_t* ctx, int prior, const float* x_nchw, float* y_nchw,
+                    int N, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGTEUN_H_ */

@@ -1,0 +1,14 @@
+"""lgteun_b200 — B200-native (sm_100a) forward of LGTEUN's stage-wise unfolding network.
+
+Public surface (mirrors the reference's hot-path interface, models/unlg_former.py):
+    Pansharpening(cfg, logger, stage)   drop-in nn.Module, forward(ms, pan) -> HrMS
+    install(...)                        plug it behind the reference's MODELS registry / UnlgFormer runner
+    shard_range / forward_sharded       batch sharding for one-process-per-GPU inference
+The compute lives in lgteun_b200/csrc (CUDA) behind the C ABI of include/lgteun.h."""
+from . import _abi
+from .module import Pansharpening, expected_state_dict_keys, param_count
+from .register import install
+from .sharding import forward_sharded, shard_range
+
+__all__ = ["Pansharpening", "install", "shard_range", "forward_sharded", "expected_state_dict_keys", "param_count", "_abi"]
+__version__ = "0.1.0"

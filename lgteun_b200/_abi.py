@@ -1,0 +1,120 @@
+"""ctypes binding of the C ABI declared in include/lgteun.h (the only way Python talks to the kernels).
+
+The library is built in-tree by ``python -m lgteun_b200.build`` into ``lgteun_b200/_lgteun_cuda.so``.
+There is no fallback of any kind: if the library is missing or a call fails, an exception is raised."""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lgteun_cuda.so")
+
+RUN_DEAD_PRIORS = 1
+NO_GRAPH = 2
+EINVAL, ECUDA, ESTATE, ENOMEM = -1, -2, -3, -4
+
+# name -> (restype, argtypes); mirrors include/lgteun.h one to one (checked by tests/test_abi.py)
+_F = c_void_p  # float* (device or host)
+SIGNATURES = {
+    "lgteun_abi_version": (c_int, []),
+    "lgteun_last_error": (c_char_p, []),
+    "lgteun_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    "lgteun_destroy": (None, [c_void_p]),
+    "lgteun_num_weights": (c_int, [c_void_p]),
+    "lgteun_weight_name": (c_char_p, [c_void_p, c_int]),
+    "lgteun_weight_numel": (c_int64, [c_void_p, c_int]),
+    "lgteun_load_weights": (c_int, [c_void_p, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p]),
+    "lgteun_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int]),
+    "lgteun_forward": (c_int, [c_void_p, _F, _F, _F, c_int, c_int, c_int, c_int, c_void_p]),
+    "lgteun_forward_host": (c_int, [c_void_p, _F, _F, _F, c_int, c_int, c_int, c_int, c_void_p]),
+    "lgteun_forward_launches": (c_int, [c_void_p, c_int, c_int, c_int, c_int]),
+    "lgteun_op_bicubic": (c_int, [c_void_p, _F, _F, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "lgteun_op_data_step": (c_int, [c_void_p, c_int, _F, _F, _F, _F, c_int, c_int, c_int, c_void_p]),
+    "lgteun_op_patch_embed": (c_int, [c_void_p, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
+    "lgteun_op_mixer": (c_int, [c_void_p, c_int, c_int, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
+    "lgteun_op_local_mixer": (c_int, [c_void_p, c_int, c_int, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
+    "lgteun_op_global_mixer": (c_int, [c_void_p, c_int, c_int, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
+    "lgteun_op_ffn": (c_int, [c_void_p, c_int, c_int, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
+    "lgteun_op_prior": (c_int, [c_void_p, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m lgteun_b200.build` "
+                "(there is no CPU or PyTorch fallback for the LGTEUN forward)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return (lib().lgteun_last_error() or b"").decode()
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc in (EINVAL,):
+        raise ValueError(f"lgteun: {msg}")
+    if rc == ENOMEM:
+        raise MemoryError(f"lgteun: {msg}")
+    raise RuntimeError(f"lgteun (code {rc}): {msg}")
+
+
+class Handle:
+    """RAII wrapper of lgteun_t* (one per device, one host thread at a time)."""
+
+    def __init__(self, device, bands, stages):
+        self._p = c_void_p()
+        self.device, self.bands, self.stages = int(device), int(bands), int(stages)
+        check(lib().lgteun_create(self.device, self.bands, self.stages, ctypes.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None) and self._p.value:
+            lib().lgteun_destroy(self._p)
+            self._p = c_void_p()
+
+    __del__ = close
+
+    @property
+    def ptr(self):
+        return self._p
+
+    def weight_table(self):
+        n = lib().lgteun_num_weights(self._p)
+        return [(lib().lgteun_weight_name(self._p, i).decode(), lib().lgteun_weight_numel(self._p, i)) for i in range(n)]
+
+    def load_weights(self, tensors, stream=0):
+        """tensors: dict name -> contiguous fp32 CUDA tensor on this handle's device."""
+        names = list(tensors)
+        n = len(names)
+        c_names = (c_char_p * n)(*[s.encode() for s in names])
+        c_ptrs = (c_void_p * n)(*[tensors[s].data_ptr() for s in names])
+        c_nums = (c_int64 * n)(*[tensors[s].numel() for s in names])
+        check(lib().lgteun_load_weights(self._p, c_names, c_ptrs, c_nums, n, c_void_p(stream)))
+
+    def forward(self, ms_ptr, pan_ptr, out_ptr, N, h, w, flags=0, stream=0):
+        check(lib().lgteun_forward(self._p, ms_ptr, pan_ptr, out_ptr, N, h, w, flags, c_void_p(stream)))
+
+    def forward_host(self, ms_ptr, pan_ptr, out_ptr, N, h, w, flags=0, stream=0):
+        check(lib().lgteun_forward_host(self._p, ms_ptr, pan_ptr, out_ptr, N, h, w, flags, c_void_p(stream)))
+
+    def launches(self, N, h, w, flags=0):
+        return lib().lgteun_forward_launches(self._p, N, h, w, flags)
+
+    def workspace_bytes(self, N, h, w):
+        return lib().lgteun_workspace_bytes(self._p, N, h, w)
+
+    def op(self, name, *args, stream=0):
+        check(getattr(lib(), "lgteun_op_" + name)(self._p, *args, c_void_p(stream)))

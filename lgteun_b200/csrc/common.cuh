@@ -1,0 +1,132 @@
+// common.cuh — shared declarations of the LGTEUN sm_100a kernels.
+//
+// Internal data layout: the data module works on NCHW planes exactly as the reference
+// boundary delivers them; everything inside the Local-Global Transformer prior is NHWC fp32
+// ([N,H,W,c], channels innermost = 64..256 B per pixel) so that a pixel's channel vector is one
+// contiguous, vectorisable run and window / tile addressing is pure index arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lg {
+
+constexpr int kWin = 8;              // window_size, models/unlg_former.py:47
+constexpr int kHeads = 2;            // num_heads,   models/unlg_former.py:48
+constexpr float kLnEps = 1e-5f;      // nn.LayerNorm default, LGT.py:58
+constexpr int kMaxStages = 8;
+
+// ---- weight views (pointers into the packed arena; native PyTorch layouts) ---------------------
+struct BlockW {                       // one LGB block: LGT.py:231-239
+  const float *ln1_w, *ln1_b;         // blocks.j.0.fn.norm
+  const float *pos;                   // local_mixer.pos_emb        [1,2,64,64]
+  const float *pos_t;                 // derived: pos transposed to [2][key j][query i]
+  const float *qkv_w, *qkv_b;         // local_mixer.to_qkv         [3c/2, c/2]
+  const float *amp_w, *amp_b;         // global_mixer.conv_amp.0    [c/2]
+  const float *pha_w, *pha_b;         // global_mixer.conv_pha.0    [c/2]
+  const float *proj_w, *proj_b;       // proj                       [c, c]
+  const float *ln2_w, *ln2_b;         // blocks.j.1.fn.norm
+  const float *f0_w, *f0_b;           // net.0                      [4c, c]
+  const float *f1_w, *f1_b;           // net.2.point_conv           [4c, 4c]
+  const float *dw_w, *dw_b;           // net.2.depth_conv           [4c, 3, 3]
+  const float *f2_w, *f2_b;           // net.4                      [c, 4c]
+  const float *f0_wt, *f1_wt, *f2_wt; // derived: the three FFN weights transposed to [in][out]
+};
+
+struct PriorW {                       // one LGT: LGT.py:251-303
+  const float *pe_dw_w, *pe_dw_b;     // patch_embed.proj.0         [B]
+  const float *pe_w, *pe_b;           // patch_embed.proj.1         [C, B]
+  const float *pe_ln_w, *pe_ln_b;     // patch_embed.norm           [C]
+  BlockW enc[2], bott[1], dec[2];
+  const float *down_w, *down_b;       // encoder_layers.0.1.1       [2C, C]
+  const float *up_w, *up_b;           // decoder_layers.0.0.1       [C, 2C]
+  const float *fuse_w, *fuse_b;       // decoder_layers.0.1         [C, 2C]   input = [upsampled | skip]
+  const float *tail_w, *tail_b;       // tail.1                     [B, C]
+};
+
+struct DataW {                        // models/unlg_former.py:29-40
+  const float *d1_w, *d1_b, *d3_w, *d3_b;       // D.1, D.3     [B,3,3]
+  const float *dt1_w, *dt1_b, *dt3_w, *dt3_b;   // DT.1, DT.3
+  const float *r_w, *r_b;                       // R            [1,B]
+  const float *rt_w, *rt_b;                     // RT           [B,1]
+  const float *eta[kMaxStages];                 // eta.i        []
+};
+
+// ---- kernel launchers (one per .cu file) ---------------------------------------------------------
+// data_step.cu
+cudaError_t launch_bicubic(const float* x, float* y, int planes, int h, int w, int num, int den, cudaStream_t s);
+cudaError_t launch_data_step(const DataW& w, int stage, int B, const float* z_in, const float* ms, const float* pan,
+                             float* resid /*[N,B,h,w] scratch*/, float* z_out, int N, int h, int wd, cudaStream_t s);
+// pixel_ops.cu
+cudaError_t launch_patch_embed(const PriorW& w, int B, const float* x_nchw, float* y, int N, int H, int W, cudaStream_t s);
+cudaError_t launch_down(const PriorW& w, int C, const float* x, float* y, int N, int H, int W, cudaStream_t s);
+cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float* skip, float* y, int N, int H, int W,
+                           cudaStream_t s);
+cudaError_t launch_tail(const PriorW& w, int B, const float* fea, const float* x_nchw, float* y_nchw, int N, int H, int W,
+                        cudaStream_t s);
+// window_msa.cu
+//  pre_ln = 1: x is the un-normalised [N,H,W,c] map, LN(blocks.j.0.fn.norm) is applied on the fly and the first
+//  c/2 channels are used;  pre_ln = 0: x is already the [N,H,W,c/2] local half.
+cudaError_t launch_window_msa(const BlockW& w, int c, const float* x, float* y_half, int pre_ln, int N, int H, int W,
+                              cudaStream_t s);
+// fft_mixer.cu
+size_t spectrum_floats(int N, int H, int W, int c2);
+cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* spec, int pre_ln, int N, int H, int W,
+                                cudaStream_t s);
+cudaError_t launch_fft_cols(const BlockW& w, int c, float* spec, int N, int H, int W, cudaStream_t s);
+//  proj = 1: y[N,H,W,c] = proj(cat(local, |irfft|)) + xres ;  proj = 0: y[N,H,W,c/2] = |irfft| only.
+cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const float* local, const float* xres,
+                                float* y, int proj, int N, int H, int W, cudaStream_t s);
+cudaError_t fft_init_tables(cudaStream_t s);
+// ffn.cu
+size_t ffn_hidden_floats(int N, int H, int W, int c);
+cudaError_t launch_ffn(const BlockW& w, int c, const float* x, float* hidden, float* y, int N, int H, int W,
+                       cudaStream_t s);
+// misc
+cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s);
+cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r] = src[r][c]
+
+// ---- device helpers -----------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() exact form, LGT.py:97,99
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// LayerNorm over C register-resident channels (biased variance, eps inside the sqrt).
+template <int C>
+__device__ __forceinline__ void layer_norm_inplace(float (&v)[C], const float* __restrict__ g,
+                                                   const float* __restrict__ b) {
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) mean += v[i];
+  mean *= (1.0f / C);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    float d = v[i] - mean;
+    var = fmaf(d, d, var);
+  }
+  float rstd = 1.0f / sqrtf(var * (1.0f / C) + kLnEps);
+#pragma unroll
+  for (int i = 0; i < C; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
+}
+
+template <int C>
+__device__ __forceinline__ void load_vec(float (&v)[C], const float* __restrict__ p) {
+  static_assert(C % 4 == 0, "channel vectors are multiples of 4");
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) {
+    float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+template <int C>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[C]) {
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i)
+    *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+#endif
+
+}  // namespace lg

@@ -1,0 +1,421 @@
+// fft_mixer.cu — the global branch of LGMixer (models/common/LGT.py:149-180), a Fourier amplitude/phase
+// mixer on the second half of the channels:
+//     fre = rfft2(x); amp = |fre|; pha = angle(fre)                               LGT.py:166-169
+//     amp' = conv_amp(amp), pha' = conv_pha(pha)     (depthwise 1x1 = per-channel affine)   LGT.py:171-172
+//     out = | irfft2( complex(amp' cos pha' + 1e-8, amp' sin pha' + 1e-8) + 1e-8 ) |        LGT.py:174-178
+// followed (when PROJ) by the rest of LGMixer + residual: proj(cat(local, global)) + x      LGT.py:212-217, :51
+//
+// True-fp32 FFTs written here (no cuFFT): the phase branch cut makes the result ill-conditioned in the
+// spectrum, so twiddles are rounded from double and the four purely-real bins
+// (ky in {0,H/2}, kx in {0,W/2}) get an exact +0.0 imaginary part like the CPU oracle's rfft2.
+//
+// Three HBM-bound passes per block (spectrum layout S[n][y][kx][ch] complex64, ch innermost):
+//   rows_fwd : LN (optional) -> two real channels packed into one complex Stockham FFT along W -> split -> S
+//   cols     : in-place radix-4 DIF FFT along H in shared memory (digit-reversed order), pointwise
+//              amp/phase mixing, radix-4 DIT inverse (consumes digit-reversed order, no permutation pass)
+//   rows_inv : Hermitian rebuild (C2R ignores Im of bins 0 and W/2) -> inverse Stockham -> |.|/(HW)
+//              -> concat with the local branch -> proj 1x1 -> + residual
+#include <math.h>
+#include "common.cuh"
+
+namespace lg {
+
+constexpr int kTwN = 1024;                               // largest supported FFT length
+__device__ float2 g_tw[kTwN];                            // e^{-2 pi i k / 1024}, rounded from double
+
+cudaError_t fft_init_tables(cudaStream_t s) {
+  static float2 host[kTwN];
+  for (int k = 0; k < kTwN; ++k) {
+    double a = -2.0 * M_PI * (double)k / (double)kTwN;
+    host[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  // exact values on the axes / diagonals
+  host[0] = make_float2(1.f, 0.f);
+  host[kTwN / 4] = make_float2(0.f, -1.f);
+  host[kTwN / 2] = make_float2(-1.f, 0.f);
+  host[3 * kTwN / 4] = make_float2(0.f, 1.f);
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_tw, host, sizeof(host), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
+
+size_t spectrum_floats(int N, int H, int W, int c2) { return (size_t)N * H * (W / 2 + 1) * c2 * 2; }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {     // a * conj(b)
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// ---- natural-order Stockham FFT of NF sequences of length L held in shared memory ----------------------
+// a, b: ping-pong buffers [NF][L]; tw[j] = e^{-2 pi i j / L}.  SIGN = -1 forward, +1 inverse (unnormalised).
+// Returns the buffer holding the result.  All threads of the CTA must call it.
+template <int SIGN>
+__device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int NF, int tid, int nthreads) {
+  for (int Ns = 1; Ns < L;) {
+    const int rem = L / Ns;
+    if ((rem & 3) == 0) {
+      const int q = L >> 2;                        // items per sequence
+      const int tws = L / (Ns * 4);                // twiddle stride: w_{4Ns}^k = tw[k * tws]
+      for (int id = tid; id < NF * q; id += nthreads) {
+        const int f = id / q, j = id - f * q;
+        const int k = j & (Ns - 1);
+        const float2* src = a + f * L + j;
+        float2 v0 = src[0], v1 = src[q], v2 = src[2 * q], v3 = src[3 * q];
+        if (k) {
+          float2 w1 = tw[k * tws], w2 = tw[2 * k * tws], w3 = tw[3 * k * tws];
+          if (SIGN < 0) { v1 = cmul(v1, w1); v2 = cmul(v2, w2); v3 = cmul(v3, w3); }
+          else          { v1 = cmul_conj(v1, w1); v2 = cmul_conj(v2, w2); v3 = cmul_conj(v3, w3); }
+        }
+        // radix-4 butterfly; forward: o1 = v0 - i v1 - v2 + i v3, inverse: o1 = v0 + i v1 - v2 - i v3
+        float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+        float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+        float2 jd = (SIGN < 0) ? make_float2(d13.y, -d13.x) : make_float2(-d13.y, d13.x);   // (-/+ i) * d13
+        float2* dst = b + f * L + (j - k) * 4 + k;
+        dst[0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+        dst[Ns] = make_float2(d02.x + jd.x, d02.y + jd.y);
+        dst[2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+        dst[3 * Ns] = make_float2(d02.x - jd.x, d02.y - jd.y);
+      }
+      Ns <<= 2;
+    } else {
+      const int q = L >> 1;
+      const int tws = L / (Ns * 2);
+      for (int id = tid; id < NF * q; id += nthreads) {
+        const int f = id / q, j = id - f * q;
+        const int k = j & (Ns - 1);
+        const float2* src = a + f * L + j;
+        float2 v0 = src[0], v1 = src[q];
+        if (k) {
+          float2 w1 = tw[k * tws];
+          v1 = (SIGN < 0) ? cmul(v1, w1) : cmul_conj(v1, w1);
+        }
+        float2* dst = b + f * L + (j - k) * 2 + k;
+        dst[0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+        dst[Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+      }
+      Ns <<= 1;
+    }
+    __syncthreads();
+    float2* t = a; a = b; b = t;
+  }
+  return a;
+}
+
+constexpr int kFftThreads = 256;
+
+// ---- pass 1: rows forward ----------------------------------------------------------------------------
+template <int C2, bool PRE_LN>
+__global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
+                                                                   BlockW w, int W) {
+  constexpr int NF = C2 / 2;
+  constexpr int CIN = PRE_LN ? 2 * C2 : C2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);       // [W]
+  float2* bufA = tw + W;                                  // [NF][W]
+  float2* bufB = bufA + NF * W;
+  const int tid = threadIdx.x;
+  const size_t row = blockIdx.x;                          // n*H + y
+  for (int j = tid; j < W; j += kFftThreads) tw[j] = g_tw[j * (kTwN / W)];
+  for (int px = tid; px < W; px += kFftThreads) {
+    const float* src = x + (row * W + px) * CIN;
+    float g[C2];
+    if constexpr (PRE_LN) {
+      float v[CIN];
+      load_vec<CIN>(v, src);
+      float mean = 0.f;
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) mean += v[i];
+      mean *= (1.0f / CIN);
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) { float d = v[i] - mean; var = fmaf(d, d, var); }
+      float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+      for (int i = 0; i < C2; ++i)
+        g[i] = (v[C2 + i] - mean) * rstd * __ldg(w.ln1_w + C2 + i) + __ldg(w.ln1_b + C2 + i);
+    } else {
+      load_vec<C2>(g, src);
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) bufA[f * W + px] = make_float2(g[2 * f], g[2 * f + 1]);
+  }
+  __syncthreads();
+  const float2* res = stockham<-1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
+  // split the packed transform: channel a = 2f (real part), b = 2f+1 (imag part)
+  const int Wf = W / 2 + 1;
+  float4* out = reinterpret_cast<float4*>(spec + row * Wf * C2);
+  for (int id = tid; id < Wf * NF; id += kFftThreads) {
+    const int k = id / NF, f = id - k * NF;
+    float2 z = res[f * W + k], zm = res[f * W + ((W - k) & (W - 1))];
+    float4 o;
+    o.x = 0.5f * (z.x + zm.x);        // Xa = (Z[k] + conj(Z[W-k])) / 2
+    o.y = 0.5f * (z.y - zm.y);
+    o.z = 0.5f * (z.y + zm.y);        // Xb = (Z[k] - conj(Z[W-k])) / (2i)
+    o.w = 0.5f * (zm.x - z.x);
+    out[k * NF + f] = o;
+  }
+}
+
+// ---- pass 2: columns (forward, pointwise, inverse) -----------------------------------------------------
+// One CTA = Q adjacent complex lanes (kx*C2+ch) of one image, all H rows, in shared memory [H][Q].
+template <int Q>
+__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restrict__ spec, BlockW w, int H, int W, int C2,
+                                                               int lanes_per_row /* Wf*C2 */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);       // [H]
+  float2* d = tw + H;                                     // [H][Q]
+  const int tid = threadIdx.x;
+  const int l0 = blockIdx.x * Q;
+  const int nl = min(Q, lanes_per_row - l0);
+  float2* base = spec + (size_t)blockIdx.y * H * lanes_per_row + l0;
+  for (int j = tid; j < H; j += kFftThreads) tw[j] = g_tw[j * (kTwN / H)];
+  for (int id = tid; id < H * Q; id += kFftThreads) {
+    const int r = id / Q, l = id - r * Q;
+    d[id] = (l < nl) ? base[(size_t)r * lanes_per_row + l] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const bool odd = (__ffs(H) - 1) & 1;                    // log2(H) odd -> one trailing radix-2 stage
+  // forward: decimation in frequency, natural in -> digit-reversed out
+  for (int L = H; L >= 4; L >>= 2) {
+    const int q = L >> 2, tws = H / L;
+    for (int id = tid; id < (H >> 2) * Q; id += kFftThreads) {
+      const int l = id % Q, bf = id / Q;
+      const int blk = bf / q, j = bf - blk * q;
+      float2* p = d + (size_t)(blk * L + j) * Q + l;
+      float2 a0 = p[0], a1 = p[(size_t)q * Q], a2 = p[(size_t)2 * q * Q], a3 = p[(size_t)3 * q * Q];
+      float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+      float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
+      float2 mjd = make_float2(d13.y, -d13.x);            // -i * (a1 - a3)
+      float2 y0 = make_float2(s02.x + s13.x, s02.y + s13.y);
+      float2 y1 = make_float2(d02.x + mjd.x, d02.y + mjd.y);
+      float2 y2 = make_float2(s02.x - s13.x, s02.y - s13.y);
+      float2 y3 = make_float2(d02.x - mjd.x, d02.y - mjd.y);
+      if (j) { y1 = cmul(y1, tw[j * tws]); y2 = cmul(y2, tw[2 * j * tws]); y3 = cmul(y3, tw[3 * j * tws]); }
+      p[0] = y0; p[(size_t)q * Q] = y1; p[(size_t)2 * q * Q] = y2; p[(size_t)3 * q * Q] = y3;
+    }
+    __syncthreads();
+  }
+  if (odd) {
+    for (int id = tid; id < (H >> 1) * Q; id += kFftThreads) {
+      const int l = id % Q, bf = id / Q;
+      float2* p = d + (size_t)(2 * bf) * Q + l;
+      float2 a0 = p[0], a1 = p[Q];
+      p[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
+      p[Q] = make_float2(a0.x - a1.x, a0.y - a1.y);
+    }
+    __syncthreads();
+  }
+  // pointwise amplitude / phase mixing.  ky = 0 sits at position 0, ky = H/2 at position 1 (odd log2 H) or 2.
+  const int pos_nyq = odd ? 1 : 2;
+  for (int id = tid; id < H * Q; id += kFftThreads) {
+    const int pos = id / Q, l = id - pos * Q;
+    if (l >= nl) continue;
+    const int lane = l0 + l;
+    const int kx = lane / C2, ch = lane - kx * C2;
+    float2 z = d[id];
+    if ((pos == 0 || pos == pos_nyq) && (kx == 0 || kx == W / 2)) z.y = 0.0f;   // exactly-real bins: +0.0 (F7)
+    float amp = hypotf(z.x, z.y);
+    float pha = atan2f(z.y, z.x);
+    amp = amp * __ldg(w.amp_w + ch) + __ldg(w.amp_b + ch);
+    pha = pha * __ldg(w.pha_w + ch) + __ldg(w.pha_b + ch);
+    float sn, cs;
+    sincosf(pha, &sn, &cs);
+    float re = amp * cs + 1e-8f;
+    float im = amp * sn + 1e-8f;
+    re = re + 1e-8f;                                       // complex(real, imag) + 1e-8 adds to the real part
+    d[id] = make_float2(re, im);
+  }
+  __syncthreads();
+  // inverse: decimation in time mirror of the forward graph, digit-reversed in -> natural out (unnormalised)
+  if (odd) {
+    for (int id = tid; id < (H >> 1) * Q; id += kFftThreads) {
+      const int l = id % Q, bf = id / Q;
+      float2* p = d + (size_t)(2 * bf) * Q + l;
+      float2 a0 = p[0], a1 = p[Q];
+      p[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
+      p[Q] = make_float2(a0.x - a1.x, a0.y - a1.y);
+    }
+    __syncthreads();
+  }
+  for (int L = odd ? 8 : 4; L <= H; L <<= 2) {
+    const int q = L >> 2, tws = H / L;
+    for (int id = tid; id < (H >> 2) * Q; id += kFftThreads) {
+      const int l = id % Q, bf = id / Q;
+      const int blk = bf / q, j = bf - blk * q;
+      float2* p = d + (size_t)(blk * L + j) * Q + l;
+      float2 a0 = p[0], a1 = p[(size_t)q * Q], a2 = p[(size_t)2 * q * Q], a3 = p[(size_t)3 * q * Q];
+      if (j) { a1 = cmul_conj(a1, tw[j * tws]); a2 = cmul_conj(a2, tw[2 * j * tws]); a3 = cmul_conj(a3, tw[3 * j * tws]); }
+      float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+      float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
+      float2 jd = make_float2(-d13.y, d13.x);             // +i * (a1 - a3)
+      p[0] = make_float2(s02.x + s13.x, s02.y + s13.y);
+      p[(size_t)q * Q] = make_float2(d02.x + jd.x, d02.y + jd.y);
+      p[(size_t)2 * q * Q] = make_float2(s02.x - s13.x, s02.y - s13.y);
+      p[(size_t)3 * q * Q] = make_float2(d02.x - jd.x, d02.y - jd.y);
+    }
+    __syncthreads();
+  }
+  for (int id = tid; id < H * Q; id += kFftThreads) {
+    const int r = id / Q, l = id - r * Q;
+    if (l < nl) base[(size_t)r * lanes_per_row + l] = d[id];
+  }
+}
+
+// ---- pass 3: rows inverse (+ proj + residual) ------------------------------------------------------------
+template <int C2, bool PROJ>
+__global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2* __restrict__ spec,
+                                                                   const float* __restrict__ local,
+                                                                   const float* __restrict__ xres, float* __restrict__ y,
+                                                                   BlockW w, int W, float scale) {
+  constexpr int NF = C2 / 2;
+  constexpr int C = 2 * C2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);       // [W]
+  float2* bufA = tw + W;                                  // [NF][W]
+  float2* bufB = bufA + NF * W;
+  float* sW = reinterpret_cast<float*>(bufB + NF * W);    // [C][C] proj weight (PROJ only)
+  float* sBias = sW + C * C;                              // [C]
+  const int tid = threadIdx.x;
+  const size_t row = blockIdx.x;
+  const int Wf = W / 2 + 1;
+  for (int j = tid; j < W; j += kFftThreads) tw[j] = g_tw[j * (kTwN / W)];
+  if constexpr (PROJ) {
+    for (int i = tid; i < C * C; i += kFftThreads) sW[i] = __ldg(w.proj_w + i);
+    for (int i = tid; i < C; i += kFftThreads) sBias[i] = __ldg(w.proj_b + i);
+  }
+  const float4* in = reinterpret_cast<const float4*>(spec + row * Wf * C2);
+  for (int id = tid; id < Wf * NF; id += kFftThreads) {
+    const int k = id / NF, f = id - k * NF;
+    float4 v = __ldg(in + k * NF + f);                    // (Xa.re, Xa.im, Xb.re, Xb.im)
+    if (k == 0 || k == W / 2) {                           // C2R ignores Im of the DC and Nyquist bins
+      bufA[f * W + k] = make_float2(v.x, v.z);
+    } else {
+      bufA[f * W + k] = make_float2(v.x - v.w, v.y + v.z);          // Xa + i Xb
+      bufA[f * W + W - k] = make_float2(v.x + v.w, v.z - v.y);      // conj(Xa) + i conj(Xb)
+    }
+  }
+  __syncthreads();
+  const float2* res = stockham<+1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
+  for (int px = tid; px < W; px += kFftThreads) {
+    float g[C2];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      float2 z = res[f * W + px];
+      g[2 * f] = fabsf(z.x * scale);
+      g[2 * f + 1] = fabsf(z.y * scale);
+    }
+    if constexpr (!PROJ) {
+      store_vec<C2>(y + (row * W + px) * C2, g);
+    } else {
+      float cat[C];
+      {
+        float t[C2];
+        load_vec<C2>(t, local + (row * W + px) * C2);
+#pragma unroll
+        for (int i = 0; i < C2; ++i) { cat[i] = t[i]; cat[C2 + i] = g[i]; }
+      }
+      const float* xr = xres + (row * W + px) * C;
+      float* dst = y + (row * W + px) * C;
+#pragma unroll 1
+      for (int o = 0; o < C; o += 4) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          a0 = fmaf(sW[(o + 0) * C + k], cat[k], a0);
+          a1 = fmaf(sW[(o + 1) * C + k], cat[k], a1);
+          a2 = fmaf(sW[(o + 2) * C + k], cat[k], a2);
+          a3 = fmaf(sW[(o + 3) * C + k], cat[k], a3);
+        }
+        float4 r = *reinterpret_cast<const float4*>(xr + o);
+        *reinterpret_cast<float4*>(dst + o) = make_float4((a0 + sBias[o]) + r.x, (a1 + sBias[o + 1]) + r.y,
+                                                          (a2 + sBias[o + 2]) + r.z, (a3 + sBias[o + 3]) + r.w);
+      }
+    }
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------------
+static bool pow2_in_range(int v) { return v >= 8 && v <= kTwN && (v & (v - 1)) == 0; }
+
+template <int C2>
+static cudaError_t rows_fwd_t(const BlockW& w, const float* x, float* spec, int pre_ln, int N, int H, int W, cudaStream_t s) {
+  size_t smem = (size_t)(W + 2 * (C2 / 2) * W) * sizeof(float2);
+  cudaError_t e;
+  if (pre_ln) {
+    e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fft_rows_fwd_kernel<C2, true><<<N * H, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
+  } else {
+    e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fft_rows_fwd_kernel<C2, false><<<N * H, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* spec, int pre_ln, int N, int H, int W,
+                                cudaStream_t s) {
+  if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  switch (c) {
+    case 16: return rows_fwd_t<8>(w, x, spec, pre_ln, N, H, W, s);
+    case 32: return rows_fwd_t<16>(w, x, spec, pre_ln, N, H, W, s);
+    case 64: return rows_fwd_t<32>(w, x, spec, pre_ln, N, H, W, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int Q>
+static cudaError_t cols_t(const BlockW& w, int c2, float* spec, int N, int H, int W, cudaStream_t s) {
+  const int lanes = (W / 2 + 1) * c2;
+  size_t smem = (size_t)(H + H * Q) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_cols_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((lanes + Q - 1) / Q, N);
+  fft_cols_kernel<Q><<<grid, kFftThreads, smem, s>>>(reinterpret_cast<float2*>(spec), w, H, W, c2, lanes);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fft_cols(const BlockW& w, int c, float* spec, int N, int H, int W, cudaStream_t s) {
+  if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  const int c2 = c / 2;
+  if (H <= 128) return cols_t<64>(w, c2, spec, N, H, W, s);
+  if (H == 256) return cols_t<32>(w, c2, spec, N, H, W, s);
+  if (H == 512) return cols_t<16>(w, c2, spec, N, H, W, s);
+  return cols_t<8>(w, c2, spec, N, H, W, s);
+}
+
+template <int C2>
+static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* local, const float* xres, float* y, int proj,
+                              int N, int H, int W, cudaStream_t s) {
+  constexpr int C = 2 * C2;
+  size_t smem = (size_t)(W + 2 * (C2 / 2) * W) * sizeof(float2) + (proj ? (size_t)(C * C + C) * sizeof(float) : 0);
+  const float scale = 1.0f / ((float)H * (float)W);
+  cudaError_t e;
+  if (proj) {
+    e = cudaFuncSetAttribute(fft_rows_inv_kernel<C2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fft_rows_inv_kernel<C2, true><<<N * H, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
+                                                                   W, scale);
+  } else {
+    e = cudaFuncSetAttribute(fft_rows_inv_kernel<C2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fft_rows_inv_kernel<C2, false><<<N * H, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y,
+                                                                    w, W, scale);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
+                                int proj, int N, int H, int W, cudaStream_t s) {
+  if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  switch (c) {
+    case 16: return rows_inv_t<8>(w, spec, local, xres, y, proj, N, H, W, s);
+    case 32: return rows_inv_t<16>(w, spec, local, xres, y, proj, N, H, W, s);
+    case 64: return rows_inv_t<32>(w, spec, local, xres, y, proj, N, H, W, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace lg

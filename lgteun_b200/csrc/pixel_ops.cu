@@ -1,0 +1,260 @@
+// pixel_ops.cu — the U-Net glue of the LGT prior (models/common/LGT.py), one thread per output pixel,
+// NHWC inside, NCHW only at the prior's boundary.  All HBM-bound (<10 FLOP/B): one read of the inputs,
+// one write of the output, weights broadcast from shared memory.
+//   patch_embed : LGT.py:72-88   depthwise 1x1 -> 1x1 B->C -> LayerNorm(C)          NCHW -> NHWC
+//   down        : LGT.py:280-281 bicubic 1/2 -> 1x1 C->2C                            NHWC -> NHWC (half res)
+//   up_fuse     : LGT.py:294-295,336-338  bicubic x2 -> 1x1 2C->C ; cat(up, skip) -> 1x1 2C->C
+//   tail        : LGT.py:302-303,342      bicubic x1 (identity taps [0,1,0,0]) -> 1x1 C->B ; + x   NHWC -> NCHW
+#include "common.cuh"
+
+namespace lg {
+
+// ---- patch embedding -------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ x, float* __restrict__ y, PriorW w,
+                                                           int HW, long long total) {
+  constexpr int C = 4 * B;
+  __shared__ float sW[C * B], sB[C], sG[C], sBeta[C], sDw[B], sDb[B];
+  for (int i = threadIdx.x; i < C * B; i += 256) sW[i] = __ldg(w.pe_w + i);
+  for (int i = threadIdx.x; i < C; i += 256) {
+    sB[i] = __ldg(w.pe_b + i); sG[i] = __ldg(w.pe_ln_w + i); sBeta[i] = __ldg(w.pe_ln_b + i);
+  }
+  if (threadIdx.x < B) { sDw[threadIdx.x] = __ldg(w.pe_dw_w + threadIdx.x); sDb[threadIdx.x] = __ldg(w.pe_dw_b + threadIdx.x); }
+  __syncthreads();
+  long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= total) return;
+  long long n = p / HW;
+  int r = (int)(p - n * HW);
+  float t[B];
+#pragma unroll
+  for (int b = 0; b < B; ++b) t[b] = fmaf(sDw[b], __ldg(x + (n * B + b) * HW + r), sDb[b]);
+  float v[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int b = 0; b < B; ++b) acc = fmaf(sW[c * B + b], t[b], acc);
+    v[c] = acc + sB[c];
+  }
+  layer_norm_inplace<C>(v, sG, sBeta);
+  store_vec<C>(y + p * C, v);
+}
+
+cudaError_t launch_patch_embed(const PriorW& w, int B, const float* x, float* y, int N, int H, int W, cudaStream_t s) {
+  long long total = (long long)N * H * W;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (B == 4) patch_embed_kernel<4><<<grid, 256, 0, s>>>(x, y, w, H * W, total);
+  else if (B == 8) patch_embed_kernel<8><<<grid, 256, 0, s>>>(x, y, w, H * W, total);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ---- dense per-pixel matvec with weights [NOUT][K] in shared memory ---------------------------------
+// out[o] = bias[o] + sum_k W[o][k] v[k]; processed 4 outputs at a time to bound live registers.
+template <int K, int NOUT>
+__device__ __forceinline__ void matvec_store(const float (&v)[K], const float* __restrict__ sW,
+                                             const float* __restrict__ sBias, float* __restrict__ dst) {
+#pragma unroll
+  for (int o = 0; o < NOUT; o += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      a0 = fmaf(sW[(o + 0) * K + k], v[k], a0);
+      a1 = fmaf(sW[(o + 1) * K + k], v[k], a1);
+      a2 = fmaf(sW[(o + 2) * K + k], v[k], a2);
+      a3 = fmaf(sW[(o + 3) * K + k], v[k], a3);
+    }
+    *reinterpret_cast<float4*>(dst + o) =
+        make_float4(a0 + sBias[o], a1 + sBias[o + 1], a2 + sBias[o + 2], a3 + sBias[o + 3]);
+  }
+}
+
+// ---- down unit -----------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) down_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                    const float* __restrict__ wt, const float* __restrict__ bias,
+                                                    int H, int W, long long total) {
+  extern __shared__ float smem[];
+  float* sW = smem;                 // [2C][C]
+  float* sB = smem + 2 * C * C;     // [2C]
+  for (int i = threadIdx.x; i < 2 * C * C; i += 128) sW[i] = __ldg(wt + i);
+  for (int i = threadIdx.x; i < 2 * C; i += 128) sB[i] = __ldg(bias + i);
+  __syncthreads();
+  const int oh = H / 2, ow = W / 2;
+  long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (p >= total) return;
+  int ox = (int)(p % ow);
+  long long q = p / ow;
+  int oy = (int)(q % oh);
+  long long n = q / oh;
+  const float dn[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
+  float v[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int gy = clampi(2 * oy - 1 + a, 0, H - 1);
+    float r[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) r[c] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int gx = clampi(2 * ox - 1 + b, 0, W - 1);
+      float t[C];
+      load_vec<C>(t, x + ((n * H + gy) * W + gx) * C);
+#pragma unroll
+      for (int c = 0; c < C; ++c) r[c] = fmaf(dn[b], t[c], r[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = fmaf(dn[a], r[c], v[c]);
+  }
+  matvec_store<C, 2 * C>(v, sW, sB, y + p * (2 * C));
+}
+
+cudaError_t launch_down(const PriorW& w, int C, const float* x, float* y, int N, int H, int W, cudaStream_t s) {
+  long long total = (long long)N * (H / 2) * (W / 2);
+  unsigned grid = (unsigned)((total + 127) / 128);
+  size_t smem = (size_t)(2 * C * C + 2 * C) * sizeof(float);
+  if (C == 16) down_kernel<16><<<grid, 128, smem, s>>>(x, y, w.down_w, w.down_b, H, W, total);
+  else if (C == 32) down_kernel<32><<<grid, 128, smem, s>>>(x, y, w.down_w, w.down_b, H, W, total);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ---- up unit + skip fusion ---------------------------------------------------------------------------
+// low [N,H/2,W/2,2C] -> bicubic x2 -> up_w (2C->C) ; y = fuse_w[:, :C] up + fuse_w[:, C:] skip + fuse_b
+template <int C>
+__global__ void __launch_bounds__(128) up_fuse_kernel(const float* __restrict__ low, const float* __restrict__ skip,
+                                                       float* __restrict__ y, PriorW w, int H, int W, long long total) {
+  extern __shared__ float smem[];
+  float* sUp = smem;                    // [C][2C]
+  float* sFu = sUp + 2 * C * C;         // [C][2C]
+  float* sUb = sFu + 2 * C * C;         // [C]
+  float* sFb = sUb + C;                 // [C]
+  for (int i = threadIdx.x; i < 2 * C * C; i += 128) { sUp[i] = __ldg(w.up_w + i); sFu[i] = __ldg(w.fuse_w + i); }
+  for (int i = threadIdx.x; i < C; i += 128) { sUb[i] = __ldg(w.up_b + i); sFb[i] = __ldg(w.fuse_b + i); }
+  __syncthreads();
+  const int lh = H / 2, lw = W / 2;
+  long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (p >= total) return;
+  int ox = (int)(p % W);
+  long long q = p / W;
+  int oy = (int)(q % H);
+  long long n = q / H;
+  // x2 taps: even dst 2q -> src q-2..q+1 (t=.75), odd dst 2q+1 -> src q-1..q+2 (t=.25)
+  const float te[4] = {-0.03515625f, 0.26171875f, 0.87890625f, -0.10546875f};
+  const float to[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
+  const int fy = (oy >> 1) - ((oy & 1) ? 1 : 2), fx = (ox >> 1) - ((ox & 1) ? 1 : 2);
+  float u[2 * C];
+#pragma unroll
+  for (int c = 0; c < 2 * C; ++c) u[c] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int gy = clampi(fy + a, 0, lh - 1);
+    float wy = (oy & 1) ? to[a] : te[a];
+    float r[2 * C];
+#pragma unroll
+    for (int c = 0; c < 2 * C; ++c) r[c] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int gx = clampi(fx + b, 0, lw - 1);
+      float wx = (ox & 1) ? to[b] : te[b];
+      const float* src = low + ((n * lh + gy) * lw + gx) * (2 * C);
+#pragma unroll
+      for (int c4 = 0; c4 < 2 * C; c4 += 4) {
+        float4 t = *reinterpret_cast<const float4*>(src + c4);
+        r[c4] = fmaf(wx, t.x, r[c4]); r[c4 + 1] = fmaf(wx, t.y, r[c4 + 1]);
+        r[c4 + 2] = fmaf(wx, t.z, r[c4 + 2]); r[c4 + 3] = fmaf(wx, t.w, r[c4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2 * C; ++c) u[c] = fmaf(wy, r[c], u[c]);
+  }
+  float cat[2 * C];                      // [up | skip]
+#pragma unroll
+  for (int o = 0; o < C; ++o) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * C; ++k) acc = fmaf(sUp[o * 2 * C + k], u[k], acc);
+    cat[o] = acc + sUb[o];
+  }
+  {
+    float t[C];
+    load_vec<C>(t, skip + p * C);
+#pragma unroll
+    for (int c = 0; c < C; ++c) cat[C + c] = t[c];
+  }
+  matvec_store<2 * C, C>(cat, sFu, sFb, y + p * C);
+}
+
+cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float* skip, float* y, int N, int H, int W,
+                           cudaStream_t s) {
+  long long total = (long long)N * H * W;
+  unsigned grid = (unsigned)((total + 127) / 128);
+  size_t smem = (size_t)(4 * C * C + 2 * C) * sizeof(float);
+  if (C == 16) up_fuse_kernel<16><<<grid, 128, smem, s>>>(low, skip, y, w, H, W, total);
+  else if (C == 32) up_fuse_kernel<32><<<grid, 128, smem, s>>>(low, skip, y, w, H, W, total);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ---- tail + global residual ----------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea, const float* __restrict__ x,
+                                                    float* __restrict__ y, const float* __restrict__ wt,
+                                                    const float* __restrict__ bias, int HW, long long total) {
+  constexpr int C = 4 * B;
+  __shared__ float sW[B * C], sB[B];
+  for (int i = threadIdx.x; i < B * C; i += 256) sW[i] = __ldg(wt + i);
+  if (threadIdx.x < B) sB[threadIdx.x] = __ldg(bias + threadIdx.x);
+  __syncthreads();
+  long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= total) return;
+  long long n = p / HW;
+  int r = (int)(p - n * HW);
+  float v[C];
+  load_vec<C>(v, fea + p * C);
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc = fmaf(sW[b * C + c], v[c], acc);
+    size_t o = (size_t)(n * B + b) * HW + r;
+    y[o] = (acc + sB[b]) + __ldg(x + o);
+  }
+}
+
+cudaError_t launch_tail(const PriorW& w, int B, const float* fea, const float* x, float* y, int N, int H, int W,
+                        cudaStream_t s) {
+  long long total = (long long)N * H * W;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (B == 4) tail_kernel<4><<<grid, 256, 0, s>>>(fea, x, y, w.tail_w, w.tail_b, H * W, total);
+  else if (B == 8) tail_kernel<8><<<grid, 256, 0, s>>>(fea, x, y, w.tail_w, w.tail_b, H * W, total);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// pos_emb [2][i][j] -> [2][j][i] so that a warp of consecutive queries reads consecutive words
+__global__ void transpose_pos_kernel(const float* __restrict__ pos, float* __restrict__ pos_t) {
+  int idx = blockIdx.x * 256 + threadIdx.x;       // over [2][64][64] of the destination
+  if (idx >= 2 * 64 * 64) return;
+  int h = idx >> 12, j = (idx >> 6) & 63, i = idx & 63;
+  pos_t[idx] = pos[(h << 12) + (i << 6) + j];
+}
+cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s) {
+  transpose_pos_kernel<<<32, 256, 0, s>>>(pos, pos_t);
+  return cudaGetLastError();
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int c = idx / rows, r = idx - c * rows;          // idx enumerates dst [cols][rows]
+  dst[idx] = src[(size_t)r * cols + c];
+}
+cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s) {
+  transpose_kernel<<<(rows * cols + 255) / 256, 256, 0, s>>>(src, dst, rows, cols);
+  return cudaGetLastError();
+}
+
+}  // namespace lg

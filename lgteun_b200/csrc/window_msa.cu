@@ -1,0 +1,193 @@
+// window_msa.cu — the local branch of LGMixer: 8x8-window multi-head self-attention on the first half of
+// the channels (models/common/LGT.py:112-146, window merge :207-208), fused with the pre-norm LayerNorm
+// (LGT.py:54-61) and the to_qkv 1x1 conv.
+//
+//   per window (64 tokens, token = i*8+j, LGT.py:135) and head (2 heads, channel = head*d + c, LGT.py:138):
+//     q,k,v = to_qkv(x_win) split in that order along out-channels (LGT.py:136)
+//     out   = softmax(q*d^-0.5 . k^T + pos_emb[head]) . v                               (LGT.py:139-143)
+//
+// The window partition / reverse rearranges of the reference (≈40 copy kernels per stage) do not exist
+// here: a window is addressed in place inside the NHWC map.  Logits never leave registers (the reference
+// materialises a [N*nWin,2,64,64] tensor in HBM).  One thread owns one (window, head, query) row:
+// 64 logits in registers, K/V rows broadcast from shared memory, pos_emb pre-transposed to [head][key][query]
+// so the per-query reads are conflict-free.
+#include "common.cuh"
+
+namespace lg {
+
+constexpr int kWinPerIter = 2;          // windows processed concurrently by one CTA (128 threads each)
+constexpr int kMsaThreads = 128 * kWinPerIter;
+
+template <int C2>
+struct MsaSmem {
+  static constexpr int D = C2 / kHeads;
+  float pos_t[kHeads * 64 * 64];                    // [h][j][i]
+  float wqkv[3 * C2 * C2];                          // [3*C2][C2]
+  float bqkv[3 * C2];
+  float xs[kWinPerIter][C2][64 + 1];                // LN'd local half, channel-major (conflict-free per-token reads)
+  float ks[kWinPerIter][kHeads][64][D];
+  float vs[kWinPerIter][kHeads][64][D];
+};
+
+template <int C2, bool PRE_LN>
+__global__ void __launch_bounds__(kMsaThreads) window_msa_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                  BlockW w, int H, int W, int total_windows,
+                                                                  int windows_per_cta) {
+  constexpr int D = C2 / kHeads;
+  constexpr int CIN = PRE_LN ? 2 * C2 : C2;         // channels per pixel of the input map
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MsaSmem<C2>& sm = *reinterpret_cast<MsaSmem<C2>*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kHeads * 64 * 64; i += kMsaThreads) sm.pos_t[i] = __ldg(w.pos_t + i);
+  for (int i = tid; i < 3 * C2 * C2; i += kMsaThreads) sm.wqkv[i] = __ldg(w.qkv_w + i);
+  for (int i = tid; i < 3 * C2; i += kMsaThreads) sm.bqkv[i] = __ldg(w.qkv_b + i);
+
+  const int nwx = W / kWin, nwy = H / kWin;
+  const int slot = tid >> 7;                        // which of the concurrent windows
+  const int lt = tid & 127;
+  const int head = lt >> 6, tok = lt & 63;
+  // head_channel ** -0.5 rounded to fp32 like the reference's python-float * tensor (LGT.py:119,139)
+  const float scale = (D == 4) ? 0.5f : (D == 8) ? 0.35355339059327379f : (D == 16) ? 0.25f : 0.17677669529663689f;
+
+  const int w_begin = blockIdx.x * windows_per_cta;
+  const int w_end = min(w_begin + windows_per_cta, total_windows);
+  for (int wbase = w_begin; wbase < w_end; wbase += kWinPerIter) {
+    const int widx = wbase + slot;
+    const bool active = widx < w_end;
+    __syncthreads();                                // previous iteration's K/V/xs fully consumed; weights loaded
+    int n = 0, wy = 0, wx = 0;
+    if (active) {
+      wx = widx % nwx;
+      int q = widx / nwx;
+      wy = q % nwy;
+      n = q / nwy;
+    }
+    // 1) load (+ LayerNorm) : threads 0..63 of each slot own one token each
+    if (active && lt < 64) {
+      const int py = wy * kWin + (lt >> 3), px = wx * kWin + (lt & 7);
+      const float* src = x + (((size_t)n * H + py) * W + px) * CIN;
+      if constexpr (PRE_LN) {
+        float v[CIN];
+        load_vec<CIN>(v, src);
+        // LayerNorm over all c channels, but only the local half is needed afterwards
+        float mean = 0.f;
+#pragma unroll
+        for (int i = 0; i < CIN; ++i) mean += v[i];
+        mean *= (1.0f / CIN);
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < CIN; ++i) { float d = v[i] - mean; var = fmaf(d, d, var); }
+        float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+        for (int i = 0; i < C2; ++i)
+          sm.xs[slot][i][lt] = (v[i] - mean) * rstd * __ldg(w.ln1_w + i) + __ldg(w.ln1_b + i);
+      } else {
+        float v[C2];
+        load_vec<C2>(v, src);
+#pragma unroll
+        for (int i = 0; i < C2; ++i) sm.xs[slot][i][lt] = v[i];
+      }
+    }
+    __syncthreads();
+    // 2) q/k/v of this thread's (head, token)
+    float q[D];
+    if (active) {
+      float kk[D], vv[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        q[j] = sm.bqkv[head * D + j];
+        kk[j] = sm.bqkv[C2 + head * D + j];
+        vv[j] = sm.bqkv[2 * C2 + head * D + j];
+      }
+#pragma unroll
+      for (int k = 0; k < C2; ++k) {
+        const float xv = sm.xs[slot][k][tok];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          q[j] = fmaf(sm.wqkv[(head * D + j) * C2 + k], xv, q[j]);
+          kk[j] = fmaf(sm.wqkv[(C2 + head * D + j) * C2 + k], xv, kk[j]);
+          vv[j] = fmaf(sm.wqkv[(2 * C2 + head * D + j) * C2 + k], xv, vv[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        q[j] *= scale;
+        sm.ks[slot][head][tok][j] = kk[j];
+        sm.vs[slot][head][tok][j] = vv[j];
+      }
+    }
+    __syncthreads();
+    // 3) logits + softmax + PV, all in registers
+    if (active) {
+      float s[64];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        float acc = sm.pos_t[(head * 64 + j) * 64 + tok];
+#pragma unroll
+        for (int c4 = 0; c4 < D; c4 += 4) {
+          float4 kv = *reinterpret_cast<const float4*>(&sm.ks[slot][head][j][c4]);
+          acc = fmaf(q[c4], kv.x, acc); acc = fmaf(q[c4 + 1], kv.y, acc);
+          acc = fmaf(q[c4 + 2], kv.z, acc); acc = fmaf(q[c4 + 3], kv.w, acc);
+        }
+        s[j] = acc;
+        mx = fmaxf(mx, acc);
+      }
+      float sum = 0.f;
+      float o[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) o[c] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        float p = expf(s[j] - mx);
+        sum += p;
+#pragma unroll
+        for (int c4 = 0; c4 < D; c4 += 4) {
+          float4 vv = *reinterpret_cast<const float4*>(&sm.vs[slot][head][j][c4]);
+          o[c4] = fmaf(p, vv.x, o[c4]); o[c4 + 1] = fmaf(p, vv.y, o[c4 + 1]);
+          o[c4 + 2] = fmaf(p, vv.z, o[c4 + 2]); o[c4 + 3] = fmaf(p, vv.w, o[c4 + 3]);
+        }
+      }
+      const float inv = 1.0f / sum;
+      const int py = wy * kWin + (tok >> 3), px = wx * kWin + (tok & 7);
+      float* dst = y + (((size_t)n * H + py) * W + px) * C2 + head * D;
+#pragma unroll
+      for (int c4 = 0; c4 < D; c4 += 4)
+        *reinterpret_cast<float4*>(dst + c4) =
+            make_float4(o[c4] * inv, o[c4 + 1] * inv, o[c4 + 2] * inv, o[c4 + 3] * inv);
+    }
+  }
+}
+
+template <int C2>
+static cudaError_t launch_msa_t(const BlockW& w, const float* x, float* y, int pre_ln, int N, int H, int W,
+                                cudaStream_t s) {
+  const int total = N * (H / kWin) * (W / kWin);
+  int per_cta = 16;                                  // amortise the 32 KB pos_emb + weight staging
+  while (per_cta > kWinPerIter && (total + per_cta - 1) / per_cta < 2 * 148) per_cta /= 2;
+  const int grid = (total + per_cta - 1) / per_cta;
+  const size_t smem = sizeof(MsaSmem<C2>);
+  cudaError_t e;
+  if (pre_ln) {
+    e = cudaFuncSetAttribute(window_msa_kernel<C2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    window_msa_kernel<C2, true><<<grid, kMsaThreads, smem, s>>>(x, y, w, H, W, total, per_cta);
+  } else {
+    e = cudaFuncSetAttribute(window_msa_kernel<C2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    window_msa_kernel<C2, false><<<grid, kMsaThreads, smem, s>>>(x, y, w, H, W, total, per_cta);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_window_msa(const BlockW& w, int c, const float* x, float* y_half, int pre_ln, int N, int H, int W,
+                              cudaStream_t s) {
+  switch (c) {
+    case 16: return launch_msa_t<8>(w, x, y_half, pre_ln, N, H, W, s);
+    case 32: return launch_msa_t<16>(w, x, y_half, pre_ln, N, H, W, s);
+    case 64: return launch_msa_t<32>(w, x, y_half, pre_ln, N, H, W, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace lg
