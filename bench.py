@@ -196,6 +196,8 @@ def run_ours(args):
     batch = args.batch or default_batch               # per GPU (weak scaling)
     H = 4 * h
     flags = 0 if args.skip_dead_priors else _abi.RUN_DEAD_PRIORS
+    if args.no_graph:
+        flags |= _abi.NO_GRAPH                         # direct launches (for ncu launch lists); never used for a reported number
     sd = golden_weights(bands)
 
     net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=2, skip_dead_priors=args.skip_dead_priors)
@@ -252,8 +254,11 @@ def run_ours(args):
     value = total_pairs / (ms_total * 1e-3)
 
     e2e_steps = max(3, min(args.steps, 10))
-    ms_e2e = timed(step_e2e, e2e_steps, 3)
-    e2e_value = sum_over_ranks(batch, dev) * e2e_steps / (ms_e2e * 1e-3)
+    if args.no_e2e:
+        ms_e2e, e2e_value = None, None
+    else:
+        ms_e2e = timed(step_e2e, e2e_steps, 3)
+        e2e_value = sum_over_ranks(batch, dev) * e2e_steps / (ms_e2e * 1e-3)
 
     launches_per_fwd = handle.launches(batch, h, h, flags)
 
@@ -286,7 +291,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"3 forwards of 2 pairs of the same workload shape (oracle port, torch CPU fp32, "
                                               f"both priors), median; {time.perf_counter() - t0:.1f}s"}
-        if world == 1 and args.other_workloads:
+        if world == 1 and args.other_workloads and not args.no_e2e:
             line["other_workloads"] = other_workload(args, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -365,6 +370,8 @@ def main():
     ap.add_argument("--skip-dead-priors", action="store_true",
                     help="skip prior_module[0..K-2] whose output the reference discards (identical result)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="profiling aid: launch kernels directly instead of the CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
     ap.add_argument("--other-workloads", action="store_true", default=True)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

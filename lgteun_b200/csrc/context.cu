@@ -55,6 +55,7 @@ struct Workspace {      // bump-allocated views for one problem size
 
 struct GraphEntry {
   int N, h, w, flags;
+  cudaGraph_t graph;              // kept alive: the copy-node handles below belong to it
   cudaGraphExec_t exec;
   cudaGraphNode_t n_ms, n_pan, n_out;
   const float *ms, *pan;
@@ -191,7 +192,7 @@ size_t ws_layout(const lgteun_ctx* c, int N, int h, int w, Workspace* out) {
 }
 
 void drop_graphs(lgteun_ctx* c) {
-  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+  for (auto& g : c->graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph); }
   c->graphs.clear();
 }
 
@@ -402,8 +403,28 @@ int lgteun_forward(lgteun_t* c, const float* ms, const float* pan, float* out, i
     return 0;
   }
   GraphEntry* ge = nullptr;
-  for (auto& g : c->graphs)
-    if (g.N == N && g.h == h && g.w == w && g.flags == flags) ge = &g;
+  for (size_t i = 0; i < c->graphs.size(); ++i) {
+    GraphEntry& g = c->graphs[i];
+    if (!(g.N == N && g.h == h && g.w == w && g.flags == flags)) continue;
+    // replay with other caller buffers: retarget the three I/O copy nodes of the instantiated graph
+    bool ok = true;
+    if (g.ms != ms)
+      ok = ok && cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_ms, ws.ms, ms, ms_bytes, cudaMemcpyDeviceToDevice) == cudaSuccess;
+    if (ok && g.pan != pan)
+      ok = ok && cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_pan, ws.pan, pan, pan_bytes, cudaMemcpyDeviceToDevice) == cudaSuccess;
+    if (ok && g.out != out)
+      ok = ok && cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_out, out, ws.out, out_bytes, cudaMemcpyDeviceToDevice) == cudaSuccess;
+    if (ok) {
+      g.ms = ms; g.pan = pan; g.out = out;
+      ge = &g;
+    } else {                       // could not retarget (driver refused): drop the entry and capture afresh
+      cudaGetLastError();
+      cudaGraphExecDestroy(g.exec);
+      cudaGraphDestroy(g.graph);
+      c->graphs.erase(c->graphs.begin() + i);
+    }
+    break;
+  }
   if (!ge) {
     // Stage chaining: the whole K-stage forward is captured once per (N, h, w) into one CUDA graph.
     // I/O goes through fixed staging buffers so that replays with different caller pointers only
@@ -423,28 +444,18 @@ int lgteun_forward(lgteun_t* c, const float* ms, const float* pan, float* out, i
       cudaGetLastError();
       return fail_cuda(e != cudaSuccess ? e : e2, "graph capture of the forward");
     }
-    GraphEntry g{N, h, w, flags, nullptr, nullptr, nullptr, nullptr, ms, pan, out, launches};
+    GraphEntry g{N, h, w, flags, graph, nullptr, nullptr, nullptr, nullptr, ms, pan, out, launches};
     rc = find_copy_nodes(graph, ws, &g);
     if (rc) { cudaGraphDestroy(graph); return rc; }
     e = cudaGraphInstantiate(&g.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate");
-    if (c->graphs.size() >= 8) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail_cuda(e, "cudaGraphInstantiate"); }
+    if (c->graphs.size() >= 8) {
+      cudaGraphExecDestroy(c->graphs.front().exec);
+      cudaGraphDestroy(c->graphs.front().graph);
+      c->graphs.erase(c->graphs.begin());
+    }
     c->graphs.push_back(g);
     ge = &c->graphs.back();
-  } else {
-    if (ge->ms != ms) {
-      CK(cudaGraphExecMemcpyNodeSetParams1D(ge->exec, ge->n_ms, ws.ms, ms, ms_bytes, cudaMemcpyDeviceToDevice));
-      ge->ms = ms;
-    }
-    if (ge->pan != pan) {
-      CK(cudaGraphExecMemcpyNodeSetParams1D(ge->exec, ge->n_pan, ws.pan, pan, pan_bytes, cudaMemcpyDeviceToDevice));
-      ge->pan = pan;
-    }
-    if (ge->out != out) {
-      CK(cudaGraphExecMemcpyNodeSetParams1D(ge->exec, ge->n_out, out, ws.out, out_bytes, cudaMemcpyDeviceToDevice));
-      ge->out = out;
-    }
   }
   c->last_launches = ge->launches;
   CK(cudaGraphLaunch(ge->exec, s));
