@@ -29,7 +29,8 @@ struct BlockW {                       // one LGB block: LGT.py:231-239
   const float *f1_w, *f1_b;           // net.2.point_conv           [4c, 4c]
   const float *dw_w, *dw_b;           // net.2.depth_conv           [4c, 3, 3]
   const float *f2_w, *f2_b;           // net.4                      [c, 4c]
-  const float *f0_wt, *f1_wt, *f2_wt; // derived: the three FFN weights transposed to [in][out]
+  const float *f0_wt, *f1_wt, *f2_wt; // derived: the three FFN weights transposed to [in][out] (CUDA-core path)
+  const float *ffn_pack;              // derived: fp16 hi/lo of W0,W1,W2 in UMMA K-major core-matrix layout (ffn_tc.cu)
 };
 
 struct PriorW {                       // one LGT: LGT.py:251-303
@@ -81,6 +82,10 @@ cudaError_t fft_init_tables(cudaStream_t s);
 size_t ffn_hidden_floats(int N, int H, int W, int c);
 cudaError_t launch_ffn(const BlockW& w, int c, const float* x, float* hidden, float* y, int N, int H, int W,
                        cudaStream_t s);
+// ffn_tc.cu — fused tcgen05/TMEM FFN (c = 16 or 32)
+size_t ffn_tc_pack_halves(int c);
+cudaError_t launch_pack_umma_f16(const float* w, void* hi, void* lo, int N, int K, cudaStream_t s);
+cudaError_t launch_ffn_tc(const BlockW& w, int c, const float* x, float* y, int N, int H, int W, cudaStream_t s);
 // misc
 cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s);
 cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r] = src[r][c]
@@ -90,6 +95,35 @@ cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, c
 __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() exact form, LGT.py:97,99
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+
+// Exact-form GELU x*Phi(x) on a PAIR of values with Blackwell's packed fp32 pipe (FFMA2/FMUL2).
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt(2)   (Abramowitz-Stegun 7.1.26)
+//   gelu(x) = relu(x) - 0.5 |x| poly(t) exp(-x^2/2)
+// Max abs error 3.3e-7 over [-12, 12] in fp32 (torch's own fp32 erf-GELU is at 1.2e-6 vs fp64) at 9 issue slots
+// per element instead of ~27 for erff(): the conv-FFN is bound by these epilogues, not by the tensor pipe.
+__device__ __forceinline__ float2 gelu_pair(float2 x) {
+  const float kPS = 0.23164189f;                 // p / sqrt(2), p = 0.3275911
+  const float kK = 0.84932180f;                  // sqrt(log2(e) / 2): exp(-x^2/2) = exp2(-(kK x)^2)
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 u = __ffma2_rn(ax, make_float2(kPS, kPS), make_float2(1.f, 1.f));
+  float2 t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 w = __fmul2_rn(ax, make_float2(kK, kK));
+  const float2 ww = __fmul2_rn(w, w);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(-ww.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(-ww.y));
+  // -0.5 * (a1..a5)
+  float2 p = make_float2(-0.5307027145f, -0.5307027145f);
+  p = __ffma2_rn(p, t, make_float2(0.7265760135f, 0.7265760135f));
+  p = __ffma2_rn(p, t, make_float2(-0.7107068705f, -0.7107068705f));
+  p = __ffma2_rn(p, t, make_float2(0.142248368f, 0.142248368f));
+  p = __ffma2_rn(p, t, make_float2(-0.127414796f, -0.127414796f));
+  p = __fmul2_rn(p, t);
+  const float2 ae = __fmul2_rn(ax, e);
+  return __ffma2_rn(ae, p, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+__device__ __forceinline__ float gelu_fast(float x) { return gelu_pair(make_float2(x, x)).x; }
 
 // LayerNorm over C register-resident channels (biased variance, eps inside the sqrt).
 template <int C>

@@ -2,6 +2,7 @@
 // (models/unlg_former.py:50-67 and models/common/LGT.py:314-344) and the CUDA-graph cache.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -41,8 +42,9 @@ struct WeightSlot {
 struct Derived {        // arena regions computed from loaded tensors
   const float* const* src;
   const float** dst;
-  int rows, cols;       // transpose [rows][cols] -> [cols][rows]; rows == 0: pos_emb transpose
+  int rows, cols;       // transpose [rows][cols] -> [cols][rows]; rows == 0: pos_emb transpose; rows == -1: FFN fp16 pack
   size_t offset;
+  const BlockW* blk;    // FFN pack only: the block whose f0/f1/f2 weights are packed, cols = channels
 };
 
 struct Workspace {      // bump-allocated views for one problem size
@@ -111,10 +113,11 @@ void add_block(lgteun_ctx* c, const std::string& p, BlockW* b, int ch) {
   add_slot(c, p + ".1.fn.fn.net.2.depth_conv.bias", c4, &b->dw_b);
   add_slot(c, p + ".1.fn.fn.net.4.weight", ch * c4, &b->f2_w);
   add_slot(c, p + ".1.fn.fn.net.4.bias", ch, &b->f2_b);
-  c->derived.push_back({&b->pos, &b->pos_t, 0, 0, 0});
-  c->derived.push_back({&b->f0_w, &b->f0_wt, c4, ch, 0});
-  c->derived.push_back({&b->f1_w, &b->f1_wt, c4, c4, 0});
-  c->derived.push_back({&b->f2_w, &b->f2_wt, ch, c4, 0});
+  c->derived.push_back({&b->pos, &b->pos_t, 0, 0, 0, nullptr});
+  c->derived.push_back({&b->f0_w, &b->f0_wt, c4, ch, 0, nullptr});
+  c->derived.push_back({&b->f1_w, &b->f1_wt, c4, c4, 0, nullptr});
+  c->derived.push_back({&b->f2_w, &b->f2_wt, ch, c4, 0, nullptr});
+  if (ch == 16 || ch == 32) c->derived.push_back({&b->f0_w, &b->ffn_pack, -1, ch, 0, b});
 }
 
 // The weight ABI: reference state_dict key grammar.
@@ -155,7 +158,11 @@ void build_table(lgteun_ctx* c) {
   }
   size_t off = 0;
   for (auto& s : c->slots) { s.offset = off; off += align4((size_t)s.numel); }
-  for (auto& d : c->derived) { d.offset = off; off += align4(d.rows ? (size_t)d.rows * d.cols : 2 * 64 * 64); }
+  for (auto& d : c->derived) {
+    d.offset = off;
+    size_t floats = d.rows > 0 ? (size_t)d.rows * d.cols : d.rows == 0 ? 2 * 64 * 64 : ffn_tc_pack_halves(d.cols) / 2;
+    off += align4(floats);
+  }
   c->arena_floats = off;
 }
 
@@ -224,6 +231,14 @@ struct Launcher {       // counts launches and stops at the first error
   bool ok() const { return err == cudaSuccess; }
 };
 
+// The conv-FFN runs as the fused tcgen05/TMEM kernel for c in {16, 32}; c = 64 (the WV-3 bottleneck) does not fit
+// its weights in shared memory and uses the CUDA-core kernels.  LGTEUN_FFN=simt selects the CUDA-core kernels for
+// every block (A/B measurement only).
+bool use_tc_ffn(int ch) {
+  static const bool simt = [] { const char* e = getenv("LGTEUN_FFN"); return e && std::string(e) == "simt"; }();
+  return !simt && (ch == 16 || ch == 32);
+}
+
 // x + LGMixer(LN(x)): window MSA on the first channel half || FFT mixer on the second, proj, residual.
 void run_mixer(Launcher& L, const BlockW& b, int ch, const float* x, float* y, const Workspace& ws, int N, int H, int W,
                cudaStream_t s) {
@@ -236,7 +251,8 @@ void run_mixer(Launcher& L, const BlockW& b, int ch, const float* x, float* y, c
 void run_block(Launcher& L, const BlockW& b, int ch, float* a, float* t, const Workspace& ws, int N, int H, int W,
                cudaStream_t s) {
   run_mixer(L, b, ch, a, t, ws, N, H, W, s);
-  L(launch_ffn(b, ch, t, ws.hidden, a, N, H, W, s), 2);
+  if (use_tc_ffn(ch)) L(launch_ffn_tc(b, ch, t, a, N, H, W, s));
+  else L(launch_ffn(b, ch, t, ws.hidden, a, N, H, W, s), 2);
 }
 // LGT.forward (LGT.py:314-344)
 void run_prior(Launcher& L, const lgteun_ctx* c, int i, const float* zin, float* zout, const Workspace& ws, int N, int H,
@@ -345,7 +361,16 @@ int lgteun_load_weights(lgteun_t* c, const char* const* names, const float* cons
   for (auto& d : c->derived) {
     float* dst = c->arena + d.offset;
     if (d.rows == 0) CK(launch_transpose_pos(*d.src, dst, s));
-    else CK(launch_transpose(*d.src, dst, d.rows, d.cols, s));
+    else if (d.rows > 0) CK(launch_transpose(*d.src, dst, d.rows, d.cols, s));
+    else {
+      // fp16 hi/lo operands of the three FFN GEMMs: w0h | w0l | w1h | w1l | w2h | w2l (halves), see ffn_tc.cu
+      const int ch = d.cols, c4 = 4 * ch;
+      char* base = reinterpret_cast<char*>(dst);
+      const size_t s0 = (size_t)c4 * ch * 2, s1 = (size_t)c4 * c4 * 2, s2 = (size_t)ch * c4 * 2;   // bytes per half-tensor
+      CK(launch_pack_umma_f16(d.blk->f0_w, base, base + s0, c4, ch, s));
+      CK(launch_pack_umma_f16(d.blk->f1_w, base + 2 * s0, base + 2 * s0 + s1, c4, c4, s));
+      CK(launch_pack_umma_f16(d.blk->f2_w, base + 2 * s0 + 2 * s1, base + 2 * s0 + 2 * s1 + s2, ch, c4, s));
+    }
   }
   c->loaded = true;
   return 0;
@@ -358,7 +383,8 @@ int64_t lgteun_workspace_bytes(const lgteun_t* c, int N, int h, int w) {
 
 int lgteun_forward_launches(lgteun_t* c, int N, int h, int w, int flags) {
   if (!c || check_shape(c, N, h, w)) return -1;
-  const int per_prior = 1 + 5 * 6 + 3;        // patch_embed, 5 blocks x (msa, 3 fft passes, 2 ffn), down, up_fuse, tail
+  // patch_embed, 5 blocks x (msa, 3 fft passes, ffn = 1 fused tcgen05 launch or 2 CUDA-core launches), down, up_fuse, tail
+  const int per_prior = 1 + 4 * (4 + (use_tc_ffn(c->C) ? 1 : 2)) + (4 + (use_tc_ffn(2 * c->C) ? 1 : 2)) + 3;
   const int priors = (flags & LGTEUN_RUN_DEAD_PRIORS) ? c->K : 1;
   return 1 + 2 * c->K + priors * per_prior;
 }
@@ -593,7 +619,8 @@ int lgteun_op_ffn(lgteun_t* c, int prior, int lgb, int block, const float* x, fl
   Workspace ws;
   int rc = op_shape(c, N * (lgb == 1 ? 4 : 1), H, W, 1, &ws);
   if (rc) return rc;
-  CK(launch_ffn(*b, ch, x, ws.hidden, y, N, H, W, s));
+  if (use_tc_ffn(ch)) CK(launch_ffn_tc(*b, ch, x, y, N, H, W, s));
+  else CK(launch_ffn(*b, ch, x, ws.hidden, y, N, H, W, s));
   return 0;
 }
 

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) ffn_expand_kernel(const float* __restrict
       }
     }
 #pragma unroll
-    for (int o = 0; o < C; ++o) h1[(og * C + o) * EP + px] = gelu_erf(acc[o]);
+    for (int o = 0; o < C; ++o) h1[(og * C + o) * EP + px] = gelu_fast(acc[o]);
   }
   float acc[C];
 #pragma unroll
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) ffn_contract_kernel(const float* __restri
           }
         }
 #pragma unroll
-      for (int c = 0; c < 16; ++c) act[(half * 16 + c) * 128 + px] = gelu_erf(g[c]);
+      for (int c = 0; c < 16; ++c) act[(half * 16 + c) * 128 + px] = gelu_fast(g[c]);
     }
     __syncthreads();
 #pragma unroll 4

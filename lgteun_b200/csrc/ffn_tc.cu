@@ -1,0 +1,479 @@
+// ffn_tc.cu — residual(pre_norm(feed_forward)) as ONE fused tcgen05/TMEM kernel (sm_100a).
+//   reference: models/common/LGT.py:91-109 (feed_forward), :45-61 (residual/pre_norm),
+//              models/common/basic_module_unformer_v2.py:37-53 (depthwise_conv = 1x1 then dw3x3, zero pad)
+//     y = x + W2 . GELU( dw3x3( W1 . GELU( W0 . LN(x) + b0 ) + b1 ) + bdw ) + b2
+//
+// Mapping to the hardware
+//   * The three 1x1 convs are GEMMs with M = pixels, N/K = channels, issued as tcgen05.mma kind::f16 by one thread,
+//     accumulating in TMEM.  fp32 parity (max |delta| <= 1e-3 end to end) rules out plain bf16/tf32 operands
+//     (SURVEY.md F8), so every operand is split x = hi + lo in fp16 (2 x 11-bit mantissas) and each GEMM issues
+//     hi*hi + hi*lo + lo*hi into the same fp32 accumulator: the accuracy of 3xTF32 at twice the MMA rate.
+//   * A 128-row MMA tile is ONE IMAGE ROW segment: TMEM lane = pixel column.  The hidden activation of the
+//     depthwise 3x3 therefore never leaves TMEM for its vertical taps (three accumulator slots = rows y-1, y, y+1
+//     in the same lane) and reaches its horizontal taps with two warp shuffles; there is no halo buffer in shared
+//     memory and no 4c-channel hidden tensor in HBM (the reference round-trips 4 x 16.8 MB per pair per block).
+//   * Each warp quarter of the tile is an independent 32-pixel strip (30 interior + 2 halo columns, recomputed);
+//     a CTA streams R+2 rows of four such strips top to bottom.  Zero padding of the conv = masking lanes/rows
+//     outside the image after the bias.
+//   * Operands are written to shared memory by the epilogue threads in the canonical no-swizzle K-major core-matrix
+//     layout [K/8][rows][8] (LBO = rows*16 B, SBO = 128 B): one 16-byte store per thread per K-chunk, conflict-free.
+//   * 128*G threads: warp w owns TMEM lanes 32*(w%4).. and the (w/4)-th slice of the channels, so all CUDA cores
+//     work on the GELU/conv epilogues, which bound this kernel (~70 instructions per hidden element; the tensor
+//     pipe is <25 % busy).  C=16 runs two CTAs per SM (2 x 256 TMEM columns) so one CTA's MMAs hide under the
+//     other's epilogue.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace lg {
+
+constexpr int kStripW = 30;          // interior pixels per warp strip (32 lanes - 2 halo lanes)
+constexpr int kRowsPerBand = 32;     // output rows streamed by one CTA pass
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 in, fp32 accumulate), M=128, cta_group::1
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[4]) {     // 8 consecutive columns of this thread's lane
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32,
+// version 1 at bit 46, layout_type 0 (SWIZZLE_NONE).  LBO = byte stride between the two 16-byte K halves of one
+// MMA (K=16 fp16), SBO = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format F16 (0), K-major A and B,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// split 8 fp32 values (4 pairs) into fp16 hi / lo parts (x = hi + lo up to 2^-22 relative), two 16-byte vectors
+__device__ __forceinline__ void split8(const float2 (&v)[4], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 hh = __float22half2_rn(v[i]);
+    float2 back = __half22float2(hh);
+    __half2 ll = __float22half2_rn(__fadd2_rn(v[i], make_float2(-back.x, -back.y)));
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- weight packing (load time): W [N][K] fp32 -> hi/lo fp16 in the UMMA K-major core-matrix layout [K/8][N][8] -----
+__global__ void pack_umma_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int N,
+                                     int K) {
+  int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= N * K) return;
+  int n = idx / K, k = idx - n * K;
+  float v = w[idx];
+  __half h = __float2half_rn(v);
+  __half l = __float2half_rn(v - __half2float(h));
+  size_t o = ((size_t)(k >> 3) * N + n) * 8 + (k & 7);
+  hi[o] = h;
+  lo[o] = l;
+}
+cudaError_t launch_pack_umma_f16(const float* w, void* hi, void* lo, int N, int K, cudaStream_t s) {
+  pack_umma_f16_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(w, (__half*)hi, (__half*)lo, N, K);
+  return cudaGetLastError();
+}
+
+// ---- shared memory plan -------------------------------------------------------------------------------------------------
+template <int C>
+struct FfnTcSmem {
+  static constexpr int C4 = 4 * C;
+  uint64_t mbar;
+  uint32_t tmem_base;
+  uint32_t pad_;
+  alignas(16) __half w0h[C4 * C], w0l[C4 * C];        // [C/8][C4][8]
+  alignas(16) __half w1h[C4 * C4], w1l[C4 * C4];      // [C4/8][C4][8]
+  alignas(16) __half w2h[C * C4], w2l[C * C4];        // [C4/8][C][8]
+  alignas(16) __half a1h[128 * C], a1l[128 * C];      // [C/8][128][8]
+  alignas(16) __half a2h[128 * C4], a2l[128 * C4];    // [C4/8][128][8]   (A2, then A3)
+  alignas(16) float b0[C4], b1[C4], dwb[C4], dww[9 * C4];   // dww: [tap][channel]
+  alignas(16) float b2[C], lng[C], lnb[C];
+};
+
+// One CTA: four 30-pixel-wide strips (one per warp quarter), rows y0-1 .. y0+R streamed through the three GEMMs.
+template <int C, int G>
+__global__ void __launch_bounds__(128 * G, (C == 16) ? 2 : 1)
+ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w, const __half* __restrict__ wpack,
+              int H, int W, int nws, int nbands, int total_units, int num_groups) {
+  constexpr int C4 = 4 * C;
+  constexpr int NT = 128 * G;
+  constexpr int CH = C4 / G;            // hidden channels per thread
+  constexpr int CO = C / G;             // output channels per thread
+  static_assert(CH % 8 == 0 && CO == 8, "channel slices are processed 8 columns at a time");
+  constexpr uint32_t D1_COL = 0;        // [0, C4): GEMM1 accumulator, later aliased by the GEMM3 accumulator [0, C)
+  constexpr uint32_t D2_COL = C4;       // three slots of C4 columns: hidden rows y-1, y, y+1
+  constexpr uint32_t TMEM_COLS = 4 * C4;        // 256 (C=16) or 512 (C=32)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FfnTcSmem<C>& sm = *reinterpret_cast<FfnTcSmem<C>*>(smem_raw);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3;               // TMEM lane quarter owned by this warp
+  const int cg = warp >> 2;             // channel slice
+  const int row = q * 32 + lane;        // row of the 128-row MMA tile
+
+  // ---- one-time setup: barrier, TMEM, weights -----------------------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(&sm.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&sm.tmem_base, TMEM_COLS);
+  {
+    // packed weights in global: w0h | w0l | w1h | w1l | w2h | w2l, contiguous, same order as the smem plan
+    constexpr int n16 = (2 * (C4 * C + C4 * C4 + C * C4)) * 2 / 16;
+    const uint4* src = reinterpret_cast<const uint4*>(wpack);
+    uint4* dst = reinterpret_cast<uint4*>(sm.w0h);
+    for (int i = tid; i < n16; i += NT) dst[i] = __ldg(src + i);
+    for (int i = tid; i < C4; i += NT) {
+      sm.b0[i] = __ldg(w.f0_b + i);
+      sm.b1[i] = __ldg(w.f1_b + i);
+      sm.dwb[i] = __ldg(w.dw_b + i);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) sm.dww[t * C4 + i] = __ldg(w.dw_w + i * 9 + t);
+    }
+    for (int i = tid; i < C; i += NT) {
+      sm.b2[i] = __ldg(w.f2_b + i);
+      sm.lng[i] = __ldg(w.ln2_w + i);
+      sm.lnb[i] = __ldg(w.ln2_b + i);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  uint32_t phase = 0;
+
+  const uint32_t a1h = smem_u32(sm.a1h), a1l = smem_u32(sm.a1l), a2h = smem_u32(sm.a2h), a2l = smem_u32(sm.a2l);
+  const uint32_t w0h = smem_u32(sm.w0h), w0l = smem_u32(sm.w0l), w1h = smem_u32(sm.w1h), w1l = smem_u32(sm.w1l);
+  const uint32_t w2h = smem_u32(sm.w2h), w2l = smem_u32(sm.w2l);
+
+  for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+    // this warp's strip
+    const int unit = grp * 4 + q;
+    const bool unit_ok = unit < total_units;
+    int n = 0, band = 0, ws = 0;
+    if (unit_ok) {
+      ws = unit % nws;
+      int t = unit / nws;
+      band = t % nbands;
+      n = t / nbands;
+    }
+    const int x = ws * kStripW + lane - 1;
+    const bool x_ok = unit_ok && x >= 0 && x < W;
+    const int y0 = band * kRowsPerBand;
+    const int rows = min(kRowsPerBand, H - y0);          // output rows of this band (uniform over the image)
+    const float* xrow0 = xin + (size_t)n * H * W * C;
+    float* yrow0 = yout + (size_t)n * H * W * C;
+
+    const int iters = min(kRowsPerBand, H) + 2;           // H is a power of two: every band has the same height
+    for (int it = 0; it < iters; ++it) {
+      const int y = y0 + it - 1;                          // row entering GEMM1/GEMM2 in this iteration
+      // ---- S_a: LayerNorm(x[row y]) -> A1 (hi/lo fp16) --------------------------------------------------------------
+      if (cg == 0) {
+        float v[C];
+        if (x_ok && y >= 0 && y < H && it < rows + 2) {
+          load_vec<C>(v, xrow0 + ((size_t)y * W + x) * C);
+          layer_norm_inplace<C>(v, sm.lng, sm.lnb);
+        } else {
+#pragma unroll
+          for (int i = 0; i < C; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int kc = 0; kc < C / 8; ++kc) {
+          float2 t8[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) t8[i] = make_float2(v[kc * 8 + 2 * i], v[kc * 8 + 2 * i + 1]);
+          uint4 hi, lo;
+          split8(t8, hi, lo);
+          *reinterpret_cast<uint4*>(&sm.a1h[(kc * 128 + row) * 8]) = hi;
+          *reinterpret_cast<uint4*>(&sm.a1l[(kc * 128 + row) * 8]) = lo;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      // ---- G1: D1 = A1 . W0^T ------------------------------------------------------------------------------------------
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc(C4);
+#pragma unroll
+        for (int ks = 0; ks < C / 16; ++ks) {
+          const uint64_t ah = umma_desc(a1h + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t al = umma_desc(a1l + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t bh = umma_desc(w0h + ks * 2 * C4 * 16, C4 * 16, 128);
+          const uint64_t bl = umma_desc(w0l + ks * 2 * C4 * 16, C4 * 16, 128);
+          umma_f16(tmem + D1_COL, ah, bh, idesc, ks > 0);
+          umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
+          umma_f16(tmem + D1_COL, al, bh, idesc, 1);
+        }
+        umma_commit(&sm.mbar);
+      }
+      mbar_wait(&sm.mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      // ---- S_b: GELU(D1 + b0) -> A2 (hi/lo fp16) ---------------------------------------------------------------------
+      {
+        float2 nxt[4];
+        tmem_ld8(lane_addr + D1_COL + cg * CH, nxt);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int c0 = cg * CH; c0 < (cg + 1) * CH; c0 += 8) {
+          float2 v[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+          if (c0 + 8 < (cg + 1) * CH) tmem_ld8(lane_addr + D1_COL + c0 + 8, nxt);    // in flight while this chunk computes
+          const float4 ba = *reinterpret_cast<const float4*>(&sm.b0[c0]);
+          const float4 bb = *reinterpret_cast<const float4*>(&sm.b0[c0 + 4]);
+          v[0] = gelu_pair(__fadd2_rn(v[0], make_float2(ba.x, ba.y)));
+          v[1] = gelu_pair(__fadd2_rn(v[1], make_float2(ba.z, ba.w)));
+          v[2] = gelu_pair(__fadd2_rn(v[2], make_float2(bb.x, bb.y)));
+          v[3] = gelu_pair(__fadd2_rn(v[3], make_float2(bb.z, bb.w)));
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(&sm.a2h[((c0 >> 3) * 128 + row) * 8]) = hi;
+          *reinterpret_cast<uint4*>(&sm.a2l[((c0 >> 3) * 128 + row) * 8]) = lo;
+          tmem_ld_wait();
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      // ---- G2: D2[it % 3] = A2 . W1^T ------------------------------------------------------------------------------------
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc(C4);
+        const uint32_t d = tmem + D2_COL + (uint32_t)(it % 3) * C4;
+#pragma unroll
+        for (int ks = 0; ks < C4 / 16; ++ks) {
+          const uint64_t ah = umma_desc(a2h + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t bh = umma_desc(w1h + ks * 2 * C4 * 16, C4 * 16, 128);
+          const uint64_t bl = umma_desc(w1l + ks * 2 * C4 * 16, C4 * 16, 128);
+          umma_f16(d, ah, bh, idesc, ks > 0);
+          umma_f16(d, ah, bl, idesc, 1);
+          umma_f16(d, al, bh, idesc, 1);
+        }
+        umma_commit(&sm.mbar);
+      }
+      mbar_wait(&sm.mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      if (it < 2) continue;                               // uniform over the CTA
+      // ---- S_c: depthwise 3x3 over hidden rows (it-2, it-1, it) + bias -> GELU -> A3 -------------------------------
+      const int yo = y0 + it - 2;                         // output row
+      // zero padding of the conv: rows outside the image are skipped (warp-uniform), columns outside the image are
+      // multiplied by 0 after the bias (lane mask folded into one FFMA)
+      bool rv[3];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yi = yo - 1 + dy;
+        rv[dy] = unit_ok && yi >= 0 && yi < H;
+      }
+      const float m = x_ok ? 1.f : 0.f;
+      const float2 m2 = make_float2(m, m);
+      uint32_t slot[3];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) slot[dy] = lane_addr + D2_COL + (uint32_t)((it - 2 + dy) % 3) * C4;
+      float2 hn[3][4];
+      tmem_ld8(slot[0] + cg * CH, hn[0]);
+      tmem_ld8(slot[1] + cg * CH, hn[1]);
+      tmem_ld8(slot[2] + cg * CH, hn[2]);
+      tmem_ld_wait();
+#pragma unroll 1
+      for (int c0 = cg * CH; c0 < (cg + 1) * CH; c0 += 8) {
+        float2 h[3][4];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[dy][i] = hn[dy][i];
+        if (c0 + 8 < (cg + 1) * CH) {                     // next chunk in flight while this one computes
+          tmem_ld8(slot[0] + c0 + 8, hn[0]);
+          tmem_ld8(slot[1] + c0 + 8, hn[1]);
+          tmem_ld8(slot[2] + c0 + 8, hn[2]);
+        }
+        float2 bm[4];                                     // masked bias of the 1x1 conv (hidden = GEMM2 + b1)
+        {
+          const float4 ba = *reinterpret_cast<const float4*>(&sm.b1[c0]);
+          const float4 bb = *reinterpret_cast<const float4*>(&sm.b1[c0 + 4]);
+          bm[0] = __fmul2_rn(make_float2(ba.x, ba.y), m2); bm[1] = __fmul2_rn(make_float2(ba.z, ba.w), m2);
+          bm[2] = __fmul2_rn(make_float2(bb.x, bb.y), m2); bm[3] = __fmul2_rn(make_float2(bb.z, bb.w), m2);
+        }
+        float2 cl[4], cc[4], cr[4];                       // per-lane column sums for the left / centre / right taps
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cl[i] = cc[i] = cr[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          if (!rv[dy]) continue;
+          const float4* wl = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 0) * C4 + c0]);
+          const float4* wc = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 1) * C4 + c0]);
+          const float4* wr = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 2) * C4 + c0]);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const float4 l4 = wl[hf], c4 = wc[hf], r4 = wr[hf];
+            const float2 ha = __ffma2_rn(h[dy][2 * hf], m2, bm[2 * hf]);
+            const float2 hb = __ffma2_rn(h[dy][2 * hf + 1], m2, bm[2 * hf + 1]);
+            // tap (dy,-1) of THIS pixel is consumed by lane+1, tap (dy,+1) by lane-1
+            cl[2 * hf] = __ffma2_rn(make_float2(l4.x, l4.y), ha, cl[2 * hf]);
+            cl[2 * hf + 1] = __ffma2_rn(make_float2(l4.z, l4.w), hb, cl[2 * hf + 1]);
+            cc[2 * hf] = __ffma2_rn(make_float2(c4.x, c4.y), ha, cc[2 * hf]);
+            cc[2 * hf + 1] = __ffma2_rn(make_float2(c4.z, c4.w), hb, cc[2 * hf + 1]);
+            cr[2 * hf] = __ffma2_rn(make_float2(r4.x, r4.y), ha, cr[2 * hf]);
+            cr[2 * hf + 1] = __ffma2_rn(make_float2(r4.z, r4.w), hb, cr[2 * hf + 1]);
+          }
+        }
+        float2 o[4];
+        const float4 da = *reinterpret_cast<const float4*>(&sm.dwb[c0]);
+        const float4 db = *reinterpret_cast<const float4*>(&sm.dwb[c0 + 4]);
+        const float2 dbv[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y), make_float2(db.z, db.w)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 left, right;
+          left.x = __shfl_up_sync(0xffffffffu, cl[i].x, 1);        // from pixel x-1
+          left.y = __shfl_up_sync(0xffffffffu, cl[i].y, 1);
+          right.x = __shfl_down_sync(0xffffffffu, cr[i].x, 1);     // from pixel x+1
+          right.y = __shfl_down_sync(0xffffffffu, cr[i].y, 1);
+          o[i] = gelu_pair(__fadd2_rn(__fadd2_rn(__fadd2_rn(cc[i], left), right), dbv[i]));
+        }
+        uint4 hi, lo;
+        split8(o, hi, lo);
+        *reinterpret_cast<uint4*>(&sm.a2h[((c0 >> 3) * 128 + row) * 8]) = hi;
+        *reinterpret_cast<uint4*>(&sm.a2l[((c0 >> 3) * 128 + row) * 8]) = lo;
+        tmem_ld_wait();
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      // ---- G3: D3 = A3 . W2^T  (D3 aliases D1) -------------------------------------------------------------------------
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc(C);
+#pragma unroll
+        for (int ks = 0; ks < C4 / 16; ++ks) {
+          const uint64_t ah = umma_desc(a2h + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t bh = umma_desc(w2h + ks * 2 * C * 16, C * 16, 128);
+          const uint64_t bl = umma_desc(w2l + ks * 2 * C * 16, C * 16, 128);
+          umma_f16(tmem + D1_COL, ah, bh, idesc, ks > 0);
+          umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
+          umma_f16(tmem + D1_COL, al, bh, idesc, 1);
+        }
+        umma_commit(&sm.mbar);
+      }
+      mbar_wait(&sm.mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      // ---- S_d: y = D3 + b2 + x  (interior lanes only) ---------------------------------------------------------------
+      {
+        float2 v2[4];
+        tmem_ld8(lane_addr + D1_COL + cg * CO, v2);
+        tmem_ld_wait();
+        const float v[8] = {v2[0].x, v2[0].y, v2[1].x, v2[1].y, v2[2].x, v2[2].y, v2[3].x, v2[3].y};
+        if (x_ok && lane >= 1 && lane <= kStripW && yo < y0 + rows) {
+          const size_t off = ((size_t)yo * W + x) * C + cg * CO;
+          const float4 r0 = *reinterpret_cast<const float4*>(xrow0 + off);
+          const float4 r1 = *reinterpret_cast<const float4*>(xrow0 + off + 4);
+          const float4 ba = *reinterpret_cast<const float4*>(&sm.b2[cg * CO]);
+          const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cg * CO + 4]);
+          *reinterpret_cast<float4*>(yrow0 + off) =
+              make_float4((v[0] + ba.x) + r0.x, (v[1] + ba.y) + r0.y, (v[2] + ba.z) + r0.z, (v[3] + ba.w) + r0.w);
+          *reinterpret_cast<float4*>(yrow0 + off + 4) =
+              make_float4((v[4] + bb.x) + r1.x, (v[5] + bb.y) + r1.y, (v[6] + bb.z) + r1.z, (v[7] + bb.w) + r1.w);
+        }
+      }
+      tc_fence_before();
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+size_t ffn_tc_pack_halves(int c) { return (size_t)2 * (4 * c * c + 16 * c * c + 4 * c * c); }
+
+template <int C, int G>
+static cudaError_t ffn_tc_t(const BlockW& w, const float* x, float* y, int N, int H, int W, cudaStream_t s) {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int nws = (W + kStripW - 1) / kStripW, nbands = (H + kRowsPerBand - 1) / kRowsPerBand;
+  const int units = N * nbands * nws;
+  const int groups = (units + 3) / 4;
+  const size_t smem = sizeof(FfnTcSmem<C>) + 128;
+  cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int per_sm = (C == 16) ? 2 : 1;
+  const int grid = groups < sm_count * per_sm ? groups : sm_count * per_sm;
+  ffn_tc_kernel<C, G><<<grid, 128 * G, smem, s>>>(x, y, w, reinterpret_cast<const __half*>(w.ffn_pack), H, W, nws, nbands,
+                                                   units, groups);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ffn_tc(const BlockW& w, int c, const float* x, float* y, int N, int H, int W, cudaStream_t s) {
+  switch (c) {
+    case 16: return ffn_tc_t<16, 2>(w, x, y, N, H, W, s);
+    case 32: return ffn_tc_t<32, 4>(w, x, y, N, H, W, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace lg

@@ -234,12 +234,13 @@ cudaError_t launch_tail(const PriorW& w, int B, const float* fea, const float* x
   return cudaGetLastError();
 }
 
-// pos_emb [2][i][j] -> [2][j][i] so that a warp of consecutive queries reads consecutive words
+// pos_emb [2][i][j] -> log2(e) * [2][j][i]: a warp of consecutive queries reads consecutive words, and the softmax
+// of window_msa.cu runs in base 2 (ex2.approx)
 __global__ void transpose_pos_kernel(const float* __restrict__ pos, float* __restrict__ pos_t) {
   int idx = blockIdx.x * 256 + threadIdx.x;       // over [2][64][64] of the destination
   if (idx >= 2 * 64 * 64) return;
   int h = idx >> 12, j = (idx >> 6) & 63, i = idx & 63;
-  pos_t[idx] = pos[(h << 12) + (i << 6) + j];
+  pos_t[idx] = pos[(h << 12) + (i << 6) + j] * 1.4426950408889634f;
 }
 cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s) {
   transpose_pos_kernel<<<32, 256, 0, s>>>(pos, pos_t);

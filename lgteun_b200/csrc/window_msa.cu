@@ -25,12 +25,12 @@ struct MsaSmem {
   float wqkv[3 * C2 * C2];                          // [3*C2][C2]
   float bqkv[3 * C2];
   float xs[kWinPerIter][C2][64 + 1];                // LN'd local half, channel-major (conflict-free per-token reads)
-  float ks[kWinPerIter][kHeads][64][D];
+  float ks[kWinPerIter][kHeads][D][64];                // channel-major: four keys per 128-bit broadcast
   float vs[kWinPerIter][kHeads][64][D];
 };
 
 template <int C2, bool PRE_LN>
-__global__ void __launch_bounds__(kMsaThreads) window_msa_kernel(const float* __restrict__ x, float* __restrict__ y,
+__global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1) window_msa_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                   BlockW w, int H, int W, int total_windows,
                                                                   int windows_per_cta) {
   constexpr int D = C2 / kHeads;
@@ -111,43 +111,59 @@ __global__ void __launch_bounds__(kMsaThreads) window_msa_kernel(const float* __
       }
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        q[j] *= scale;
-        sm.ks[slot][head][tok][j] = kk[j];
+        q[j] *= scale * 1.4426950408889634f;              // logits in base-2 units: softmax via ex2.approx
+        sm.ks[slot][head][j][tok] = kk[j];
         sm.vs[slot][head][tok][j] = vv[j];
       }
     }
     __syncthreads();
     // 3) logits + softmax + PV, all in registers
     if (active) {
-      float s[64];
+      // logits for 4 keys at a time on the packed fp32 pipe; pos_t already holds pos_emb * log2(e), transposed
+      float2 s2[32];
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float acc = sm.pos_t[(head * 64 + j) * 64 + tok];
+      for (int j = 0; j < 64; j += 4) {
+        float2 a01 = make_float2(sm.pos_t[(head * 64 + j) * 64 + tok], sm.pos_t[(head * 64 + j + 1) * 64 + tok]);
+        float2 a23 = make_float2(sm.pos_t[(head * 64 + j + 2) * 64 + tok], sm.pos_t[(head * 64 + j + 3) * 64 + tok]);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const float4 kv = *reinterpret_cast<const float4*>(&sm.ks[slot][head][c][j]);
+          const float2 qc = make_float2(q[c], q[c]);
+          a01 = __ffma2_rn(qc, make_float2(kv.x, kv.y), a01);
+          a23 = __ffma2_rn(qc, make_float2(kv.z, kv.w), a23);
+        }
+        s2[j / 2] = a01;
+        s2[j / 2 + 1] = a23;
+        mx = fmaxf(mx, fmaxf(fmaxf(a01.x, a01.y), fmaxf(a23.x, a23.y)));
+      }
+      float2 sum2 = make_float2(0.f, 0.f);
+      float2 o2[D / 2];
+#pragma unroll
+      for (int c = 0; c < D / 2; ++c) o2[c] = make_float2(0.f, 0.f);
+      const float2 nmx = make_float2(-mx, -mx);
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const float2 d = __fadd2_rn(s2[jj], nmx);
+        float2 p;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.x) : "f"(d.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.y) : "f"(d.y));
+        sum2 = __fadd2_rn(sum2, p);
 #pragma unroll
         for (int c4 = 0; c4 < D; c4 += 4) {
-          float4 kv = *reinterpret_cast<const float4*>(&sm.ks[slot][head][j][c4]);
-          acc = fmaf(q[c4], kv.x, acc); acc = fmaf(q[c4 + 1], kv.y, acc);
-          acc = fmaf(q[c4 + 2], kv.z, acc); acc = fmaf(q[c4 + 3], kv.w, acc);
+          const float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][2 * jj][c4]);
+          const float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][2 * jj + 1][c4]);
+          const float2 p0 = make_float2(p.x, p.x), p1 = make_float2(p.y, p.y);
+          o2[c4 / 2] = __ffma2_rn(p0, make_float2(v0.x, v0.y), o2[c4 / 2]);
+          o2[c4 / 2 + 1] = __ffma2_rn(p0, make_float2(v0.z, v0.w), o2[c4 / 2 + 1]);
+          o2[c4 / 2] = __ffma2_rn(p1, make_float2(v1.x, v1.y), o2[c4 / 2]);
+          o2[c4 / 2 + 1] = __ffma2_rn(p1, make_float2(v1.z, v1.w), o2[c4 / 2 + 1]);
         }
-        s[j] = acc;
-        mx = fmaxf(mx, acc);
       }
-      float sum = 0.f;
+      const float sum = sum2.x + sum2.y;
       float o[D];
 #pragma unroll
-      for (int c = 0; c < D; ++c) o[c] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float p = expf(s[j] - mx);
-        sum += p;
-#pragma unroll
-        for (int c4 = 0; c4 < D; c4 += 4) {
-          float4 vv = *reinterpret_cast<const float4*>(&sm.vs[slot][head][j][c4]);
-          o[c4] = fmaf(p, vv.x, o[c4]); o[c4 + 1] = fmaf(p, vv.y, o[c4 + 1]);
-          o[c4 + 2] = fmaf(p, vv.z, o[c4 + 2]); o[c4 + 3] = fmaf(p, vv.w, o[c4 + 3]);
-        }
-      }
+      for (int c = 0; c < D / 2; ++c) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
       const float inv = 1.0f / sum;
       const int py = wy * kWin + (tok >> 3), px = wx * kWin + (tok & 7);
       float* dst = y + (((size_t)n * H + py) * W + px) * C2 + head * D;
