@@ -60,8 +60,8 @@ cudaError_t launch_data_step(const DataW& w, int stage, int B, const float* z_in
 // pixel_ops.cu
 cudaError_t launch_patch_embed(const PriorW& w, int B, const float* x_nchw, float* y, int N, int H, int W, cudaStream_t s);
 cudaError_t launch_down(const PriorW& w, int C, const float* x, float* y, int N, int H, int W, cudaStream_t s);
-cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float* skip, float* y, int N, int H, int W,
-                           cudaStream_t s);
+cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float* skip, float* t_low /*[N,H/2,W/2,C] scratch*/,
+                           float* y, int N, int H, int W, cudaStream_t s);
 cudaError_t launch_tail(const PriorW& w, int B, const float* fea, const float* x_nchw, float* y_nchw, int N, int H, int W,
                         cudaStream_t s);
 // window_msa.cu

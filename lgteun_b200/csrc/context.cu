@@ -263,7 +263,7 @@ void run_prior(Launcher& L, const lgteun_ctx* c, int i, const float* zin, float*
   for (int j = 0; j < 2; ++j) run_block(L, p.enc[j], C, ws.X0, ws.X1, ws, N, H, W, s);       // skip = X0
   L(launch_down(p, C, ws.X0, ws.L0, N, H, W, s));
   run_block(L, p.bott[0], 2 * C, ws.L0, ws.L1, ws, N, H / 2, W / 2, s);
-  L(launch_up_fuse(p, C, ws.L0, ws.X0, ws.X1, N, H, W, s));
+  L(launch_up_fuse(p, C, ws.L0, ws.X0, ws.L1, ws.X1, N, H, W, s), 2);
   for (int j = 0; j < 2; ++j) run_block(L, p.dec[j], C, ws.X1, ws.X2, ws, N, H, W, s);
   L(launch_tail(p, c->B, ws.X1, zin, zout, N, H, W, s));
 }
@@ -384,7 +384,7 @@ int64_t lgteun_workspace_bytes(const lgteun_t* c, int N, int h, int w) {
 int lgteun_forward_launches(lgteun_t* c, int N, int h, int w, int flags) {
   if (!c || check_shape(c, N, h, w)) return -1;
   // patch_embed, 5 blocks x (msa, 3 fft passes, ffn = 1 fused tcgen05 launch or 2 CUDA-core launches), down, up_fuse, tail
-  const int per_prior = 1 + 4 * (4 + (use_tc_ffn(c->C) ? 1 : 2)) + (4 + (use_tc_ffn(2 * c->C) ? 1 : 2)) + 3;
+  const int per_prior = 1 + 4 * (4 + (use_tc_ffn(c->C) ? 1 : 2)) + (4 + (use_tc_ffn(2 * c->C) ? 1 : 2)) + 4;
   const int priors = (flags & LGTEUN_RUN_DEAD_PRIORS) ? c->K : 1;
   return 1 + 2 * c->K + priors * per_prior;
 }

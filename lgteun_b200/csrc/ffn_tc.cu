@@ -135,9 +135,9 @@ cudaError_t launch_pack_umma_f16(const float* w, void* hi, void* lo, int N, int 
 template <int C>
 struct FfnTcSmem {
   static constexpr int C4 = 4 * C;
-  uint64_t mbar;
+  uint64_t mbar[3];                                   // MMA-completion barriers of G1, G2, G3
   uint32_t tmem_base;
-  uint32_t pad_;
+  uint32_t pad_[3];
   alignas(16) __half w0h[C4 * C], w0l[C4 * C];        // [C/8][C4][8]
   alignas(16) __half w1h[C4 * C4], w1l[C4 * C4];      // [C4/8][C4][8]
   alignas(16) __half w2h[C * C4], w2l[C * C4];        // [C4/8][C][8]
@@ -145,6 +145,7 @@ struct FfnTcSmem {
   alignas(16) __half a2h[128 * C4], a2l[128 * C4];    // [C4/8][128][8]   (A2, then A3)
   alignas(16) float b0[C4], b1[C4], dwb[C4], dww[9 * C4];   // dww: [tap][channel]
   alignas(16) float b2[C], lng[C], lnb[C];
+  alignas(16) float2 part[C / 8][128];                // LayerNorm partials (mean, M2) of each 8-channel slice of a pixel
 };
 
 // One CTA: four 30-pixel-wide strips (one per warp quarter), rows y0-1 .. y0+R streamed through the three GEMMs.
@@ -157,8 +158,8 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   constexpr int CH = C4 / G;            // hidden channels per thread
   constexpr int CO = C / G;             // output channels per thread
   static_assert(CH % 8 == 0 && CO == 8, "channel slices are processed 8 columns at a time");
-  constexpr uint32_t D1_COL = 0;        // [0, C4): GEMM1 accumulator, later aliased by the GEMM3 accumulator [0, C)
-  constexpr uint32_t D2_COL = C4;       // three slots of C4 columns: hidden rows y-1, y, y+1
+  constexpr uint32_t D1_COL = 0;        // [0, C4): GEMM1 accumulator
+  constexpr uint32_t D2_COL = C4;       // three slots of C4 columns: hidden rows y-1, y, y+1 (the dead slot hosts GEMM3's accumulator)
   constexpr uint32_t TMEM_COLS = 4 * C4;        // 256 (C=16) or 512 (C=32)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FfnTcSmem<C>& sm = *reinterpret_cast<FfnTcSmem<C>*>(smem_raw);
@@ -170,7 +171,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
 
   // ---- one-time setup: barrier, TMEM, weights -----------------------------------------------------------------------
   if (tid == 0) {
-    mbar_init(&sm.mbar, 1);
+    mbar_init(&sm.mbar[0], 1);
+    mbar_init(&sm.mbar[1], 1);
+    mbar_init(&sm.mbar[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, TMEM_COLS);
@@ -199,11 +202,12 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-  uint32_t phase = 0;
 
   const uint32_t a1h = smem_u32(sm.a1h), a1l = smem_u32(sm.a1l), a2h = smem_u32(sm.a2h), a2l = smem_u32(sm.a2l);
   const uint32_t w0h = smem_u32(sm.w0h), w0l = smem_u32(sm.w0l), w1h = smem_u32(sm.w1h), w1l = smem_u32(sm.w1l);
   const uint32_t w2h = smem_u32(sm.w2h), w2l = smem_u32(sm.w2l);
+
+  uint32_t ph1 = 0, ph2 = 0, ph3 = 0;   // phases of the three MMA-completion barriers (G1, G2, G3)
 
   for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
     // this warp's strip
@@ -222,54 +226,98 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     const int rows = min(kRowsPerBand, H - y0);          // output rows of this band (uniform over the image)
     const float* xrow0 = xin + (size_t)n * H * W * C;
     float* yrow0 = yout + (size_t)n * H * W * C;
-
+    const float2 m2 = x_ok ? make_float2(1.f, 1.f) : make_float2(0.f, 0.f);
     const int iters = min(kRowsPerBand, H) + 2;           // H is a power of two: every band has the same height
+
+    // ---- S_a: LayerNorm(x[row]) -> A1 (hi/lo fp16), spread over all warps -------------------------------------------
+    // Thread (pixel row, cg) owns channels [8cg, 8cg+8): the global load is issued one row ahead (prefetch_x), the
+    // statistics of the G slices are combined with Chan's formula through shared memory (publish_stats), and each
+    // thread normalises / splits / stores only its own K-chunk of A1 (stage_a).
+    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+    bool xvalid = false;
+    auto prefetch_x = [&](int it) {
+      const int y = y0 + it - 1;
+      xvalid = x_ok && y >= 0 && y < H && it < rows + 2;
+      if (xvalid) {
+        const float4* src = reinterpret_cast<const float4*>(xrow0 + ((size_t)y * W + x) * C + cg * 8);
+        xa = __ldg(src);
+        xb = __ldg(src + 1);
+      }
+    };
+    auto publish_stats = [&]() {
+      const float mean = (((xa.x + xa.y) + (xa.z + xa.w)) + ((xb.x + xb.y) + (xb.z + xb.w))) * 0.125f;
+      float m2 = 0.f, d;
+      d = xa.x - mean; m2 = fmaf(d, d, m2); d = xa.y - mean; m2 = fmaf(d, d, m2);
+      d = xa.z - mean; m2 = fmaf(d, d, m2); d = xa.w - mean; m2 = fmaf(d, d, m2);
+      d = xb.x - mean; m2 = fmaf(d, d, m2); d = xb.y - mean; m2 = fmaf(d, d, m2);
+      d = xb.z - mean; m2 = fmaf(d, d, m2); d = xb.w - mean; m2 = fmaf(d, d, m2);
+      sm.part[cg][row] = make_float2(mean, m2);
+    };
+    auto stage_a = [&]() {
+      float2 t8[4];
+      if (xvalid) {
+        float2 pr[G];
+        float mean = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) { pr[g] = sm.part[g][row]; mean += pr[g].x; }
+        mean *= (1.0f / G);
+        float m2 = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) { const float dm = pr[g].x - mean; m2 += fmaf(8.0f * dm, dm, pr[g].y); }
+        const float rstd = 1.0f / sqrtf(m2 * (1.0f / C) + kLnEps);
+        const float4 ga = *reinterpret_cast<const float4*>(&sm.lng[cg * 8]), gb = *reinterpret_cast<const float4*>(&sm.lng[cg * 8 + 4]);
+        const float4 ba = *reinterpret_cast<const float4*>(&sm.lnb[cg * 8]), bb = *reinterpret_cast<const float4*>(&sm.lnb[cg * 8 + 4]);
+        t8[0] = make_float2((xa.x - mean) * rstd * ga.x + ba.x, (xa.y - mean) * rstd * ga.y + ba.y);
+        t8[1] = make_float2((xa.z - mean) * rstd * ga.z + ba.z, (xa.w - mean) * rstd * ga.w + ba.w);
+        t8[2] = make_float2((xb.x - mean) * rstd * gb.x + bb.x, (xb.y - mean) * rstd * gb.y + bb.y);
+        t8[3] = make_float2((xb.z - mean) * rstd * gb.z + bb.z, (xb.w - mean) * rstd * gb.w + bb.w);
+      } else {
+        t8[0] = t8[1] = t8[2] = t8[3] = make_float2(0.f, 0.f);
+      }
+      uint4 hi, lo;
+      split8(t8, hi, lo);
+      *reinterpret_cast<uint4*>(&sm.a1h[(cg * 128 + row) * 8]) = hi;
+      *reinterpret_cast<uint4*>(&sm.a1l[(cg * 128 + row) * 8]) = lo;
+    };
+    // ---- G1: D1 = A1 . W0^T ----------------------------------------------------------------------------------------------
+    auto issue_g1 = [&]() {
+      constexpr uint32_t idesc = umma_idesc(C4);
+#pragma unroll
+      for (int ks = 0; ks < C / 16; ++ks) {
+        const uint64_t ah = umma_desc(a1h + ks * 2 * 128 * 16, 128 * 16, 128);
+        const uint64_t al = umma_desc(a1l + ks * 2 * 128 * 16, 128 * 16, 128);
+        const uint64_t bh = umma_desc(w0h + ks * 2 * C4 * 16, C4 * 16, 128);
+        const uint64_t bl = umma_desc(w0l + ks * 2 * C4 * 16, C4 * 16, 128);
+        umma_f16(tmem + D1_COL, ah, bh, idesc, ks > 0);
+        umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
+        umma_f16(tmem + D1_COL, al, bh, idesc, 1);
+      }
+      umma_commit(&sm.mbar[0]);
+    };
+    // publish generic-proxy smem writes + finished TMEM reads, then let one thread issue MMAs
+#define LG_SYNC_THEN_ISSUE(stmt)      \
+  do {                                \
+    fence_proxy_async();              \
+    tc_fence_before();                \
+    __syncthreads();                  \
+    if (tid == 0) {                   \
+      tc_fence_after();               \
+      stmt;                           \
+    }                                 \
+  } while (0)
+
+    prefetch_x(0);
+    publish_stats();
+    __syncthreads();
+    stage_a();
+    LG_SYNC_THEN_ISSUE(issue_g1());
+
     for (int it = 0; it < iters; ++it) {
-      const int y = y0 + it - 1;                          // row entering GEMM1/GEMM2 in this iteration
-      // ---- S_a: LayerNorm(x[row y]) -> A1 (hi/lo fp16) --------------------------------------------------------------
-      if (cg == 0) {
-        float v[C];
-        if (x_ok && y >= 0 && y < H && it < rows + 2) {
-          load_vec<C>(v, xrow0 + ((size_t)y * W + x) * C);
-          layer_norm_inplace<C>(v, sm.lng, sm.lnb);
-        } else {
-#pragma unroll
-          for (int i = 0; i < C; ++i) v[i] = 0.f;
-        }
-#pragma unroll
-        for (int kc = 0; kc < C / 8; ++kc) {
-          float2 t8[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) t8[i] = make_float2(v[kc * 8 + 2 * i], v[kc * 8 + 2 * i + 1]);
-          uint4 hi, lo;
-          split8(t8, hi, lo);
-          *reinterpret_cast<uint4*>(&sm.a1h[(kc * 128 + row) * 8]) = hi;
-          *reinterpret_cast<uint4*>(&sm.a1l[(kc * 128 + row) * 8]) = lo;
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      // ---- G1: D1 = A1 . W0^T ------------------------------------------------------------------------------------------
-      if (tid == 0) {
-        tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc(C4);
-#pragma unroll
-        for (int ks = 0; ks < C / 16; ++ks) {
-          const uint64_t ah = umma_desc(a1h + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t al = umma_desc(a1l + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t bh = umma_desc(w0h + ks * 2 * C4 * 16, C4 * 16, 128);
-          const uint64_t bl = umma_desc(w0l + ks * 2 * C4 * 16, C4 * 16, 128);
-          umma_f16(tmem + D1_COL, ah, bh, idesc, ks > 0);
-          umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
-          umma_f16(tmem + D1_COL, al, bh, idesc, 1);
-        }
-        umma_commit(&sm.mbar);
-      }
-      mbar_wait(&sm.mbar, phase);
-      phase ^= 1;
-      tc_fence_after();
+      if (it + 1 < iters) prefetch_x(it + 1);             // global load of the next row flies under the wait + S_b
       // ---- S_b: GELU(D1 + b0) -> A2 (hi/lo fp16) ---------------------------------------------------------------------
+      mbar_wait(&sm.mbar[0], ph1);
+      ph1 ^= 1;
+      tc_fence_after();
       {
         float2 nxt[4];
         tmem_ld8(lane_addr + D1_COL + cg * CH, nxt);
@@ -291,12 +339,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           tmem_ld_wait();
         }
       }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      // ---- G2: D2[it % 3] = A2 . W1^T ------------------------------------------------------------------------------------
-      if (tid == 0) {
-        tc_fence_after();
+      if (it + 1 < iters) publish_stats();
+      // ---- G2: D2[it % 3] = A2 . W1^T  (runs under S_a of the next row) -------------------------------------------------
+      LG_SYNC_THEN_ISSUE({
         constexpr uint32_t idesc = umma_idesc(C4);
         const uint32_t d = tmem + D2_COL + (uint32_t)(it % 3) * C4;
 #pragma unroll
@@ -309,10 +354,15 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           umma_f16(d, ah, bl, idesc, 1);
           umma_f16(d, al, bh, idesc, 1);
         }
-        umma_commit(&sm.mbar);
+        umma_commit(&sm.mbar[1]);
+      });
+      // ---- S_a + G1 of the next row: G1 runs under the depthwise stage below -------------------------------------------
+      if (it + 1 < iters) {
+        stage_a();
+        LG_SYNC_THEN_ISSUE(issue_g1());
       }
-      mbar_wait(&sm.mbar, phase);
-      phase ^= 1;
+      mbar_wait(&sm.mbar[1], ph2);
+      ph2 ^= 1;
       tc_fence_after();
       if (it < 2) continue;                               // uniform over the CTA
       // ---- S_c: depthwise 3x3 over hidden rows (it-2, it-1, it) + bias -> GELU -> A3 -------------------------------
@@ -325,8 +375,6 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         const int yi = yo - 1 + dy;
         rv[dy] = unit_ok && yi >= 0 && yi < H;
       }
-      const float m = x_ok ? 1.f : 0.f;
-      const float2 m2 = make_float2(m, m);
       uint32_t slot[3];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) slot[dy] = lane_addr + D2_COL + (uint32_t)((it - 2 + dy) % 3) * C4;
@@ -396,12 +444,17 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         *reinterpret_cast<uint4*>(&sm.a2l[((c0 >> 3) * 128 + row) * 8]) = lo;
         tmem_ld_wait();
       }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      // ---- G3: D3 = A3 . W2^T  (D3 aliases D1) -------------------------------------------------------------------------
-      if (tid == 0) {
-        tc_fence_after();
+      // residual for S_d: issued now, consumed after GEMM3
+      const bool st_ok = x_ok && lane >= 1 && lane <= kStripW && yo < y0 + rows;
+      const size_t off = ((size_t)yo * W + x) * C + cg * CO;
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+      if (st_ok) {
+        r0 = __ldg(reinterpret_cast<const float4*>(xrow0 + off));
+        r1 = __ldg(reinterpret_cast<const float4*>(xrow0 + off) + 1);
+      }
+      // ---- G3: D3 = A3 . W2^T, accumulated in the first C columns of the hidden-row slot that just died ------------
+      const uint32_t d3 = D2_COL + (uint32_t)((it + 1) % 3) * C4;
+      LG_SYNC_THEN_ISSUE({
         constexpr uint32_t idesc = umma_idesc(C);
 #pragma unroll
         for (int ks = 0; ks < C4 / 16; ++ks) {
@@ -409,25 +462,22 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
           const uint64_t bh = umma_desc(w2h + ks * 2 * C * 16, C * 16, 128);
           const uint64_t bl = umma_desc(w2l + ks * 2 * C * 16, C * 16, 128);
-          umma_f16(tmem + D1_COL, ah, bh, idesc, ks > 0);
-          umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
-          umma_f16(tmem + D1_COL, al, bh, idesc, 1);
+          umma_f16(tmem + d3, ah, bh, idesc, ks > 0);
+          umma_f16(tmem + d3, ah, bl, idesc, 1);
+          umma_f16(tmem + d3, al, bh, idesc, 1);
         }
-        umma_commit(&sm.mbar);
-      }
-      mbar_wait(&sm.mbar, phase);
-      phase ^= 1;
+        umma_commit(&sm.mbar[2]);
+      });
+      mbar_wait(&sm.mbar[2], ph3);
+      ph3 ^= 1;
       tc_fence_after();
       // ---- S_d: y = D3 + b2 + x  (interior lanes only) ---------------------------------------------------------------
       {
         float2 v2[4];
-        tmem_ld8(lane_addr + D1_COL + cg * CO, v2);
+        tmem_ld8(lane_addr + d3 + cg * CO, v2);
         tmem_ld_wait();
         const float v[8] = {v2[0].x, v2[0].y, v2[1].x, v2[1].y, v2[2].x, v2[2].y, v2[3].x, v2[3].y};
-        if (x_ok && lane >= 1 && lane <= kStripW && yo < y0 + rows) {
-          const size_t off = ((size_t)yo * W + x) * C + cg * CO;
-          const float4 r0 = *reinterpret_cast<const float4*>(xrow0 + off);
-          const float4 r1 = *reinterpret_cast<const float4*>(xrow0 + off + 4);
+        if (st_ok) {
           const float4 ba = *reinterpret_cast<const float4*>(&sm.b2[cg * CO]);
           const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cg * CO + 4]);
           *reinterpret_cast<float4*>(yrow0 + off) =
@@ -440,6 +490,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     }
     __syncthreads();
   }
+#undef LG_SYNC_THEN_ISSUE
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);

@@ -103,12 +103,67 @@ __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int N
   return a;
 }
 
+// ---- compile-time specialised Stockham (sizes used by the headline shapes): strides and trip counts are constants,
+// butterflies run on the packed fp32 pipe (one FADD2 / FFMA2 per complex add / half complex multiply) -------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+template <int SIGN>
+__device__ __forceinline__ float2 ctw(float2 a, float2 w) {            // a * w (SIGN < 0) or a * conj(w) (SIGN > 0)
+  const float2 t = __fmul2_rn(a, make_float2(w.x, w.x));
+  return (SIGN < 0) ? __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), t)
+                    : __ffma2_rn(make_float2(a.y, -a.x), make_float2(w.y, w.y), t);
+}
+
+template <int L, int NF, int SIGN, int NT, int Ns>
+__device__ __forceinline__ float2* stockham_ct(float2* a, float2* b, const float2* tw, int tid) {
+  if constexpr (Ns >= L) {
+    return a;
+  } else {
+    constexpr int R = (((L / Ns) & 3) == 0) ? 4 : 2;
+    constexpr int q = L / R;                       // butterflies per sequence
+    constexpr int tws = L / (Ns * R);
+    constexpr int ITEMS = NF * q;
+#pragma unroll
+    for (int base = 0; base < ITEMS; base += NT) {
+      const int id = base + tid;
+      if (ITEMS % NT == 0 || id < ITEMS) {
+        const int f = id / q, j = id % q;
+        const int k = j & (Ns - 1);
+        const float2* src = a + f * L + j;
+        float2* dst = b + f * L + (j - k) * R + k;
+        if constexpr (R == 4) {
+          float2 v0 = src[0], v1 = src[q], v2 = src[2 * q], v3 = src[3 * q];
+          if constexpr (Ns > 1) {
+            v1 = ctw<SIGN>(v1, tw[k * tws]);
+            v2 = ctw<SIGN>(v2, tw[2 * k * tws]);
+            v3 = ctw<SIGN>(v3, tw[3 * k * tws]);
+          }
+          const float2 s02 = cadd(v0, v2), d02 = csub(v0, v2), s13 = cadd(v1, v3), d13 = csub(v1, v3);
+          const float2 jd = (SIGN < 0) ? make_float2(d13.y, -d13.x) : make_float2(-d13.y, d13.x);
+          dst[0] = cadd(s02, s13);
+          dst[Ns] = cadd(d02, jd);
+          dst[2 * Ns] = csub(s02, s13);
+          dst[3 * Ns] = csub(d02, jd);
+        } else {
+          float2 v0 = src[0], v1 = src[q];
+          if constexpr (Ns > 1) v1 = ctw<SIGN>(v1, tw[k * tws]);
+          dst[0] = cadd(v0, v1);
+          dst[Ns] = csub(v0, v1);
+        }
+      }
+    }
+    __syncthreads();
+    return stockham_ct<L, NF, SIGN, NT, Ns * R>(b, a, tw, tid);
+  }
+}
+
 constexpr int kFftThreads = 256;
 
 // ---- pass 1: rows forward ----------------------------------------------------------------------------
-template <int C2, bool PRE_LN>
+template <int C2, bool PRE_LN, int WCT>
 __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
-                                                                   BlockW w, int W) {
+                                                                   BlockW w, int Wrt) {
+  const int W = WCT ? WCT : Wrt;                          // WCT != 0: compile-time row length (fast path)
   constexpr int NF = C2 / 2;
   constexpr int CIN = PRE_LN ? 2 * C2 : C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -142,7 +197,9 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* 
     for (int f = 0; f < NF; ++f) bufA[f * W + px] = make_float2(g[2 * f], g[2 * f + 1]);
   }
   __syncthreads();
-  const float2* res = stockham<-1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
+  const float2* res;
+  if constexpr (WCT != 0) res = stockham_ct<WCT, NF, -1, kFftThreads, 1>(bufA, bufB, tw, tid);
+  else res = stockham<-1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
   // split the packed transform: channel a = 2f (real part), b = 2f+1 (imag part)
   const int Wf = W / 2 + 1;
   float4* out = reinterpret_cast<float4*>(spec + row * Wf * C2);
@@ -160,9 +217,10 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* 
 
 // ---- pass 2: columns (forward, pointwise, inverse) -----------------------------------------------------
 // One CTA = Q adjacent complex lanes (kx*C2+ch) of one image, all H rows, in shared memory [H][Q].
-template <int Q>
-__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restrict__ spec, BlockW w, int H, int W, int C2,
+template <int Q, int HCT>
+__global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restrict__ spec, BlockW w, int Hrt, int W, int C2,
                                                                int lanes_per_row /* Wf*C2 */) {
+  const int H = HCT ? HCT : Hrt;                          // HCT != 0: compile-time column length (fast path, loops unroll)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);       // [H]
   float2* d = tw + H;                                     // [H][Q]
@@ -171,6 +229,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
   const int nl = min(Q, lanes_per_row - l0);
   float2* base = spec + (size_t)blockIdx.y * H * lanes_per_row + l0;
   for (int j = tid; j < H; j += kFftThreads) tw[j] = g_tw[j * (kTwN / H)];
+#pragma unroll 4
   for (int id = tid; id < H * Q; id += kFftThreads) {
     const int r = id / Q, l = id - r * Q;
     d[id] = (l < nl) ? base[(size_t)r * lanes_per_row + l] : make_float2(0.f, 0.f);
@@ -178,37 +237,39 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
   __syncthreads();
   const bool odd = (__ffs(H) - 1) & 1;                    // log2(H) odd -> one trailing radix-2 stage
   // forward: decimation in frequency, natural in -> digit-reversed out
+#pragma unroll
   for (int L = H; L >= 4; L >>= 2) {
     const int q = L >> 2, tws = H / L;
+#pragma unroll
     for (int id = tid; id < (H >> 2) * Q; id += kFftThreads) {
       const int l = id % Q, bf = id / Q;
       const int blk = bf / q, j = bf - blk * q;
       float2* p = d + (size_t)(blk * L + j) * Q + l;
-      float2 a0 = p[0], a1 = p[(size_t)q * Q], a2 = p[(size_t)2 * q * Q], a3 = p[(size_t)3 * q * Q];
-      float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
-      float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
-      float2 mjd = make_float2(d13.y, -d13.x);            // -i * (a1 - a3)
-      float2 y0 = make_float2(s02.x + s13.x, s02.y + s13.y);
-      float2 y1 = make_float2(d02.x + mjd.x, d02.y + mjd.y);
-      float2 y2 = make_float2(s02.x - s13.x, s02.y - s13.y);
-      float2 y3 = make_float2(d02.x - mjd.x, d02.y - mjd.y);
-      if (j) { y1 = cmul(y1, tw[j * tws]); y2 = cmul(y2, tw[2 * j * tws]); y3 = cmul(y3, tw[3 * j * tws]); }
-      p[0] = y0; p[(size_t)q * Q] = y1; p[(size_t)2 * q * Q] = y2; p[(size_t)3 * q * Q] = y3;
+      const float2 a0 = p[0], a1 = p[(size_t)q * Q], a2 = p[(size_t)2 * q * Q], a3 = p[(size_t)3 * q * Q];
+      const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+      const float2 mjd = make_float2(d13.y, -d13.x);      // -i * (a1 - a3)
+      float2 y1 = cadd(d02, mjd), y2 = csub(s02, s13), y3 = csub(d02, mjd);
+      if (q > 1) {                                         // j == 0 twiddles are exactly 1: multiplying is harmless
+        y1 = ctw<-1>(y1, tw[j * tws]); y2 = ctw<-1>(y2, tw[2 * j * tws]); y3 = ctw<-1>(y3, tw[3 * j * tws]);
+      }
+      p[0] = cadd(s02, s13); p[(size_t)q * Q] = y1; p[(size_t)2 * q * Q] = y2; p[(size_t)3 * q * Q] = y3;
     }
     __syncthreads();
   }
   if (odd) {
+#pragma unroll
     for (int id = tid; id < (H >> 1) * Q; id += kFftThreads) {
       const int l = id % Q, bf = id / Q;
       float2* p = d + (size_t)(2 * bf) * Q + l;
-      float2 a0 = p[0], a1 = p[Q];
-      p[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
-      p[Q] = make_float2(a0.x - a1.x, a0.y - a1.y);
+      const float2 a0 = p[0], a1 = p[Q];
+      p[0] = cadd(a0, a1);
+      p[Q] = csub(a0, a1);
     }
     __syncthreads();
   }
   // pointwise amplitude / phase mixing.  ky = 0 sits at position 0, ky = H/2 at position 1 (odd log2 H) or 2.
   const int pos_nyq = odd ? 1 : 2;
+#pragma unroll 4
   for (int id = tid; id < H * Q; id += kFftThreads) {
     const int pos = id / Q, l = id - pos * Q;
     if (l >= nl) continue;
@@ -230,33 +291,38 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
   __syncthreads();
   // inverse: decimation in time mirror of the forward graph, digit-reversed in -> natural out (unnormalised)
   if (odd) {
+#pragma unroll
     for (int id = tid; id < (H >> 1) * Q; id += kFftThreads) {
       const int l = id % Q, bf = id / Q;
       float2* p = d + (size_t)(2 * bf) * Q + l;
-      float2 a0 = p[0], a1 = p[Q];
-      p[0] = make_float2(a0.x + a1.x, a0.y + a1.y);
-      p[Q] = make_float2(a0.x - a1.x, a0.y - a1.y);
+      const float2 a0 = p[0], a1 = p[Q];
+      p[0] = cadd(a0, a1);
+      p[Q] = csub(a0, a1);
     }
     __syncthreads();
   }
+#pragma unroll
   for (int L = odd ? 8 : 4; L <= H; L <<= 2) {
     const int q = L >> 2, tws = H / L;
+#pragma unroll
     for (int id = tid; id < (H >> 2) * Q; id += kFftThreads) {
       const int l = id % Q, bf = id / Q;
       const int blk = bf / q, j = bf - blk * q;
       float2* p = d + (size_t)(blk * L + j) * Q + l;
       float2 a0 = p[0], a1 = p[(size_t)q * Q], a2 = p[(size_t)2 * q * Q], a3 = p[(size_t)3 * q * Q];
-      if (j) { a1 = cmul_conj(a1, tw[j * tws]); a2 = cmul_conj(a2, tw[2 * j * tws]); a3 = cmul_conj(a3, tw[3 * j * tws]); }
-      float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
-      float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
-      float2 jd = make_float2(-d13.y, d13.x);             // +i * (a1 - a3)
-      p[0] = make_float2(s02.x + s13.x, s02.y + s13.y);
-      p[(size_t)q * Q] = make_float2(d02.x + jd.x, d02.y + jd.y);
-      p[(size_t)2 * q * Q] = make_float2(s02.x - s13.x, s02.y - s13.y);
-      p[(size_t)3 * q * Q] = make_float2(d02.x - jd.x, d02.y - jd.y);
+      if (q > 1) {
+        a1 = ctw<+1>(a1, tw[j * tws]); a2 = ctw<+1>(a2, tw[2 * j * tws]); a3 = ctw<+1>(a3, tw[3 * j * tws]);
+      }
+      const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = csub(a1, a3);
+      const float2 jd = make_float2(-d13.y, d13.x);       // +i * (a1 - a3)
+      p[0] = cadd(s02, s13);
+      p[(size_t)q * Q] = cadd(d02, jd);
+      p[(size_t)2 * q * Q] = csub(s02, s13);
+      p[(size_t)3 * q * Q] = csub(d02, jd);
     }
     __syncthreads();
   }
+#pragma unroll 4
   for (int id = tid; id < H * Q; id += kFftThreads) {
     const int r = id / Q, l = id - r * Q;
     if (l < nl) base[(size_t)r * lanes_per_row + l] = d[id];
@@ -264,11 +330,12 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
 }
 
 // ---- pass 3: rows inverse (+ proj + residual) ------------------------------------------------------------
-template <int C2, bool PROJ>
+template <int C2, bool PROJ, int WCT>
 __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2* __restrict__ spec,
                                                                    const float* __restrict__ local,
                                                                    const float* __restrict__ xres, float* __restrict__ y,
-                                                                   BlockW w, int W, float scale) {
+                                                                   BlockW w, int Wrt, float scale) {
+  const int W = WCT ? WCT : Wrt;
   constexpr int NF = C2 / 2;
   constexpr int C = 2 * C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -297,7 +364,9 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2*
     }
   }
   __syncthreads();
-  const float2* res = stockham<+1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
+  const float2* res;
+  if constexpr (WCT != 0) res = stockham_ct<WCT, NF, +1, kFftThreads, 1>(bufA, bufB, tw, tid);
+  else res = stockham<+1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
   for (int px = tid; px < W; px += kFftThreads) {
     float g[C2];
 #pragma unroll
@@ -339,20 +408,22 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2*
 // ---- launchers ---------------------------------------------------------------------------------------------
 static bool pow2_in_range(int v) { return v >= 8 && v <= kTwN && (v & (v - 1)) == 0; }
 
+template <int C2, bool PRE_LN, int WCT>
+static cudaError_t rows_fwd_launch(const BlockW& w, const float* x, float* spec, int N, int H, int W, cudaStream_t s) {
+  size_t smem = (size_t)(W + 2 * (C2 / 2) * W) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, PRE_LN, WCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_rows_fwd_kernel<C2, PRE_LN, WCT><<<N * H, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
+  return cudaGetLastError();
+}
 template <int C2>
 static cudaError_t rows_fwd_t(const BlockW& w, const float* x, float* spec, int pre_ln, int N, int H, int W, cudaStream_t s) {
-  size_t smem = (size_t)(W + 2 * (C2 / 2) * W) * sizeof(float2);
-  cudaError_t e;
   if (pre_ln) {
-    e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fft_rows_fwd_kernel<C2, true><<<N * H, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
-  } else {
-    e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fft_rows_fwd_kernel<C2, false><<<N * H, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
+    if (W == 256) return rows_fwd_launch<C2, true, 256>(w, x, spec, N, H, W, s);
+    if (W == 128) return rows_fwd_launch<C2, true, 128>(w, x, spec, N, H, W, s);
+    return rows_fwd_launch<C2, true, 0>(w, x, spec, N, H, W, s);
   }
-  return cudaGetLastError();
+  return rows_fwd_launch<C2, false, 0>(w, x, spec, N, H, W, s);
 }
 
 cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* spec, int pre_ln, int N, int H, int W,
@@ -366,24 +437,25 @@ cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* s
   }
 }
 
-template <int Q>
+template <int Q, int HCT>
 static cudaError_t cols_t(const BlockW& w, int c2, float* spec, int N, int H, int W, cudaStream_t s) {
   const int lanes = (W / 2 + 1) * c2;
   size_t smem = (size_t)(H + H * Q) * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(fft_cols_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(fft_cols_kernel<Q, HCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((lanes + Q - 1) / Q, N);
-  fft_cols_kernel<Q><<<grid, kFftThreads, smem, s>>>(reinterpret_cast<float2*>(spec), w, H, W, c2, lanes);
+  fft_cols_kernel<Q, HCT><<<grid, kFftThreads, smem, s>>>(reinterpret_cast<float2*>(spec), w, H, W, c2, lanes);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fft_cols(const BlockW& w, int c, float* spec, int N, int H, int W, cudaStream_t s) {
   if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
   const int c2 = c / 2;
-  if (H <= 128) return cols_t<64>(w, c2, spec, N, H, W, s);
-  if (H == 256) return cols_t<32>(w, c2, spec, N, H, W, s);
-  if (H == 512) return cols_t<16>(w, c2, spec, N, H, W, s);
-  return cols_t<8>(w, c2, spec, N, H, W, s);
+  if (H == 128) return cols_t<64, 128>(w, c2, spec, N, H, W, s);
+  if (H < 128) return cols_t<64, 0>(w, c2, spec, N, H, W, s);
+  if (H == 256) return cols_t<32, 256>(w, c2, spec, N, H, W, s);
+  if (H == 512) return cols_t<16, 0>(w, c2, spec, N, H, W, s);
+  return cols_t<8, 0>(w, c2, spec, N, H, W, s);
 }
 
 template <int C2>
@@ -392,19 +464,18 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
   constexpr int C = 2 * C2;
   size_t smem = (size_t)(W + 2 * (C2 / 2) * W) * sizeof(float2) + (proj ? (size_t)(C * C + C) * sizeof(float) : 0);
   const float scale = 1.0f / ((float)H * (float)W);
-  cudaError_t e;
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<N * H, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w, W, scale);
+    return cudaGetLastError();
+  };
   if (proj) {
-    e = cudaFuncSetAttribute(fft_rows_inv_kernel<C2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fft_rows_inv_kernel<C2, true><<<N * H, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
-                                                                   W, scale);
-  } else {
-    e = cudaFuncSetAttribute(fft_rows_inv_kernel<C2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fft_rows_inv_kernel<C2, false><<<N * H, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y,
-                                                                    w, W, scale);
+    if (W == 256) return go(fft_rows_inv_kernel<C2, true, 256>);
+    if (W == 128) return go(fft_rows_inv_kernel<C2, true, 128>);
+    return go(fft_rows_inv_kernel<C2, true, 0>);
   }
-  return cudaGetLastError();
+  return go(fft_rows_inv_kernel<C2, false, 0>);
 }
 
 cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,

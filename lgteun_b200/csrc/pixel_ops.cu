@@ -122,62 +122,84 @@ cudaError_t launch_down(const PriorW& w, int C, const float* x, float* y, int N,
 }
 
 // ---- up unit + skip fusion ---------------------------------------------------------------------------
-// low [N,H/2,W/2,2C] -> bicubic x2 -> up_w (2C->C) ; y = fuse_w[:, :C] up + fuse_w[:, C:] skip + fuse_b
-template <int C>
-__global__ void __launch_bounds__(128) up_fuse_kernel(const float* __restrict__ low, const float* __restrict__ skip,
-                                                       float* __restrict__ y, PriorW w, int H, int W, long long total) {
+// reference (LGT.py:294-295,336-338): fea = up_conv(bicubic_x2(low)); y = fuse_conv(cat[fea, skip]).
+// A per-pixel affine map commutes with the bicubic resize (its taps sum to 1 and index clamping is linear), so the
+// 2C->C conv runs at LOW resolution (4x fewer pixels, fp32 rounding differs by ~1e-7 relative), then one kernel does
+// bicubic x2 from a shared-memory patch, the concat with the skip map and the 2C->C fusion conv.
+template <int K, int NOUT>
+__global__ void __launch_bounds__(128) pw_conv_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       const float* __restrict__ wt, const float* __restrict__ bias,
+                                                       long long total) {
   extern __shared__ float smem[];
-  float* sUp = smem;                    // [C][2C]
-  float* sFu = sUp + 2 * C * C;         // [C][2C]
-  float* sUb = sFu + 2 * C * C;         // [C]
-  float* sFb = sUb + C;                 // [C]
-  for (int i = threadIdx.x; i < 2 * C * C; i += 128) { sUp[i] = __ldg(w.up_w + i); sFu[i] = __ldg(w.fuse_w + i); }
-  for (int i = threadIdx.x; i < C; i += 128) { sUb[i] = __ldg(w.up_b + i); sFb[i] = __ldg(w.fuse_b + i); }
+  float* sW = smem;                 // [NOUT][K]
+  float* sB = smem + NOUT * K;
+  for (int i = threadIdx.x; i < NOUT * K; i += 128) sW[i] = __ldg(wt + i);
+  for (int i = threadIdx.x; i < NOUT; i += 128) sB[i] = __ldg(bias + i);
   __syncthreads();
-  const int lh = H / 2, lw = W / 2;
   long long p = (long long)blockIdx.x * 128 + threadIdx.x;
   if (p >= total) return;
-  int ox = (int)(p % W);
-  long long q = p / W;
-  int oy = (int)(q % H);
-  long long n = q / H;
+  float v[K];
+  load_vec<K>(v, x + p * K);
+  matvec_store<K, NOUT>(v, sW, sB, y + p * NOUT);
+}
+
+constexpr int UFH = 8, UFW = 32;                  // output tile (rows x cols), one thread per pixel
+constexpr int UFPH = UFH / 2 + 4, UFPW = UFW / 2 + 4;   // low-res patch 8 x 20
+
+template <int C>
+__global__ void __launch_bounds__(256) up_fuse_kernel(const float* __restrict__ t_low, const float* __restrict__ skip,
+                                                       float* __restrict__ y, PriorW w, int H, int W) {
+  constexpr int PS = C + 4;                       // padded pixel stride: conflict-free 128-bit reads
+  extern __shared__ __align__(16) float smem[];
+  float* sP = smem;                               // [UFPH*UFPW][PS]
+  float* sFu = sP + UFPH * UFPW * PS;             // [C][2C]
+  float* sFb = sFu + 2 * C * C;                   // [C]
+  const int tid = threadIdx.x;
+  const int lh = H / 2, lw = W / 2;
+  const int n = blockIdx.z;
+  const int Y0 = blockIdx.y * UFH, X0 = blockIdx.x * UFW;
+  const int py0 = Y0 / 2 - 2, px0 = X0 / 2 - 2;   // low-res origin of the patch (replicated borders)
+  for (int i = tid; i < 2 * C * C; i += 256) sFu[i] = __ldg(w.fuse_w + i);
+  for (int i = tid; i < C; i += 256) sFb[i] = __ldg(w.fuse_b + i);
+  for (int i = tid; i < UFPH * UFPW * (C / 4); i += 256) {
+    const int pix = i / (C / 4), c4 = i - pix * (C / 4);
+    const int pr = pix / UFPW, pc = pix - pr * UFPW;
+    const int gy = clampi(py0 + pr, 0, lh - 1), gx = clampi(px0 + pc, 0, lw - 1);
+    *reinterpret_cast<float4*>(sP + pix * PS + 4 * c4) =
+        __ldg(reinterpret_cast<const float4*>(t_low + (((size_t)n * lh + gy) * lw + gx) * C) + c4);
+  }
+  __syncthreads();
+  const int ty = tid >> 5, tx = tid & 31;
+  const int oy = Y0 + ty, ox = X0 + tx;
+  if (oy >= H || ox >= W) return;
   // x2 taps: even dst 2q -> src q-2..q+1 (t=.75), odd dst 2q+1 -> src q-1..q+2 (t=.25)
   const float te[4] = {-0.03515625f, 0.26171875f, 0.87890625f, -0.10546875f};
   const float to[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
-  const int fy = (oy >> 1) - ((oy & 1) ? 1 : 2), fx = (ox >> 1) - ((ox & 1) ? 1 : 2);
-  float u[2 * C];
+  const int fy = (oy >> 1) - ((oy & 1) ? 1 : 2) - py0, fx = (ox >> 1) - ((ox & 1) ? 1 : 2) - px0;
+  float cat[2 * C];                               // [upsampled | skip]
 #pragma unroll
-  for (int c = 0; c < 2 * C; ++c) u[c] = 0.f;
+  for (int c = 0; c < C; ++c) cat[c] = 0.f;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    int gy = clampi(fy + a, 0, lh - 1);
-    float wy = (oy & 1) ? to[a] : te[a];
-    float r[2 * C];
+    const float wy = (oy & 1) ? to[a] : te[a];
+    float r[C];
 #pragma unroll
-    for (int c = 0; c < 2 * C; ++c) r[c] = 0.f;
+    for (int c = 0; c < C; ++c) r[c] = 0.f;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      int gx = clampi(fx + b, 0, lw - 1);
-      float wx = (ox & 1) ? to[b] : te[b];
-      const float* src = low + ((n * lh + gy) * lw + gx) * (2 * C);
+      const float wx = (ox & 1) ? to[b] : te[b];
+      const float* src = sP + ((fy + a) * UFPW + fx + b) * PS;
 #pragma unroll
-      for (int c4 = 0; c4 < 2 * C; c4 += 4) {
-        float4 t = *reinterpret_cast<const float4*>(src + c4);
+      for (int c4 = 0; c4 < C; c4 += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src + c4);
         r[c4] = fmaf(wx, t.x, r[c4]); r[c4 + 1] = fmaf(wx, t.y, r[c4 + 1]);
         r[c4 + 2] = fmaf(wx, t.z, r[c4 + 2]); r[c4 + 3] = fmaf(wx, t.w, r[c4 + 3]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < 2 * C; ++c) u[c] = fmaf(wy, r[c], u[c]);
+    for (int c = 0; c < C; ++c) cat[c] = fmaf(wy, r[c], cat[c]);
   }
-  float cat[2 * C];                      // [up | skip]
-#pragma unroll
-  for (int o = 0; o < C; ++o) {
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < 2 * C; ++k) acc = fmaf(sUp[o * 2 * C + k], u[k], acc);
-    cat[o] = acc + sUb[o];
-  }
+  const size_t p = ((size_t)n * H + oy) * W + ox;
   {
     float t[C];
     load_vec<C>(t, skip + p * C);
@@ -187,14 +209,22 @@ __global__ void __launch_bounds__(128) up_fuse_kernel(const float* __restrict__ 
   matvec_store<2 * C, C>(cat, sFu, sFb, y + p * C);
 }
 
-cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float* skip, float* y, int N, int H, int W,
-                           cudaStream_t s) {
-  long long total = (long long)N * H * W;
-  unsigned grid = (unsigned)((total + 127) / 128);
-  size_t smem = (size_t)(4 * C * C + 2 * C) * sizeof(float);
-  if (C == 16) up_fuse_kernel<16><<<grid, 128, smem, s>>>(low, skip, y, w, H, W, total);
-  else if (C == 32) up_fuse_kernel<32><<<grid, 128, smem, s>>>(low, skip, y, w, H, W, total);
-  else return cudaErrorInvalidValue;
+cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float* skip, float* t_low, float* y, int N, int H,
+                           int W, cudaStream_t s) {
+  const long long low_px = (long long)N * (H / 2) * (W / 2);
+  const unsigned g0 = (unsigned)((low_px + 127) / 128);
+  dim3 grid((W + UFW - 1) / UFW, (H + UFH - 1) / UFH, N);
+  if (C == 16) {
+    pw_conv_kernel<32, 16><<<g0, 128, (32 * 16 + 16) * sizeof(float), s>>>(low, t_low, w.up_w, w.up_b, low_px);
+    size_t smem = (size_t)(UFPH * UFPW * (16 + 4) + 2 * 16 * 16 + 16) * sizeof(float);
+    up_fuse_kernel<16><<<grid, 256, smem, s>>>(t_low, skip, y, w, H, W);
+  } else if (C == 32) {
+    pw_conv_kernel<64, 32><<<g0, 128, (64 * 32 + 32) * sizeof(float), s>>>(low, t_low, w.up_w, w.up_b, low_px);
+    size_t smem = (size_t)(UFPH * UFPW * (32 + 4) + 2 * 32 * 32 + 32) * sizeof(float);
+    up_fuse_kernel<32><<<grid, 256, smem, s>>>(t_low, skip, y, w, H, W);
+  } else {
+    return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
