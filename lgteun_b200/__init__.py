@@ -8,7 +8,8 @@ The compute lives in lgteun_b200/csrc (CUDA) behind the C ABI of include/lgteun.
 from . import _abi
 from .module import Pansharpening, expected_state_dict_keys, param_count
 from .register import install
+from .hostio import HostPipeline
 from .sharding import forward_sharded, shard_range
 
-__all__ = ["Pansharpening", "install", "shard_range", "forward_sharded", "expected_state_dict_keys", "param_count", "_abi"]
+__all__ = ["Pansharpening", "install", "shard_range", "forward_sharded", "HostPipeline", "expected_state_dict_keys", "param_count", "_abi"]
 __version__ = "0.1.0"

@@ -28,7 +28,7 @@
 namespace lg {
 
 constexpr int kStripW = 30;          // interior pixels per warp strip (32 lanes - 2 halo lanes)
-constexpr int kRowsPerBand = 32;     // output rows streamed by one CTA pass
+// output rows streamed by one CTA pass (band_rows) are chosen per launch: 64 when the grid is deep, fewer for small batches
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -152,7 +152,7 @@ struct FfnTcSmem {
 template <int C, int G>
 __global__ void __launch_bounds__(128 * G, (C == 16) ? 2 : 1)
 ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w, const __half* __restrict__ wpack,
-              int H, int W, int nws, int nbands, int total_units, int num_groups) {
+              int H, int W, int nws, int nbands, int band_rows, int total_units, int num_groups) {
   constexpr int C4 = 4 * C;
   constexpr int NT = 128 * G;
   constexpr int CH = C4 / G;            // hidden channels per thread
@@ -222,12 +222,12 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     }
     const int x = ws * kStripW + lane - 1;
     const bool x_ok = unit_ok && x >= 0 && x < W;
-    const int y0 = band * kRowsPerBand;
-    const int rows = min(kRowsPerBand, H - y0);          // output rows of this band (uniform over the image)
+    const int y0 = band * band_rows;
+    const int rows = min(band_rows, H - y0);              // output rows of this band (uniform over the image)
     const float* xrow0 = xin + (size_t)n * H * W * C;
     float* yrow0 = yout + (size_t)n * H * W * C;
     const float2 m2 = x_ok ? make_float2(1.f, 1.f) : make_float2(0.f, 0.f);
-    const int iters = min(kRowsPerBand, H) + 2;           // H is a power of two: every band has the same height
+    const int iters = min(band_rows, H) + 2;              // H and band_rows are powers of two: every band has the same height
 
     // ---- S_a: LayerNorm(x[row]) -> A1 (hi/lo fp16), spread over all warps -------------------------------------------
     // Thread (pixel row, cg) owns channels [8cg, 8cg+8): the global load is issued one row ahead (prefetch_x), the
@@ -506,16 +506,21 @@ static cudaError_t ffn_tc_t(const BlockW& w, const float* x, float* y, int N, in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int nws = (W + kStripW - 1) / kStripW, nbands = (H + kRowsPerBand - 1) / kRowsPerBand;
+  const int per_sm = (C == 16) ? 2 : 1;
+  const int nws = (W + kStripW - 1) / kStripW;
+  // taller bands amortise the two halo rows (66/64 vs 34/32 vs 18/16) but need about one full wave of groups
+  int band_rows = 64;
+  while (band_rows > 8 && (band_rows > H || (N * ((H + band_rows - 1) / band_rows) * nws + 3) / 4 < (9 * sm_count * per_sm) / 10))
+    band_rows >>= 1;
+  const int nbands = (H + band_rows - 1) / band_rows;
   const int units = N * nbands * nws;
   const int groups = (units + 3) / 4;
   const size_t smem = sizeof(FfnTcSmem<C>) + 128;
   cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int per_sm = (C == 16) ? 2 : 1;
   const int grid = groups < sm_count * per_sm ? groups : sm_count * per_sm;
   ffn_tc_kernel<C, G><<<grid, 128 * G, smem, s>>>(x, y, w, reinterpret_cast<const __half*>(w.ffn_pack), H, W, nws, nbands,
-                                                   units, groups);
+                                                   band_rows, units, groups);
   return cudaGetLastError();
 }
 

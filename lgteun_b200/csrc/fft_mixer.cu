@@ -389,17 +389,24 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2*
       float* dst = y + (row * W + px) * C;
 #pragma unroll 1
       for (int o = 0; o < C; o += 4) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        const float4* r0 = reinterpret_cast<const float4*>(sW + (o + 0) * C);
+        const float4* r1 = reinterpret_cast<const float4*>(sW + (o + 1) * C);
+        const float4* r2 = reinterpret_cast<const float4*>(sW + (o + 2) * C);
+        const float4* r3 = reinterpret_cast<const float4*>(sW + (o + 3) * C);
 #pragma unroll
-        for (int k = 0; k < C; ++k) {
-          a0 = fmaf(sW[(o + 0) * C + k], cat[k], a0);
-          a1 = fmaf(sW[(o + 1) * C + k], cat[k], a1);
-          a2 = fmaf(sW[(o + 2) * C + k], cat[k], a2);
-          a3 = fmaf(sW[(o + 3) * C + k], cat[k], a3);
+        for (int k4 = 0; k4 < C / 4; ++k4) {
+          const float2 va = make_float2(cat[4 * k4], cat[4 * k4 + 1]), vb = make_float2(cat[4 * k4 + 2], cat[4 * k4 + 3]);
+          const float4 w0 = r0[k4], w1 = r1[k4], w2 = r2[k4], w3 = r3[k4];
+          a0 = __ffma2_rn(make_float2(w0.x, w0.y), va, a0); a0 = __ffma2_rn(make_float2(w0.z, w0.w), vb, a0);
+          a1 = __ffma2_rn(make_float2(w1.x, w1.y), va, a1); a1 = __ffma2_rn(make_float2(w1.z, w1.w), vb, a1);
+          a2 = __ffma2_rn(make_float2(w2.x, w2.y), va, a2); a2 = __ffma2_rn(make_float2(w2.z, w2.w), vb, a2);
+          a3 = __ffma2_rn(make_float2(w3.x, w3.y), va, a3); a3 = __ffma2_rn(make_float2(w3.z, w3.w), vb, a3);
         }
         float4 r = *reinterpret_cast<const float4*>(xr + o);
-        *reinterpret_cast<float4*>(dst + o) = make_float4((a0 + sBias[o]) + r.x, (a1 + sBias[o + 1]) + r.y,
-                                                          (a2 + sBias[o + 2]) + r.z, (a3 + sBias[o + 3]) + r.w);
+        *reinterpret_cast<float4*>(dst + o) =
+            make_float4(((a0.x + a0.y) + sBias[o]) + r.x, ((a1.x + a1.y) + sBias[o + 1]) + r.y,
+                        ((a2.x + a2.y) + sBias[o + 2]) + r.z, ((a3.x + a3.y) + sBias[o + 3]) + r.w);
       }
     }
   }

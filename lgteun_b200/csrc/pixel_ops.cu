@@ -50,22 +50,30 @@ cudaError_t launch_patch_embed(const PriorW& w, int B, const float* x, float* y,
 }
 
 // ---- dense per-pixel matvec with weights [NOUT][K] in shared memory ---------------------------------
-// out[o] = bias[o] + sum_k W[o][k] v[k]; processed 4 outputs at a time to bound live registers.
+// out[o] = bias[o] + sum_k W[o][k] v[k]; four outputs at a time, weights as 128-bit broadcasts, dot products on the
+// packed fp32 pipe (two k per FFMA2).  sW must be 16-byte aligned and K a multiple of 4.
 template <int K, int NOUT>
 __device__ __forceinline__ void matvec_store(const float (&v)[K], const float* __restrict__ sW,
                                              const float* __restrict__ sBias, float* __restrict__ dst) {
-#pragma unroll
+  static_assert(K % 4 == 0 && NOUT % 4 == 0, "matvec tiles are 4x4");
+#pragma unroll 1
   for (int o = 0; o < NOUT; o += 4) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    const float4* r0 = reinterpret_cast<const float4*>(sW + (o + 0) * K);
+    const float4* r1 = reinterpret_cast<const float4*>(sW + (o + 1) * K);
+    const float4* r2 = reinterpret_cast<const float4*>(sW + (o + 2) * K);
+    const float4* r3 = reinterpret_cast<const float4*>(sW + (o + 3) * K);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      a0 = fmaf(sW[(o + 0) * K + k], v[k], a0);
-      a1 = fmaf(sW[(o + 1) * K + k], v[k], a1);
-      a2 = fmaf(sW[(o + 2) * K + k], v[k], a2);
-      a3 = fmaf(sW[(o + 3) * K + k], v[k], a3);
+    for (int k4 = 0; k4 < K / 4; ++k4) {
+      const float2 va = make_float2(v[4 * k4], v[4 * k4 + 1]), vb = make_float2(v[4 * k4 + 2], v[4 * k4 + 3]);
+      const float4 w0 = r0[k4], w1 = r1[k4], w2 = r2[k4], w3 = r3[k4];
+      a0 = __ffma2_rn(make_float2(w0.x, w0.y), va, a0); a0 = __ffma2_rn(make_float2(w0.z, w0.w), vb, a0);
+      a1 = __ffma2_rn(make_float2(w1.x, w1.y), va, a1); a1 = __ffma2_rn(make_float2(w1.z, w1.w), vb, a1);
+      a2 = __ffma2_rn(make_float2(w2.x, w2.y), va, a2); a2 = __ffma2_rn(make_float2(w2.z, w2.w), vb, a2);
+      a3 = __ffma2_rn(make_float2(w3.x, w3.y), va, a3); a3 = __ffma2_rn(make_float2(w3.z, w3.w), vb, a3);
     }
-    *reinterpret_cast<float4*>(dst + o) =
-        make_float4(a0 + sBias[o], a1 + sBias[o + 1], a2 + sBias[o + 2], a3 + sBias[o + 3]);
+    *reinterpret_cast<float4*>(dst + o) = make_float4((a0.x + a0.y) + sBias[o], (a1.x + a1.y) + sBias[o + 1],
+                                                      (a2.x + a2.y) + sBias[o + 2], (a3.x + a3.y) + sBias[o + 3]);
   }
 }
 
@@ -74,7 +82,7 @@ template <int C>
 __global__ void __launch_bounds__(128) down_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                     const float* __restrict__ wt, const float* __restrict__ bias,
                                                     int H, int W, long long total) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* sW = smem;                 // [2C][C]
   float* sB = smem + 2 * C * C;     // [2C]
   for (int i = threadIdx.x; i < 2 * C * C; i += 128) sW[i] = __ldg(wt + i);
@@ -130,7 +138,7 @@ template <int K, int NOUT>
 __global__ void __launch_bounds__(128) pw_conv_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                        const float* __restrict__ wt, const float* __restrict__ bias,
                                                        long long total) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* sW = smem;                 // [NOUT][K]
   float* sB = smem + NOUT * K;
   for (int i = threadIdx.x; i < NOUT * K; i += 128) sW[i] = __ldg(wt + i);
@@ -269,7 +277,9 @@ cudaError_t launch_tail(const PriorW& w, int B, const float* fea, const float* x
 __global__ void transpose_pos_kernel(const float* __restrict__ pos, float* __restrict__ pos_t) {
   int idx = blockIdx.x * 256 + threadIdx.x;       // over [2][64][64] of the destination
   if (idx >= 2 * 64 * 64) return;
-  int h = idx >> 12, j = (idx >> 6) & 63, i = idx & 63;
+  // destination layout [head][key/4][query][key%4]: one 128-bit load per query thread fetches four keys
+  int h = idx >> 12, jq = (idx >> 8) & 15, i = (idx >> 2) & 63, jr = idx & 3;
+  int j = 4 * jq + jr;
   pos_t[idx] = pos[(h << 12) + (i << 6) + j] * 1.4426950408889634f;
 }
 cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s) {

@@ -17,11 +17,12 @@ namespace lg {
 
 constexpr int kWinPerIter = 2;          // windows processed concurrently by one CTA (128 threads each)
 constexpr int kMsaThreads = 128 * kWinPerIter;
+constexpr bool kRecomputeLogits = false;   // two-pass softmax that recomputes q.k instead of keeping 64 logits in registers
 
 template <int C2>
 struct MsaSmem {
   static constexpr int D = C2 / kHeads;
-  float pos_t[kHeads * 64 * 64];                    // [h][j][i]
+  alignas(16) float pos_t[kHeads * 64 * 64];        // [h][j/4][i][j%4], pre-scaled by log2(e)
   float wqkv[3 * C2 * C2];                          // [3*C2][C2]
   float bqkv[3 * C2];
   float xs[kWinPerIter][C2][64 + 1];                // LN'd local half, channel-major (conflict-free per-token reads)
@@ -120,12 +121,10 @@ __global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1) window_msa_ke
     // 3) logits + softmax + PV, all in registers
     if (active) {
       // logits for 4 keys at a time on the packed fp32 pipe; pos_t already holds pos_emb * log2(e), transposed
-      float2 s2[32];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        float2 a01 = make_float2(sm.pos_t[(head * 64 + j) * 64 + tok], sm.pos_t[(head * 64 + j + 1) * 64 + tok]);
-        float2 a23 = make_float2(sm.pos_t[(head * 64 + j + 2) * 64 + tok], sm.pos_t[(head * 64 + j + 3) * 64 + tok]);
+      auto logits4 = [&](int j, float2& a01, float2& a23) {
+        const float4 p4 = *reinterpret_cast<const float4*>(&sm.pos_t[((head * 16 + (j >> 2)) * 64 + tok) * 4]);
+        a01 = make_float2(p4.x, p4.y);
+        a23 = make_float2(p4.z, p4.w);
 #pragma unroll
         for (int c = 0; c < D; ++c) {
           const float4 kv = *reinterpret_cast<const float4*>(&sm.ks[slot][head][c][j]);
@@ -133,32 +132,56 @@ __global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1) window_msa_ke
           a01 = __ffma2_rn(qc, make_float2(kv.x, kv.y), a01);
           a23 = __ffma2_rn(qc, make_float2(kv.z, kv.w), a23);
         }
-        s2[j / 2] = a01;
-        s2[j / 2 + 1] = a23;
-        mx = fmaxf(mx, fmaxf(fmaxf(a01.x, a01.y), fmaxf(a23.x, a23.y)));
-      }
+      };
       float2 sum2 = make_float2(0.f, 0.f);
       float2 o2[D / 2];
 #pragma unroll
       for (int c = 0; c < D / 2; ++c) o2[c] = make_float2(0.f, 0.f);
-      const float2 nmx = make_float2(-mx, -mx);
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const float2 d = __fadd2_rn(s2[jj], nmx);
+      auto accumulate2 = [&](int j, float2 s, float2 nmx) {      // keys j, j+1
+        const float2 d = __fadd2_rn(s, nmx);
         float2 p;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.x) : "f"(d.x));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.y) : "f"(d.y));
         sum2 = __fadd2_rn(sum2, p);
 #pragma unroll
         for (int c4 = 0; c4 < D; c4 += 4) {
-          const float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][2 * jj][c4]);
-          const float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][2 * jj + 1][c4]);
+          const float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][j][c4]);
+          const float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][j + 1][c4]);
           const float2 p0 = make_float2(p.x, p.x), p1 = make_float2(p.y, p.y);
           o2[c4 / 2] = __ffma2_rn(p0, make_float2(v0.x, v0.y), o2[c4 / 2]);
           o2[c4 / 2 + 1] = __ffma2_rn(p0, make_float2(v0.z, v0.w), o2[c4 / 2 + 1]);
           o2[c4 / 2] = __ffma2_rn(p1, make_float2(v1.x, v1.y), o2[c4 / 2]);
           o2[c4 / 2 + 1] = __ffma2_rn(p1, make_float2(v1.z, v1.w), o2[c4 / 2 + 1]);
         }
+      };
+      float mx = -INFINITY;
+      if constexpr (kRecomputeLogits && D == 4) {
+        // measured slower (175 vs 135 us / 16 pairs): the doubled K / pos_emb shared-memory traffic outweighs the
+        // occupancy gained from ~64 registers per thread, so this variant is compiled out
+#pragma unroll 4
+        for (int j = 0; j < 64; j += 4) {
+          float2 a01, a23;
+          logits4(j, a01, a23);
+          mx = fmaxf(mx, fmaxf(fmaxf(a01.x, a01.y), fmaxf(a23.x, a23.y)));
+        }
+        const float2 nmx = make_float2(-mx, -mx);
+#pragma unroll 4
+        for (int j = 0; j < 64; j += 4) {
+          float2 a01, a23;
+          logits4(j, a01, a23);
+          accumulate2(j, a01, nmx);
+          accumulate2(j + 2, a23, nmx);
+        }
+      } else {
+        float2 s2[32];
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          logits4(j, s2[j / 2], s2[j / 2 + 1]);
+          mx = fmaxf(mx, fmaxf(fmaxf(s2[j / 2].x, s2[j / 2].y), fmaxf(s2[j / 2 + 1].x, s2[j / 2 + 1].y)));
+        }
+        const float2 nmx = make_float2(-mx, -mx);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) accumulate2(2 * jj, s2[jj], nmx);
       }
       const float sum = sum2.x + sum2.y;
       float o[D];

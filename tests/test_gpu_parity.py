@@ -238,6 +238,24 @@ def test_forward_host_buffers(abi, h4):
     assert _maxdiff(out, g["out"]) <= E2E_TOL
 
 
+def test_host_pipeline_matches_direct_forward(abi):
+    """Chunked H2D / forward / D2H on three streams == one direct forward (pairs are independent), bitwise."""
+    import lgteun_b200
+    from types import SimpleNamespace
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=4), None, stage=2)
+    net.load_state_dict(load_weights(4))
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    ms = torch.rand(7, 4, 16, 16, generator=g).pin_memory()
+    pan = torch.rand(7, 1, 64, 64, generator=g).pin_memory()
+    with torch.no_grad():
+        direct = net(ms.cuda(), pan.cuda()).cpu()
+    pipe = lgteun_b200.HostPipeline(net, chunk=3)           # 3 + 3 + 1: exercises buffer reuse and a ragged tail
+    for _ in range(2):
+        out = pipe(ms, pan)
+        assert torch.equal(out, direct)
+
+
 def test_metrics_within_tolerance(abi, h4):
     from oracle import metrics_oracle as M
     g = load_case("gf2_metric")
