@@ -319,24 +319,26 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       ph1 ^= 1;
       tc_fence_after();
       {
-        float2 nxt[4];
-        tmem_ld8(lane_addr + D1_COL + cg * CH, nxt);
+        // all CH accumulator columns of this thread in one go (one wait), then CH/8 independent chunks the
+        // scheduler can interleave: the epilogue is latency-bound, not issue-bound
+        float2 acc[CH / 8][4];
+#pragma unroll
+        for (int c = 0; c < CH / 8; ++c) tmem_ld8(lane_addr + D1_COL + cg * CH + 8 * c, acc[c]);
         tmem_ld_wait();
-#pragma unroll 1
-        for (int c0 = cg * CH; c0 < (cg + 1) * CH; c0 += 8) {
-          float2 v[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
-          if (c0 + 8 < (cg + 1) * CH) tmem_ld8(lane_addr + D1_COL + c0 + 8, nxt);    // in flight while this chunk computes
+#pragma unroll
+        for (int c = 0; c < CH / 8; ++c) {
+          const int c0 = cg * CH + 8 * c;
           const float4 ba = *reinterpret_cast<const float4*>(&sm.b0[c0]);
           const float4 bb = *reinterpret_cast<const float4*>(&sm.b0[c0 + 4]);
-          v[0] = gelu_pair(__fadd2_rn(v[0], make_float2(ba.x, ba.y)));
-          v[1] = gelu_pair(__fadd2_rn(v[1], make_float2(ba.z, ba.w)));
-          v[2] = gelu_pair(__fadd2_rn(v[2], make_float2(bb.x, bb.y)));
-          v[3] = gelu_pair(__fadd2_rn(v[3], make_float2(bb.z, bb.w)));
+          float2 v[4];
+          v[0] = gelu_pair(__fadd2_rn(acc[c][0], make_float2(ba.x, ba.y)));
+          v[1] = gelu_pair(__fadd2_rn(acc[c][1], make_float2(ba.z, ba.w)));
+          v[2] = gelu_pair(__fadd2_rn(acc[c][2], make_float2(bb.x, bb.y)));
+          v[3] = gelu_pair(__fadd2_rn(acc[c][3], make_float2(bb.z, bb.w)));
           uint4 hi, lo;
           split8(v, hi, lo);
           *reinterpret_cast<uint4*>(&sm.a2h[((c0 >> 3) * 128 + row) * 8]) = hi;
           *reinterpret_cast<uint4*>(&sm.a2l[((c0 >> 3) * 128 + row) * 8]) = lo;
-          tmem_ld_wait();
         }
       }
       if (it + 1 < iters) publish_stats();

@@ -140,10 +140,13 @@ __device__ __forceinline__ float2* stockham_ct(float2* a, float2* b, const float
           }
           const float2 s02 = cadd(v0, v2), d02 = csub(v0, v2), s13 = cadd(v1, v3), d13 = csub(v1, v3);
           const float2 jd = (SIGN < 0) ? make_float2(d13.y, -d13.x) : make_float2(-d13.y, d13.x);
-          dst[0] = cadd(s02, s13);
-          dst[Ns] = cadd(d02, jd);
-          dst[2 * Ns] = csub(s02, s13);
-          dst[3 * Ns] = csub(d02, jd);
+          const float2 o0 = cadd(s02, s13), o1 = cadd(d02, jd), o2 = csub(s02, s13), o3 = csub(d02, jd);
+          if constexpr (Ns == 1) {                   // the four outputs are contiguous: two conflict-free 128-bit stores
+            reinterpret_cast<float4*>(dst)[0] = make_float4(o0.x, o0.y, o1.x, o1.y);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(o2.x, o2.y, o3.x, o3.y);
+          } else {
+            dst[0] = o0; dst[Ns] = o1; dst[2 * Ns] = o2; dst[3 * Ns] = o3;
+          }
         } else {
           float2 v0 = src[0], v1 = src[q];
           if constexpr (Ns > 1) v1 = ctw<SIGN>(v1, tw[k * tws]);
@@ -160,21 +163,23 @@ __device__ __forceinline__ float2* stockham_ct(float2* a, float2* b, const float
 constexpr int kFftThreads = 256;
 
 // ---- pass 1: rows forward ----------------------------------------------------------------------------
-template <int C2, bool PRE_LN, int WCT>
+template <int C2, bool PRE_LN, int WCT, int ROWS>
 __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
                                                                    BlockW w, int Wrt) {
   const int W = WCT ? WCT : Wrt;                          // WCT != 0: compile-time row length (fast path)
-  constexpr int NF = C2 / 2;
+  constexpr int NF1 = C2 / 2;                             // complex sequences per image row (two real channels each)
+  constexpr int NF = NF1 * ROWS;                          // ROWS consecutive image rows per CTA: more work per barrier
   constexpr int CIN = PRE_LN ? 2 * C2 : C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);       // [W]
   float2* bufA = tw + W;                                  // [NF][W]
   float2* bufB = bufA + NF * W;
   const int tid = threadIdx.x;
-  const size_t row = blockIdx.x;                          // n*H + y
+  const size_t row0 = (size_t)blockIdx.x * ROWS;          // n*H + y of the first row
   for (int j = tid; j < W; j += kFftThreads) tw[j] = g_tw[j * (kTwN / W)];
-  for (int px = tid; px < W; px += kFftThreads) {
-    const float* src = x + (row * W + px) * CIN;
+  for (int p = tid; p < ROWS * W; p += kFftThreads) {
+    const int rl = p / W, px = p - rl * W;
+    const float* src = x + ((row0 + rl) * W + px) * CIN;
     float g[C2];
     if constexpr (PRE_LN) {
       float v[CIN];
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* 
       load_vec<C2>(g, src);
     }
 #pragma unroll
-    for (int f = 0; f < NF; ++f) bufA[f * W + px] = make_float2(g[2 * f], g[2 * f + 1]);
+    for (int f = 0; f < NF1; ++f) bufA[(rl * NF1 + f) * W + px] = make_float2(g[2 * f], g[2 * f + 1]);
   }
   __syncthreads();
   const float2* res;
@@ -202,16 +207,17 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* 
   else res = stockham<-1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
   // split the packed transform: channel a = 2f (real part), b = 2f+1 (imag part)
   const int Wf = W / 2 + 1;
-  float4* out = reinterpret_cast<float4*>(spec + row * Wf * C2);
-  for (int id = tid; id < Wf * NF; id += kFftThreads) {
-    const int k = id / NF, f = id - k * NF;
+  float4* out = reinterpret_cast<float4*>(spec + row0 * Wf * C2);      // ROWS rows are contiguous in the spectrum
+  for (int id = tid; id < ROWS * Wf * NF1; id += kFftThreads) {
+    const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
+    const int k = rem / NF1, f = rl * NF1 + (rem - k * NF1);
     float2 z = res[f * W + k], zm = res[f * W + ((W - k) & (W - 1))];
     float4 o;
     o.x = 0.5f * (z.x + zm.x);        // Xa = (Z[k] + conj(Z[W-k])) / 2
     o.y = 0.5f * (z.y - zm.y);
     o.z = 0.5f * (z.y + zm.y);        // Xb = (Z[k] - conj(Z[W-k])) / (2i)
     o.w = 0.5f * (zm.x - z.x);
-    out[k * NF + f] = o;
+    out[id] = o;
   }
 }
 
@@ -277,12 +283,14 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
     const int kx = lane / C2, ch = lane - kx * C2;
     float2 z = d[id];
     if ((pos == 0 || pos == pos_nyq) && (kx == 0 || kx == W / 2)) z.y = 0.0f;   // exactly-real bins: +0.0 (F7)
-    float amp = hypotf(z.x, z.y);
+    // |z| by sqrt (no overflow risk at these magnitudes); the angle keeps the accurate atan2f because the phase weight
+    // amplifies its error (F7); sin/cos of the mixed phase go to the SFU: |pha'| stays within a few radians, where
+    // sin.approx / cos.approx are good to ~4e-7 absolute, i.e. below the fp32 rounding noise of the FFT itself
+    float amp = sqrtf(fmaf(z.x, z.x, z.y * z.y));
     float pha = atan2f(z.y, z.x);
     amp = amp * __ldg(w.amp_w + ch) + __ldg(w.amp_b + ch);
     pha = pha * __ldg(w.pha_w + ch) + __ldg(w.pha_b + ch);
-    float sn, cs;
-    sincosf(pha, &sn, &cs);
+    const float sn = __sinf(pha), cs = __cosf(pha);
     float re = amp * cs + 1e-8f;
     float im = amp * sn + 1e-8f;
     re = re + 1e-8f;                                       // complex(real, imag) + 1e-8 adds to the real part
@@ -330,13 +338,14 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
 }
 
 // ---- pass 3: rows inverse (+ proj + residual) ------------------------------------------------------------
-template <int C2, bool PROJ, int WCT>
+template <int C2, bool PROJ, int WCT, int ROWS>
 __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2* __restrict__ spec,
                                                                    const float* __restrict__ local,
                                                                    const float* __restrict__ xres, float* __restrict__ y,
                                                                    BlockW w, int Wrt, float scale) {
   const int W = WCT ? WCT : Wrt;
-  constexpr int NF = C2 / 2;
+  constexpr int NF1 = C2 / 2;
+  constexpr int NF = NF1 * ROWS;                          // ROWS consecutive image rows per CTA
   constexpr int C = 2 * C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);       // [W]
@@ -345,17 +354,18 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2*
   float* sW = reinterpret_cast<float*>(bufB + NF * W);    // [C][C] proj weight (PROJ only)
   float* sBias = sW + C * C;                              // [C]
   const int tid = threadIdx.x;
-  const size_t row = blockIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * ROWS;
   const int Wf = W / 2 + 1;
   for (int j = tid; j < W; j += kFftThreads) tw[j] = g_tw[j * (kTwN / W)];
   if constexpr (PROJ) {
     for (int i = tid; i < C * C; i += kFftThreads) sW[i] = __ldg(w.proj_w + i);
     for (int i = tid; i < C; i += kFftThreads) sBias[i] = __ldg(w.proj_b + i);
   }
-  const float4* in = reinterpret_cast<const float4*>(spec + row * Wf * C2);
-  for (int id = tid; id < Wf * NF; id += kFftThreads) {
-    const int k = id / NF, f = id - k * NF;
-    float4 v = __ldg(in + k * NF + f);                    // (Xa.re, Xa.im, Xb.re, Xb.im)
+  const float4* in = reinterpret_cast<const float4*>(spec + row0 * Wf * C2);
+  for (int id = tid; id < ROWS * Wf * NF1; id += kFftThreads) {
+    const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
+    const int k = rem / NF1, f = rl * NF1 + (rem - k * NF1);
+    float4 v = __ldg(in + id);                            // (Xa.re, Xa.im, Xb.re, Xb.im)
     if (k == 0 || k == W / 2) {                           // C2R ignores Im of the DC and Nyquist bins
       bufA[f * W + k] = make_float2(v.x, v.z);
     } else {
@@ -367,11 +377,13 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2*
   const float2* res;
   if constexpr (WCT != 0) res = stockham_ct<WCT, NF, +1, kFftThreads, 1>(bufA, bufB, tw, tid);
   else res = stockham<+1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
-  for (int px = tid; px < W; px += kFftThreads) {
+  for (int p = tid; p < ROWS * W; p += kFftThreads) {
+    const int rl = p / W, px = p - rl * W;
+    const size_t row = row0 + rl;
     float g[C2];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      float2 z = res[f * W + px];
+    for (int f = 0; f < NF1; ++f) {
+      float2 z = res[(rl * NF1 + f) * W + px];
       g[2 * f] = fabsf(z.x * scale);
       g[2 * f + 1] = fabsf(z.y * scale);
     }
@@ -415,22 +427,25 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2*
 // ---- launchers ---------------------------------------------------------------------------------------------
 static bool pow2_in_range(int v) { return v >= 8 && v <= kTwN && (v & (v - 1)) == 0; }
 
-template <int C2, bool PRE_LN, int WCT>
+// rows per CTA on the fast path: 16 complex sequences per CTA (C2=8: 4 rows, C2=16: 2 rows, C2=32: 1 row)
+template <int C2> constexpr int fast_rows() { return (16 / (C2 / 2)) > 0 ? 16 / (C2 / 2) : 1; }
+
+template <int C2, bool PRE_LN, int WCT, int ROWS>
 static cudaError_t rows_fwd_launch(const BlockW& w, const float* x, float* spec, int N, int H, int W, cudaStream_t s) {
-  size_t smem = (size_t)(W + 2 * (C2 / 2) * W) * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, PRE_LN, WCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = (size_t)(W + 2 * ROWS * (C2 / 2) * W) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  fft_rows_fwd_kernel<C2, PRE_LN, WCT><<<N * H, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
+  fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS><<<N * H / ROWS, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
   return cudaGetLastError();
 }
 template <int C2>
 static cudaError_t rows_fwd_t(const BlockW& w, const float* x, float* spec, int pre_ln, int N, int H, int W, cudaStream_t s) {
   if (pre_ln) {
-    if (W == 256) return rows_fwd_launch<C2, true, 256>(w, x, spec, N, H, W, s);
-    if (W == 128) return rows_fwd_launch<C2, true, 128>(w, x, spec, N, H, W, s);
-    return rows_fwd_launch<C2, true, 0>(w, x, spec, N, H, W, s);
+    if (W == 256 && H % fast_rows<C2>() == 0) return rows_fwd_launch<C2, true, 256, fast_rows<C2>()>(w, x, spec, N, H, W, s);
+    if (W == 128 && H % fast_rows<C2>() == 0) return rows_fwd_launch<C2, true, 128, fast_rows<C2>()>(w, x, spec, N, H, W, s);
+    return rows_fwd_launch<C2, true, 0, 1>(w, x, spec, N, H, W, s);
   }
-  return rows_fwd_launch<C2, false, 0>(w, x, spec, N, H, W, s);
+  return rows_fwd_launch<C2, false, 0, 1>(w, x, spec, N, H, W, s);
 }
 
 cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* spec, int pre_ln, int N, int H, int W,
@@ -469,20 +484,25 @@ template <int C2>
 static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* local, const float* xres, float* y, int proj,
                               int N, int H, int W, cudaStream_t s) {
   constexpr int C = 2 * C2;
-  size_t smem = (size_t)(W + 2 * (C2 / 2) * W) * sizeof(float2) + (proj ? (size_t)(C * C + C) * sizeof(float) : 0);
+  // measured: several rows per CTA do not pay here (the proj weights + 64 KB of buffers cut residency: 89 vs 67 us per
+  // 16 pairs), so the inverse pass keeps one row per CTA
+  const int fr = 1;
+  size_t smem = (size_t)(W + 2 * fr * (C2 / 2) * W) * sizeof(float2) + (proj ? (size_t)(C * C + C) * sizeof(float) : 0);
   const float scale = 1.0f / ((float)H * (float)W);
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<N * H, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w, W, scale);
+    kern<<<N * H / fr, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w, W, scale);
     return cudaGetLastError();
   };
   if (proj) {
-    if (W == 256) return go(fft_rows_inv_kernel<C2, true, 256>);
-    if (W == 128) return go(fft_rows_inv_kernel<C2, true, 128>);
-    return go(fft_rows_inv_kernel<C2, true, 0>);
+    if (W == 256 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 256, fast_rows<C2>()>);
+    if (W == 128 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 128, fast_rows<C2>()>);
+    if (W == 256) return go(fft_rows_inv_kernel<C2, true, 256, 1>);
+    if (W == 128) return go(fft_rows_inv_kernel<C2, true, 128, 1>);
+    return go(fft_rows_inv_kernel<C2, true, 0, 1>);
   }
-  return go(fft_rows_inv_kernel<C2, false, 0>);
+  return go(fft_rows_inv_kernel<C2, false, 0, 1>);
 }
 
 cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,

@@ -23,7 +23,7 @@ template <int C2>
 struct MsaSmem {
   static constexpr int D = C2 / kHeads;
   alignas(16) float pos_t[kHeads * 64 * 64];        // [h][j/4][i][j%4], pre-scaled by log2(e)
-  float wqkv[3 * C2 * C2];                          // [3*C2][C2]
+  alignas(16) float wqkv[3 * C2 * C2];              // [3*C2][C2]
   float bqkv[3 * C2];
   float xs[kWinPerIter][C2][64 + 1];                // LN'd local half, channel-major (conflict-free per-token reads)
   float ks[kWinPerIter][kHeads][D][64];                // channel-major: four keys per 128-bit broadcast
@@ -94,21 +94,26 @@ __global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1) window_msa_ke
     float q[D];
     if (active) {
       float kk[D], vv[D];
+      float2 xv[C2 / 2];
+#pragma unroll
+      for (int k = 0; k < C2 / 2; ++k) xv[k] = make_float2(sm.xs[slot][2 * k][tok], sm.xs[slot][2 * k + 1][tok]);
+      // one output channel = one weight row [C2] read as 128-bit broadcasts, dot product on the packed fp32 pipe
+      auto dot = [&](int o) {
+        const float4* wr = reinterpret_cast<const float4*>(&sm.wqkv[o * C2]);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k4 = 0; k4 < C2 / 4; ++k4) {
+          const float4 w4 = wr[k4];
+          acc = __ffma2_rn(make_float2(w4.x, w4.y), xv[2 * k4], acc);
+          acc = __ffma2_rn(make_float2(w4.z, w4.w), xv[2 * k4 + 1], acc);
+        }
+        return (acc.x + acc.y) + sm.bqkv[o];
+      };
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        q[j] = sm.bqkv[head * D + j];
-        kk[j] = sm.bqkv[C2 + head * D + j];
-        vv[j] = sm.bqkv[2 * C2 + head * D + j];
-      }
-#pragma unroll
-      for (int k = 0; k < C2; ++k) {
-        const float xv = sm.xs[slot][k][tok];
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          q[j] = fmaf(sm.wqkv[(head * D + j) * C2 + k], xv, q[j]);
-          kk[j] = fmaf(sm.wqkv[(C2 + head * D + j) * C2 + k], xv, kk[j]);
-          vv[j] = fmaf(sm.wqkv[(2 * C2 + head * D + j) * C2 + k], xv, vv[j]);
-        }
+        q[j] = dot(head * D + j);
+        kk[j] = dot(C2 + head * D + j);
+        vv[j] = dot(2 * C2 + head * D + j);
       }
 #pragma unroll
       for (int j = 0; j < D; ++j) {
