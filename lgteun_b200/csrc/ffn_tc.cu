@@ -27,6 +27,8 @@
 
 namespace lg {
 
+constexpr int kG16 = 2;              // channel slices (thread groups of 128) per CTA at c = 16.  Measured: 4 (512 threads, 64-register
+                                     // cap, ~0.5 KB of spills per thread) runs 2.6x slower than 2 (256 threads, 128 registers)
 constexpr int kStripW = 30;          // interior pixels per warp strip (32 lanes - 2 halo lanes)
 // output rows streamed by one CTA pass (band_rows) are chosen per launch: 64 when the grid is deep, fewer for small batches
 
@@ -156,8 +158,8 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   constexpr int C4 = 4 * C;
   constexpr int NT = 128 * G;
   constexpr int CH = C4 / G;            // hidden channels per thread
-  constexpr int CO = C / G;             // output channels per thread
-  static_assert(CH % 8 == 0 && CO == 8, "channel slices are processed 8 columns at a time");
+  static_assert(CH % 8 == 0, "channel slices are processed 8 columns at a time");
+  constexpr int LG = C / 8;             // thread groups (cg < LG) that own an 8-channel slice of x / y (LayerNorm, residual, store)
   constexpr uint32_t D1_COL = 0;        // [0, C4): GEMM1 accumulator
   constexpr uint32_t D2_COL = C4;       // three slots of C4 columns: hidden rows y-1, y, y+1 (the dead slot hosts GEMM3's accumulator)
   constexpr uint32_t TMEM_COLS = 4 * C4;        // 256 (C=16) or 512 (C=32)
@@ -236,6 +238,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
     bool xvalid = false;
     auto prefetch_x = [&](int it) {
+      if (cg >= LG) return;
       const int y = y0 + it - 1;
       xvalid = x_ok && y >= 0 && y < H && it < rows + 2;
       if (xvalid) {
@@ -245,6 +248,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       }
     };
     auto publish_stats = [&]() {
+      if (cg >= LG) return;
       const float mean = (((xa.x + xa.y) + (xa.z + xa.w)) + ((xb.x + xb.y) + (xb.z + xb.w))) * 0.125f;
       float m2 = 0.f, d;
       d = xa.x - mean; m2 = fmaf(d, d, m2); d = xa.y - mean; m2 = fmaf(d, d, m2);
@@ -254,16 +258,17 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       sm.part[cg][row] = make_float2(mean, m2);
     };
     auto stage_a = [&]() {
+      if (cg >= LG) return;
       float2 t8[4];
       if (xvalid) {
-        float2 pr[G];
+        float2 pr[LG];
         float mean = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) { pr[g] = sm.part[g][row]; mean += pr[g].x; }
-        mean *= (1.0f / G);
+        for (int g = 0; g < LG; ++g) { pr[g] = sm.part[g][row]; mean += pr[g].x; }
+        mean *= (1.0f / LG);
         float m2 = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) { const float dm = pr[g].x - mean; m2 += fmaf(8.0f * dm, dm, pr[g].y); }
+        for (int g = 0; g < LG; ++g) { const float dm = pr[g].x - mean; m2 += fmaf(8.0f * dm, dm, pr[g].y); }
         const float rstd = 1.0f / sqrtf(m2 * (1.0f / C) + kLnEps);
         const float4 ga = *reinterpret_cast<const float4*>(&sm.lng[cg * 8]), gb = *reinterpret_cast<const float4*>(&sm.lng[cg * 8 + 4]);
         const float4 ba = *reinterpret_cast<const float4*>(&sm.lnb[cg * 8]), bb = *reinterpret_cast<const float4*>(&sm.lnb[cg * 8 + 4]);
@@ -447,8 +452,8 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         tmem_ld_wait();
       }
       // residual for S_d: issued now, consumed after GEMM3
-      const bool st_ok = x_ok && lane >= 1 && lane <= kStripW && yo < y0 + rows;
-      const size_t off = ((size_t)yo * W + x) * C + cg * CO;
+      const bool st_ok = cg < LG && x_ok && lane >= 1 && lane <= kStripW && yo < y0 + rows;
+      const size_t off = ((size_t)yo * W + x) * C + cg * 8;
       float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
       if (st_ok) {
         r0 = __ldg(reinterpret_cast<const float4*>(xrow0 + off));
@@ -476,12 +481,12 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       // ---- S_d: y = D3 + b2 + x  (interior lanes only) ---------------------------------------------------------------
       {
         float2 v2[4];
-        tmem_ld8(lane_addr + d3 + cg * CO, v2);
+        tmem_ld8(lane_addr + d3 + (cg < LG ? cg : 0) * 8, v2);
         tmem_ld_wait();
         const float v[8] = {v2[0].x, v2[0].y, v2[1].x, v2[1].y, v2[2].x, v2[2].y, v2[3].x, v2[3].y};
         if (st_ok) {
-          const float4 ba = *reinterpret_cast<const float4*>(&sm.b2[cg * CO]);
-          const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cg * CO + 4]);
+          const float4 ba = *reinterpret_cast<const float4*>(&sm.b2[cg * 8]);
+          const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cg * 8 + 4]);
           *reinterpret_cast<float4*>(yrow0 + off) =
               make_float4((v[0] + ba.x) + r0.x, (v[1] + ba.y) + r0.y, (v[2] + ba.z) + r0.z, (v[3] + ba.w) + r0.w);
           *reinterpret_cast<float4*>(yrow0 + off + 4) =
@@ -528,7 +533,7 @@ static cudaError_t ffn_tc_t(const BlockW& w, const float* x, float* y, int N, in
 
 cudaError_t launch_ffn_tc(const BlockW& w, int c, const float* x, float* y, int N, int H, int W, cudaStream_t s) {
   switch (c) {
-    case 16: return ffn_tc_t<16, 2>(w, x, y, N, H, W, s);
+    case 16: return ffn_tc_t<16, kG16>(w, x, y, N, H, W, s);
     case 32: return ffn_tc_t<32, 4>(w, x, y, N, H, W, s);
     default: return cudaErrorInvalidValue;
   }

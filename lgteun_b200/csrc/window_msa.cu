@@ -8,16 +8,18 @@
 //
 // The window partition / reverse rearranges of the reference (≈40 copy kernels per stage) do not exist
 // here: a window is addressed in place inside the NHWC map.  Logits never leave registers (the reference
-// materialises a [N*nWin,2,64,64] tensor in HBM).  One thread owns one (window, head, query) row:
-// 64 logits in registers, K/V rows broadcast from shared memory, pos_emb pre-transposed to [head][key][query]
-// so the per-query reads are conflict-free.
+// materialises a [N*nWin,2,64,64] tensor in HBM).
+//
+// Mapping: one warp = one (window, head); a lane owns TWO query rows (tokens lane and lane+32) so every K / V row
+// fetched from shared memory (128-bit broadcasts) feeds two queries — the kernel is bound by the shared-memory
+// instruction queue, not by math.  Softmax is computed online over blocks of 16 (d=4) or 8 keys in base 2
+// (pos_emb and the q scale are pre-multiplied by log2 e; ex2.approx), all dot products on the packed fp32 pipe.
 #include "common.cuh"
 
 namespace lg {
 
-constexpr int kWinPerIter = 2;          // windows processed concurrently by one CTA (128 threads each)
-constexpr int kMsaThreads = 128 * kWinPerIter;
-constexpr bool kRecomputeLogits = false;   // two-pass softmax that recomputes q.k instead of keeping 64 logits in registers
+constexpr int kWinPerIter = 4;          // windows processed concurrently by one CTA (2 warps each)
+constexpr int kMsaThreads = 64 * kWinPerIter;
 
 template <int C2>
 struct MsaSmem {
@@ -26,14 +28,15 @@ struct MsaSmem {
   alignas(16) float wqkv[3 * C2 * C2];              // [3*C2][C2]
   float bqkv[3 * C2];
   float xs[kWinPerIter][C2][64 + 1];                // LN'd local half, channel-major (conflict-free per-token reads)
-  float ks[kWinPerIter][kHeads][D][64];                // channel-major: four keys per 128-bit broadcast
-  float vs[kWinPerIter][kHeads][64][D];
+  alignas(16) float ks[kWinPerIter][kHeads][D][64]; // channel-major: four keys per 128-bit broadcast
+  alignas(16) float vs[kWinPerIter][kHeads][64][D];
+  alignas(16) float qs[kWinPerIter][kHeads][64][D]; // scaled queries (staged so the projection loop need not be unrolled)
 };
 
 template <int C2, bool PRE_LN>
-__global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1) window_msa_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                                  BlockW w, int H, int W, int total_windows,
-                                                                  int windows_per_cta) {
+__global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1)
+window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, int H, int W, int total_windows,
+                  int windows_per_cta) {
   constexpr int D = C2 / kHeads;
   constexpr int CIN = PRE_LN ? 2 * C2 : C2;         // channels per pixel of the input map
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -44,161 +47,176 @@ __global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1) window_msa_ke
   for (int i = tid; i < 3 * C2; i += kMsaThreads) sm.bqkv[i] = __ldg(w.qkv_b + i);
 
   const int nwx = W / kWin, nwy = H / kWin;
-  const int slot = tid >> 7;                        // which of the concurrent windows
-  const int lt = tid & 127;
-  const int head = lt >> 6, tok = lt & 63;
-  // head_channel ** -0.5 rounded to fp32 like the reference's python-float * tensor (LGT.py:119,139)
-  const float scale = (D == 4) ? 0.5f : (D == 8) ? 0.35355339059327379f : (D == 16) ? 0.25f : 0.17677669529663689f;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int slot = warp >> 1, head = warp & 1;      // attention phase: warp = (window slot, head)
+  const int lslot = tid >> 6, ltok = tid & 63;      // load phase: thread = (window slot, token)
+  // head_channel ** -0.5 rounded to fp32 like the reference's python-float * tensor (LGT.py:119,139), times log2(e)
+  const float scale = ((D == 4) ? 0.5f : (D == 8) ? 0.35355339059327379f : (D == 16) ? 0.25f : 0.17677669529663689f) *
+                      1.4426950408889634f;
 
   const int w_begin = blockIdx.x * windows_per_cta;
   const int w_end = min(w_begin + windows_per_cta, total_windows);
   for (int wbase = w_begin; wbase < w_end; wbase += kWinPerIter) {
-    const int widx = wbase + slot;
-    const bool active = widx < w_end;
     __syncthreads();                                // previous iteration's K/V/xs fully consumed; weights loaded
-    int n = 0, wy = 0, wx = 0;
-    if (active) {
-      wx = widx % nwx;
-      int q = widx / nwx;
-      wy = q % nwy;
-      n = q / nwy;
-    }
-    // 1) load (+ LayerNorm) : threads 0..63 of each slot own one token each
-    if (active && lt < 64) {
-      const int py = wy * kWin + (lt >> 3), px = wx * kWin + (lt & 7);
-      const float* src = x + (((size_t)n * H + py) * W + px) * CIN;
-      if constexpr (PRE_LN) {
-        float v[CIN];
-        load_vec<CIN>(v, src);
-        // LayerNorm over all c channels, but only the local half is needed afterwards
-        float mean = 0.f;
+    // 1) load (+ LayerNorm): one thread per (window, token)
+    {
+      const int widx = wbase + lslot;
+      if (widx < w_end) {
+        const int wx = widx % nwx, t = widx / nwx, wy = t % nwy, n = t / nwy;
+        const int py = wy * kWin + (ltok >> 3), px = wx * kWin + (ltok & 7);
+        const float* src = x + (((size_t)n * H + py) * W + px) * CIN;
+        if constexpr (PRE_LN) {
+          float v[CIN];
+          load_vec<CIN>(v, src);
+          // LayerNorm over all c channels, but only the local half is needed afterwards
+          float mean = 0.f;
 #pragma unroll
-        for (int i = 0; i < CIN; ++i) mean += v[i];
-        mean *= (1.0f / CIN);
-        float var = 0.f;
+          for (int i = 0; i < CIN; ++i) mean += v[i];
+          mean *= (1.0f / CIN);
+          float var = 0.f;
 #pragma unroll
-        for (int i = 0; i < CIN; ++i) { float d = v[i] - mean; var = fmaf(d, d, var); }
-        float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
+          for (int i = 0; i < CIN; ++i) { float d = v[i] - mean; var = fmaf(d, d, var); }
+          float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
 #pragma unroll
-        for (int i = 0; i < C2; ++i)
-          sm.xs[slot][i][lt] = (v[i] - mean) * rstd * __ldg(w.ln1_w + i) + __ldg(w.ln1_b + i);
-      } else {
-        float v[C2];
-        load_vec<C2>(v, src);
+          for (int i = 0; i < C2; ++i)
+            sm.xs[lslot][i][ltok] = (v[i] - mean) * rstd * __ldg(w.ln1_w + i) + __ldg(w.ln1_b + i);
+        } else {
+          float v[C2];
+          load_vec<C2>(v, src);
 #pragma unroll
-        for (int i = 0; i < C2; ++i) sm.xs[slot][i][lt] = v[i];
+          for (int i = 0; i < C2; ++i) sm.xs[lslot][i][ltok] = v[i];
+        }
       }
     }
     __syncthreads();
-    // 2) q/k/v of this thread's (head, token)
-    float q[D];
+    const int widx = wbase + slot;
+    const bool active = widx < w_end;               // warp-uniform
+    // 2) q/k/v of this lane's two tokens for this warp's head
     if (active) {
-      float kk[D], vv[D];
-      float2 xv[C2 / 2];
+#pragma unroll 1
+      for (int r = 0; r < 2; ++r) {
+        const int tok = lane + 32 * r;
+        float2 xv[C2 / 2];
 #pragma unroll
-      for (int k = 0; k < C2 / 2; ++k) xv[k] = make_float2(sm.xs[slot][2 * k][tok], sm.xs[slot][2 * k + 1][tok]);
-      // one output channel = one weight row [C2] read as 128-bit broadcasts, dot product on the packed fp32 pipe
-      auto dot = [&](int o) {
-        const float4* wr = reinterpret_cast<const float4*>(&sm.wqkv[o * C2]);
-        float2 acc = make_float2(0.f, 0.f);
+        for (int k = 0; k < C2 / 2; ++k) xv[k] = make_float2(sm.xs[slot][2 * k][tok], sm.xs[slot][2 * k + 1][tok]);
+        // one output channel = one weight row [C2] read as 128-bit broadcasts, dot product on the packed fp32 pipe
+        auto dot = [&](int o) {
+          const float4* wr = reinterpret_cast<const float4*>(&sm.wqkv[o * C2]);
+          float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k4 = 0; k4 < C2 / 4; ++k4) {
-          const float4 w4 = wr[k4];
-          acc = __ffma2_rn(make_float2(w4.x, w4.y), xv[2 * k4], acc);
-          acc = __ffma2_rn(make_float2(w4.z, w4.w), xv[2 * k4 + 1], acc);
+          for (int k4 = 0; k4 < C2 / 4; ++k4) {
+            const float4 w4 = wr[k4];
+            acc = __ffma2_rn(make_float2(w4.x, w4.y), xv[2 * k4], acc);
+            acc = __ffma2_rn(make_float2(w4.z, w4.w), xv[2 * k4 + 1], acc);
+          }
+          return (acc.x + acc.y) + sm.bqkv[o];
+        };
+#pragma unroll 2
+        for (int j = 0; j < D; ++j) {
+          sm.qs[slot][head][tok][j] = dot(head * D + j) * scale;
+          sm.ks[slot][head][j][tok] = dot(C2 + head * D + j);
+          sm.vs[slot][head][tok][j] = dot(2 * C2 + head * D + j);
         }
-        return (acc.x + acc.y) + sm.bqkv[o];
-      };
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        q[j] = dot(head * D + j);
-        kk[j] = dot(C2 + head * D + j);
-        vv[j] = dot(2 * C2 + head * D + j);
-      }
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        q[j] *= scale * 1.4426950408889634f;              // logits in base-2 units: softmax via ex2.approx
-        sm.ks[slot][head][j][tok] = kk[j];
-        sm.vs[slot][head][tok][j] = vv[j];
       }
     }
-    __syncthreads();
-    // 3) logits + softmax + PV, all in registers
+    __syncwarp();                                   // K / V of a (window, head) are produced and consumed by one warp
+    // 3) online softmax over blocks of KB keys, two queries per lane
     if (active) {
-      // logits for 4 keys at a time on the packed fp32 pipe; pos_t already holds pos_emb * log2(e), transposed
-      auto logits4 = [&](int j, float2& a01, float2& a23) {
-        const float4 p4 = *reinterpret_cast<const float4*>(&sm.pos_t[((head * 16 + (j >> 2)) * 64 + tok) * 4]);
-        a01 = make_float2(p4.x, p4.y);
-        a23 = make_float2(p4.z, p4.w);
+      float q[2][D];
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-          const float4 kv = *reinterpret_cast<const float4*>(&sm.ks[slot][head][c][j]);
-          const float2 qc = make_float2(q[c], q[c]);
-          a01 = __ffma2_rn(qc, make_float2(kv.x, kv.y), a01);
-          a23 = __ffma2_rn(qc, make_float2(kv.z, kv.w), a23);
-        }
-      };
-      float2 sum2 = make_float2(0.f, 0.f);
-      float2 o2[D / 2];
-#pragma unroll
-      for (int c = 0; c < D / 2; ++c) o2[c] = make_float2(0.f, 0.f);
-      auto accumulate2 = [&](int j, float2 s, float2 nmx) {      // keys j, j+1
-        const float2 d = __fadd2_rn(s, nmx);
-        float2 p;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.x) : "f"(d.x));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.y) : "f"(d.y));
-        sum2 = __fadd2_rn(sum2, p);
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c4 = 0; c4 < D; c4 += 4) {
-          const float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][j][c4]);
-          const float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][j + 1][c4]);
-          const float2 p0 = make_float2(p.x, p.x), p1 = make_float2(p.y, p.y);
-          o2[c4 / 2] = __ffma2_rn(p0, make_float2(v0.x, v0.y), o2[c4 / 2]);
-          o2[c4 / 2 + 1] = __ffma2_rn(p0, make_float2(v0.z, v0.w), o2[c4 / 2 + 1]);
-          o2[c4 / 2] = __ffma2_rn(p1, make_float2(v1.x, v1.y), o2[c4 / 2]);
-          o2[c4 / 2 + 1] = __ffma2_rn(p1, make_float2(v1.z, v1.w), o2[c4 / 2 + 1]);
+          const float4 t = *reinterpret_cast<const float4*>(&sm.qs[slot][head][lane + 32 * r][c4]);
+          q[r][c4] = t.x; q[r][c4 + 1] = t.y; q[r][c4 + 2] = t.z; q[r][c4 + 3] = t.w;
         }
-      };
-      float mx = -INFINITY;
-      if constexpr (kRecomputeLogits && D == 4) {
-        // measured slower (175 vs 135 us / 16 pairs): the doubled K / pos_emb shared-memory traffic outweighs the
-        // occupancy gained from ~64 registers per thread, so this variant is compiled out
-#pragma unroll 4
-        for (int j = 0; j < 64; j += 4) {
-          float2 a01, a23;
-          logits4(j, a01, a23);
-          mx = fmaxf(mx, fmaxf(fmaxf(a01.x, a01.y), fmaxf(a23.x, a23.y)));
-        }
-        const float2 nmx = make_float2(-mx, -mx);
-#pragma unroll 4
-        for (int j = 0; j < 64; j += 4) {
-          float2 a01, a23;
-          logits4(j, a01, a23);
-          accumulate2(j, a01, nmx);
-          accumulate2(j + 2, a23, nmx);
-        }
-      } else {
-        float2 s2[32];
+      float m[2] = {-INFINITY, -INFINITY};
+      float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float2 o2[2][D / 2];
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          logits4(j, s2[j / 2], s2[j / 2 + 1]);
-          mx = fmaxf(mx, fmaxf(fmaxf(s2[j / 2].x, s2[j / 2].y), fmaxf(s2[j / 2 + 1].x, s2[j / 2 + 1].y)));
-        }
-        const float2 nmx = make_float2(-mx, -mx);
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) accumulate2(2 * jj, s2[jj], nmx);
+        for (int c = 0; c < D / 2; ++c) o2[r][c] = make_float2(0.f, 0.f);
+      constexpr int KB = (D == 4) ? 16 : 8;         // keys per online-softmax block (register budget: 2*KB logits live)
+#pragma unroll 1
+      for (int jb = 0; jb < 64; jb += KB) {
+        float2 s[2][KB / 2];
+        float bm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j4 = 0; j4 < KB / 4; ++j4) {
+          const int j = jb + 4 * j4;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float4 p4 =
+                *reinterpret_cast<const float4*>(&sm.pos_t[((head * 16 + (j >> 2)) * 64 + lane + 32 * r) * 4]);
+            s[r][2 * j4] = make_float2(p4.x, p4.y);
+            s[r][2 * j4 + 1] = make_float2(p4.z, p4.w);
+          }
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            const float4 kv = *reinterpret_cast<const float4*>(&sm.ks[slot][head][c][j]);
+            const float2 k01 = make_float2(kv.x, kv.y), k23 = make_float2(kv.z, kv.w);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const float2 qc = make_float2(q[r][c], q[r][c]);
+              s[r][2 * j4] = __ffma2_rn(qc, k01, s[r][2 * j4]);
+              s[r][2 * j4 + 1] = __ffma2_rn(qc, k23, s[r][2 * j4 + 1]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            bm[r] = fmaxf(bm[r], fmaxf(fmaxf(s[r][2 * j4].x, s[r][2 * j4].y), fmaxf(s[r][2 * j4 + 1].x, s[r][2 * j4 + 1].y)));
+        }
+        float2 nm[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {                 // rescale the running sums to the new maximum
+          const float mn = fmaxf(m[r], bm[r]);
+          float corr;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"(m[r] - mn));     // 0 on the first block (m = -inf)
+          m[r] = mn;
+          nm[r] = make_float2(-mn, -mn);
+          const float2 c2 = make_float2(corr, corr);
+          sum2[r] = __fmul2_rn(sum2[r], c2);
+#pragma unroll
+          for (int c = 0; c < D / 2; ++c) o2[r][c] = __fmul2_rn(o2[r][c], c2);
+        }
+#pragma unroll
+        for (int jj = 0; jj < KB / 2; ++jj) {         // keys jb + 2jj, jb + 2jj + 1
+          float2 p[2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const float2 d = __fadd2_rn(s[r][jj], nm[r]);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[r].x) : "f"(d.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[r].y) : "f"(d.y));
+            sum2[r] = __fadd2_rn(sum2[r], p[r]);
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < D; c4 += 4) {
+            const float4 v0 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][jb + 2 * jj][c4]);
+            const float4 v1 = *reinterpret_cast<const float4*>(&sm.vs[slot][head][jb + 2 * jj + 1][c4]);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const float2 p0 = make_float2(p[r].x, p[r].x), p1 = make_float2(p[r].y, p[r].y);
+              o2[r][c4 / 2] = __ffma2_rn(p0, make_float2(v0.x, v0.y), o2[r][c4 / 2]);
+              o2[r][c4 / 2 + 1] = __ffma2_rn(p0, make_float2(v0.z, v0.w), o2[r][c4 / 2 + 1]);
+              o2[r][c4 / 2] = __ffma2_rn(p1, make_float2(v1.x, v1.y), o2[r][c4 / 2]);
+              o2[r][c4 / 2 + 1] = __ffma2_rn(p1, make_float2(v1.z, v1.w), o2[r][c4 / 2 + 1]);
+            }
+          }
+        }
       }
-      const float sum = sum2.x + sum2.y;
-      float o[D];
+      const int wx = widx % nwx, t = widx / nwx, wy = t % nwy, n = t / nwy;
 #pragma unroll
-      for (int c = 0; c < D / 2; ++c) { o[2 * c] = o2[c].x; o[2 * c + 1] = o2[c].y; }
-      const float inv = 1.0f / sum;
-      const int py = wy * kWin + (tok >> 3), px = wx * kWin + (tok & 7);
-      float* dst = y + (((size_t)n * H + py) * W + px) * C2 + head * D;
+      for (int r = 0; r < 2; ++r) {
+        const int tok = lane + 32 * r;
+        const float inv = 1.0f / (sum2[r].x + sum2[r].y);
+        const int py = wy * kWin + (tok >> 3), px = wx * kWin + (tok & 7);
+        float* dst = y + (((size_t)n * H + py) * W + px) * C2 + head * D;
 #pragma unroll
-      for (int c4 = 0; c4 < D; c4 += 4)
-        *reinterpret_cast<float4*>(dst + c4) =
-            make_float4(o[c4] * inv, o[c4 + 1] * inv, o[c4 + 2] * inv, o[c4 + 3] * inv);
+        for (int c4 = 0; c4 < D; c4 += 4)
+          *reinterpret_cast<float4*>(dst + c4) = make_float4(o2[r][c4 / 2].x * inv, o2[r][c4 / 2].y * inv,
+                                                             o2[r][c4 / 2 + 1].x * inv, o2[r][c4 / 2 + 1].y * inv);
+      }
     }
   }
 }
@@ -207,7 +225,7 @@ template <int C2>
 static cudaError_t launch_msa_t(const BlockW& w, const float* x, float* y, int pre_ln, int N, int H, int W,
                                 cudaStream_t s) {
   const int total = N * (H / kWin) * (W / kWin);
-  int per_cta = 16;                                  // amortise the 32 KB pos_emb + weight staging
+  int per_cta = 32;                                  // amortise the 32 KB pos_emb + weight staging
   while (per_cta > kWinPerIter && (total + per_cta - 1) / per_cta < 2 * 148) per_cta /= 2;
   const int grid = (total + per_cta - 1) / per_cta;
   const size_t smem = sizeof(MsaSmem<C2>);

@@ -298,6 +298,30 @@ def test_full_size_batch_properties(abi, h8, O):
     assert _maxdiff(out[:2], ref) <= E2E_TOL
 
 
+def test_scene_tile_config3(abi, h8, O):
+    """BASELINE.json configs[3]: full-resolution scene tile PAN 1024x1024 + LrMS 256x256x8 (large-window FFT stress:
+    1024- and 512-point passes, 16384 windows).  One tile against the oracle (the CPU needs ~20-60 s for it)."""
+    sd = load_weights(8)
+    g = torch.Generator().manual_seed(4)
+    ms = torch.rand(1, 8, 256, 256, generator=g)
+    pan = torch.rand(1, 1, 1024, 1024, generator=g)
+    out = _forward(h8, abi, ms, pan)
+    ref = O.forward(sd, ms, pan)
+    assert _maxdiff(out, ref) <= E2E_TOL
+
+
+def test_rect_and_small_shapes(abi, h4, O):
+    """Ragged shapes the reference accepts: non-square maps, the smallest legal PAN (16x16: one window at the
+    bottleneck), and a PAN 512 map (512/256-point FFT passes of the generic path)."""
+    sd = load_weights(4)
+    for n, h, w in ((2, 4, 4), (1, 4, 16), (1, 32, 8), (1, 128, 128)):
+        g = torch.Generator().manual_seed(h * 131 + w)
+        ms = torch.rand(n, 4, h, w, generator=g)
+        pan = torch.rand(n, 1, 4 * h, 4 * w, generator=g)
+        out = _forward(h4, abi, ms, pan)
+        assert _maxdiff(out, O.forward(sd, ms, pan)) <= E2E_TOL, (n, h, w)
+
+
 def test_module_dropin(abi):
     """The nn.Module mirror: same constructor, same state_dict, forward(ms, pan) on CUDA tensors."""
     import lgteun_b200
