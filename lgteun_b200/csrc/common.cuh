@@ -86,16 +86,15 @@ cudaError_t launch_ffn(const BlockW& w, int c, const float* x, float* hidden, fl
 size_t ffn_tc_pack_halves(int c);
 cudaError_t launch_pack_umma_f16(const float* w, void* hi, void* lo, int N, int K, cudaStream_t s);
 cudaError_t launch_ffn_tc(const BlockW& w, int c, const float* x, float* y, int N, int H, int W, cudaStream_t s);
+// pwgemm_tc.cu — conv-FFN of the widest level (c = 64) as tcgen05 pixel-GEMMs; buf_a / buf_b: N*H*W*256 floats each
+cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, float* buf_b, float* y, int N, int H, int W,
+                               cudaStream_t s);
 // misc
 cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s);
 cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r] = src[r][c]
 
 // ---- device helpers -----------------------------------------------------------------------------
 #ifdef __CUDACC__
-__device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() exact form, LGT.py:97,99
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-
 // Exact-form GELU x*Phi(x) on a PAIR of values with Blackwell's packed fp32 pipe (FFMA2/FMUL2).
 //   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt(2)   (Abramowitz-Stegun 7.1.26)
 //   gelu(x) = relu(x) - 0.5 |x| poly(t) exp(-x^2/2)

@@ -117,7 +117,7 @@ void add_block(lgteun_ctx* c, const std::string& p, BlockW* b, int ch) {
   c->derived.push_back({&b->f0_w, &b->f0_wt, c4, ch, 0, nullptr});
   c->derived.push_back({&b->f1_w, &b->f1_wt, c4, c4, 0, nullptr});
   c->derived.push_back({&b->f2_w, &b->f2_wt, ch, c4, 0, nullptr});
-  if (ch == 16 || ch == 32) c->derived.push_back({&b->f0_w, &b->ffn_pack, -1, ch, 0, b});
+  if (ch == 16 || ch == 32 || ch == 64) c->derived.push_back({&b->f0_w, &b->ffn_pack, -1, ch, 0, b});
 }
 
 // The weight ABI: reference state_dict key grammar.
@@ -232,11 +232,19 @@ struct Launcher {       // counts launches and stops at the first error
 };
 
 // The conv-FFN runs as the fused tcgen05/TMEM kernel for c in {16, 32}; c = 64 (the WV-3 bottleneck) does not fit
-// its weights in shared memory and uses the CUDA-core kernels.  LGTEUN_FFN=simt selects the CUDA-core kernels for
-// every block (A/B measurement only).
-bool use_tc_ffn(int ch) {
+// its weights / hidden rows on chip and runs as three tcgen05 pixel-GEMMs + one depthwise kernel (pwgemm_tc.cu).
+// LGTEUN_FFN=simt selects the fp32 CUDA-core kernels of ffn.cu for every block (A/B measurement only).
+bool ffn_simt() {
   static const bool simt = [] { const char* e = getenv("LGTEUN_FFN"); return e && std::string(e) == "simt"; }();
-  return !simt && (ch == 16 || ch == 32);
+  return simt;
+}
+bool use_tc_ffn(int ch) { return !ffn_simt() && (ch == 16 || ch == 32); }
+bool use_wide_tc_ffn(int ch) { return !ffn_simt() && ch == 64; }
+int ffn_launches(int ch) { return use_tc_ffn(ch) ? 1 : use_wide_tc_ffn(ch) ? 4 : 2; }
+cudaError_t run_ffn(const BlockW& b, int ch, const float* x, float* y, float* hidden, int N, int H, int W, cudaStream_t s) {
+  if (use_tc_ffn(ch)) return launch_ffn_tc(b, ch, x, y, N, H, W, s);
+  if (use_wide_tc_ffn(ch)) return launch_ffn_wide_tc(b, x, hidden, hidden + (size_t)N * H * W * 256, y, N, H, W, s);
+  return launch_ffn(b, ch, x, hidden, y, N, H, W, s);
 }
 
 // x + LGMixer(LN(x)): window MSA on the first channel half || FFT mixer on the second, proj, residual.
@@ -251,8 +259,7 @@ void run_mixer(Launcher& L, const BlockW& b, int ch, const float* x, float* y, c
 void run_block(Launcher& L, const BlockW& b, int ch, float* a, float* t, const Workspace& ws, int N, int H, int W,
                cudaStream_t s) {
   run_mixer(L, b, ch, a, t, ws, N, H, W, s);
-  if (use_tc_ffn(ch)) L(launch_ffn_tc(b, ch, t, a, N, H, W, s));
-  else L(launch_ffn(b, ch, t, ws.hidden, a, N, H, W, s), 2);
+  L(run_ffn(b, ch, t, a, ws.hidden, N, H, W, s), ffn_launches(ch));
 }
 // LGT.forward (LGT.py:314-344)
 void run_prior(Launcher& L, const lgteun_ctx* c, int i, const float* zin, float* zout, const Workspace& ws, int N, int H,
@@ -384,7 +391,7 @@ int64_t lgteun_workspace_bytes(const lgteun_t* c, int N, int h, int w) {
 int lgteun_forward_launches(lgteun_t* c, int N, int h, int w, int flags) {
   if (!c || check_shape(c, N, h, w)) return -1;
   // patch_embed, 5 blocks x (msa, 3 fft passes, ffn = 1 fused tcgen05 launch or 2 CUDA-core launches), down, up_fuse, tail
-  const int per_prior = 1 + 4 * (4 + (use_tc_ffn(c->C) ? 1 : 2)) + (4 + (use_tc_ffn(2 * c->C) ? 1 : 2)) + 4;
+  const int per_prior = 1 + 4 * (4 + ffn_launches(c->C)) + (4 + ffn_launches(2 * c->C)) + 4;
   const int priors = (flags & LGTEUN_RUN_DEAD_PRIORS) ? c->K : 1;
   return 1 + 2 * c->K + priors * per_prior;
 }
@@ -619,8 +626,7 @@ int lgteun_op_ffn(lgteun_t* c, int prior, int lgb, int block, const float* x, fl
   Workspace ws;
   int rc = op_shape(c, N * (lgb == 1 ? 4 : 1), H, W, 1, &ws);
   if (rc) return rc;
-  if (use_tc_ffn(ch)) CK(launch_ffn_tc(*b, ch, x, y, N, H, W, s));
-  else CK(launch_ffn(*b, ch, x, ws.hidden, y, N, H, W, s));
+  CK(run_ffn(*b, ch, x, y, ws.hidden, N, H, W, s));
   return 0;
 }
 

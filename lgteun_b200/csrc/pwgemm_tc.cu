@@ -1,0 +1,339 @@
+// pwgemm_tc.cu — per-pixel GEMM (1x1 convolution) on the tcgen05 tensor cores with split-fp16 operands, used for the
+// conv-FFN of the widest level (c = 64, the WV-3 bottleneck: hidden = 256 channels), whose weights (384 KB as fp16
+// hi/lo) and hidden rows (3 x 256 TMEM columns) do not fit the fused row-streaming kernel of ffn_tc.cu.
+//
+//   reference: feed_forward, models/common/LGT.py:95-109;  depthwise_conv, basic_module_unformer_v2.py:37-53
+//   y = x + W2 . GELU( dw3x3( W1 . GELU( W0 . LN(x) + b0 ) + b1 ) + bdw ) + b2     as four launches:
+//     pwgemm<K=64,  N=256, LN prologue,  bias+GELU epilogue>      x      -> h1
+//     pwgemm<K=256, N=256, plain,        bias epilogue>           h1     -> hidden
+//     dwconv_gelu (CUDA cores, HBM-bound)                         hidden -> act
+//     pwgemm<K=256, N=64,  plain,        bias+residual epilogue>  act, x -> y
+//   The 256-channel intermediates go through HBM/L2 in fp32; at the bottleneck resolution (1/4 of the pixels) that is
+//   5 x 16.8 MB per pair, ~13 us at HBM speed, against ~160 us for the CUDA-core kernels this replaces.
+//
+// One CTA = 128 pixels (M = 128 = TMEM lanes).  A (activations) is loaded from global memory, optionally
+// LayerNorm'ed, split x = hi + lo in fp16 and written to shared memory in the no-swizzle K-major core-matrix layout;
+// B (weights, pre-packed hi/lo at load time) is streamed in slices of 64 output channels; every slice issues
+// hi*hi + hi*lo + lo*hi into its 64 TMEM columns (fp32 accumulate).  See ffn_tc.cu for the descriptor formats.
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace lg {
+
+// (PTX wrappers duplicated from ffn_tc.cu on purpose: both files are self-contained translation units)
+namespace pw {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[4]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ void split8(const float2 (&v)[4], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 hh = __float22half2_rn(v[i]);
+    float2 back = __half22float2(hh);
+    __half2 ll = __float22half2_rn(__fadd2_rn(v[i], make_float2(-back.x, -back.y)));
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+}  // namespace pw
+
+enum { PRO_PLAIN = 0, PRO_LN = 1 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2 };
+constexpr int kNS = 64;                 // output channels per weight slice
+constexpr int kPwThreads = 256;
+
+// wpack: hi [K/8][N][8] then lo [K/8][N][8] (fp16), as written by launch_pack_umma_f16
+template <int K, int N, int PRO, int EPI>
+__global__ void __launch_bounds__(kPwThreads, 1)
+pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __half* __restrict__ wpack,
+                 const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                 const float* __restrict__ resid, long long total_px, int num_tiles) {
+  using namespace pw;
+  static_assert(K % 16 == 0 && N % kNS == 0 && N <= 256, "tile shape");
+  constexpr int KC = K / 8;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
+  float* sbias = reinterpret_cast<float*>(smem_raw + 16);                       // [N]
+  __half* ah = reinterpret_cast<__half*>(smem_raw + 16 + N * 4);                // [KC][128][8]
+  __half* al = ah + 128 * K;
+  __half* wh = al + 128 * K;                                                    // [KC][kNS][8]
+  __half* wl = wh + kNS * K;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;                                     // TMEM lane quarter / column half
+  const int row = q * 32 + lane;
+  constexpr uint32_t TCOLS = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+  for (int i = tid; i < N; i += kPwThreads) sbias[i] = __ldg(bias + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  const uint32_t a_h = smem_u32(ah), a_l = smem_u32(al), w_h = smem_u32(wh), w_l = smem_u32(wl);
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const long long p = (long long)tile * 128 + row;
+    const bool live = p < total_px;
+    // ---- prologue: this thread converts channels [half*K/2, (half+1)*K/2) of its pixel ------------------------------
+    {
+      const float* src = A + p * K;
+      float mean = 0.f, rstd = 1.f;
+      if constexpr (PRO == PRO_LN) {
+        float s = 0.f, ss = 0.f;
+        if (live) {
+#pragma unroll 4
+          for (int c = 0; c < K; c += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src + c));
+            s += (t.x + t.y) + (t.z + t.w);
+          }
+          mean = s * (1.0f / K);
+#pragma unroll 4
+          for (int c = 0; c < K; c += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src + c));
+            const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
+            ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          }
+          rstd = 1.0f / sqrtf(ss * (1.0f / K) + kLnEps);
+        }
+      }
+#pragma unroll 2
+      for (int kc = half * (KC / 2); kc < (half + 1) * (KC / 2); ++kc) {
+        float2 v[4];
+        if (live) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kc * 8));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kc * 8 + 4));
+          v[0] = make_float2(t0.x, t0.y); v[1] = make_float2(t0.z, t0.w);
+          v[2] = make_float2(t1.x, t1.y); v[3] = make_float2(t1.z, t1.w);
+          if constexpr (PRO == PRO_LN) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(ln_g + kc * 8)), g1 = __ldg(reinterpret_cast<const float4*>(ln_g + kc * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ln_b + kc * 8)), b1 = __ldg(reinterpret_cast<const float4*>(ln_b + kc * 8 + 4));
+            v[0] = make_float2((v[0].x - mean) * rstd * g0.x + b0.x, (v[0].y - mean) * rstd * g0.y + b0.y);
+            v[1] = make_float2((v[1].x - mean) * rstd * g0.z + b0.z, (v[1].y - mean) * rstd * g0.w + b0.w);
+            v[2] = make_float2((v[2].x - mean) * rstd * g1.x + b1.x, (v[2].y - mean) * rstd * g1.y + b1.y);
+            v[3] = make_float2((v[3].x - mean) * rstd * g1.z + b1.z, (v[3].y - mean) * rstd * g1.w + b1.w);
+          }
+        } else {
+          v[0] = v[1] = v[2] = v[3] = make_float2(0.f, 0.f);
+        }
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(ah + (kc * 128 + row) * 8) = hi;
+        *reinterpret_cast<uint4*>(al + (kc * 128 + row) * 8) = lo;
+      }
+    }
+    // ---- main loop over weight slices ------------------------------------------------------------------------------------
+#pragma unroll 1
+    for (int ns = 0; ns < N / kNS; ++ns) {
+      // stage the slice: for every K-chunk, kNS rows of 16 bytes are contiguous in the packed weights
+      {
+        const uint4* gh = reinterpret_cast<const uint4*>(wpack);
+        const uint4* gl = reinterpret_cast<const uint4*>(wpack + (size_t)N * K);
+        uint4* sh = reinterpret_cast<uint4*>(wh);
+        uint4* sl = reinterpret_cast<uint4*>(wl);
+        for (int i = tid; i < KC * kNS; i += kPwThreads) {
+          const int kc = i / kNS, n = i - kc * kNS;
+          sh[i] = __ldg(gh + kc * N + ns * kNS + n);
+          sl[i] = __ldg(gl + kc * N + ns * kNS + n);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc(kNS);
+        const uint32_t d = tmem + ns * kNS;
+#pragma unroll
+        for (int ks = 0; ks < K / 16; ++ks) {
+          const uint64_t dah = umma_desc(a_h + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t dal = umma_desc(a_l + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t dbh = umma_desc(w_h + ks * 2 * kNS * 16, kNS * 16, 128);
+          const uint64_t dbl = umma_desc(w_l + ks * 2 * kNS * 16, kNS * 16, 128);
+          umma_f16(d, dah, dbh, idesc, ks > 0);
+          umma_f16(d, dah, dbl, idesc, 1);
+          umma_f16(d, dal, dbh, idesc, 1);
+        }
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);                      // the slice buffer (and, after the last slice, A) may be overwritten
+      phase ^= 1;
+    }
+    tc_fence_after();
+    // ---- epilogue: this thread owns columns [half*N/2, (half+1)*N/2) of its pixel ----------------------------------
+    {
+      float* dst = Out + p * N;
+      const float* res = (EPI == EPI_BIAS_RESID) ? resid + p * N : nullptr;
+#pragma unroll 2
+      for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 8) {
+        float2 v[4];
+        tmem_ld8(lane_addr + c0, v);
+        tmem_ld_wait();
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 4);
+        v[0] = __fadd2_rn(v[0], make_float2(b0.x, b0.y)); v[1] = __fadd2_rn(v[1], make_float2(b0.z, b0.w));
+        v[2] = __fadd2_rn(v[2], make_float2(b1.x, b1.y)); v[3] = __fadd2_rn(v[3], make_float2(b1.z, b1.w));
+        if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = gelu_pair(v[i]);
+        }
+        if (live) {
+          if constexpr (EPI == EPI_BIAS_RESID) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+            v[0] = __fadd2_rn(v[0], make_float2(r0.x, r0.y)); v[1] = __fadd2_rn(v[1], make_float2(r0.z, r0.w));
+            v[2] = __fadd2_rn(v[2], make_float2(r1.x, r1.y)); v[3] = __fadd2_rn(v[3], make_float2(r1.z, r1.w));
+          }
+          *reinterpret_cast<float4*>(dst + c0) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+          *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                               // TMEM columns and the A tile are free for the next tile
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+// ---- depthwise 3x3 (+bias, zero pad) + GELU on an NHWC map, 4 channels per thread (HBM-bound) ---------------------------
+__global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ hid, float* __restrict__ act,
+                                                           const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                           int H, int W, int C4, long long total_vec) {
+  extern __shared__ __align__(16) float s_dw[];     // [9][C4] taps then [C4] bias
+  for (int i = threadIdx.x; i < C4; i += 256) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s_dw[t * C4 + i] = __ldg(dw_w + i * 9 + t);
+    s_dw[9 * C4 + i] = __ldg(dw_b + i);
+  }
+  __syncthreads();
+  const long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (v >= total_vec) return;
+  const int vecs = C4 / 4;
+  const int c = (int)(v % vecs) * 4;
+  const long long pix = v / vecs;
+  const int x = (int)(pix % W);
+  const long long t = pix / W;
+  const int y = (int)(t % H);
+  const long long n = t / H;
+  float4 b = *reinterpret_cast<const float4*>(s_dw + 9 * C4 + c);
+  float2 a0 = make_float2(b.x, b.y), a1 = make_float2(b.z, b.w);
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(hid + ((n * H + yy) * W + xx) * C4 + c));
+      const float4 wv = *reinterpret_cast<const float4*>(s_dw + ((dy + 1) * 3 + dx + 1) * C4 + c);
+      a0 = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(hv.x, hv.y), a0);
+      a1 = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(hv.z, hv.w), a1);
+    }
+  }
+  a0 = gelu_pair(a0);
+  a1 = gelu_pair(a1);
+  *reinterpret_cast<float4*>(act + pix * C4 + c) = make_float4(a0.x, a0.y, a1.x, a1.y);
+}
+
+template <int K, int N, int PRO, int EPI>
+static cudaError_t pwgemm_launch(const float* A, float* Out, const void* wpack, const float* bias, const float* ln_g,
+                                 const float* ln_b, const float* resid, long long total_px, cudaStream_t s) {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = (int)((total_px + 127) / 128);
+  const size_t smem = 16 + (size_t)N * 4 + (size_t)(2 * 128 * K + 2 * kNS * K) * 2 + 128;
+  cudaError_t e = cudaFuncSetAttribute(pwgemm_tc_kernel<K, N, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  pwgemm_tc_kernel<K, N, PRO, EPI><<<grid, kPwThreads, smem, s>>>(A, Out, reinterpret_cast<const __half*>(wpack), bias, ln_g,
+                                                                  ln_b, resid, total_px, tiles);
+  return cudaGetLastError();
+}
+
+// conv-FFN of a c = 64 block.  scratch: two buffers of N*H*W*256 floats (h1 / act, hidden).
+cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, float* buf_b, float* y, int N, int H, int W,
+                               cudaStream_t s) {
+  constexpr int C = 64, C4 = 256;
+  const long long px = (long long)N * H * W;
+  const char* pack = reinterpret_cast<const char*>(w.ffn_pack);
+  const size_t s0 = (size_t)C4 * C * 2, s1 = (size_t)C4 * C4 * 2;       // bytes per half-tensor (hi or lo)
+  cudaError_t e;
+  e = pwgemm_launch<C, C4, PRO_LN, EPI_BIAS_GELU>(x, buf_a, pack, w.f0_b, w.ln2_w, w.ln2_b, nullptr, px, s);
+  if (e != cudaSuccess) return e;
+  e = pwgemm_launch<C4, C4, PRO_PLAIN, EPI_BIAS>(buf_a, buf_b, pack + 2 * s0, w.f1_b, nullptr, nullptr, nullptr, px, s);
+  if (e != cudaSuccess) return e;
+  const long long vec = px * (C4 / 4);
+  dwconv_gelu_kernel<<<(unsigned)((vec + 255) / 256), 256, 10 * C4 * sizeof(float), s>>>(buf_b, buf_a, w.dw_w, w.dw_b, H, W, C4, vec);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return pwgemm_launch<C4, C, PRO_PLAIN, EPI_BIAS_RESID>(buf_a, y, pack + 2 * s0 + 2 * s1, w.f2_b, nullptr, nullptr, x, px, s);
+}
+
+}  // namespace lg
