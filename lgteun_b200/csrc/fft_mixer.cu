@@ -486,7 +486,7 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
   constexpr int C = 2 * C2;
   // measured: several rows per CTA do not pay here (the proj weights + 64 KB of buffers cut residency: 89 vs 67 us per
   // 16 pairs), so the inverse pass keeps one row per CTA
-  const int fr = 1;
+  const int fr = (proj && (W == 256 || W == 128) && fast_rows<C2>() >= 2 && H % 2 == 0) ? 2 : 1;
   size_t smem = (size_t)(W + 2 * fr * (C2 / 2) * W) * sizeof(float2) + (proj ? (size_t)(C * C + C) * sizeof(float) : 0);
   const float scale = 1.0f / ((float)H * (float)W);
   auto go = [&](auto kern) -> cudaError_t {
@@ -496,8 +496,8 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
     return cudaGetLastError();
   };
   if (proj) {
-    if (W == 256 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 256, fast_rows<C2>()>);
-    if (W == 128 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 128, fast_rows<C2>()>);
+    if (W == 256 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 256, 2>);
+    if (W == 128 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 128, 2>);
     if (W == 256) return go(fft_rows_inv_kernel<C2, true, 256, 1>);
     if (W == 128) return go(fft_rows_inv_kernel<C2, true, 128, 1>);
     return go(fft_rows_inv_kernel<C2, true, 0, 1>);
