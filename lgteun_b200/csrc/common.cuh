@@ -78,6 +78,12 @@ cudaError_t launch_fft_cols(const BlockW& w, int c, float* spec, int N, int H, i
 cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const float* local, const float* xres,
                                 float* y, int proj, int N, int H, int W, cudaStream_t s);
 cudaError_t fft_init_tables(cudaStream_t s);
+// fft256.cu — register-resident radix-16 passes for 256-point transforms
+cudaError_t fft256_init_tables(cudaStream_t s);
+cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s);
+cudaError_t launch_fft_rows_fwd256(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s);
+cudaError_t launch_fft_rows_inv256(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
+                                   int N, int H, cudaStream_t s);
 // ffn.cu
 size_t ffn_hidden_floats(int N, int H, int W, int c);
 cudaError_t launch_ffn(const BlockW& w, int c, const float* x, float* hidden, float* y, int N, int H, int W,

@@ -1,0 +1,388 @@
+// fft256.cu — register-resident 256-point FFT passes for the global mixer (models/common/LGT.py:162-180) at the
+// headline resolution (H = 256 columns / W = 256 rows).  256 = 16 x 16: a thread holds 16 complex values, runs a
+// 16-point FFT (two radix-4 levels, compile-time twiddles) entirely in registers, exchanges once through shared memory
+// and runs the second 16-point FFT.  Compared with the shared-memory Stockham passes of fft_mixer.cu (8 stages, a barrier
+// and runtime index arithmetic per stage) this needs ~3x fewer instructions and 2-3 barriers per transform, which is
+// what bounded those kernels (issue / barrier latency, 14-36 % of HBM speed).
+//
+// Column pass (this file): forward FFT along H, amplitude/phase mixing on the registers that hold the spectrum,
+// inverse FFT along H, in place on S[n][y][kx][ch].  The forward transform leaves thread k1 with X[k1 + 16 k2]
+// (k2 = register index) — exactly the "fixed low index, stride-16" distribution the inverse transform consumes, so no
+// reordering is needed between the two.
+#include <math.h>
+#include "common.cuh"
+
+namespace lg {
+
+__device__ float2 g_tw256[256];                          // e^{-2 pi i k / 256}, rounded from double
+
+cudaError_t fft256_init_tables(cudaStream_t s) {
+  static float2 host[256];
+  for (int k = 0; k < 256; ++k) {
+    double a = -2.0 * M_PI * (double)k / 256.0;
+    host[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  host[0] = make_float2(1.f, 0.f);
+  host[64] = make_float2(0.f, -1.f);
+  host[128] = make_float2(-1.f, 0.f);
+  host[192] = make_float2(0.f, 1.f);
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_tw256, host, sizeof(host), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
+
+namespace f256 {
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a * w (SIGN < 0: forward twiddle) or a * conj(w) (SIGN > 0: inverse)
+template <int SIGN>
+__device__ __forceinline__ float2 ctw(float2 a, float2 w) {
+  const float2 t = __fmul2_rn(a, make_float2(w.x, w.x));
+  return (SIGN < 0) ? __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), t)
+                    : __ffma2_rn(make_float2(a.y, -a.x), make_float2(w.y, w.y), t);
+}
+// multiply by -i (SIGN < 0) or +i (SIGN > 0)
+template <int SIGN>
+__device__ __forceinline__ float2 rot(float2 a) { return (SIGN < 0) ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x); }
+
+template <int SIGN>
+__device__ __forceinline__ void radix4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = rot<SIGN>(csub(a1, a3));
+  a0 = cadd(s02, s13);
+  a1 = cadd(d02, d13);
+  a2 = csub(s02, s13);
+  a3 = csub(d02, d13);
+}
+
+// 16-point FFT in registers, natural order in and out (n = j + 4q, k = m + 4p).  Unnormalised; SIGN = -1 forward.
+template <int SIGN>
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+  // level 1: over q for each j -> t[j][m] stored at v[j + 4m]
+#pragma unroll
+  for (int j = 0; j < 4; ++j) radix4<SIGN>(v[j], v[j + 4], v[j + 8], v[j + 12]);
+  // twiddles W16^{j m}, j,m in 1..3  (forward values; ctw conjugates them for the inverse)
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R = 0.70710678118654752f;
+  v[1 + 4 * 1] = ctw<SIGN>(v[1 + 4 * 1], make_float2(C1, -S1));      // W^1
+  v[1 + 4 * 2] = ctw<SIGN>(v[1 + 4 * 2], make_float2(R, -R));        // W^2
+  v[1 + 4 * 3] = ctw<SIGN>(v[1 + 4 * 3], make_float2(S1, -C1));      // W^3
+  v[2 + 4 * 1] = ctw<SIGN>(v[2 + 4 * 1], make_float2(R, -R));        // W^2
+  v[2 + 4 * 2] = rot<SIGN>(v[2 + 4 * 2]);                            // W^4 = -i
+  v[2 + 4 * 3] = ctw<SIGN>(v[2 + 4 * 3], make_float2(-R, -R));       // W^6
+  v[3 + 4 * 1] = ctw<SIGN>(v[3 + 4 * 1], make_float2(S1, -C1));      // W^3
+  v[3 + 4 * 2] = ctw<SIGN>(v[3 + 4 * 2], make_float2(-R, -R));       // W^6
+  v[3 + 4 * 3] = ctw<SIGN>(v[3 + 4 * 3], make_float2(-C1, S1));      // W^9
+  // level 2: over j for each m: inputs v[0+4m], v[1+4m], v[2+4m], v[3+4m] -> X[m], X[m+4], X[m+8], X[m+12]
+  float2 o[16];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float2 b0 = v[4 * m], b1 = v[4 * m + 1], b2 = v[4 * m + 2], b3 = v[4 * m + 3];
+    radix4<SIGN>(b0, b1, b2, b3);
+    o[m] = b0; o[m + 4] = b1; o[m + 8] = b2; o[m + 12] = b3;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = o[i];
+}
+}  // namespace f256
+
+// ---- column pass at H = 256 ---------------------------------------------------------------------------------------------
+// CTA = Q adjacent complex lanes (kx*C2 + ch) of one image; thread = (lane, low index); 16 * Q threads.
+template <int Q>
+__global__ void __launch_bounds__(16 * Q) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
+                                                             int lanes_per_row) {
+  using namespace f256;
+  constexpr int H = 256;
+  __shared__ float2 tw[256];
+  extern __shared__ __align__(16) float2 ex[];            // exchange buffer [16][16][Q]
+  const int tid = threadIdx.x;
+  const int l = tid % Q, lo = tid / Q;                    // lane within the CTA, low index (n2 / k1 / m2 / j1)
+  const int l0 = blockIdx.x * Q;
+  const bool live = l0 + l < lanes_per_row;
+  float2* base = spec + (size_t)blockIdx.y * H * lanes_per_row + l0 + l;
+  for (int j = tid; j < 256; j += 16 * Q) tw[j] = g_tw256[j];
+
+  // load rows y = 16 n1 + lo
+  float2 v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1)
+    v[n1] = live ? base[(size_t)(16 * n1 + lo) * lanes_per_row] : make_float2(0.f, 0.f);
+  __syncthreads();                                        // twiddle table staged
+  // forward pass A over n1, twiddle W256^{lo k1}, exchange, pass B over n2
+  fft16<-1>(v);
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[lo * k1]);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) ex[(k1 * 16 + lo) * Q + l] = v[k1];
+  __syncthreads();
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) v[n2] = ex[(lo * 16 + n2) * Q + l];
+  fft16<-1>(v);                                           // v[k2] = X[ky = lo + 16 k2]
+
+  // amplitude / phase mixing (LGT.py:168-177)
+  {
+    const int lane = l0 + l;
+    const int kx = lane / C2, ch = lane - kx * C2;
+    const float aw = live ? __ldg(w.amp_w + ch) : 0.f, ab = live ? __ldg(w.amp_b + ch) : 0.f;
+    const float pw = live ? __ldg(w.pha_w + ch) : 0.f, pb = live ? __ldg(w.pha_b + ch) : 0.f;
+    const bool real_col = (kx == 0 || kx == W / 2);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      float2 z = v[k2];
+      if (real_col && lo == 0 && (k2 == 0 || k2 == 8)) z.y = 0.0f;     // ky in {0, 128}: exactly-real bins get +0.0 (F7)
+      float amp = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+      float pha = atan2f(z.y, z.x);
+      amp = amp * aw + ab;
+      pha = pha * pw + pb;
+      const float sn = __sinf(pha), cs = __cosf(pha);
+      float re = amp * cs + 1e-8f;
+      const float im = amp * sn + 1e-8f;
+      re = re + 1e-8f;                                    // complex(real, imag) + 1e-8 adds to the real part
+      v[k2] = make_float2(re, im);
+    }
+  }
+  // inverse: input index m = 16 m1 + m2 with m2 = lo (thread), m1 = k2 (register): same distribution as the forward input
+  fft16<+1>(v);
+#pragma unroll
+  for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[lo * j1]);
+  __syncthreads();                                        // everyone has consumed the first exchange
+#pragma unroll
+  for (int j1 = 0; j1 < 16; ++j1) ex[(j1 * 16 + lo) * Q + l] = v[j1];
+  __syncthreads();
+#pragma unroll
+  for (int m2 = 0; m2 < 16; ++m2) v[m2] = ex[(lo * 16 + m2) * Q + l];
+  fft16<+1>(v);                                           // v[j2] = x[y = lo + 16 j2]  (unnormalised)
+  if (live) {
+#pragma unroll
+    for (int j2 = 0; j2 < 16; ++j2) base[(size_t)(lo + 16 * j2) * lanes_per_row] = v[j2];
+  }
+}
+
+cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s) {
+  constexpr int Q = 16;
+  const int lanes = (W / 2 + 1) * c2;
+  const size_t smem = (size_t)256 * Q * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_cols256_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((lanes + Q - 1) / Q, N);
+  fft_cols256_kernel<Q><<<grid, 16 * Q, smem, s>>>(reinterpret_cast<float2*>(spec), w, W, c2, lanes);
+  return cudaGetLastError();
+}
+
+}  // namespace lg
+
+namespace lg {
+
+// ---- row passes at W = 256 ----------------------------------------------------------------------------------------------
+// A CTA owns 16 complex sequences (two real channels each) = 32/C2 consecutive image rows; thread = (sequence, low index).
+constexpr int kRowPad = 272;                              // 256 + one pad slot per 16: conflict-free stride-16 register loads
+__device__ __forceinline__ int padded(int i) { return i + (i >> 4); }
+
+template <int C2, bool PRE_LN>
+__global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __restrict__ x, float2* __restrict__ spec,
+                                                               BlockW w) {
+  using namespace f256;
+  constexpr int W = 256, Wf = 129;
+  constexpr int NF1 = C2 / 2;                             // sequences per image row
+  constexpr int RW = 16 / NF1;                            // image rows per CTA
+  constexpr int CIN = PRE_LN ? 2 * C2 : C2;
+  __shared__ float2 tw[256];
+  extern __shared__ __align__(16) float2 smf[];
+  float2* X = smf;                                        // [16][kRowPad]  input sequences, later the natural-order spectrum
+  float2* E = smf;                                        // [16][16*17]    exchange between the two radix-16 passes: the SAME
+                                                          // storage (35 KB per CTA instead of 70: twice the resident CTAs)
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * RW;
+  tw[tid] = g_tw256[tid];
+  // phase 0: LayerNorm, pack channel pairs (2f, 2f+1) of the global half as complex samples
+#pragma unroll
+  for (int i = 0; i < RW; ++i) {
+    const int p = tid + 256 * i, rl = p >> 8, px = p & 255;
+    const float* src = x + ((row0 + rl) * W + px) * CIN;
+    float g[C2];
+    if constexpr (PRE_LN) {
+      float v[CIN];
+      load_vec<CIN>(v, src);
+      float mean = 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) mean += v[c];
+      mean *= (1.0f / CIN);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) { float d = v[c] - mean; var = fmaf(d, d, var); }
+      const float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+      for (int c = 0; c < C2; ++c) g[c] = (v[C2 + c] - mean) * rstd * __ldg(w.ln1_w + C2 + c) + __ldg(w.ln1_b + C2 + c);
+    } else {
+      load_vec<C2>(g, src);
+    }
+#pragma unroll
+    for (int f = 0; f < NF1; ++f) X[(rl * NF1 + f) * kRowPad + padded(px)] = make_float2(g[2 * f], g[2 * f + 1]);
+  }
+  __syncthreads();
+  const int seq = tid >> 4, lo = tid & 15;
+  float2 v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[seq * kRowPad + 17 * n1 + lo];       // padded(16 n1 + lo)
+  fft16<-1>(v);
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[lo * k1]);
+  __syncthreads();                                        // all inputs are in registers: the buffer becomes the exchange
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) E[seq * 272 + k1 * 17 + lo] = v[k1];
+  __syncthreads();
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) v[n2] = E[seq * 272 + lo * 17 + n2];
+  fft16<-1>(v);                                           // v[k2] = Z[lo + 16 k2]
+  __syncthreads();
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) X[seq * kRowPad + lo + 16 * k2] = v[k2];       // natural order, unpadded
+  __syncthreads();
+  // split the packed transforms: channel a = 2f (real input), b = 2f+1 (imaginary input)
+  float4* out = reinterpret_cast<float4*>(spec + row0 * Wf * C2);
+  for (int id = tid; id < RW * Wf * NF1; id += 256) {
+    const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
+    const int k = rem / NF1, s = rl * NF1 + (rem - k * NF1);
+    const float2 z = X[s * kRowPad + k], zm = X[s * kRowPad + ((W - k) & (W - 1))];
+    float4 o;
+    o.x = 0.5f * (z.x + zm.x);        // Xa = (Z[k] + conj(Z[W-k])) / 2
+    o.y = 0.5f * (z.y - zm.y);
+    o.z = 0.5f * (z.y + zm.y);        // Xb = (Z[k] - conj(Z[W-k])) / (2i)
+    o.w = 0.5f * (zm.x - z.x);
+    out[id] = o;
+  }
+}
+
+template <int C2>
+__global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __restrict__ spec, const float* __restrict__ local,
+                                                               const float* __restrict__ xres, float* __restrict__ y,
+                                                               BlockW w, float scale) {
+  using namespace f256;
+  constexpr int W = 256, Wf = 129;
+  constexpr int NF1 = C2 / 2, RW = 16 / NF1, C = 2 * C2;
+  __shared__ float2 tw[256];
+  extern __shared__ __align__(16) float2 smf[];
+  float2* X = smf;                                        // [16][kRowPad]
+  float2* E = smf;                                        // [16][272] exchange, same storage
+  float* sW = reinterpret_cast<float*>(smf + 16 * kRowPad);     // [C][C] proj weight
+  float* sBias = sW + C * C;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * RW;
+  tw[tid] = g_tw256[tid];
+  for (int i = tid; i < C * C / 4; i += 256) reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(w.proj_w) + i);
+  for (int i = tid; i < C; i += 256) sBias[i] = __ldg(w.proj_b + i);
+  // phase 0: Hermitian rebuild of the packed spectra (C2R ignores Im of the DC and Nyquist bins)
+  const float4* in = reinterpret_cast<const float4*>(spec + row0 * Wf * C2);
+  for (int id = tid; id < RW * Wf * NF1; id += 256) {
+    const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
+    const int k = rem / NF1, s = rl * NF1 + (rem - k * NF1);
+    const float4 v = __ldg(in + id);                      // (Xa.re, Xa.im, Xb.re, Xb.im)
+    if (k == 0 || k == W / 2) {
+      X[s * kRowPad + padded(k)] = make_float2(v.x, v.z);
+    } else {
+      X[s * kRowPad + padded(k)] = make_float2(v.x - v.w, v.y + v.z);           // Xa + i Xb
+      X[s * kRowPad + padded(W - k)] = make_float2(v.x + v.w, v.z - v.y);       // conj(Xa) + i conj(Xb)
+    }
+  }
+  __syncthreads();
+  const int seq = tid >> 4, lo = tid & 15;
+  float2 v[16];
+#pragma unroll
+  for (int m1 = 0; m1 < 16; ++m1) v[m1] = X[seq * kRowPad + 17 * m1 + lo];
+  fft16<+1>(v);
+#pragma unroll
+  for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[lo * j1]);
+  __syncthreads();
+#pragma unroll
+  for (int j1 = 0; j1 < 16; ++j1) E[seq * 272 + j1 * 17 + lo] = v[j1];
+  __syncthreads();
+#pragma unroll
+  for (int m2 = 0; m2 < 16; ++m2) v[m2] = E[seq * 272 + lo * 17 + m2];
+  fft16<+1>(v);                                           // v[j2] = (xa + i xb)[lo + 16 j2], unnormalised
+  __syncthreads();
+#pragma unroll
+  for (int j2 = 0; j2 < 16; ++j2)
+    X[seq * kRowPad + lo + 16 * j2] = make_float2(fabsf(v[j2].x * scale), fabsf(v[j2].y * scale));
+  __syncthreads();
+  // phase 3: concat(local, global) -> proj 1x1 -> + residual, one pixel per thread and row
+#pragma unroll 1
+  for (int i = 0; i < RW; ++i) {
+    const int p = tid + 256 * i, rl = p >> 8, px = p & 255;
+    const size_t pix = (row0 + rl) * W + px;
+    float cat[C];
+    {
+      float t[C2];
+      load_vec<C2>(t, local + pix * C2);
+#pragma unroll
+      for (int c = 0; c < C2; ++c) cat[c] = t[c];
+#pragma unroll
+      for (int f = 0; f < NF1; ++f) {
+        const float2 g = X[(rl * NF1 + f) * kRowPad + px];
+        cat[C2 + 2 * f] = g.x;
+        cat[C2 + 2 * f + 1] = g.y;
+      }
+    }
+    const float* xr = xres + pix * C;
+    float* dst = y + pix * C;
+#pragma unroll 1
+    for (int o = 0; o < C; o += 4) {
+      float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+      const float4* r0 = reinterpret_cast<const float4*>(sW + (o + 0) * C);
+      const float4* r1 = reinterpret_cast<const float4*>(sW + (o + 1) * C);
+      const float4* r2 = reinterpret_cast<const float4*>(sW + (o + 2) * C);
+      const float4* r3 = reinterpret_cast<const float4*>(sW + (o + 3) * C);
+#pragma unroll
+      for (int k4 = 0; k4 < C / 4; ++k4) {
+        const float2 va = make_float2(cat[4 * k4], cat[4 * k4 + 1]), vb = make_float2(cat[4 * k4 + 2], cat[4 * k4 + 3]);
+        const float4 w0 = r0[k4], w1 = r1[k4], w2 = r2[k4], w3 = r3[k4];
+        a0 = __ffma2_rn(make_float2(w0.x, w0.y), va, a0); a0 = __ffma2_rn(make_float2(w0.z, w0.w), vb, a0);
+        a1 = __ffma2_rn(make_float2(w1.x, w1.y), va, a1); a1 = __ffma2_rn(make_float2(w1.z, w1.w), vb, a1);
+        a2 = __ffma2_rn(make_float2(w2.x, w2.y), va, a2); a2 = __ffma2_rn(make_float2(w2.z, w2.w), vb, a2);
+        a3 = __ffma2_rn(make_float2(w3.x, w3.y), va, a3); a3 = __ffma2_rn(make_float2(w3.z, w3.w), vb, a3);
+      }
+      const float4 r = *reinterpret_cast<const float4*>(xr + o);
+      *reinterpret_cast<float4*>(dst + o) = make_float4(((a0.x + a0.y) + sBias[o]) + r.x, ((a1.x + a1.y) + sBias[o + 1]) + r.y,
+                                                        ((a2.x + a2.y) + sBias[o + 2]) + r.z, ((a3.x + a3.y) + sBias[o + 3]) + r.w);
+    }
+  }
+}
+
+template <int C2>
+static cudaError_t rows256_fwd_t(const BlockW& w, const float* x, float* spec, int N, int H, cudaStream_t s) {
+  constexpr int RW = 16 / (C2 / 2);
+  const size_t smem = (size_t)(16 * kRowPad) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd256_kernel<C2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_rows_fwd256_kernel<C2, true><<<N * H / RW, 256, smem, s>>>(x, reinterpret_cast<float2*>(spec), w);
+  return cudaGetLastError();
+}
+template <int C2>
+static cudaError_t rows256_inv_t(const BlockW& w, const float* spec, const float* local, const float* xres, float* y, int N,
+                                 int H, cudaStream_t s) {
+  constexpr int RW = 16 / (C2 / 2), C = 2 * C2;
+  const size_t smem = (size_t)(16 * kRowPad) * sizeof(float2) + (size_t)(C * C + C) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_inv256_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_rows_inv256_kernel<C2><<<N * H / RW, 256, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
+                                                           1.0f / ((float)H * 256.0f));
+  return cudaGetLastError();
+}
+
+// W == 256, LayerNorm prologue; H must be a multiple of 32 / C2 rows
+cudaError_t launch_fft_rows_fwd256(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s) {
+  switch (c) {
+    case 16: return rows256_fwd_t<8>(w, x, spec, N, H, s);
+    case 32: return rows256_fwd_t<16>(w, x, spec, N, H, s);
+    case 64: return rows256_fwd_t<32>(w, x, spec, N, H, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+cudaError_t launch_fft_rows_inv256(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
+                                   int N, int H, cudaStream_t s) {
+  switch (c) {
+    case 16: return rows256_inv_t<8>(w, spec, local, xres, y, N, H, s);
+    case 32: return rows256_inv_t<16>(w, spec, local, xres, y, N, H, s);
+    case 64: return rows256_inv_t<32>(w, spec, local, xres, y, N, H, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace lg

@@ -16,6 +16,7 @@
 //   rows_inv : Hermitian rebuild (C2R ignores Im of bins 0 and W/2) -> inverse Stockham -> |.|/(HW)
 //              -> concat with the local branch -> proj 1x1 -> + residual
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace lg {
@@ -36,7 +37,9 @@ cudaError_t fft_init_tables(cudaStream_t s) {
   host[3 * kTwN / 4] = make_float2(0.f, 1.f);
   cudaError_t e = cudaMemcpyToSymbolAsync(g_tw, host, sizeof(host), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
-  return cudaStreamSynchronize(s);
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return e;
+  return fft256_init_tables(s);
 }
 
 size_t spectrum_floats(int N, int H, int W, int c2) { return (size_t)N * H * (W / 2 + 1) * c2 * 2; }
@@ -448,9 +451,15 @@ static cudaError_t rows_fwd_t(const BlockW& w, const float* x, float* spec, int 
   return rows_fwd_launch<C2, false, 0, 1>(w, x, spec, N, H, W, s);
 }
 
+static bool stockham_only() {                            // LGTEUN_FFT=stockham: A/B switch back to the shared-memory passes
+  static const bool v = [] { const char* e = getenv("LGTEUN_FFT"); return e && e[0] == 's'; }();
+  return v;
+}
+
 cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* spec, int pre_ln, int N, int H, int W,
                                 cudaStream_t s) {
   if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  if (W == 256 && pre_ln && H % 4 == 0 && !stockham_only()) return launch_fft_rows_fwd256(w, c, x, spec, N, H, s);
   switch (c) {
     case 16: return rows_fwd_t<8>(w, x, spec, pre_ln, N, H, W, s);
     case 32: return rows_fwd_t<16>(w, x, spec, pre_ln, N, H, W, s);
@@ -475,6 +484,7 @@ cudaError_t launch_fft_cols(const BlockW& w, int c, float* spec, int N, int H, i
   const int c2 = c / 2;
   if (H == 128) return cols_t<64, 128>(w, c2, spec, N, H, W, s);
   if (H < 128) return cols_t<64, 0>(w, c2, spec, N, H, W, s);
+  if (H == 256 && !stockham_only()) return launch_fft_cols256(w, c2, spec, N, W, s);
   if (H == 256) return cols_t<32, 256>(w, c2, spec, N, H, W, s);
   if (H == 512) return cols_t<16, 0>(w, c2, spec, N, H, W, s);
   return cols_t<8, 0>(w, c2, spec, N, H, W, s);
@@ -508,6 +518,7 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
 cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
                                 int proj, int N, int H, int W, cudaStream_t s) {
   if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  if (W == 256 && proj && H % 4 == 0 && !stockham_only()) return launch_fft_rows_inv256(w, c, spec, local, xres, y, N, H, s);
   switch (c) {
     case 16: return rows_inv_t<8>(w, spec, local, xres, y, proj, N, H, W, s);
     case 32: return rows_inv_t<16>(w, spec, local, xres, y, proj, N, H, W, s);
