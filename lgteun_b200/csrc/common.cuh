@@ -39,6 +39,7 @@ struct PriorW {                       // one LGT: LGT.py:251-303
   const float *pe_ln_w, *pe_ln_b;     // patch_embed.norm           [C]
   BlockW enc[2], bott[1], dec[2];
   const float *down_w, *down_b;       // encoder_layers.0.1.1       [2C, C]
+  const float *down_wt;               // derived: down_w transposed to [C][2C]
   const float *up_w, *up_b;           // decoder_layers.0.0.1       [C, 2C]
   const float *fuse_w, *fuse_b;       // decoder_layers.0.1         [C, 2C]   input = [upsampled | skip]
   const float *tail_w, *tail_b;       // tail.1                     [B, C]

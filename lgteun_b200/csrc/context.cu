@@ -147,6 +147,7 @@ void build_table(lgteun_ctx* c) {
     for (int j = 0; j < 2; ++j) add_block(c, pre + ".encoder_layers.0.0.blocks." + std::to_string(j), &p->enc[j], C);
     add_slot(c, pre + ".encoder_layers.0.1.1.weight", 2 * C * C, &p->down_w);
     add_slot(c, pre + ".encoder_layers.0.1.1.bias", 2 * C, &p->down_b);
+    c->derived.push_back({&p->down_w, &p->down_wt, 2 * C, C, 0, nullptr});
     add_block(c, pre + ".bottleneck.blocks.0", &p->bott[0], 2 * C);
     add_slot(c, pre + ".decoder_layers.0.0.1.weight", 2 * C * C, &p->up_w);
     add_slot(c, pre + ".decoder_layers.0.0.1.bias", C, &p->up_b);
@@ -222,14 +223,58 @@ int ensure_ws(lgteun_ctx* c, int N, int h, int w, Workspace* ws) {
   return 0;
 }
 
-struct Launcher {       // counts launches and stops at the first error
+struct Launcher {       // counts launches and stops at the first error; optional per-launch CUDA-event timing
   cudaError_t err = cudaSuccess;
   int count = 0;
+  cudaStream_t stream = nullptr;
+  bool timing = false;    // LGTEUN_TIMING=1 with LGTEUN_NO_GRAPH: warm-cache device time per kernel family (stderr)
+  struct Rec { std::string tag; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  cudaEvent_t pending = nullptr;
+  std::string pending_tag;
+  void begin(const char* call, int ch = 0) {
+    if (!timing) return;
+    std::string t(call);
+    t = t.substr(0, t.find('('));
+    if (ch) t += " c=" + std::to_string(ch);
+    pending_tag = t;
+    cudaEventCreate(&pending);
+    cudaEventRecord(pending, stream);
+  }
   void operator()(cudaError_t e, int kernels = 1) {
     if (err == cudaSuccess) { err = e; count += kernels; }
+    if (timing && pending) {
+      cudaEvent_t e1;
+      cudaEventCreate(&e1);
+      cudaEventRecord(e1, stream);
+      recs.push_back({pending_tag, pending, e1});
+      pending = nullptr;
+    }
   }
   bool ok() const { return err == cudaSuccess; }
+  void report() {
+    if (!timing || recs.empty()) return;
+    cudaStreamSynchronize(stream);
+    std::map<std::string, std::pair<int, float>> agg;
+    float total = 0.f;
+    for (auto& r : recs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      agg[r.tag].first++;
+      agg[r.tag].second += ms;
+      total += ms;
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    fprintf(stderr, "[lgteun timing] %-34s %5s %10s %7s\n", "launch", "n", "total_us", "share");
+    for (auto& kv : agg)
+      fprintf(stderr, "[lgteun timing] %-34s %5d %10.1f %6.1f%%\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e3f,
+              100.f * kv.second.second / total);
+    fprintf(stderr, "[lgteun timing] %-34s %5s %10.1f\n", "total", "", total * 1e3f);
+    recs.clear();
+  }
 };
+#define LG_L(L, ch, call, ...) do { (L).begin(#call, (ch)); (L)((call), ##__VA_ARGS__); } while (0)
 
 // The conv-FFN runs as the fused tcgen05/TMEM kernel for c in {16, 32}; c = 64 (the WV-3 bottleneck) does not fit
 // its weights / hidden rows on chip and runs as three tcgen05 pixel-GEMMs + one depthwise kernel (pwgemm_tc.cu).
@@ -250,39 +295,41 @@ cudaError_t run_ffn(const BlockW& b, int ch, const float* x, float* y, float* hi
 // x + LGMixer(LN(x)): window MSA on the first channel half || FFT mixer on the second, proj, residual.
 void run_mixer(Launcher& L, const BlockW& b, int ch, const float* x, float* y, const Workspace& ws, int N, int H, int W,
                cudaStream_t s) {
-  L(launch_window_msa(b, ch, x, ws.loc, 1, N, H, W, s));
-  L(launch_fft_rows_fwd(b, ch, x, ws.spec, 1, N, H, W, s));
-  L(launch_fft_cols(b, ch, ws.spec, N, H, W, s));
-  L(launch_fft_rows_inv(b, ch, ws.spec, ws.loc, x, y, 1, N, H, W, s));
+  LG_L(L, ch, launch_window_msa(b, ch, x, ws.loc, 1, N, H, W, s));
+  LG_L(L, ch, launch_fft_rows_fwd(b, ch, x, ws.spec, 1, N, H, W, s));
+  LG_L(L, ch, launch_fft_cols(b, ch, ws.spec, N, H, W, s));
+  LG_L(L, ch, launch_fft_rows_inv(b, ch, ws.spec, ws.loc, x, y, 1, N, H, W, s));
 }
 // one LGB block: a -> (mixer) -> t -> (ffn) -> a
 void run_block(Launcher& L, const BlockW& b, int ch, float* a, float* t, const Workspace& ws, int N, int H, int W,
                cudaStream_t s) {
   run_mixer(L, b, ch, a, t, ws, N, H, W, s);
-  L(run_ffn(b, ch, t, a, ws.hidden, N, H, W, s), ffn_launches(ch));
+  LG_L(L, ch, run_ffn(b, ch, t, a, ws.hidden, N, H, W, s), ffn_launches(ch));
 }
 // LGT.forward (LGT.py:314-344)
 void run_prior(Launcher& L, const lgteun_ctx* c, int i, const float* zin, float* zout, const Workspace& ws, int N, int H,
                int W, cudaStream_t s) {
   const PriorW& p = c->prior[i];
   const int C = c->C;
-  L(launch_patch_embed(p, c->B, zin, ws.X0, N, H, W, s));
+  LG_L(L, 0, launch_patch_embed(p, c->B, zin, ws.X0, N, H, W, s));
   for (int j = 0; j < 2; ++j) run_block(L, p.enc[j], C, ws.X0, ws.X1, ws, N, H, W, s);       // skip = X0
-  L(launch_down(p, C, ws.X0, ws.L0, N, H, W, s));
+  LG_L(L, 0, launch_down(p, C, ws.X0, ws.L0, N, H, W, s));
   run_block(L, p.bott[0], 2 * C, ws.L0, ws.L1, ws, N, H / 2, W / 2, s);
-  L(launch_up_fuse(p, C, ws.L0, ws.X0, ws.L1, ws.X1, N, H, W, s), 2);
+  LG_L(L, 0, launch_up_fuse(p, C, ws.L0, ws.X0, ws.L1, ws.X1, N, H, W, s), 2);
   for (int j = 0; j < 2; ++j) run_block(L, p.dec[j], C, ws.X1, ws.X2, ws, N, H, W, s);
-  L(launch_tail(p, c->B, ws.X1, zin, zout, N, H, W, s));
+  LG_L(L, 0, launch_tail(p, c->B, ws.X1, zin, zout, N, H, W, s));
 }
 // Pansharpening.forward (unlg_former.py:50-67)
 cudaError_t run_forward(const lgteun_ctx* c, const float* ms, const float* pan, float* out, const Workspace& ws, int N,
-                        int h, int w, int flags, cudaStream_t s, int* launches) {
+                        int h, int w, int flags, cudaStream_t s, int* launches, bool timing = false) {
   Launcher L;
+  L.stream = s;
+  L.timing = timing;
   const int H = 4 * h, W = 4 * w;
-  L(launch_bicubic(ms, ws.zA, N * c->B, h, w, 4, 1, s));
+  LG_L(L, 0, launch_bicubic(ms, ws.zA, N * c->B, h, w, 4, 1, s));
   float *za = ws.zA, *zb = ws.zB;
   for (int i = 0; i < c->K; ++i) {
-    L(launch_data_step(c->dw, i, c->B, za, ms, pan, ws.resid, zb, N, h, w, s), 2);
+    LG_L(L, 0, launch_data_step(c->dw, i, c->B, za, ms, pan, ws.resid, zb, N, h, w, s), 2);
     float* t = za; za = zb; zb = t;
     const bool last = (i == c->K - 1);
     // the reference discards the priors of stages 0..K-2 (unlg_former.py:63-67); run them only on request
@@ -290,6 +337,7 @@ cudaError_t run_forward(const lgteun_ctx* c, const float* ms, const float* pan, 
     else if (flags & LGTEUN_RUN_DEAD_PRIORS) run_prior(L, c, i, za, zb, ws, N, H, W, s);   // zb is scratch here
   }
   if (launches) *launches = L.count;
+  L.report();
   return L.err;
 }
 
@@ -431,7 +479,8 @@ int lgteun_forward(lgteun_t* c, const float* ms, const float* pan, float* out, i
   const size_t ms_bytes = N * B * h * w * sizeof(float), pan_bytes = N * P * sizeof(float), out_bytes = N * B * P * sizeof(float);
 
   if (flags & LGTEUN_NO_GRAPH) {
-    cudaError_t e = run_forward(c, ms, pan, out, ws, N, h, w, flags, s, &c->last_launches);
+    static const bool timing = [] { const char* e = getenv("LGTEUN_TIMING"); return e && e[0] == '1'; }();
+    cudaError_t e = run_forward(c, ms, pan, out, ws, N, h, w, flags, s, &c->last_launches, timing);
     if (e != cudaSuccess) return fail_cuda(e, "forward launch");
     return 0;
   }

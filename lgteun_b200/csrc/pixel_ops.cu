@@ -78,98 +78,177 @@ __device__ __forceinline__ void matvec_store(const float (&v)[K], const float* _
 }
 
 // ---- down unit -----------------------------------------------------------------------------------------
+// bicubic 1/2 (taps [-3,19,19,-3]/32, clamped) then 1x1 C->2C.  C/4 lanes share one output pixel: a lane owns four
+// channels during the resize (its 16 tap loads are 128-bit and coalesced with its neighbours') and eight output
+// channels during the 1x1 conv (inputs exchanged through shared memory).
+constexpr int kDownIters = 8;
 template <int C>
 __global__ void __launch_bounds__(128) down_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                     const float* __restrict__ wt, const float* __restrict__ bias,
                                                     int H, int W, long long total) {
+  constexpr int LPP = C / 4;                       // lanes per pixel
+  constexpr int PPB = 128 / LPP;                   // pixels per block
   extern __shared__ __align__(16) float smem[];
-  float* sW = smem;                 // [2C][C]
-  float* sB = smem + 2 * C * C;     // [2C]
-  for (int i = threadIdx.x; i < 2 * C * C; i += 128) sW[i] = __ldg(wt + i);
+  float* sW = smem;                                // [C][2C]  (transposed at load time: PriorW::down_wt)
+  float* sB = sW + 2 * C * C;                      // [2C]
+  float* sV = sB + 2 * C;                          // [PPB][C + 4]  resized pixel vectors (padded rows)
+  for (int i = threadIdx.x; i < 2 * C * C / 4; i += 128) reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
   for (int i = threadIdx.x; i < 2 * C; i += 128) sB[i] = __ldg(bias + i);
-  __syncthreads();
   const int oh = H / 2, ow = W / 2;
-  long long p = (long long)blockIdx.x * 128 + threadIdx.x;
-  if (p >= total) return;
-  int ox = (int)(p % ow);
-  long long q = p / ow;
-  int oy = (int)(q % oh);
-  long long n = q / oh;
-  const float dn[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
-  float v[C];
+  const int lp = threadIdx.x / LPP, q = threadIdx.x % LPP;
+#pragma unroll 1
+  for (int it = 0; it < kDownIters; ++it) {        // several pixel groups per CTA amortise the weight staging
+  const long long p = ((long long)blockIdx.x * kDownIters + it) * PPB + lp;
+  const bool live = p < total;
+  __syncthreads();                                 // weights staged / previous group's vectors consumed
+  if (live) {
+    const int ox = (int)(p % ow);
+    const long long t = p / ow;
+    const int oy = (int)(t % oh);
+    const long long n = t / oh;
+    const float dn[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < C; ++c) v[c] = 0.f;
+    for (int a = 0; a < 4; ++a) {
+      const int gy = clampi(2 * oy - 1 + a, 0, H - 1);
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    int gy = clampi(2 * oy - 1 + a, 0, H - 1);
-    float r[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) r[c] = 0.f;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      int gx = clampi(2 * ox - 1 + b, 0, W - 1);
-      float t[C];
-      load_vec<C>(t, x + ((n * H + gy) * W + gx) * C);
-#pragma unroll
-      for (int c = 0; c < C; ++c) r[c] = fmaf(dn[b], t[c], r[c]);
+      for (int b = 0; b < 4; ++b) {
+        const int gx = clampi(2 * ox - 1 + b, 0, W - 1);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((n * H + gy) * W + gx) * C) + q);
+        r.x = fmaf(dn[b], v.x, r.x); r.y = fmaf(dn[b], v.y, r.y); r.z = fmaf(dn[b], v.z, r.z); r.w = fmaf(dn[b], v.w, r.w);
+      }
+      acc.x = fmaf(dn[a], r.x, acc.x); acc.y = fmaf(dn[a], r.y, acc.y);
+      acc.z = fmaf(dn[a], r.z, acc.z); acc.w = fmaf(dn[a], r.w, acc.w);
     }
-#pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = fmaf(dn[a], r[c], v[c]);
+    *reinterpret_cast<float4*>(sV + lp * (C + 4) + 4 * q) = acc;
   }
-  matvec_store<C, 2 * C>(v, sW, sB, y + p * (2 * C));
+  __syncthreads();
+  if (!live) continue;
+  // 2C outputs per pixel, 8 per lane (o = 8q .. 8q+7).  Weights are staged TRANSPOSED [k][2C]: for a fixed k the four
+  // lanes of a pixel read one contiguous 128-byte row and all pixels of the warp read the same row (one wavefront).
+  const float* v = sV + lp * (C + 4);
+  float2 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_float2(sB[8 * q + 2 * j], sB[8 * q + 2 * j + 1]);
+#pragma unroll
+  for (int k4 = 0; k4 < C / 4; ++k4) {
+    const float4 v4 = *reinterpret_cast<const float4*>(v + 4 * k4);
+    const float vk[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4* wr = reinterpret_cast<const float4*>(sW + (4 * k4 + kk) * (2 * C) + 8 * q);
+      const float4 wa = wr[0], wb = wr[1];
+      const float2 vv = make_float2(vk[kk], vk[kk]);
+      acc[0] = __ffma2_rn(make_float2(wa.x, wa.y), vv, acc[0]);
+      acc[1] = __ffma2_rn(make_float2(wa.z, wa.w), vv, acc[1]);
+      acc[2] = __ffma2_rn(make_float2(wb.x, wb.y), vv, acc[2]);
+      acc[3] = __ffma2_rn(make_float2(wb.z, wb.w), vv, acc[3]);
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(y + p * (2 * C) + 8 * q);
+  dst[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+  dst[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+  }
 }
 
 cudaError_t launch_down(const PriorW& w, int C, const float* x, float* y, int N, int H, int W, cudaStream_t s) {
   long long total = (long long)N * (H / 2) * (W / 2);
-  unsigned grid = (unsigned)((total + 127) / 128);
-  size_t smem = (size_t)(2 * C * C + 2 * C) * sizeof(float);
-  if (C == 16) down_kernel<16><<<grid, 128, smem, s>>>(x, y, w.down_w, w.down_b, H, W, total);
-  else if (C == 32) down_kernel<32><<<grid, 128, smem, s>>>(x, y, w.down_w, w.down_b, H, W, total);
-  else return cudaErrorInvalidValue;
+  if (C == 16) {
+    constexpr int PPB = 128 / 4;
+    size_t smem = (size_t)(2 * 16 * 16 + 2 * 16 + PPB * 20) * sizeof(float);
+    down_kernel<16><<<(unsigned)((total + PPB * kDownIters - 1) / (PPB * kDownIters)), 128, smem, s>>>(x, y, w.down_wt, w.down_b, H, W, total);
+  } else if (C == 32) {
+    constexpr int PPB = 128 / 8;
+    size_t smem = (size_t)(2 * 32 * 32 + 2 * 32 + PPB * 36) * sizeof(float);
+    down_kernel<32><<<(unsigned)((total + PPB * kDownIters - 1) / (PPB * kDownIters)), 128, smem, s>>>(x, y, w.down_wt, w.down_b, H, W, total);
+  } else {
+    return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
 // ---- up unit + skip fusion ---------------------------------------------------------------------------
 // reference (LGT.py:294-295,336-338): fea = up_conv(bicubic_x2(low)); y = fuse_conv(cat[fea, skip]).
-// A per-pixel affine map commutes with the bicubic resize (its taps sum to 1 and index clamping is linear), so the
-// 2C->C conv runs at LOW resolution (4x fewer pixels, fp32 rounding differs by ~1e-7 relative), then one kernel does
-// bicubic x2 from a shared-memory patch, the concat with the skip map and the 2C->C fusion conv.
-template <int K, int NOUT>
-__global__ void __launch_bounds__(128) pw_conv_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                       const float* __restrict__ wt, const float* __restrict__ bias,
-                                                       long long total) {
+// A per-pixel affine map commutes with the bicubic resize (its taps sum to 1 and index clamping is linear), so both
+// the 2C->C up conv and the [:, :C] half of the fusion conv run at LOW resolution (4x fewer pixels; fp32 rounding
+// differs by ~1e-7 relative):   T = Wf[:, :C] (Wu low + bu)          (low res, low_conv2_kernel)
+//                               y = bicubic_x2(T) + Wf[:, C:] skip + bf   (full res, up_fuse_kernel)
+// The full-res kernel gives each thread a 2x2 output block: the four pixels share a 5x5 low-res neighbourhood
+// (25 shared-memory vector loads per block instead of 4 x 16).
+template <int C>
+__global__ void __launch_bounds__(128) low_conv2_kernel(const float* __restrict__ x, float* __restrict__ y, PriorW w,
+                                                         long long total) {
   extern __shared__ __align__(16) float smem[];
-  float* sW = smem;                 // [NOUT][K]
-  float* sB = smem + NOUT * K;
-  for (int i = threadIdx.x; i < NOUT * K; i += 128) sW[i] = __ldg(wt + i);
-  for (int i = threadIdx.x; i < NOUT; i += 128) sB[i] = __ldg(bias + i);
+  float* sU = smem;                 // [C][2C]   up conv
+  float* sF = sU + 2 * C * C;       // [C][C]    left half of the fusion conv
+  float* sUb = sF + C * C;          // [C]
+  for (int i = threadIdx.x; i < 2 * C * C; i += 128) sU[i] = __ldg(w.up_w + i);
+  for (int i = threadIdx.x; i < C * C; i += 128) sF[i] = __ldg(w.fuse_w + (i / C) * 2 * C + (i % C));
+  for (int i = threadIdx.x; i < C; i += 128) sUb[i] = __ldg(w.up_b + i);
   __syncthreads();
   long long p = (long long)blockIdx.x * 128 + threadIdx.x;
   if (p >= total) return;
-  float v[K];
-  load_vec<K>(v, x + p * K);
-  matvec_store<K, NOUT>(v, sW, sB, y + p * NOUT);
+  float v[2 * C];
+  load_vec<2 * C>(v, x + p * 2 * C);
+  float t[C];
+#pragma unroll
+  for (int o = 0; o < C; o += 4) {
+    float2 a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k4 = 0; k4 < 2 * C / 4; ++k4) {
+      const float2 va = make_float2(v[4 * k4], v[4 * k4 + 1]), vb = make_float2(v[4 * k4 + 2], v[4 * k4 + 3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(sU + (o + j) * 2 * C + 4 * k4);
+        a[j] = __ffma2_rn(make_float2(w4.x, w4.y), va, a[j]);
+        a[j] = __ffma2_rn(make_float2(w4.z, w4.w), vb, a[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[o + j] = (a[j].x + a[j].y) + sUb[o + j];
+  }
+  // second map (no bias: the fusion bias is added at full resolution)
+#pragma unroll
+  for (int o = 0; o < C; o += 4) {
+    float2 a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k4 = 0; k4 < C / 4; ++k4) {
+      const float2 va = make_float2(t[4 * k4], t[4 * k4 + 1]), vb = make_float2(t[4 * k4 + 2], t[4 * k4 + 3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(sF + (o + j) * C + 4 * k4);
+        a[j] = __ffma2_rn(make_float2(w4.x, w4.y), va, a[j]);
+        a[j] = __ffma2_rn(make_float2(w4.z, w4.w), vb, a[j]);
+      }
+    }
+    *reinterpret_cast<float4*>(y + p * C + o) = make_float4(a[0].x + a[0].y, a[1].x + a[1].y, a[2].x + a[2].y, a[3].x + a[3].y);
+  }
 }
 
-constexpr int UFH = 8, UFW = 32;                  // output tile (rows x cols), one thread per pixel
-constexpr int UFPH = UFH / 2 + 4, UFPW = UFW / 2 + 4;   // low-res patch 8 x 20
+constexpr int UFH = 16, UFW = 32;                 // output tile (rows x cols); one thread per 2x2 block -> 128 threads
+constexpr int UFPH = UFH / 2 + 4, UFPW = UFW / 2 + 4;   // low-res patch 12 x 20
 
 template <int C>
-__global__ void __launch_bounds__(256) up_fuse_kernel(const float* __restrict__ t_low, const float* __restrict__ skip,
+__global__ void __launch_bounds__(128) up_fuse_kernel(const float* __restrict__ t_low, const float* __restrict__ skip,
                                                        float* __restrict__ y, PriorW w, int H, int W) {
   constexpr int PS = C + 4;                       // padded pixel stride: conflict-free 128-bit reads
   extern __shared__ __align__(16) float smem[];
   float* sP = smem;                               // [UFPH*UFPW][PS]
-  float* sFu = sP + UFPH * UFPW * PS;             // [C][2C]
-  float* sFb = sFu + 2 * C * C;                   // [C]
+  float* sFu = sP + UFPH * UFPW * PS;             // [C][C]  right (skip) half of the fusion conv
+  float* sFb = sFu + C * C;                       // [C]
   const int tid = threadIdx.x;
   const int lh = H / 2, lw = W / 2;
   const int n = blockIdx.z;
   const int Y0 = blockIdx.y * UFH, X0 = blockIdx.x * UFW;
   const int py0 = Y0 / 2 - 2, px0 = X0 / 2 - 2;   // low-res origin of the patch (replicated borders)
-  for (int i = tid; i < 2 * C * C; i += 256) sFu[i] = __ldg(w.fuse_w + i);
-  for (int i = tid; i < C; i += 256) sFb[i] = __ldg(w.fuse_b + i);
-  for (int i = tid; i < UFPH * UFPW * (C / 4); i += 256) {
+  for (int i = tid; i < C * C; i += 128) sFu[i] = __ldg(w.fuse_w + (i / C) * 2 * C + C + (i % C));
+  for (int i = tid; i < C; i += 128) sFb[i] = __ldg(w.fuse_b + i);
+  for (int i = tid; i < UFPH * UFPW * (C / 4); i += 128) {
     const int pix = i / (C / 4), c4 = i - pix * (C / 4);
     const int pr = pix / UFPW, pc = pix - pr * UFPW;
     const int gy = clampi(py0 + pr, 0, lh - 1), gx = clampi(px0 + pc, 0, lw - 1);
@@ -177,44 +256,80 @@ __global__ void __launch_bounds__(256) up_fuse_kernel(const float* __restrict__ 
         __ldg(reinterpret_cast<const float4*>(t_low + (((size_t)n * lh + gy) * lw + gx) * C) + c4);
   }
   __syncthreads();
-  const int ty = tid >> 5, tx = tid & 31;
-  const int oy = Y0 + ty, ox = X0 + tx;
-  if (oy >= H || ox >= W) return;
-  // x2 taps: even dst 2q -> src q-2..q+1 (t=.75), odd dst 2q+1 -> src q-1..q+2 (t=.25)
+  const int by = tid >> 4, bx = tid & 15;         // 2x2 block: low-res cell (Y0/2 + by, X0/2 + bx)
+  // x2 taps: even dst 2q -> src q-2..q+1 (t=.75), odd dst 2q+1 -> src q-1..q+2 (t=.25); patch rows/cols by+r, bx+c
+  // hold src q-2+r: even uses r = 0..3, odd uses r = 1..4
   const float te[4] = {-0.03515625f, 0.26171875f, 0.87890625f, -0.10546875f};
   const float to[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
-  const int fy = (oy >> 1) - ((oy & 1) ? 1 : 2) - py0, fx = (ox >> 1) - ((ox & 1) ? 1 : 2) - px0;
-  float cat[2 * C];                               // [upsampled | skip]
+#pragma unroll 1
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    float acc[2][2][16];
 #pragma unroll
-  for (int c = 0; c < C; ++c) cat[c] = 0.f;
+    for (int i = 0; i < 16; ++i) acc[0][0][i] = acc[0][1][i] = acc[1][0][i] = acc[1][1][i] = 0.f;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const float wy = (oy & 1) ? to[a] : te[a];
-    float r[C];
+    for (int r = 0; r < 5; ++r) {
+      float rs_e[16], rs_o[16];
 #pragma unroll
-    for (int c = 0; c < C; ++c) r[c] = 0.f;
+      for (int i = 0; i < 16; ++i) rs_e[i] = rs_o[i] = 0.f;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const float wx = (ox & 1) ? to[b] : te[b];
-      const float* src = sP + ((fy + a) * UFPW + fx + b) * PS;
+      for (int c = 0; c < 5; ++c) {
+        const float4* src = reinterpret_cast<const float4*>(sP + ((by + r) * UFPW + bx + c) * PS + c0);
 #pragma unroll
-      for (int c4 = 0; c4 < C; c4 += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(src + c4);
-        r[c4] = fmaf(wx, t.x, r[c4]); r[c4 + 1] = fmaf(wx, t.y, r[c4 + 1]);
-        r[c4 + 2] = fmaf(wx, t.z, r[c4 + 2]); r[c4 + 3] = fmaf(wx, t.w, r[c4 + 3]);
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 t = src[i4];
+          const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (c < 4) rs_e[4 * i4 + k] = fmaf(te[c < 4 ? c : 0], tv[k], rs_e[4 * i4 + k]);
+            if (c >= 1) rs_o[4 * i4 + k] = fmaf(to[c >= 1 ? c - 1 : 0], tv[k], rs_o[4 * i4 + k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (r < 4) {
+          acc[0][0][i] = fmaf(te[r < 4 ? r : 0], rs_e[i], acc[0][0][i]);
+          acc[0][1][i] = fmaf(te[r < 4 ? r : 0], rs_o[i], acc[0][1][i]);
+        }
+        if (r >= 1) {
+          acc[1][0][i] = fmaf(to[r >= 1 ? r - 1 : 0], rs_e[i], acc[1][0][i]);
+          acc[1][1][i] = fmaf(to[r >= 1 ? r - 1 : 0], rs_o[i], acc[1][1][i]);
+        }
       }
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) cat[c] = fmaf(wy, r[c], cat[c]);
-  }
-  const size_t p = ((size_t)n * H + oy) * W + ox;
-  {
-    float t[C];
-    load_vec<C>(t, skip + p * C);
+    for (int ey = 0; ey < 2; ++ey)
 #pragma unroll
-    for (int c = 0; c < C; ++c) cat[C + c] = t[c];
+      for (int ex = 0; ex < 2; ++ex) {
+        const int oy = Y0 + 2 * by + ey, ox = X0 + 2 * bx + ex;
+        if (oy >= H || ox >= W) continue;
+        const size_t p = ((size_t)n * H + oy) * W + ox;
+        float sk[C];
+        load_vec<C>(sk, skip + p * C);
+#pragma unroll
+        for (int o = 0; o < 16; o += 4) {
+          float2 a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k4 = 0; k4 < C / 4; ++k4) {
+            const float2 va = make_float2(sk[4 * k4], sk[4 * k4 + 1]), vb = make_float2(sk[4 * k4 + 2], sk[4 * k4 + 3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w4 = *reinterpret_cast<const float4*>(sFu + (c0 + o + j) * C + 4 * k4);
+              a[j] = __ffma2_rn(make_float2(w4.x, w4.y), va, a[j]);
+              a[j] = __ffma2_rn(make_float2(w4.z, w4.w), vb, a[j]);
+            }
+          }
+          float up[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) up[j] = ey ? (ex ? acc[1][1][o + j] : acc[1][0][o + j]) : (ex ? acc[0][1][o + j] : acc[0][0][o + j]);
+          *reinterpret_cast<float4*>(y + p * C + c0 + o) =
+              make_float4((up[0] + (a[0].x + a[0].y)) + sFb[c0 + o], (up[1] + (a[1].x + a[1].y)) + sFb[c0 + o + 1],
+                          (up[2] + (a[2].x + a[2].y)) + sFb[c0 + o + 2], (up[3] + (a[3].x + a[3].y)) + sFb[c0 + o + 3]);
+        }
+      }
   }
-  matvec_store<2 * C, C>(cat, sFu, sFb, y + p * C);
 }
 
 cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float* skip, float* t_low, float* y, int N, int H,
@@ -223,13 +338,13 @@ cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float
   const unsigned g0 = (unsigned)((low_px + 127) / 128);
   dim3 grid((W + UFW - 1) / UFW, (H + UFH - 1) / UFH, N);
   if (C == 16) {
-    pw_conv_kernel<32, 16><<<g0, 128, (32 * 16 + 16) * sizeof(float), s>>>(low, t_low, w.up_w, w.up_b, low_px);
-    size_t smem = (size_t)(UFPH * UFPW * (16 + 4) + 2 * 16 * 16 + 16) * sizeof(float);
-    up_fuse_kernel<16><<<grid, 256, smem, s>>>(t_low, skip, y, w, H, W);
+    low_conv2_kernel<16><<<g0, 128, (size_t)(3 * 16 * 16 + 16) * sizeof(float), s>>>(low, t_low, w, low_px);
+    size_t smem = (size_t)(UFPH * UFPW * (16 + 4) + 16 * 16 + 16) * sizeof(float);
+    up_fuse_kernel<16><<<grid, 128, smem, s>>>(t_low, skip, y, w, H, W);
   } else if (C == 32) {
-    pw_conv_kernel<64, 32><<<g0, 128, (64 * 32 + 32) * sizeof(float), s>>>(low, t_low, w.up_w, w.up_b, low_px);
-    size_t smem = (size_t)(UFPH * UFPW * (32 + 4) + 2 * 32 * 32 + 32) * sizeof(float);
-    up_fuse_kernel<32><<<grid, 256, smem, s>>>(t_low, skip, y, w, H, W);
+    low_conv2_kernel<32><<<g0, 128, (size_t)(3 * 32 * 32 + 32) * sizeof(float), s>>>(low, t_low, w, low_px);
+    size_t smem = (size_t)(UFPH * UFPW * (32 + 4) + 32 * 32 + 32) * sizeof(float);
+    up_fuse_kernel<32><<<grid, 128, smem, s>>>(t_low, skip, y, w, H, W);
   } else {
     return cudaErrorInvalidValue;
   }
