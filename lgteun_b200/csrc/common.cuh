@@ -31,6 +31,7 @@ struct BlockW {                       // one LGB block: LGT.py:231-239
   const float *f2_w, *f2_b;           // net.4                      [c, 4c]
   const float *f0_wt, *f1_wt, *f2_wt; // derived: the three FFN weights transposed to [in][out] (CUDA-core path)
   const float *ffn_pack;              // derived: fp16 hi/lo of W0,W1,W2 in UMMA K-major core-matrix layout (ffn_tc.cu)
+  const float *proj_pack;             // derived: fp16 hi | lo of proj_w in the same layout (fft256.cu)
 };
 
 struct PriorW {                       // one LGT: LGT.py:251-303

@@ -118,6 +118,7 @@ void add_block(lgteun_ctx* c, const std::string& p, BlockW* b, int ch) {
   c->derived.push_back({&b->f1_w, &b->f1_wt, c4, c4, 0, nullptr});
   c->derived.push_back({&b->f2_w, &b->f2_wt, ch, c4, 0, nullptr});
   if (ch == 16 || ch == 32 || ch == 64) c->derived.push_back({&b->f0_w, &b->ffn_pack, -1, ch, 0, b});
+  c->derived.push_back({&b->proj_w, &b->proj_pack, -2, ch, 0, b});      // proj [c][c] as fp16 hi | lo
 }
 
 // The weight ABI: reference state_dict key grammar.
@@ -161,7 +162,8 @@ void build_table(lgteun_ctx* c) {
   for (auto& s : c->slots) { s.offset = off; off += align4((size_t)s.numel); }
   for (auto& d : c->derived) {
     d.offset = off;
-    size_t floats = d.rows > 0 ? (size_t)d.rows * d.cols : d.rows == 0 ? 2 * 64 * 64 : ffn_tc_pack_halves(d.cols) / 2;
+    size_t floats = d.rows > 0 ? (size_t)d.rows * d.cols : d.rows == 0 ? 2 * 64 * 64
+                    : d.rows == -1 ? ffn_tc_pack_halves(d.cols) / 2 : (size_t)d.cols * d.cols;
     off += align4(floats);
   }
   c->arena_floats = off;
@@ -417,7 +419,10 @@ int lgteun_load_weights(lgteun_t* c, const char* const* names, const float* cons
     float* dst = c->arena + d.offset;
     if (d.rows == 0) CK(launch_transpose_pos(*d.src, dst, s));
     else if (d.rows > 0) CK(launch_transpose(*d.src, dst, d.rows, d.cols, s));
-    else {
+    else if (d.rows == -2) {
+      char* base = reinterpret_cast<char*>(dst);
+      CK(launch_pack_umma_f16(*d.src, base, base + (size_t)d.cols * d.cols * 2, d.cols, d.cols, s));
+    } else {
       // fp16 hi/lo operands of the three FFN GEMMs: w0h | w0l | w1h | w1l | w2h | w2l (halves), see ffn_tc.cu
       const int ch = d.cols, c4 = 4 * ch;
       char* base = reinterpret_cast<char*>(dst);

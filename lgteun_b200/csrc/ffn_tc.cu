@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace lg {
 
@@ -32,88 +33,7 @@ constexpr int kG16 = 2;              // channel slices (thread groups of 128) pe
 constexpr int kStripW = 30;          // interior pixels per warp strip (32 lanes - 2 halo lanes)
 // output rows streamed by one CTA pass (band_rows) are chosen per launch: 64 when the grid is deep, fewer for small batches
 
-// ---- PTX wrappers ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 in, fp32 accumulate), M=128, cta_group::1
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[4]) {     // 8 consecutive columns of this thread's lane
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32,
-// version 1 at bit 46, layout_type 0 (SWIZZLE_NONE).  LBO = byte stride between the two 16-byte K halves of one
-// MMA (K=16 fp16), SBO = byte stride between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format F16 (0), K-major A and B,
-// N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
-
-// split 8 fp32 values (4 pairs) into fp16 hi / lo parts (x = hi + lo up to 2^-22 relative), two 16-byte vectors
-__device__ __forceinline__ void split8(const float2 (&v)[4], uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half2 hh = __float22half2_rn(v[i]);
-    float2 back = __half22float2(hh);
-    __half2 ll = __float22half2_rn(__fadd2_rn(v[i], make_float2(-back.x, -back.y)));
-    h[i] = *reinterpret_cast<uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
+using namespace tc;   // PTX wrappers, descriptors and the fp16 hi/lo split: tc_ptx.cuh
 
 // ---- weight packing (load time): W [N][K] fp32 -> hi/lo fp16 in the UMMA K-major core-matrix layout [K/8][N][8] -----
 __global__ void pack_umma_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int N,

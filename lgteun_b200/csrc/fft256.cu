@@ -11,6 +11,7 @@
 // reordering is needed between the two.
 #include <math.h>
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace lg {
 
@@ -251,23 +252,39 @@ __global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __res
   }
 }
 
+// Inverse row pass + the rest of LGMixer: y = proj(cat(local, |irfft|)) + xres.  The c x c projection runs on the
+// tensor cores (split-fp16 3xMMA, see tc_ptx.cuh): a 128-pixel tile of the concatenated map is written to shared memory
+// as the A operand, the accumulator comes back from TMEM for the bias + residual epilogue.  (The CUDA-core matvec this
+// replaces was 60 % of the kernel and stalled on shared-memory latency.)
 template <int C2>
 __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __restrict__ spec, const float* __restrict__ local,
                                                                const float* __restrict__ xres, float* __restrict__ y,
                                                                BlockW w, float scale) {
   using namespace f256;
+  using namespace tc;
   constexpr int W = 256, Wf = 129;
   constexpr int NF1 = C2 / 2, RW = 16 / NF1, C = 2 * C2;
+  constexpr int TILES = RW * 2;                           // 128-pixel tiles per CTA, two in flight (warps 0-3 / 4-7)
+  constexpr uint32_t TCOLS = (2 * C < 32) ? 32 : 2 * C;   // TMEM columns: two accumulators of C columns
   __shared__ float2 tw[256];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
   extern __shared__ __align__(16) float2 smf[];
   float2* X = smf;                                        // [16][kRowPad]
   float2* E = smf;                                        // [16][272] exchange, same storage
-  float* sW = reinterpret_cast<float*>(smf + 16 * kRowPad);     // [C][C] proj weight
-  float* sBias = sW + C * C;
-  const int tid = threadIdx.x;
+  __half* wh = reinterpret_cast<__half*>(smf + 16 * kRowPad);   // proj weight hi [C/8][C][8], then lo
+  __half* wl = wh + C * C;
+  __half* ah = wl + C * C;                                // A operand: [2 tiles][hi | lo][C/8][128][8]
+  float* sBias = reinterpret_cast<float*>(ah + 2 * 2 * 128 * C);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t row0 = (size_t)blockIdx.x * RW;
   tw[tid] = g_tw256[tid];
-  for (int i = tid; i < C * C / 4; i += 256) reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(w.proj_w) + i);
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+  for (int i = tid; i < 2 * C * C * 2 / 16; i += 256) reinterpret_cast<uint4*>(wh)[i] = __ldg(reinterpret_cast<const uint4*>(w.proj_pack) + i);
   for (int i = tid; i < C; i += 256) sBias[i] = __ldg(w.proj_b + i);
   // phase 0: Hermitian rebuild of the packed spectra (C2R ignores Im of the DC and Nyquist bins)
   const float4* in = reinterpret_cast<const float4*>(spec + row0 * Wf * C2);
@@ -282,7 +299,10 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
       X[s * kRowPad + padded(W - k)] = make_float2(v.x + v.w, v.z - v.y);       // conj(Xa) + i conj(Xb)
     }
   }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
   const int seq = tid >> 4, lo = tid & 15;
   float2 v[16];
 #pragma unroll
@@ -302,47 +322,82 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   for (int j2 = 0; j2 < 16; ++j2)
     X[seq * kRowPad + lo + 16 * j2] = make_float2(fabsf(v[j2].x * scale), fabsf(v[j2].y * scale));
   __syncthreads();
-  // phase 3: concat(local, global) -> proj 1x1 -> + residual, one pixel per thread and row
+  // phase 3: concat(local, global) -> proj 1x1 (tensor cores) -> + bias + residual
+  const int t = warp >> 2;                                // which of the two tiles in flight
+  const int trow = (warp & 3) * 32 + lane;                // row of the tile = TMEM lane
+  __half* a_hi = ah + t * (2 * 128 * C);
+  __half* a_lo = a_hi + 128 * C;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C;
+  uint32_t phase = 0;
 #pragma unroll 1
-  for (int i = 0; i < RW; ++i) {
-    const int p = tid + 256 * i, rl = p >> 8, px = p & 255;
+  for (int round = 0; round < TILES / 2; ++round) {
+    const int p = (round * 2 + t) * 128 + trow, rl = p >> 8, px = p & 255;
     const size_t pix = (row0 + rl) * W + px;
-    float cat[C];
     {
-      float t[C2];
-      load_vec<C2>(t, local + pix * C2);
+      const float4* lsrc = reinterpret_cast<const float4*>(local + pix * C2);
 #pragma unroll
-      for (int c = 0; c < C2; ++c) cat[c] = t[c];
+      for (int kc = 0; kc < C2 / 8; ++kc) {               // local half: channels [0, C2)
+        const float4 t0 = __ldg(lsrc + 2 * kc), t1 = __ldg(lsrc + 2 * kc + 1);
+        const float2 q[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
+        uint4 hi, lo4;
+        split8(q, hi, lo4);
+        *reinterpret_cast<uint4*>(a_hi + (kc * 128 + trow) * 8) = hi;
+        *reinterpret_cast<uint4*>(a_lo + (kc * 128 + trow) * 8) = lo4;
+      }
 #pragma unroll
-      for (int f = 0; f < NF1; ++f) {
-        const float2 g = X[(rl * NF1 + f) * kRowPad + px];
-        cat[C2 + 2 * f] = g.x;
-        cat[C2 + 2 * f + 1] = g.y;
+      for (int kc = 0; kc < C2 / 8; ++kc) {               // global half: channels [C2, C), pairs (2f, 2f+1) per sequence
+        float2 q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = X[(rl * NF1 + 4 * kc + i) * kRowPad + px];
+        uint4 hi, lo4;
+        split8(q, hi, lo4);
+        *reinterpret_cast<uint4*>(a_hi + ((C2 / 8 + kc) * 128 + trow) * 8) = hi;
+        *reinterpret_cast<uint4*>(a_lo + ((C2 / 8 + kc) * 128 + trow) * 8) = lo4;
       }
     }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc(C);
+#pragma unroll
+      for (int tt = 0; tt < 2; ++tt) {
+        const uint32_t ab = smem_u32(ah + tt * (2 * 128 * C));
+#pragma unroll
+        for (int ks = 0; ks < C / 16; ++ks) {
+          const uint64_t dah = umma_desc(ab + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t dal = umma_desc(ab + 128 * C * 2 + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t dbh = umma_desc(smem_u32(wh) + ks * 2 * C * 16, C * 16, 128);
+          const uint64_t dbl = umma_desc(smem_u32(wl) + ks * 2 * C * 16, C * 16, 128);
+          umma_f16(tmem + tt * C, dah, dbh, idesc, ks > 0);
+          umma_f16(tmem + tt * C, dah, dbl, idesc, 1);
+          umma_f16(tmem + tt * C, dal, dbh, idesc, 1);
+        }
+      }
+      umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
     const float* xr = xres + pix * C;
     float* dst = y + pix * C;
-#pragma unroll 1
-    for (int o = 0; o < C; o += 4) {
-      float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-      const float4* r0 = reinterpret_cast<const float4*>(sW + (o + 0) * C);
-      const float4* r1 = reinterpret_cast<const float4*>(sW + (o + 1) * C);
-      const float4* r2 = reinterpret_cast<const float4*>(sW + (o + 2) * C);
-      const float4* r3 = reinterpret_cast<const float4*>(sW + (o + 3) * C);
 #pragma unroll
-      for (int k4 = 0; k4 < C / 4; ++k4) {
-        const float2 va = make_float2(cat[4 * k4], cat[4 * k4 + 1]), vb = make_float2(cat[4 * k4 + 2], cat[4 * k4 + 3]);
-        const float4 w0 = r0[k4], w1 = r1[k4], w2 = r2[k4], w3 = r3[k4];
-        a0 = __ffma2_rn(make_float2(w0.x, w0.y), va, a0); a0 = __ffma2_rn(make_float2(w0.z, w0.w), vb, a0);
-        a1 = __ffma2_rn(make_float2(w1.x, w1.y), va, a1); a1 = __ffma2_rn(make_float2(w1.z, w1.w), vb, a1);
-        a2 = __ffma2_rn(make_float2(w2.x, w2.y), va, a2); a2 = __ffma2_rn(make_float2(w2.z, w2.w), vb, a2);
-        a3 = __ffma2_rn(make_float2(w3.x, w3.y), va, a3); a3 = __ffma2_rn(make_float2(w3.z, w3.w), vb, a3);
-      }
-      const float4 r = *reinterpret_cast<const float4*>(xr + o);
-      *reinterpret_cast<float4*>(dst + o) = make_float4(((a0.x + a0.y) + sBias[o]) + r.x, ((a1.x + a1.y) + sBias[o + 1]) + r.y,
-                                                        ((a2.x + a2.y) + sBias[o + 2]) + r.z, ((a3.x + a3.y) + sBias[o + 3]) + r.w);
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float2 acc[4];
+      tmem_ld8(lane_addr + c0, acc);
+      tmem_ld_wait();
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(xr + c0)), r1 = __ldg(reinterpret_cast<const float4*>(xr + c0 + 4));
+      const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0), b1 = *reinterpret_cast<const float4*>(sBias + c0 + 4);
+      *reinterpret_cast<float4*>(dst + c0) =
+          make_float4((acc[0].x + b0.x) + r0.x, (acc[0].y + b0.y) + r0.y, (acc[1].x + b0.z) + r0.z, (acc[1].y + b0.w) + r0.w);
+      *reinterpret_cast<float4*>(dst + c0 + 4) =
+          make_float4((acc[2].x + b1.x) + r1.x, (acc[2].y + b1.y) + r1.y, (acc[3].x + b1.z) + r1.z, (acc[3].y + b1.w) + r1.w);
     }
+    tc_fence_before();
   }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
 template <int C2>
@@ -358,7 +413,7 @@ template <int C2>
 static cudaError_t rows256_inv_t(const BlockW& w, const float* spec, const float* local, const float* xres, float* y, int N,
                                  int H, cudaStream_t s) {
   constexpr int RW = 16 / (C2 / 2), C = 2 * C2;
-  const size_t smem = (size_t)(16 * kRowPad) * sizeof(float2) + (size_t)(C * C + C) * sizeof(float);
+  const size_t smem = (size_t)(16 * kRowPad) * sizeof(float2) + (size_t)(2 * C * C + 2 * 2 * 128 * C) * 2 + (size_t)C * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(fft_rows_inv256_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   fft_rows_inv256_kernel<C2><<<N * H / RW, 256, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
