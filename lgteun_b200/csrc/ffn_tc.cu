@@ -310,7 +310,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       tmem_ld8(slot[1] + cg * CH, hn[1]);
       tmem_ld8(slot[2] + cg * CH, hn[2]);
       tmem_ld_wait();
-#pragma unroll 1
+#pragma unroll
       for (int c0 = cg * CH; c0 < (cg + 1) * CH; c0 += 8) {
         float2 h[3][4];
 #pragma unroll
@@ -330,11 +330,15 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           bm[2] = __fmul2_rn(make_float2(bb.x, bb.y), m2); bm[3] = __fmul2_rn(make_float2(bb.z, bb.w), m2);
         }
         float2 cl[4], cc[4], cr[4];                       // per-lane column sums for the left / centre / right taps
+        const float4 da = *reinterpret_cast<const float4*>(&sm.dwb[c0]);
+        const float4 db = *reinterpret_cast<const float4*>(&sm.dwb[c0 + 4]);
+        const float2 dbv[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y), make_float2(db.z, db.w)};
+        // the centre row (dy = 1) always lies inside the image for a live strip: it initialises the sums (the conv bias
+        // rides in the centre tap); the rows above / below are added when they exist (warp-uniform test)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cl[i] = cc[i] = cr[i] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          if (!rv[dy]) continue;
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const int dy = (dyi == 0) ? 1 : (dyi == 1 ? 0 : 2);
+          if (dy != 1 && !rv[dy]) continue;
           const float4* wl = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 0) * C4 + c0]);
           const float4* wc = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 1) * C4 + c0]);
           const float4* wr = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 2) * C4 + c0]);
@@ -344,18 +348,24 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
             const float2 ha = __ffma2_rn(h[dy][2 * hf], m2, bm[2 * hf]);
             const float2 hb = __ffma2_rn(h[dy][2 * hf + 1], m2, bm[2 * hf + 1]);
             // tap (dy,-1) of THIS pixel is consumed by lane+1, tap (dy,+1) by lane-1
-            cl[2 * hf] = __ffma2_rn(make_float2(l4.x, l4.y), ha, cl[2 * hf]);
-            cl[2 * hf + 1] = __ffma2_rn(make_float2(l4.z, l4.w), hb, cl[2 * hf + 1]);
-            cc[2 * hf] = __ffma2_rn(make_float2(c4.x, c4.y), ha, cc[2 * hf]);
-            cc[2 * hf + 1] = __ffma2_rn(make_float2(c4.z, c4.w), hb, cc[2 * hf + 1]);
-            cr[2 * hf] = __ffma2_rn(make_float2(r4.x, r4.y), ha, cr[2 * hf]);
-            cr[2 * hf + 1] = __ffma2_rn(make_float2(r4.z, r4.w), hb, cr[2 * hf + 1]);
+            if (dy == 1) {
+              cl[2 * hf] = __fmul2_rn(make_float2(l4.x, l4.y), ha);
+              cl[2 * hf + 1] = __fmul2_rn(make_float2(l4.z, l4.w), hb);
+              cc[2 * hf] = __ffma2_rn(make_float2(c4.x, c4.y), ha, dbv[2 * hf]);
+              cc[2 * hf + 1] = __ffma2_rn(make_float2(c4.z, c4.w), hb, dbv[2 * hf + 1]);
+              cr[2 * hf] = __fmul2_rn(make_float2(r4.x, r4.y), ha);
+              cr[2 * hf + 1] = __fmul2_rn(make_float2(r4.z, r4.w), hb);
+            } else {
+              cl[2 * hf] = __ffma2_rn(make_float2(l4.x, l4.y), ha, cl[2 * hf]);
+              cl[2 * hf + 1] = __ffma2_rn(make_float2(l4.z, l4.w), hb, cl[2 * hf + 1]);
+              cc[2 * hf] = __ffma2_rn(make_float2(c4.x, c4.y), ha, cc[2 * hf]);
+              cc[2 * hf + 1] = __ffma2_rn(make_float2(c4.z, c4.w), hb, cc[2 * hf + 1]);
+              cr[2 * hf] = __ffma2_rn(make_float2(r4.x, r4.y), ha, cr[2 * hf]);
+              cr[2 * hf + 1] = __ffma2_rn(make_float2(r4.z, r4.w), hb, cr[2 * hf + 1]);
+            }
           }
         }
         float2 o[4];
-        const float4 da = *reinterpret_cast<const float4*>(&sm.dwb[c0]);
-        const float4 db = *reinterpret_cast<const float4*>(&sm.dwb[c0 + 4]);
-        const float2 dbv[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y), make_float2(db.z, db.w)};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float2 left, right;
@@ -363,7 +373,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           left.y = __shfl_up_sync(0xffffffffu, cl[i].y, 1);
           right.x = __shfl_down_sync(0xffffffffu, cr[i].x, 1);     // from pixel x+1
           right.y = __shfl_down_sync(0xffffffffu, cr[i].y, 1);
-          o[i] = gelu_pair(__fadd2_rn(__fadd2_rn(__fadd2_rn(cc[i], left), right), dbv[i]));
+          o[i] = gelu_pair(__fadd2_rn(__fadd2_rn(cc[i], left), right));
         }
         uint4 hi, lo;
         split8(o, hi, lo);
