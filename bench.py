@@ -330,8 +330,17 @@ def roofline_ffn(handle, bands, batch, H, dev, stream, peaks, args):
     flops = (48 * c * c + 72 * c) * n * H * H
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    traffic = None                      # dram__bytes_read + write per launch from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_final_ffn_tc_traffic.json")) as f:
+            t = json.load(f)
+        if t["bands"] == bands and t["pairs"] == n and t["H"] == H:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
     return {"bound": "tensor", "kernel": f"ffn (LN+1x1+GELU+1x1+dw3x3+GELU+1x1+res), c={c}, {n}x{H}x{H} px",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "algorithmic_bytes": 2 * 4 * c * n * H * H,
             "ms_per_launch": ms, "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json)",
             "note": "fp32 parity needs 3-way split operands on the tensor pipe: the reachable ceiling is peak/3"}
 
