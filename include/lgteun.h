@@ -123,6 +123,14 @@ int lgteun_op_ffn(lgteun_t* ctx, int prior, int lgb, int block, const float* x, 
 int lgteun_op_prior(lgteun_t* ctx, int prior, const float* x_nchw, float* y_nchw,
                     int N, int H, int W, void* stream);
 
+/* ---- eval glue next to the hot path -------------------------------------------------
+ * Full-reference metrics of Base_model.test (models/base/base_model.py:304-327 -> models/base/metrics.py: psnr :39-48,
+ * sam :22-35, ergas :166-182) on the device, in float64 like the reference: pred / gt are normalised NCHW tensors
+ * [N,B,H,W]; they are de-normalised with max_value = 2**bit_depth - .5 (dataset/utils.py:252-263) first.
+ * out_dev receives N x {PSNR, SAM, ERGAS} doubles (device memory). */
+int lgteun_op_metrics(lgteun_t* ctx, const float* pred, const float* gt, double* out_dev, int N, int H, int W,
+                      float max_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

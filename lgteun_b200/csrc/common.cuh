@@ -97,6 +97,9 @@ cudaError_t launch_ffn_tc(const BlockW& w, int c, const float* x, float* y, int 
 // pwgemm_tc.cu — conv-FFN of the widest level (c = 64) as tcgen05 pixel-GEMMs; buf_a / buf_b: N*H*W*256 floats each
 cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, float* buf_b, float* y, int N, int H, int W,
                                cudaStream_t s);
+// metrics.cu — PSNR / SAM / ERGAS per image in fp64 (acc: N*(2+2B) doubles scratch, out: N*3 doubles)
+cudaError_t launch_metrics(const float* pred, const float* gt, double* acc, double* out, int N, int B, int H, int W,
+                           float max_value, cudaStream_t s);
 // misc
 cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s);
 cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r] = src[r][c]

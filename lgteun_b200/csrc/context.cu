@@ -80,6 +80,8 @@ struct lgteun_ctx {
   size_t ws_bytes = 0;
   std::vector<GraphEntry> graphs;
   cudaStream_t cap_stream = nullptr;   // capture never runs on the caller's stream (it may be the legacy stream)
+  double* metric_acc = nullptr;        // scratch of lgteun_op_metrics
+  size_t metric_acc_doubles = 0;
   int last_launches = 0;
 };
 
@@ -385,6 +387,7 @@ void lgteun_destroy(lgteun_t* c) {
   cudaDeviceSynchronize();
   drop_graphs(c);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  if (c->metric_acc) cudaFree(c->metric_acc);
   if (c->ws_base) cudaFree(c->ws_base);
   if (c->arena) cudaFree(c->arena);
   delete c;
@@ -696,6 +699,25 @@ int lgteun_op_prior(lgteun_t* c, int prior, const float* x, float* y, int N, int
   Launcher L;
   run_prior(L, c, prior, x, y, ws, N, H, W, s);
   if (!L.ok()) return fail_cuda(L.err, "prior launch");
+  return 0;
+}
+
+int lgteun_op_metrics(lgteun_t* c, const float* pred, const float* gt, double* out_dev, int N, int H, int W, float max_value,
+                      void* stream) {
+  if (!c || !pred || !gt || !out_dev) return fail(LGTEUN_EINVAL, "NULL argument");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(LGTEUN_EINVAL, "bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  const size_t need = (size_t)N * (2 + 2 * c->B);
+  if (need > c->metric_acc_doubles) {
+    CK(cudaStreamSynchronize(s));
+    if (c->metric_acc) cudaFree(c->metric_acc);
+    c->metric_acc = nullptr;
+    c->metric_acc_doubles = 0;
+    CK(cudaMalloc(&c->metric_acc, need * sizeof(double)));
+    c->metric_acc_doubles = need;
+  }
+  CK(launch_metrics(pred, gt, c->metric_acc, out_dev, N, c->B, H, W, max_value, s));
   return 0;
 }
 

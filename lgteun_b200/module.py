@@ -216,6 +216,23 @@ class Pansharpening(nn.Module):
                            torch.cuda.current_stream(ms.device).cuda_stream)
         return out
 
+    def evaluate(self, pred: torch.Tensor, gt: torch.Tensor, bit_depth: int = 11) -> torch.Tensor:
+        """PSNR / SAM / ERGAS per image on the device, float64 — the reduced-resolution metrics the reference's test
+        loop computes per image with numpy (models/base/base_model.py:304-327, models/base/metrics.py).  pred / gt are
+        the normalised [N,B,H,W] CUDA tensors of the eval loop; returns a float64 CUDA tensor [N, 3]."""
+        if pred.shape != gt.shape or pred.dim() != 4 or pred.shape[1] != self.in_channels:
+            raise ValueError("pred and gt must both be [N,B,H,W]")
+        if pred.device.type != "cuda" or gt.device != pred.device or pred.dtype != torch.float32 or gt.dtype != torch.float32:
+            raise RuntimeError("evaluate() needs float32 CUDA tensors on one device")
+        with torch.cuda.device(pred.device):
+            handle = self._runtime(pred.device)
+            n, _, h, w = pred.shape
+            out = torch.empty((n, 3), dtype=torch.float64, device=pred.device)
+            pc, gc = pred.contiguous(), gt.contiguous()
+            handle.op("metrics", pc.data_ptr(), gc.data_ptr(), out.data_ptr(), n, h, w, float(2 ** bit_depth - 0.5),
+                      stream=torch.cuda.current_stream(pred.device).cuda_stream)
+        return out
+
     def extra_repr(self):
         return f"bands={self.in_channels}, stage={self.stage}, backend=sm_100a C-ABI ({_abi.LIB_PATH})"
 

@@ -164,7 +164,8 @@ def test_global_mixer_golden(h4):
     assert _maxdiff(y, g["enc0_global"]) <= 1e-4
 
 
-@pytest.mark.parametrize("bands,lgb,shape", [(4, 0, (1, 64, 64)), (4, 1, (2, 16, 32)), (8, 0, (1, 32, 32)), (8, 1, (1, 16, 16))])
+@pytest.mark.parametrize("bands,lgb,shape", [(4, 0, (1, 64, 64)), (4, 1, (2, 16, 32)), (8, 0, (1, 32, 32)), (8, 1, (1, 16, 16)),
+                                             (4, 0, (1, 256, 256)), (8, 0, (1, 64, 256)), (8, 1, (1, 32, 256))])
 def test_mixer_and_ffn(h4, h8, O, bands, lgb, shape):
     hd, sd = (h4, load_weights(4)) if bands == 4 else (h8, load_weights(8))
     n, H, W = shape
@@ -265,6 +266,33 @@ def test_metrics_within_tolerance(abi, h4):
     assert np.all(np.abs(ours - ref) <= 0.01), (ours, ref)
 
 
+def test_device_metrics_match_reference(abi, h4):
+    """lgteun_op_metrics (fp64 PSNR/SAM/ERGAS on the device) against the numpy restatement per image and against the
+    metrics the reference's own functions produced for the golden case (models/base/metrics.py)."""
+    from oracle import metrics_oracle as M
+    g = load_case("gf2_metric")
+    out = _forward(h4, abi, g["ms"], g["pan"])
+    gt = g["gt"].cuda()
+    n, _, hh, ww = out.shape
+    res = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    h4.op("metrics", out.data_ptr(), gt.data_ptr(), res.data_ptr(), n, hh, ww, 2047.5)
+    torch.cuda.synchronize()
+    res = res.cpu().numpy()
+    o, t = out.cpu().numpy(), g["gt"].numpy()
+    for i in range(n):
+        want = M.evaluate(o[i:i + 1], t[i:i + 1])
+        assert np.allclose(res[i], want, rtol=1e-9, atol=1e-9), (i, res[i], want)
+    ref = g["ref_metrics_psnr_sam_ergas"].numpy()
+    assert np.all(np.abs(res.mean(axis=0) - ref) <= 0.01), (res.mean(axis=0), ref)
+    # identical images: PSNR is +inf, SAM ~ 0 (arccos of a clipped 1), ERGAS 0 — metrics.py:41-42
+    same =torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    h4.op("metrics", gt.data_ptr(), gt.data_ptr(), same.data_ptr(), n, hh, ww, 2047.5)
+    same = same.cpu().numpy()
+    assert np.all(np.isinf(same[:, 0])) and np.all(same[:, 2] == 0.0)
+    want_sam = M.sam(np.transpose(t[0], (1, 2, 0)) * 2047.5, np.transpose(t[0], (1, 2, 0)) * 2047.5)
+    assert abs(same[0, 1] - want_sam) <= 1e-9
+
+
 def test_small_residual_regime(abi, O):
     """second weight set with the last prior's tail scaled by 0.05 (prior = small residual around the
     data-step output, outputs near [0,1])."""
@@ -334,6 +362,10 @@ def test_module_dropin(abi):
     with torch.no_grad():
         out = net(g["ms"].cuda(), g["pan"].cuda())
         assert _maxdiff(out, g["out"]) <= E2E_TOL
+        from oracle import metrics_oracle as M
+        m = net.evaluate(out, g["out"].cuda()).cpu().numpy()
+        assert m.shape == (out.shape[0], 3)
+        assert np.allclose(m.mean(axis=0), M.evaluate(out.cpu().numpy(), g["out"].numpy()), rtol=1e-9, atol=1e-9)
         # weight refresh after an in-place parameter update
         net.prior_module[1].tail[1].bias.add_(0.25)
         out2 = net(g["ms"].cuda(), g["pan"].cuda())
@@ -361,3 +393,31 @@ def test_error_behaviour(abi, h4):
     with pytest.raises(RuntimeError):
         fresh.load_weights({"R.weight": torch.zeros(4, device="cuda")})       # missing keys
     fresh.close()
+
+
+@pytest.mark.parametrize("env", [{"LGTEUN_FFN": "simt"}, {"LGTEUN_FFT": "stockham"}])
+def test_ab_switch_paths_stay_correct(env):
+    """The A/B switches (CUDA-core FFN, shared-memory Stockham FFT passes) select other kernels of the SAME library for
+    measurement; they are read once per process, so they are exercised in a child process against the golden output."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from types import SimpleNamespace\n"
+        "import lgteun_b200\n"
+        f"z = np.load({os.path.join(ROOT, 'tests', 'golden', 'weights_b4.npz')!r})\n"
+        f"g = np.load({os.path.join(ROOT, 'tests', 'golden', 'case_gf2_full.npz')!r})\n"
+        "net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=4), None, stage=2)\n"
+        "net.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files})\n"
+        "net = net.cuda().eval()\n"
+        "with torch.no_grad():\n"
+        "    out = net(torch.from_numpy(g['ms']).cuda(), torch.from_numpy(g['pan']).cuda()).cpu().numpy()\n"
+        "print('MAXDIFF', float(np.abs(out - g['out']).max()))\n"
+    )
+    res = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    diff = float(res.stdout.strip().split("MAXDIFF")[-1])
+    assert diff <= E2E_TOL, (env, diff)
