@@ -106,32 +106,28 @@ cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, c
 
 // ---- device helpers -----------------------------------------------------------------------------
 #ifdef __CUDACC__
-// Exact-form GELU x*Phi(x) on a PAIR of values with Blackwell's packed fp32 pipe (FFMA2/FMUL2).
-//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt(2)   (Abramowitz-Stegun 7.1.26)
-//   gelu(x) = relu(x) - 0.5 |x| poly(t) exp(-x^2/2)
-// Max abs error 3.3e-7 over [-12, 12] in fp32 (torch's own fp32 erf-GELU is at 1.2e-6 vs fp64) at 9 issue slots
-// per element instead of ~27 for erff(): the conv-FFN is bound by these epilogues, not by the tensor pipe.
+// Exact-form (erf) GELU x*Phi(x) on a PAIR of values with Blackwell's packed fp32 pipe.
+//   gelu(x) = relu(x) - |x| * Phi(-|x|),   Phi(-a) = erfc(a / sqrt 2) / 2 = 2^(-Q(a))
+// -log2 Phi(-a) is smooth (1 at 0, ~ a^2 log2(e)/2 for large a), so a degree-5 polynomial Q fitted with weight
+// a * Phi(-a) reproduces GELU to 4.8e-7 absolute over the whole real line (6.4e-7 including fp32 rounding; torch's own
+// fp32 erf-GELU is 1.2e-6 from the fp64 value).  The leading coefficient is positive: Q grows without bound, the
+// correction underflows to 0 for large |x| and gelu(x) -> relu(x) exactly.  The polynomial is evaluated in n = -|x|
+// (odd coefficients negated), which also is the factor of the correction term.
+// Cost per pair: 2 LOP3 + 5 FFMA2 + 2 MUFU.EX2 + 2 FMNMX + 1 FFMA2 = 12 issue slots and ONE special-function op per
+// element (the Abramowitz-Stegun 7.1.26 form used before needed 18 slots and two MUFU ops; erff() needs ~27/element).
+// The conv-FFN is bound by these epilogues, not by the tensor pipe.
 __device__ __forceinline__ float2 gelu_pair(float2 x) {
-  const float kPS = 0.23164189f;                 // p / sqrt(2), p = 0.3275911
-  const float kK = 0.84932180f;                  // sqrt(log2(e) / 2): exp(-x^2/2) = exp2(-(kK x)^2)
-  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-  const float2 u = __ffma2_rn(ax, make_float2(kPS, kPS), make_float2(1.f, 1.f));
-  float2 t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
-  const float2 w = __fmul2_rn(ax, make_float2(kK, kK));
-  const float2 ww = __fmul2_rn(w, w);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(-ww.x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(-ww.y));
-  // -0.5 * (a1..a5)
-  float2 p = make_float2(-0.5307027145f, -0.5307027145f);
-  p = __ffma2_rn(p, t, make_float2(0.7265760135f, 0.7265760135f));
-  p = __ffma2_rn(p, t, make_float2(-0.7107068705f, -0.7107068705f));
-  p = __ffma2_rn(p, t, make_float2(0.142248368f, 0.142248368f));
-  p = __ffma2_rn(p, t, make_float2(-0.127414796f, -0.127414796f));
-  p = __fmul2_rn(p, t);
-  const float2 ae = __fmul2_rn(ax, e);
-  return __ffma2_rn(ae, p, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+  const float2 n = make_float2(__int_as_float(__float_as_int(x.x) | 0x80000000), __int_as_float(__float_as_int(x.y) | 0x80000000));
+  float2 q = make_float2(4.7329402712e-04f, 4.7329402712e-04f);
+  q = __ffma2_rn(q, n, make_float2(7.0844612347e-03f, 7.0844612347e-03f));
+  q = __ffma2_rn(q, n, make_float2(5.1827168585e-02f, 5.1827168585e-02f));
+  q = __ffma2_rn(q, n, make_float2(-4.5999264548e-01f, -4.5999264548e-01f));
+  q = __ffma2_rn(q, n, make_float2(1.1507877699e+00f, 1.1507877699e+00f));
+  q = __ffma2_rn(q, n, make_float2(-1.0000376324e+00f, -1.0000376324e+00f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  return __ffma2_rn(n, e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 __device__ __forceinline__ float gelu_fast(float x) { return gelu_pair(make_float2(x, x)).x; }
 

@@ -56,8 +56,12 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
 
   const int w_begin = blockIdx.x * windows_per_cta;
   const int w_end = min(w_begin + windows_per_cta, total_windows);
+  __syncthreads();                                  // weights staged
+  // A window slot is loaded, projected and attended by the SAME two warps (threads 64*slot .. 64*slot+63), so the
+  // slots run free of each other: their hand-offs use a 64-thread named barrier, not a CTA-wide one.
+  auto slot_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(lslot + 1) : "memory"); };
   for (int wbase = w_begin; wbase < w_end; wbase += kWinPerIter) {
-    __syncthreads();                                // previous iteration's K/V/xs fully consumed; weights loaded
+    slot_sync();                                    // previous iteration's xs of this slot fully consumed
     // 1) load (+ LayerNorm): one thread per (window, token)
     {
       const int widx = wbase + lslot;
@@ -88,7 +92,7 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
         }
       }
     }
-    __syncthreads();
+    slot_sync();
     const int widx = wbase + slot;
     const bool active = widx < w_end;               // warp-uniform
     // 2) q/k/v of this lane's two tokens for this warp's head
