@@ -35,13 +35,15 @@ constexpr int kStripW = 30;          // interior pixels per warp strip (32 lanes
 
 using namespace tc;   // PTX wrappers, descriptors and the fp16 hi/lo split: tc_ptx.cuh
 
-// ---- weight packing (load time): W [N][K] fp32 -> hi/lo fp16 in the UMMA K-major core-matrix layout [K/8][N][8] -----
-__global__ void pack_umma_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int N,
-                                     int K) {
+// ---- weight packing (load time): W [N][K] fp32 -> hi/lo fp16 in the UMMA K-major core-matrix layout [Kext/8][N][8] ---
+// Kext > K appends the bias as column K (the A operand carries a matching column of ones, so the GEMM adds the bias and
+// a zeroed A row yields an exactly zero output row) and zero columns up to Kext.
+__global__ void pack_umma_f16_kernel(const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ hi,
+                                     __half* __restrict__ lo, int N, int K, int Kext) {
   int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= N * K) return;
-  int n = idx / K, k = idx - n * K;
-  float v = w[idx];
+  if (idx >= N * Kext) return;
+  int n = idx / Kext, k = idx - n * Kext;
+  float v = k < K ? w[n * K + k] : (k == K && bias) ? bias[n] : 0.f;
   __half h = __float2half_rn(v);
   __half l = __float2half_rn(v - __half2float(h));
   size_t o = ((size_t)(k >> 3) * N + n) * 8 + (k & 7);
@@ -49,7 +51,11 @@ __global__ void pack_umma_f16_kernel(const float* __restrict__ w, __half* __rest
   lo[o] = l;
 }
 cudaError_t launch_pack_umma_f16(const float* w, void* hi, void* lo, int N, int K, cudaStream_t s) {
-  pack_umma_f16_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(w, (__half*)hi, (__half*)lo, N, K);
+  pack_umma_f16_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(w, nullptr, (__half*)hi, (__half*)lo, N, K, K);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_umma_f16_bias(const float* w, const float* bias, void* hi, void* lo, int N, int K, cudaStream_t s) {
+  pack_umma_f16_kernel<<<(N * (K + 16) + 255) / 256, 256, 0, s>>>(w, bias, (__half*)hi, (__half*)lo, N, K, K + 16);
   return cudaGetLastError();
 }
 
@@ -60,12 +66,14 @@ struct FfnTcSmem {
   uint64_t mbar[3];                                   // MMA-completion barriers of G1, G2, G3
   uint32_t tmem_base;
   uint32_t pad_[3];
-  alignas(16) __half w0h[C4 * C], w0l[C4 * C];        // [C/8][C4][8]
-  alignas(16) __half w1h[C4 * C4], w1l[C4 * C4];      // [C4/8][C4][8]
-  alignas(16) __half w2h[C * C4], w2l[C * C4];        // [C4/8][C][8]
-  alignas(16) __half a1h[128 * C], a1l[128 * C];      // [C/8][128][8]
-  alignas(16) __half a2h[128 * C4], a2l[128 * C4];    // [C4/8][128][8]   (A2, then A3)
-  alignas(16) float b0[C4], b1[C4], dwb[C4], dww[9 * C4];   // dww: [tap][channel]
+  // K of GEMM1 / GEMM2 is extended by one 16-wide step whose first column is the bias (weights) / the pixel-valid flag
+  // (activations): the bias add and the zero padding of the conv ride in the MMA
+  alignas(16) __half w0h[C4 * (C + 16)], w0l[C4 * (C + 16)];        // [(C+16)/8][C4][8]
+  alignas(16) __half w1h[C4 * (C4 + 16)], w1l[C4 * (C4 + 16)];      // [(C4+16)/8][C4][8]
+  alignas(16) __half w2h[C * C4], w2l[C * C4];                      // [C4/8][C][8]
+  alignas(16) __half a1h[128 * (C + 16)], a1l[128 * C];             // [K/8][128][8]; the flag step has no lo part
+  alignas(16) __half a2h[128 * (C4 + 16)], a2l[128 * C4];           // A2, then A3 (first C4 columns)
+  alignas(16) float dwb[C4], dww[9 * C4];                           // dww: [tap][channel]
   alignas(16) float b2[C], lng[C], lnb[C];
   alignas(16) float2 part[C / 8][128];                // LayerNorm partials (mean, M2) of each 8-channel slice of a pixel
 };
@@ -101,13 +109,11 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   if (warp == 0) tmem_alloc(&sm.tmem_base, TMEM_COLS);
   {
     // packed weights in global: w0h | w0l | w1h | w1l | w2h | w2l, contiguous, same order as the smem plan
-    constexpr int n16 = (2 * (C4 * C + C4 * C4 + C * C4)) * 2 / 16;
+    constexpr int n16 = (2 * (C4 * (C + 16) + C4 * (C4 + 16) + C * C4)) * 2 / 16;
     const uint4* src = reinterpret_cast<const uint4*>(wpack);
     uint4* dst = reinterpret_cast<uint4*>(sm.w0h);
     for (int i = tid; i < n16; i += NT) dst[i] = __ldg(src + i);
     for (int i = tid; i < C4; i += NT) {
-      sm.b0[i] = __ldg(w.f0_b + i);
-      sm.b1[i] = __ldg(w.f1_b + i);
       sm.dwb[i] = __ldg(w.dw_b + i);
 #pragma unroll
       for (int t = 0; t < 9; ++t) sm.dww[t * C4 + i] = __ldg(w.dw_w + i * 9 + t);
@@ -116,6 +122,11 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       sm.b2[i] = __ldg(w.f2_b + i);
       sm.lng[i] = __ldg(w.ln2_w + i);
       sm.lnb[i] = __ldg(w.ln2_b + i);
+    }
+    // second half of the two flag K-steps: always zero
+    for (int i = tid; i < 128; i += NT) {
+      *reinterpret_cast<uint4*>(&sm.a1h[((C / 8 + 1) * 128 + i) * 8]) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(&sm.a2h[((C4 / 8 + 1) * 128 + i) * 8]) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   fence_proxy_async();
@@ -148,7 +159,6 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     const int rows = min(band_rows, H - y0);              // output rows of this band (uniform over the image)
     const float* xrow0 = xin + (size_t)n * H * W * C;
     float* yrow0 = yout + (size_t)n * H * W * C;
-    const float2 m2 = x_ok ? make_float2(1.f, 1.f) : make_float2(0.f, 0.f);
     const int iters = min(band_rows, H) + 2;              // H and band_rows are powers of two: every band has the same height
 
     // ---- S_a: LayerNorm(x[row]) -> A1 (hi/lo fp16), spread over all warps -------------------------------------------
@@ -158,10 +168,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
     bool xvalid = false;
     auto prefetch_x = [&](int it) {
-      if (cg >= LG) return;
       const int y = y0 + it - 1;
       xvalid = x_ok && y >= 0 && y < H && it < rows + 2;
-      if (xvalid) {
+      if (xvalid && cg < LG) {
         const float4* src = reinterpret_cast<const float4*>(xrow0 + ((size_t)y * W + x) * C + cg * 8);
         xa = __ldg(src);
         xb = __ldg(src + 1);
@@ -177,8 +186,11 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       d = xb.z - mean; m2 = fmaf(d, d, m2); d = xb.w - mean; m2 = fmaf(d, d, m2);
       sm.part[cg][row] = make_float2(mean, m2);
     };
+    const uint4 kFlagOn = make_uint4(0x00003C00u, 0u, 0u, 0u);   // fp16 {1, 0, 0, 0, 0, 0, 0, 0}
+    const uint4 kFlagOff = make_uint4(0u, 0u, 0u, 0u);
     auto stage_a = [&]() {
       if (cg >= LG) return;
+      if (cg == 0) *reinterpret_cast<uint4*>(&sm.a1h[((C / 8) * 128 + row) * 8]) = xvalid ? kFlagOn : kFlagOff;
       float2 t8[4];
       if (xvalid) {
         float2 pr[LG];
@@ -217,6 +229,11 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
         umma_f16(tmem + D1_COL, al, bh, idesc, 1);
       }
+      {                                                   // + valid * b0
+        const uint64_t ah = umma_desc(a1h + (C / 16) * 2 * 128 * 16, 128 * 16, 128);
+        umma_f16(tmem + D1_COL, ah, umma_desc(w0h + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+        umma_f16(tmem + D1_COL, ah, umma_desc(w0l + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+      }
       umma_commit(&sm.mbar[0]);
     };
     // publish generic-proxy smem writes + finished TMEM reads, then let one thread issue MMAs
@@ -238,8 +255,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     LG_SYNC_THEN_ISSUE(issue_g1());
 
     for (int it = 0; it < iters; ++it) {
+      const bool row_valid = xvalid;                      // this row's pixel lies inside the image
       if (it + 1 < iters) prefetch_x(it + 1);             // global load of the next row flies under the wait + S_b
-      // ---- S_b: GELU(D1 + b0) -> A2 (hi/lo fp16) ---------------------------------------------------------------------
+      // ---- S_b: GELU(D1) -> A2 (hi/lo fp16); D1 already holds the bias, and is exactly 0 outside the image ------------
       mbar_wait(&sm.mbar[0], ph1);
       ph1 ^= 1;
       tc_fence_after();
@@ -253,18 +271,15 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
 #pragma unroll
         for (int c = 0; c < CH / 8; ++c) {
           const int c0 = cg * CH + 8 * c;
-          const float4 ba = *reinterpret_cast<const float4*>(&sm.b0[c0]);
-          const float4 bb = *reinterpret_cast<const float4*>(&sm.b0[c0 + 4]);
           float2 v[4];
-          v[0] = gelu_pair(__fadd2_rn(acc[c][0], make_float2(ba.x, ba.y)));
-          v[1] = gelu_pair(__fadd2_rn(acc[c][1], make_float2(ba.z, ba.w)));
-          v[2] = gelu_pair(__fadd2_rn(acc[c][2], make_float2(bb.x, bb.y)));
-          v[3] = gelu_pair(__fadd2_rn(acc[c][3], make_float2(bb.z, bb.w)));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = gelu_pair(acc[c][i]);
           uint4 hi, lo;
           split8(v, hi, lo);
           *reinterpret_cast<uint4*>(&sm.a2h[((c0 >> 3) * 128 + row) * 8]) = hi;
           *reinterpret_cast<uint4*>(&sm.a2l[((c0 >> 3) * 128 + row) * 8]) = lo;
         }
+        if (cg == 0) *reinterpret_cast<uint4*>(&sm.a2h[((C4 / 8) * 128 + row) * 8]) = row_valid ? kFlagOn : kFlagOff;
       }
       if (it + 1 < iters) publish_stats();
       // ---- G2: D2[it % 3] = A2 . W1^T  (runs under S_a of the next row) -------------------------------------------------
@@ -281,6 +296,11 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           umma_f16(d, ah, bl, idesc, 1);
           umma_f16(d, al, bh, idesc, 1);
         }
+        {                                                 // + valid * b1: hidden rows / columns outside the image stay 0
+          const uint64_t ah = umma_desc(a2h + (C4 / 16) * 2 * 128 * 16, 128 * 16, 128);
+          umma_f16(d, ah, umma_desc(w1h + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+          umma_f16(d, ah, umma_desc(w1l + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+        }
         umma_commit(&sm.mbar[1]);
       });
       // ---- S_a + G1 of the next row: G1 runs under the depthwise stage below -------------------------------------------
@@ -294,14 +314,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       if (it < 2) continue;                               // uniform over the CTA
       // ---- S_c: depthwise 3x3 over hidden rows (it-2, it-1, it) + bias -> GELU -> A3 -------------------------------
       const int yo = y0 + it - 2;                         // output row
-      // zero padding of the conv: rows outside the image are skipped (warp-uniform), columns outside the image are
-      // multiplied by 0 after the bias (lane mask folded into one FFMA)
-      bool rv[3];
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int yi = yo - 1 + dy;
-        rv[dy] = unit_ok && yi >= 0 && yi < H;
-      }
+      // zero padding of the conv: hidden rows / columns outside the image are exactly 0 in TMEM (flag column of GEMM2)
       uint32_t slot[3];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) slot[dy] = lane_addr + D2_COL + (uint32_t)((it - 2 + dy) % 3) * C4;
@@ -322,31 +335,21 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           tmem_ld8(slot[1] + c0 + 8, hn[1]);
           tmem_ld8(slot[2] + c0 + 8, hn[2]);
         }
-        float2 bm[4];                                     // masked bias of the 1x1 conv (hidden = GEMM2 + b1)
-        {
-          const float4 ba = *reinterpret_cast<const float4*>(&sm.b1[c0]);
-          const float4 bb = *reinterpret_cast<const float4*>(&sm.b1[c0 + 4]);
-          bm[0] = __fmul2_rn(make_float2(ba.x, ba.y), m2); bm[1] = __fmul2_rn(make_float2(ba.z, ba.w), m2);
-          bm[2] = __fmul2_rn(make_float2(bb.x, bb.y), m2); bm[3] = __fmul2_rn(make_float2(bb.z, bb.w), m2);
-        }
         float2 cl[4], cc[4], cr[4];                       // per-lane column sums for the left / centre / right taps
         const float4 da = *reinterpret_cast<const float4*>(&sm.dwb[c0]);
         const float4 db = *reinterpret_cast<const float4*>(&sm.dwb[c0 + 4]);
         const float2 dbv[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y), make_float2(db.z, db.w)};
-        // the centre row (dy = 1) always lies inside the image for a live strip: it initialises the sums (the conv bias
-        // rides in the centre tap); the rows above / below are added when they exist (warp-uniform test)
+        // the centre row initialises the sums (the conv bias rides in the centre tap)
 #pragma unroll
         for (int dyi = 0; dyi < 3; ++dyi) {
           const int dy = (dyi == 0) ? 1 : (dyi == 1 ? 0 : 2);
-          if (dy != 1 && !rv[dy]) continue;
           const float4* wl = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 0) * C4 + c0]);
           const float4* wc = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 1) * C4 + c0]);
           const float4* wr = reinterpret_cast<const float4*>(&sm.dww[(dy * 3 + 2) * C4 + c0]);
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const float4 l4 = wl[hf], c4 = wc[hf], r4 = wr[hf];
-            const float2 ha = __ffma2_rn(h[dy][2 * hf], m2, bm[2 * hf]);
-            const float2 hb = __ffma2_rn(h[dy][2 * hf + 1], m2, bm[2 * hf + 1]);
+            const float2 ha = h[dy][2 * hf], hb = h[dy][2 * hf + 1];
             // tap (dy,-1) of THIS pixel is consumed by lane+1, tap (dy,+1) by lane-1
             if (dy == 1) {
               cl[2 * hf] = __fmul2_rn(make_float2(l4.x, l4.y), ha);
@@ -433,7 +436,12 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-size_t ffn_tc_pack_halves(int c) { return (size_t)2 * (4 * c * c + 16 * c * c + 4 * c * c); }
+// halves of the packed operand block: the fused kernel (c = 16, 32) carries the bias K-steps of GEMM1 / GEMM2, the
+// wide path (c = 64, pwgemm_tc.cu) the plain matrices
+size_t ffn_tc_pack_halves(int c) {
+  if (c == 64) return (size_t)2 * (4 * c * c + 16 * c * c + 4 * c * c);
+  return (size_t)2 * (4 * c * (c + 16) + 4 * c * (4 * c + 16) + 4 * c * c);
+}
 
 template <int C, int G>
 static cudaError_t ffn_tc_t(const BlockW& w, const float* x, float* y, int N, int H, int W, cudaStream_t s) {
