@@ -34,7 +34,7 @@ struct MsaSmem {
 };
 
 template <int C2, bool PRE_LN>
-__global__ void __launch_bounds__(kMsaThreads, (C2 <= 16) ? 2 : 1)
+__global__ void __launch_bounds__(kMsaThreads, (C2 <= 8) ? 3 : (C2 <= 16) ? 2 : 1)
 window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, int H, int W, int total_windows,
                   int windows_per_cta) {
   constexpr int D = C2 / kHeads;
@@ -59,7 +59,14 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
   __syncthreads();                                  // weights staged
   // A window slot is loaded, projected and attended by the SAME two warps (threads 64*slot .. 64*slot+63), so the
   // slots run free of each other: their hand-offs use a 64-thread named barrier, not a CTA-wide one.
-  auto slot_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(lslot + 1) : "memory"); };
+  auto slot_sync = [&]() {
+    switch (lslot) {                                // immediate barrier ids: the kernel reserves 5 barriers, not all 16
+      case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+      case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+      case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+      default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+  };
   for (int wbase = w_begin; wbase < w_end; wbase += kWinPerIter) {
     slot_sync();                                    // previous iteration's xs of this slot fully consumed
     // 1) load (+ LayerNorm): one thread per (window, token)
@@ -141,7 +148,7 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
       for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < D / 2; ++c) o2[r][c] = make_float2(0.f, 0.f);
-      constexpr int KB = (D == 4) ? 16 : 8;         // keys per online-softmax block (register budget: 2*KB logits live)
+      constexpr int KB = 8;          // keys per online-softmax block (register budget: 2*KB logits live)
 #pragma unroll 1
       for (int jb = 0; jb < 64; jb += KB) {
         float2 s[2][KB / 2];
