@@ -63,7 +63,8 @@ cudaError_t launch_pack_umma_f16_bias(const float* w, const float* bias, void* h
 template <int C>
 struct FfnTcSmem {
   static constexpr int C4 = 4 * C;
-  uint64_t mbar[3];                                   // MMA-completion barriers of G1, G2, G3
+  uint64_t mbar[3];                                   // MMA-completion barriers of G1, G2, G3 (tcgen05.commit arrives)
+  uint64_t ready[3];                                  // operand-ready barriers A1, A2, A3 (every epilogue thread arrives)
   uint32_t tmem_base;
   uint32_t pad_[3];
   // K of GEMM1 / GEMM2 is extended by one 16-wide step whose first column is the bias (weights) / the pixel-valid flag
@@ -80,11 +81,11 @@ struct FfnTcSmem {
 
 // One CTA: four 30-pixel-wide strips (one per warp quarter), rows y0-1 .. y0+R streamed through the three GEMMs.
 template <int C, int G>
-__global__ void __launch_bounds__(128 * G, (C == 16) ? 2 : 1)
+__global__ void __launch_bounds__(128 * G + 32, (C == 16) ? 2 : 1)
 ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w, const __half* __restrict__ wpack,
               int H, int W, int nws, int nbands, int band_rows, int total_units, int num_groups) {
   constexpr int C4 = 4 * C;
-  constexpr int NT = 128 * G;
+  constexpr int NT = 128 * G;           // epilogue threads (warps 0 .. 4G-1); warp 4G only issues the MMAs
   constexpr int CH = C4 / G;            // hidden channels per thread
   static_assert(CH % 8 == 0, "channel slices are processed 8 columns at a time");
   constexpr int LG = C / 8;             // thread groups (cg < LG) that own an 8-channel slice of x / y (LayerNorm, residual, store)
@@ -104,6 +105,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     mbar_init(&sm.mbar[0], 1);
     mbar_init(&sm.mbar[1], 1);
     mbar_init(&sm.mbar[2], 1);
+    mbar_init(&sm.ready[0], NT);
+    mbar_init(&sm.ready[1], NT);
+    mbar_init(&sm.ready[2], NT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&sm.tmem_base, TMEM_COLS);
@@ -112,19 +116,19 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     constexpr int n16 = (2 * (C4 * (C + 16) + C4 * (C4 + 16) + C * C4)) * 2 / 16;
     const uint4* src = reinterpret_cast<const uint4*>(wpack);
     uint4* dst = reinterpret_cast<uint4*>(sm.w0h);
-    for (int i = tid; i < n16; i += NT) dst[i] = __ldg(src + i);
-    for (int i = tid; i < C4; i += NT) {
+    for (int i = tid; i < n16; i += NT + 32) dst[i] = __ldg(src + i);
+    for (int i = tid; i < C4; i += NT + 32) {
       sm.dwb[i] = __ldg(w.dw_b + i);
 #pragma unroll
       for (int t = 0; t < 9; ++t) sm.dww[t * C4 + i] = __ldg(w.dw_w + i * 9 + t);
     }
-    for (int i = tid; i < C; i += NT) {
+    for (int i = tid; i < C; i += NT + 32) {
       sm.b2[i] = __ldg(w.f2_b + i);
       sm.lng[i] = __ldg(w.ln2_w + i);
       sm.lnb[i] = __ldg(w.ln2_b + i);
     }
     // second half of the two flag K-steps: always zero
-    for (int i = tid; i < 128; i += NT) {
+    for (int i = tid; i < 128; i += NT + 32) {
       *reinterpret_cast<uint4*>(&sm.a1h[((C / 8 + 1) * 128 + i) * 8]) = make_uint4(0u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(&sm.a2h[((C4 / 8 + 1) * 128 + i) * 8]) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -140,7 +144,103 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   const uint32_t w0h = smem_u32(sm.w0h), w0l = smem_u32(sm.w0l), w1h = smem_u32(sm.w1h), w1l = smem_u32(sm.w1l);
   const uint32_t w2h = smem_u32(sm.w2h), w2l = smem_u32(sm.w2l);
 
+  const int iters = min(band_rows, H) + 2;                // H and band_rows are powers of two: every band has the same height
+
+  // ---- the three GEMMs (issued by the dedicated warp) ----------------------------------------------------------------------
+  // G1: D1 = [A1 | valid] . [W0 | b0]^T
+  auto issue_g1 = [&]() {
+    constexpr uint32_t idesc = umma_idesc(C4);
+#pragma unroll
+    for (int ks = 0; ks < C / 16; ++ks) {
+      const uint64_t ah = umma_desc(a1h + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t al = umma_desc(a1l + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t bh = umma_desc(w0h + ks * 2 * C4 * 16, C4 * 16, 128);
+      const uint64_t bl = umma_desc(w0l + ks * 2 * C4 * 16, C4 * 16, 128);
+      umma_f16(tmem + D1_COL, ah, bh, idesc, ks > 0);
+      umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
+      umma_f16(tmem + D1_COL, al, bh, idesc, 1);
+    }
+    {                                                     // + valid * b0
+      const uint64_t ah = umma_desc(a1h + (C / 16) * 2 * 128 * 16, 128 * 16, 128);
+      umma_f16(tmem + D1_COL, ah, umma_desc(w0h + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+      umma_f16(tmem + D1_COL, ah, umma_desc(w0l + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+    }
+    umma_commit(&sm.mbar[0]);
+  };
+  // G2: D2[it % 3] = [A2 | valid] . [W1 | b1]^T: hidden rows / columns outside the image stay exactly 0
+  auto issue_g2 = [&](int it) {
+    constexpr uint32_t idesc = umma_idesc(C4);
+    const uint32_t d = tmem + D2_COL + (uint32_t)(it % 3) * C4;
+#pragma unroll
+    for (int ks = 0; ks < C4 / 16; ++ks) {
+      const uint64_t ah = umma_desc(a2h + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t bh = umma_desc(w1h + ks * 2 * C4 * 16, C4 * 16, 128);
+      const uint64_t bl = umma_desc(w1l + ks * 2 * C4 * 16, C4 * 16, 128);
+      umma_f16(d, ah, bh, idesc, ks > 0);
+      umma_f16(d, ah, bl, idesc, 1);
+      umma_f16(d, al, bh, idesc, 1);
+    }
+    {
+      const uint64_t ah = umma_desc(a2h + (C4 / 16) * 2 * 128 * 16, 128 * 16, 128);
+      umma_f16(d, ah, umma_desc(w1h + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+      umma_f16(d, ah, umma_desc(w1l + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+    }
+    umma_commit(&sm.mbar[1]);
+  };
+  // G3: D3 = A3 . W2^T, accumulated in the first C columns of the hidden-row slot that just died
+  auto issue_g3 = [&](int it) {
+    constexpr uint32_t idesc = umma_idesc(C);
+    const uint32_t d = tmem + D2_COL + (uint32_t)((it + 1) % 3) * C4;
+#pragma unroll
+    for (int ks = 0; ks < C4 / 16; ++ks) {
+      const uint64_t ah = umma_desc(a2h + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t bh = umma_desc(w2h + ks * 2 * C * 16, C * 16, 128);
+      const uint64_t bl = umma_desc(w2l + ks * 2 * C * 16, C * 16, 128);
+      umma_f16(d, ah, bh, idesc, ks > 0);
+      umma_f16(d, ah, bl, idesc, 1);
+      umma_f16(d, al, bh, idesc, 1);
+    }
+    umma_commit(&sm.mbar[2]);
+  };
+
+  if (warp == 4 * G) {
+    // ---- MMA issuer: one thread waits for the operand-ready barriers in the order the epilogue warps raise them and
+    // feeds the tensor pipe, so no epilogue warp ever carries the issue sequence on its critical path
+    if (lane == 0) {
+      uint32_t pa1 = 0, pa2 = 0, pa3 = 0;
+      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        mbar_wait(&sm.ready[0], pa1); pa1 ^= 1;
+        tc_fence_after();
+        issue_g1();
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&sm.ready[1], pa2); pa2 ^= 1;
+          tc_fence_after();
+          issue_g2(it);
+          if (it + 1 < iters) {
+            mbar_wait(&sm.ready[0], pa1); pa1 ^= 1;
+            tc_fence_after();
+            issue_g1();
+          }
+          if (it >= 2) {
+            mbar_wait(&sm.ready[2], pa3); pa3 ^= 1;
+            tc_fence_after();
+            issue_g3(it);
+          }
+        }
+      }
+    }
+  } else {
+  // ---- epilogue warps ------------------------------------------------------------------------------------------------------
   uint32_t ph1 = 0, ph2 = 0, ph3 = 0;   // phases of the three MMA-completion barriers (G1, G2, G3)
+  // operands written (generic proxy) and TMEM reads finished: publish both, then count this thread in
+  auto signal = [&](uint64_t* bar) {
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(bar);
+  };
+  auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); };   // LayerNorm partials exchanged
 
   for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
     // this warp's strip
@@ -159,7 +259,6 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     const int rows = min(band_rows, H - y0);              // output rows of this band (uniform over the image)
     const float* xrow0 = xin + (size_t)n * H * W * C;
     float* yrow0 = yout + (size_t)n * H * W * C;
-    const int iters = min(band_rows, H) + 2;              // H and band_rows are powers of two: every band has the same height
 
     // ---- S_a: LayerNorm(x[row]) -> A1 (hi/lo fp16), spread over all warps -------------------------------------------
     // Thread (pixel row, cg) owns channels [8cg, 8cg+8): the global load is issued one row ahead (prefetch_x), the
@@ -216,44 +315,11 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       *reinterpret_cast<uint4*>(&sm.a1h[(cg * 128 + row) * 8]) = hi;
       *reinterpret_cast<uint4*>(&sm.a1l[(cg * 128 + row) * 8]) = lo;
     };
-    // ---- G1: D1 = A1 . W0^T ----------------------------------------------------------------------------------------------
-    auto issue_g1 = [&]() {
-      constexpr uint32_t idesc = umma_idesc(C4);
-#pragma unroll
-      for (int ks = 0; ks < C / 16; ++ks) {
-        const uint64_t ah = umma_desc(a1h + ks * 2 * 128 * 16, 128 * 16, 128);
-        const uint64_t al = umma_desc(a1l + ks * 2 * 128 * 16, 128 * 16, 128);
-        const uint64_t bh = umma_desc(w0h + ks * 2 * C4 * 16, C4 * 16, 128);
-        const uint64_t bl = umma_desc(w0l + ks * 2 * C4 * 16, C4 * 16, 128);
-        umma_f16(tmem + D1_COL, ah, bh, idesc, ks > 0);
-        umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
-        umma_f16(tmem + D1_COL, al, bh, idesc, 1);
-      }
-      {                                                   // + valid * b0
-        const uint64_t ah = umma_desc(a1h + (C / 16) * 2 * 128 * 16, 128 * 16, 128);
-        umma_f16(tmem + D1_COL, ah, umma_desc(w0h + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
-        umma_f16(tmem + D1_COL, ah, umma_desc(w0l + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
-      }
-      umma_commit(&sm.mbar[0]);
-    };
-    // publish generic-proxy smem writes + finished TMEM reads, then let one thread issue MMAs.  (Measured: issuing from
-    // `warp == 0 && elect.sync` removes the compiler's per-MMA ELECT/BRA.U.ANY loops but runs 2 % slower.)
-#define LG_SYNC_THEN_ISSUE(stmt)      \
-  do {                                \
-    fence_proxy_async();              \
-    tc_fence_before();                \
-    __syncthreads();                  \
-    if (tid == 0) {                   \
-      tc_fence_after();               \
-      stmt;                           \
-    }                                 \
-  } while (0)
-
     prefetch_x(0);
     publish_stats();
-    __syncthreads();
+    epi_sync();
     stage_a();
-    LG_SYNC_THEN_ISSUE(issue_g1());
+    signal(&sm.ready[0]);
 
     for (int it = 0; it < iters; ++it) {
       const bool row_valid = xvalid;                      // this row's pixel lies inside the image
@@ -283,31 +349,13 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         if (cg == 0) *reinterpret_cast<uint4*>(&sm.a2h[((C4 / 8) * 128 + row) * 8]) = row_valid ? kFlagOn : kFlagOff;
       }
       if (it + 1 < iters) publish_stats();
-      // ---- G2: D2[it % 3] = A2 . W1^T  (runs under S_a of the next row) -------------------------------------------------
-      LG_SYNC_THEN_ISSUE({
-        constexpr uint32_t idesc = umma_idesc(C4);
-        const uint32_t d = tmem + D2_COL + (uint32_t)(it % 3) * C4;
-#pragma unroll
-        for (int ks = 0; ks < C4 / 16; ++ks) {
-          const uint64_t ah = umma_desc(a2h + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t bh = umma_desc(w1h + ks * 2 * C4 * 16, C4 * 16, 128);
-          const uint64_t bl = umma_desc(w1l + ks * 2 * C4 * 16, C4 * 16, 128);
-          umma_f16(d, ah, bh, idesc, ks > 0);
-          umma_f16(d, ah, bl, idesc, 1);
-          umma_f16(d, al, bh, idesc, 1);
-        }
-        {                                                 // + valid * b1: hidden rows / columns outside the image stay 0
-          const uint64_t ah = umma_desc(a2h + (C4 / 16) * 2 * 128 * 16, 128 * 16, 128);
-          umma_f16(d, ah, umma_desc(w1h + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
-          umma_f16(d, ah, umma_desc(w1l + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
-        }
-        umma_commit(&sm.mbar[1]);
-      });
+      // ---- G2 runs under S_a of the next row ------------------------------------------------------------------------------
+      signal(&sm.ready[1]);
       // ---- S_a + G1 of the next row: G1 runs under the depthwise stage below -------------------------------------------
       if (it + 1 < iters) {
+        epi_sync();
         stage_a();
-        LG_SYNC_THEN_ISSUE(issue_g1());
+        signal(&sm.ready[0]);
       }
       mbar_wait(&sm.mbar[1], ph2);
       ph2 ^= 1;
@@ -393,22 +441,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         r0 = __ldg(reinterpret_cast<const float4*>(xrow0 + off));
         r1 = __ldg(reinterpret_cast<const float4*>(xrow0 + off) + 1);
       }
-      // ---- G3: D3 = A3 . W2^T, accumulated in the first C columns of the hidden-row slot that just died ------------
+      // ---- G3 (accumulator: first C columns of the hidden-row slot that just died) -----------------------------------------
       const uint32_t d3 = D2_COL + (uint32_t)((it + 1) % 3) * C4;
-      LG_SYNC_THEN_ISSUE({
-        constexpr uint32_t idesc = umma_idesc(C);
-#pragma unroll
-        for (int ks = 0; ks < C4 / 16; ++ks) {
-          const uint64_t ah = umma_desc(a2h + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t bh = umma_desc(w2h + ks * 2 * C * 16, C * 16, 128);
-          const uint64_t bl = umma_desc(w2l + ks * 2 * C * 16, C * 16, 128);
-          umma_f16(tmem + d3, ah, bh, idesc, ks > 0);
-          umma_f16(tmem + d3, ah, bl, idesc, 1);
-          umma_f16(tmem + d3, al, bh, idesc, 1);
-        }
-        umma_commit(&sm.mbar[2]);
-      });
+      signal(&sm.ready[2]);
       mbar_wait(&sm.mbar[2], ph3);
       ph3 ^= 1;
       tc_fence_after();
@@ -427,11 +462,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
               make_float4((v[4] + bb.x) + r1.x, (v[5] + bb.y) + r1.y, (v[6] + bb.z) + r1.z, (v[7] + bb.w) + r1.w);
         }
       }
-      tc_fence_before();
     }
-    __syncthreads();
   }
-#undef LG_SYNC_THEN_ISSUE
+  }   // role
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
@@ -465,7 +498,7 @@ static cudaError_t ffn_tc_t(const BlockW& w, const float* x, float* y, int N, in
   cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int grid = groups < sm_count * per_sm ? groups : sm_count * per_sm;
-  ffn_tc_kernel<C, G><<<grid, 128 * G, smem, s>>>(x, y, w, reinterpret_cast<const __half*>(w.ffn_pack), H, W, nws, nbands,
+  ffn_tc_kernel<C, G><<<grid, 128 * G + 32, smem, s>>>(x, y, w, reinterpret_cast<const __half*>(w.ffn_pack), H, W, nws, nbands,
                                                    band_rows, units, groups);
   return cudaGetLastError();
 }
