@@ -435,7 +435,7 @@ int lgteun_load_weights(lgteun_t* c, const char* const* names, const float* cons
         CK(launch_pack_umma_f16(d.blk->f1_w, base + 2 * s0, base + 2 * s0 + s1, c4, c4, s));
         CK(launch_pack_umma_f16(d.blk->f2_w, base + 2 * s0 + 2 * s1, base + 2 * s0 + 2 * s1 + s2, ch, c4, s));
       } else {                     // fused kernel: GEMM1 / GEMM2 carry their bias as an extra K-step
-        const size_t s0 = (size_t)c4 * (ch + 16) * 2, s1 = (size_t)c4 * (c4 + 16) * 2, s2 = (size_t)ch * c4 * 2;
+        const size_t s0 = (size_t)c4 * (ch + 8) * 2, s1 = (size_t)c4 * (c4 + 8) * 2, s2 = (size_t)ch * c4 * 2;
         CK(launch_pack_umma_f16_bias(d.blk->f0_w, d.blk->f0_b, base, base + s0, c4, ch, s));
         CK(launch_pack_umma_f16_bias(d.blk->f1_w, d.blk->f1_b, base + 2 * s0, base + 2 * s0 + s1, c4, c4, s));
         CK(launch_pack_umma_f16(d.blk->f2_w, base + 2 * s0 + 2 * s1, base + 2 * s0 + 2 * s1 + s2, ch, c4, s));

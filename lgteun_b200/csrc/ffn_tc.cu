@@ -36,8 +36,8 @@ constexpr int kStripW = 30;          // interior pixels per warp strip (32 lanes
 using namespace tc;   // PTX wrappers, descriptors and the fp16 hi/lo split: tc_ptx.cuh
 
 // ---- weight packing (load time): W [N][K] fp32 -> hi/lo fp16 in the UMMA K-major core-matrix layout [Kext/8][N][8] ---
-// Kext > K appends the bias as column K (the A operand carries a matching column of ones, so the GEMM adds the bias and
-// a zeroed A row yields an exactly zero output row) and zero columns up to Kext.
+// Kext = K + 8 appends one core-matrix chunk whose first column is the bias (the A operand carries a matching column of
+// ones, so the GEMM adds the bias and a zeroed A row yields an exactly zero output row).
 __global__ void pack_umma_f16_kernel(const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ hi,
                                      __half* __restrict__ lo, int N, int K, int Kext) {
   int idx = blockIdx.x * 256 + threadIdx.x;
@@ -55,7 +55,7 @@ cudaError_t launch_pack_umma_f16(const float* w, void* hi, void* lo, int N, int 
   return cudaGetLastError();
 }
 cudaError_t launch_pack_umma_f16_bias(const float* w, const float* bias, void* hi, void* lo, int N, int K, cudaStream_t s) {
-  pack_umma_f16_kernel<<<(N * (K + 16) + 255) / 256, 256, 0, s>>>(w, bias, (__half*)hi, (__half*)lo, N, K, K + 16);
+  pack_umma_f16_kernel<<<(N * (K + 8) + 255) / 256, 256, 0, s>>>(w, bias, (__half*)hi, (__half*)lo, N, K, K + 8);
   return cudaGetLastError();
 }
 
@@ -68,16 +68,23 @@ struct FfnTcSmem {
   uint32_t tmem_base;
   uint32_t pad_[3];
   // K of GEMM1 / GEMM2 is extended by one 16-wide step whose first column is the bias (weights) / the pixel-valid flag
-  // (activations): the bias add and the zero padding of the conv ride in the MMA
-  alignas(16) __half w0h[C4 * (C + 16)], w0l[C4 * (C + 16)];        // [(C+16)/8][C4][8]
-  alignas(16) __half w1h[C4 * (C4 + 16)], w1l[C4 * (C4 + 16)];      // [(C4+16)/8][C4][8]
+  // (activations): the bias add and the zero padding of the conv ride in the MMA.  Only the first 8-column chunk of that
+  // step is stored; its second chunk is the shared block `zero` (reached through the descriptor's leading-dimension offset)
+  static constexpr bool kOwnA3 = (C == 16);                         // room for A3 next to A2: GEMM3 overlaps the next row's S_b
+  alignas(16) __half w0h[C4 * (C + 8)], w0l[C4 * (C + 8)];          // [(C+8)/8][C4][8]
+  alignas(16) __half w1h[C4 * (C4 + 8)], w1l[C4 * (C4 + 8)];        // [(C4+8)/8][C4][8]
   alignas(16) __half w2h[C * C4], w2l[C * C4];                      // [C4/8][C][8]
-  alignas(16) __half a1h[128 * (C + 16)], a1l[128 * C];             // [K/8][128][8]; the flag step has no lo part
-  alignas(16) __half a2h[128 * (C4 + 16)], a2l[128 * C4];           // A2, then A3 (first C4 columns)
+  alignas(16) __half a1h[128 * (C + 8)], a1l[128 * C];              // [K/8][128][8]; the flag step has no lo part
+  alignas(16) __half a2h[128 * (C4 + 8)], a2l[128 * C4];            // A2 (and A3 when it has no buffer of its own)
+  alignas(16) __half a3h[kOwnA3 ? 128 * C4 : 8], a3l[kOwnA3 ? 128 * C4 : 8];
   alignas(16) float dwb[C4], dww[9 * C4];                           // dww: [tap][channel]
   alignas(16) float b2[C], lng[C], lnb[C];
   alignas(16) float2 part[C / 8][128];                // LayerNorm partials (mean, M2) of each 8-channel slice of a pixel
+  alignas(16) __half zero[128 * 8];                   // second chunk of the flag K-steps (must lie above every operand)
 };
+
+static_assert(sizeof(FfnTcSmem<16>) + 128 + 1024 <= 114 * 1024, "c = 16 must keep two CTAs per SM (228 KB, 1 KB reserved each)");
+static_assert(sizeof(FfnTcSmem<32>) + 128 <= 227 * 1024, "c = 32: one CTA per SM");
 
 // One CTA: four 30-pixel-wide strips (one per warp quarter), rows y0-1 .. y0+R streamed through the three GEMMs.
 template <int C, int G>
@@ -113,7 +120,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   if (warp == 0) tmem_alloc(&sm.tmem_base, TMEM_COLS);
   {
     // packed weights in global: w0h | w0l | w1h | w1l | w2h | w2l, contiguous, same order as the smem plan
-    constexpr int n16 = (2 * (C4 * (C + 16) + C4 * (C4 + 16) + C * C4)) * 2 / 16;
+    constexpr int n16 = (2 * (C4 * (C + 8) + C4 * (C4 + 8) + C * C4)) * 2 / 16;
     const uint4* src = reinterpret_cast<const uint4*>(wpack);
     uint4* dst = reinterpret_cast<uint4*>(sm.w0h);
     for (int i = tid; i < n16; i += NT + 32) dst[i] = __ldg(src + i);
@@ -127,11 +134,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       sm.lng[i] = __ldg(w.ln2_w + i);
       sm.lnb[i] = __ldg(w.ln2_b + i);
     }
-    // second half of the two flag K-steps: always zero
-    for (int i = tid; i < 128; i += NT + 32) {
-      *reinterpret_cast<uint4*>(&sm.a1h[((C / 8 + 1) * 128 + i) * 8]) = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(&sm.a2h[((C4 / 8 + 1) * 128 + i) * 8]) = make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int i = tid; i < 128; i += NT + 32) *reinterpret_cast<uint4*>(&sm.zero[i * 8]) = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -142,7 +145,9 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
 
   const uint32_t a1h = smem_u32(sm.a1h), a1l = smem_u32(sm.a1l), a2h = smem_u32(sm.a2h), a2l = smem_u32(sm.a2l);
   const uint32_t w0h = smem_u32(sm.w0h), w0l = smem_u32(sm.w0l), w1h = smem_u32(sm.w1h), w1l = smem_u32(sm.w1l);
-  const uint32_t w2h = smem_u32(sm.w2h), w2l = smem_u32(sm.w2l);
+  const uint32_t w2h = smem_u32(sm.w2h), w2l = smem_u32(sm.w2l), zero = smem_u32(sm.zero);
+  constexpr bool kOwnA3 = FfnTcSmem<C>::kOwnA3;
+  const uint32_t a3h = kOwnA3 ? smem_u32(sm.a3h) : a2h, a3l = kOwnA3 ? smem_u32(sm.a3l) : a2l;
 
   const int iters = min(band_rows, H) + 2;                // H and band_rows are powers of two: every band has the same height
 
@@ -160,10 +165,11 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       umma_f16(tmem + D1_COL, ah, bl, idesc, 1);
       umma_f16(tmem + D1_COL, al, bh, idesc, 1);
     }
-    {                                                     // + valid * b0
-      const uint64_t ah = umma_desc(a1h + (C / 16) * 2 * 128 * 16, 128 * 16, 128);
-      umma_f16(tmem + D1_COL, ah, umma_desc(w0h + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
-      umma_f16(tmem + D1_COL, ah, umma_desc(w0l + (C / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+    {                                                     // + valid * b0 (second K chunk = the zero block)
+      const uint32_t fa = a1h + (C / 8) * 128 * 16, fh = w0h + (C / 8) * C4 * 16, fl = w0l + (C / 8) * C4 * 16;
+      const uint64_t ah = umma_desc(fa, zero - fa, 128);
+      umma_f16(tmem + D1_COL, ah, umma_desc(fh, zero - fh, 128), idesc, 1);
+      umma_f16(tmem + D1_COL, ah, umma_desc(fl, zero - fl, 128), idesc, 1);
     }
     umma_commit(&sm.mbar[0]);
   };
@@ -182,9 +188,10 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       umma_f16(d, al, bh, idesc, 1);
     }
     {
-      const uint64_t ah = umma_desc(a2h + (C4 / 16) * 2 * 128 * 16, 128 * 16, 128);
-      umma_f16(d, ah, umma_desc(w1h + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
-      umma_f16(d, ah, umma_desc(w1l + (C4 / 16) * 2 * C4 * 16, C4 * 16, 128), idesc, 1);
+      const uint32_t fa = a2h + (C4 / 8) * 128 * 16, fh = w1h + (C4 / 8) * C4 * 16, fl = w1l + (C4 / 8) * C4 * 16;
+      const uint64_t ah = umma_desc(fa, zero - fa, 128);
+      umma_f16(d, ah, umma_desc(fh, zero - fh, 128), idesc, 1);
+      umma_f16(d, ah, umma_desc(fl, zero - fl, 128), idesc, 1);
     }
     umma_commit(&sm.mbar[1]);
   };
@@ -194,8 +201,8 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     const uint32_t d = tmem + D2_COL + (uint32_t)((it + 1) % 3) * C4;
 #pragma unroll
     for (int ks = 0; ks < C4 / 16; ++ks) {
-      const uint64_t ah = umma_desc(a2h + ks * 2 * 128 * 16, 128 * 16, 128);
-      const uint64_t al = umma_desc(a2l + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t ah = umma_desc(a3h + ks * 2 * 128 * 16, 128 * 16, 128);
+      const uint64_t al = umma_desc(a3l + ks * 2 * 128 * 16, 128 * 16, 128);
       const uint64_t bh = umma_desc(w2h + ks * 2 * C * 16, C * 16, 128);
       const uint64_t bl = umma_desc(w2l + ks * 2 * C * 16, C * 16, 128);
       umma_f16(d, ah, bh, idesc, ks > 0);
@@ -315,6 +322,35 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       *reinterpret_cast<uint4*>(&sm.a1h[(cg * 128 + row) * 8]) = hi;
       *reinterpret_cast<uint4*>(&sm.a1l[(cg * 128 + row) * 8]) = lo;
     };
+    // ---- S_d: y = D3 + b2 + x for the output row produced by iteration `itr` (interior lanes only) -----------------------
+    __half* const a3h_p = kOwnA3 ? sm.a3h : sm.a2h;
+    __half* const a3l_p = kOwnA3 ? sm.a3l : sm.a2l;
+    auto row_store_ok = [&](int itr) { return cg < LG && x_ok && lane >= 1 && lane <= kStripW && itr >= 2 && itr - 2 < rows; };
+    auto load_residual = [&](int itr, float4& r0, float4& r1) {
+      r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      r1 = r0;
+      if (row_store_ok(itr)) {
+        const float4* src = reinterpret_cast<const float4*>(xrow0 + ((size_t)(y0 + itr - 2) * W + x) * C + cg * 8);
+        r0 = __ldg(src);
+        r1 = __ldg(src + 1);
+      }
+    };
+    auto store_row = [&](int itr, const float4& r0, const float4& r1) {
+      const uint32_t d3 = D2_COL + (uint32_t)((itr + 1) % 3) * C4;   // GEMM3's accumulator: the hidden-row slot that died
+      float2 v2[4];
+      tmem_ld8(lane_addr + d3 + (cg < LG ? cg : 0) * 8, v2);
+      tmem_ld_wait();
+      if (row_store_ok(itr)) {
+        float* dst = yrow0 + ((size_t)(y0 + itr - 2) * W + x) * C + cg * 8;
+        const float4 ba = *reinterpret_cast<const float4*>(&sm.b2[cg * 8]);
+        const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cg * 8 + 4]);
+        *reinterpret_cast<float4*>(dst) = make_float4((v2[0].x + ba.x) + r0.x, (v2[0].y + ba.y) + r0.y,
+                                                      (v2[1].x + ba.z) + r0.z, (v2[1].y + ba.w) + r0.w);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4((v2[2].x + bb.x) + r1.x, (v2[2].y + bb.y) + r1.y,
+                                                          (v2[3].x + bb.z) + r1.z, (v2[3].y + bb.w) + r1.w);
+      }
+    };
+
     prefetch_x(0);
     publish_stats();
     epi_sync();
@@ -324,6 +360,8 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     for (int it = 0; it < iters; ++it) {
       const bool row_valid = xvalid;                      // this row's pixel lies inside the image
       if (it + 1 < iters) prefetch_x(it + 1);             // global load of the next row flies under the wait + S_b
+      float4 pr0, pr1;                                    // residual of the previous output row (stored after S_b)
+      if constexpr (kOwnA3) load_residual(it - 1, pr0, pr1);
       // ---- S_b: GELU(D1) -> A2 (hi/lo fp16); D1 already holds the bias, and is exactly 0 outside the image ------------
       mbar_wait(&sm.mbar[0], ph1);
       ph1 ^= 1;
@@ -348,6 +386,15 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         }
         if (cg == 0) *reinterpret_cast<uint4*>(&sm.a2h[((C4 / 8) * 128 + row) * 8]) = row_valid ? kFlagOn : kFlagOff;
       }
+      if constexpr (kOwnA3) {
+        // the previous row's GEMM3 ran under this S_b; its accumulator sits in the slot GEMM2 of this row overwrites
+        if (it >= 3) {
+          mbar_wait(&sm.mbar[2], ph3);
+          ph3 ^= 1;
+          tc_fence_after();
+          store_row(it - 1, pr0, pr1);
+        }
+      }
       if (it + 1 < iters) publish_stats();
       // ---- G2 runs under S_a of the next row ------------------------------------------------------------------------------
       signal(&sm.ready[1]);
@@ -362,7 +409,6 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       tc_fence_after();
       if (it < 2) continue;                               // uniform over the CTA
       // ---- S_c: depthwise 3x3 over hidden rows (it-2, it-1, it) + bias -> GELU -> A3 -------------------------------
-      const int yo = y0 + it - 2;                         // output row
       // zero padding of the conv: hidden rows / columns outside the image are exactly 0 in TMEM (flag column of GEMM2)
       uint32_t slot[3];
 #pragma unroll
@@ -429,39 +475,28 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         }
         uint4 hi, lo;
         split8(o, hi, lo);
-        *reinterpret_cast<uint4*>(&sm.a2h[((c0 >> 3) * 128 + row) * 8]) = hi;
-        *reinterpret_cast<uint4*>(&sm.a2l[((c0 >> 3) * 128 + row) * 8]) = lo;
+        *reinterpret_cast<uint4*>(&a3h_p[((c0 >> 3) * 128 + row) * 8]) = hi;
+        *reinterpret_cast<uint4*>(&a3l_p[((c0 >> 3) * 128 + row) * 8]) = lo;
         tmem_ld_wait();
       }
-      // residual for S_d: issued now, consumed after GEMM3
-      const bool st_ok = cg < LG && x_ok && lane >= 1 && lane <= kStripW && yo < y0 + rows;
-      const size_t off = ((size_t)yo * W + x) * C + cg * 8;
-      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-      if (st_ok) {
-        r0 = __ldg(reinterpret_cast<const float4*>(xrow0 + off));
-        r1 = __ldg(reinterpret_cast<const float4*>(xrow0 + off) + 1);
+      signal(&sm.ready[2]);                               // -> G3(it)
+      if constexpr (!kOwnA3) {
+        // A3 shares A2's buffer: GEMM3 has to finish before the next row's S_b may overwrite it
+        float4 r0, r1;
+        load_residual(it, r0, r1);
+        mbar_wait(&sm.mbar[2], ph3);
+        ph3 ^= 1;
+        tc_fence_after();
+        store_row(it, r0, r1);
       }
-      // ---- G3 (accumulator: first C columns of the hidden-row slot that just died) -----------------------------------------
-      const uint32_t d3 = D2_COL + (uint32_t)((it + 1) % 3) * C4;
-      signal(&sm.ready[2]);
+    }
+    if constexpr (kOwnA3) {                               // drain: the last row's GEMM3
+      float4 r0, r1;
+      load_residual(iters - 1, r0, r1);
       mbar_wait(&sm.mbar[2], ph3);
       ph3 ^= 1;
       tc_fence_after();
-      // ---- S_d: y = D3 + b2 + x  (interior lanes only) ---------------------------------------------------------------
-      {
-        float2 v2[4];
-        tmem_ld8(lane_addr + d3 + (cg < LG ? cg : 0) * 8, v2);
-        tmem_ld_wait();
-        const float v[8] = {v2[0].x, v2[0].y, v2[1].x, v2[1].y, v2[2].x, v2[2].y, v2[3].x, v2[3].y};
-        if (st_ok) {
-          const float4 ba = *reinterpret_cast<const float4*>(&sm.b2[cg * 8]);
-          const float4 bb = *reinterpret_cast<const float4*>(&sm.b2[cg * 8 + 4]);
-          *reinterpret_cast<float4*>(yrow0 + off) =
-              make_float4((v[0] + ba.x) + r0.x, (v[1] + ba.y) + r0.y, (v[2] + ba.z) + r0.z, (v[3] + ba.w) + r0.w);
-          *reinterpret_cast<float4*>(yrow0 + off + 4) =
-              make_float4((v[4] + bb.x) + r1.x, (v[5] + bb.y) + r1.y, (v[6] + bb.z) + r1.z, (v[7] + bb.w) + r1.w);
-        }
-      }
+      store_row(iters - 1, r0, r1);
     }
   }
   }   // role
@@ -474,7 +509,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
 // wide path (c = 64, pwgemm_tc.cu) the plain matrices
 size_t ffn_tc_pack_halves(int c) {
   if (c == 64) return (size_t)2 * (4 * c * c + 16 * c * c + 4 * c * c);
-  return (size_t)2 * (4 * c * (c + 16) + 4 * c * (4 * c + 16) + 4 * c * c);
+  return (size_t)2 * (4 * c * (c + 8) + 4 * c * (4 * c + 8) + 4 * c * c);
 }
 
 template <int C, int G>
