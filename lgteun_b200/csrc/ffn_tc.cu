@@ -247,7 +247,16 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     tc_fence_before();
     mbar_arrive(bar);
   };
-  auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); };   // LayerNorm partials exchanged
+  // LayerNorm partials are exchanged between the G warps that own the same 32 pixels (warps q, q+4, ...): one named
+  // barrier per TMEM lane quarter, 32*G threads each
+  auto epi_sync = [&]() {
+    switch (q) {
+      case 0: asm volatile("bar.sync 1, %0;" ::"n"(32 * G) : "memory"); break;
+      case 1: asm volatile("bar.sync 2, %0;" ::"n"(32 * G) : "memory"); break;
+      case 2: asm volatile("bar.sync 3, %0;" ::"n"(32 * G) : "memory"); break;
+      default: asm volatile("bar.sync 4, %0;" ::"n"(32 * G) : "memory"); break;
+    }
+  };
 
   for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
     // this warp's strip
