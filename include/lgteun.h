@@ -131,6 +131,15 @@ int lgteun_op_prior(lgteun_t* ctx, int prior, const float* x_nchw, float* y_nchw
 int lgteun_op_metrics(lgteun_t* ctx, const float* pred, const float* gt, double* out_dev, int N, int H, int W,
                       float max_value, void* stream);
 
+/* data_normalize (dataset/utils.py:232-248): out[i] = raw[i] / max_value, max_value = 2**bit_depth - .5; n elements,
+ * device pointers (in place allowed). */
+int lgteun_op_normalize(lgteun_t* ctx, const float* raw, float* out, int64_t n, float max_value, void* stream);
+
+/* torch2np + data_denormalize (models/base/utils.py:28-39, dataset/utils.py:252-263): NCHW [N,C,H,W] -> NHWC
+ * [N,H,W,C] times `scale` (max_value, or 1 to only change the layout); C in {1, 4, 8}; device pointers, no aliasing. */
+int lgteun_op_to_nhwc(lgteun_t* ctx, const float* nchw, float* nhwc, int N, int C, int H, int W, float scale,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

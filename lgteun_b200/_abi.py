@@ -37,6 +37,8 @@ SIGNATURES = {
     "lgteun_op_ffn": (c_int, [c_void_p, c_int, c_int, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
     "lgteun_op_prior": (c_int, [c_void_p, c_int, _F, _F, c_int, c_int, c_int, c_void_p]),
     "lgteun_op_metrics": (c_int, [c_void_p, _F, _F, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_void_p]),
+    "lgteun_op_normalize": (c_int, [c_void_p, _F, _F, c_int64, ctypes.c_float, c_void_p]),
+    "lgteun_op_to_nhwc": (c_int, [c_void_p, _F, _F, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p]),
 }
 
 _lib = None

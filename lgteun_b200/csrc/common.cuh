@@ -101,6 +101,8 @@ cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, fl
 // metrics.cu — PSNR / SAM / ERGAS per image in fp64 (acc: N*(2+2B) doubles scratch, out: N*3 doubles)
 cudaError_t launch_metrics(const float* pred, const float* gt, double* acc, double* out, int N, int B, int H, int W,
                            float max_value, cudaStream_t s);
+cudaError_t launch_normalize(const float* raw, float* out, size_t n, float max_value, cudaStream_t s);
+cudaError_t launch_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, float scale, cudaStream_t s);
 // misc
 cudaError_t launch_transpose_pos(const float* pos, float* pos_t, cudaStream_t s);
 cudaError_t launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r] = src[r][c]

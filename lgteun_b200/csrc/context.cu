@@ -728,4 +728,20 @@ int lgteun_op_metrics(lgteun_t* c, const float* pred, const float* gt, double* o
   return 0;
 }
 
+int lgteun_op_normalize(lgteun_t* c, const float* raw, float* out, int64_t n, float max_value, void* stream) {
+  if (!c || !raw || !out) return fail(LGTEUN_EINVAL, "NULL argument");
+  if (n <= 0 || !(max_value > 0.f)) return fail(LGTEUN_EINVAL, "bad size or max_value");
+  CK(cudaSetDevice(c->device));
+  CK(launch_normalize(raw, out, (size_t)n, max_value, (cudaStream_t)stream));
+  return 0;
+}
+
+int lgteun_op_to_nhwc(lgteun_t* c, const float* nchw, float* nhwc, int N, int C, int H, int W, float scale, void* stream) {
+  if (!c || !nchw || !nhwc) return fail(LGTEUN_EINVAL, "NULL argument");
+  if (N <= 0 || H <= 0 || W <= 0 || !(C == 1 || C == 4 || C == 8)) return fail(LGTEUN_EINVAL, "bad shape (C must be 1, 4 or 8)");
+  CK(cudaSetDevice(c->device));
+  CK(launch_to_nhwc(nchw, nhwc, N, C, H, W, scale, (cudaStream_t)stream));
+  return 0;
+}
+
 }  // extern "C"

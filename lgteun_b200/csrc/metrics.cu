@@ -74,6 +74,47 @@ __global__ void metrics_finalize_kernel(const double* __restrict__ acc, double* 
   out[3 * n + 2] = 100.0 / 4.0 * sqrt(e / B);                                                      // ergas (scale 4)
 }
 
+// data_normalize (dataset/utils.py:232-248): img / (2**bit_depth - .5), a true fp32 division like torch's
+__global__ void normalize_kernel(const float* __restrict__ raw, float* __restrict__ out, size_t n, float max_value) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __fdiv_rn(__ldg(raw + i), max_value);
+}
+cudaError_t launch_normalize(const float* raw, float* out, size_t n, float max_value, cudaStream_t s) {
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  normalize_kernel<<<(unsigned)blocks, 256, 0, s>>>(raw, out, n, max_value);
+  return cudaGetLastError();
+}
+
+// torch2np + data_denormalize (models/base/utils.py:28-39, dataset/utils.py:252-263): NCHW -> NHWC, times max_value.
+// A 32-pixel x C tile goes through shared memory so both the NCHW reads and the NHWC writes are coalesced.
+template <int C>
+__global__ void __launch_bounds__(256) to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int HW, float scale) {
+  __shared__ float tile[C][256 + 1];
+  const int n = blockIdx.y, p0 = blockIdx.x * 256;
+  const float* s = src + (size_t)n * C * HW;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const int p = p0 + threadIdx.x;
+    tile[c][threadIdx.x] = p < HW ? __ldg(s + (size_t)c * HW + p) * scale : 0.f;
+  }
+  __syncthreads();
+  float* d = dst + ((size_t)n * HW + p0) * C;
+  const int lim = (HW - p0 < 256 ? HW - p0 : 256) * C;
+  for (int i = threadIdx.x; i < lim; i += 256) d[i] = tile[i % C][i / C];
+}
+cudaError_t launch_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, float scale, cudaStream_t s) {
+  const int HW = H * W;
+  dim3 grid((HW + 255) / 256, N);
+  switch (C) {
+    case 1: to_nhwc_kernel<1><<<grid, 256, 0, s>>>(src, dst, HW, scale); break;
+    case 4: to_nhwc_kernel<4><<<grid, 256, 0, s>>>(src, dst, HW, scale); break;
+    case 8: to_nhwc_kernel<8><<<grid, 256, 0, s>>>(src, dst, HW, scale); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_metrics(const float* pred, const float* gt, double* acc, double* out, int N, int B, int H, int W,
                            float max_value, cudaStream_t s) {
   const int HW = H * W;

@@ -233,6 +233,34 @@ class Pansharpening(nn.Module):
                       stream=torch.cuda.current_stream(pred.device).cuda_stream)
         return out
 
+    def normalize(self, raw: torch.Tensor, bit_depth: int = 11) -> torch.Tensor:
+        """``data_normalize`` of the reference's loops (dataset/utils.py:232-248) on the device: raw / (2**bit_depth - .5)."""
+        if raw.device.type != "cuda" or raw.dtype != torch.float32:
+            raise RuntimeError("normalize() needs a float32 CUDA tensor")
+        with torch.cuda.device(raw.device):
+            handle = self._runtime(raw.device)
+            src = raw.contiguous()
+            out = torch.empty_like(src)
+            handle.op("normalize", src.data_ptr(), out.data_ptr(), src.numel(), float(2 ** bit_depth - 0.5),
+                      stream=torch.cuda.current_stream(raw.device).cuda_stream)
+        return out
+
+    def to_numpy_layout(self, x: torch.Tensor, bit_depth=None) -> torch.Tensor:
+        """``torch2np`` (+ ``data_denormalize`` when bit_depth is given) of the reference's test loop on the device
+        (models/base/utils.py:28-39, dataset/utils.py:252-263): [N,C,H,W] -> [N,H,W,C] (C == 1: [N,H,W]), still a
+        CUDA tensor, so that one contiguous D2H copy replaces the strided host transpose."""
+        if x.dim() != 4 or x.device.type != "cuda" or x.dtype != torch.float32:
+            raise RuntimeError("to_numpy_layout() needs a float32 CUDA tensor [N,C,H,W]")
+        n, c, h, w = x.shape
+        with torch.cuda.device(x.device):
+            handle = self._runtime(x.device)
+            src = x.contiguous()
+            out = torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+            handle.op("to_nhwc", src.data_ptr(), out.data_ptr(), n, c, h, w,
+                      1.0 if bit_depth is None else float(2 ** bit_depth - 0.5),
+                      stream=torch.cuda.current_stream(x.device).cuda_stream)
+        return out.squeeze(-1) if c == 1 else out
+
     def extra_repr(self):
         return f"bands={self.in_channels}, stage={self.stage}, backend=sm_100a C-ABI ({_abi.LIB_PATH})"
 

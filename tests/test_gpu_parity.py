@@ -293,6 +293,26 @@ def test_device_metrics_match_reference(abi, h4):
     assert abs(same[0, 1] - want_sam) <= 1e-9
 
 
+def test_eval_glue_normalize_and_layout(abi):
+    """data_normalize and torch2np + data_denormalize on the device are bit-exact with the reference's torch / numpy
+    expressions (dataset/utils.py:232-263, models/base/utils.py:28-39)."""
+    import lgteun_b200
+    from types import SimpleNamespace
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=4), None, stage=2)
+    net.load_state_dict(load_weights(4))
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    raw = torch.randint(0, 2047, (3, 4, 40, 24), generator=g).float()
+    max_value = 2 ** 11 - .5
+    assert torch.equal(net.normalize(raw.cuda(), 11).cpu(), raw / max_value)
+    x = torch.rand(3, 4, 40, 24, generator=g)
+    want = x.numpy().transpose(0, 2, 3, 1) * max_value
+    assert np.array_equal(net.to_numpy_layout(x.cuda(), 11).cpu().numpy(), want)
+    assert np.array_equal(net.to_numpy_layout(x.cuda()).cpu().numpy(), x.numpy().transpose(0, 2, 3, 1))
+    pan = torch.rand(2, 1, 33, 17, generator=g)
+    assert np.array_equal(net.to_numpy_layout(pan.cuda()).cpu().numpy(), pan.squeeze(1).numpy())
+
+
 def test_small_residual_regime(abi, O):
     """second weight set with the last prior's tail scaled by 0.05 (prior = small residual around the
     data-step output, outputs near [0,1])."""
