@@ -230,71 +230,106 @@ __global__ void __launch_bounds__(128) low_conv2_kernel(const float* __restrict_
   }
 }
 
-constexpr int UFH = 16, UFW = 32;                 // output tile (rows x cols); one thread per 2x2 block -> 128 threads
+constexpr int UFH = 16, UFW = 32;                 // output tile (rows x cols) = 128 blocks of 2x2 pixels
 constexpr int UFPH = UFH / 2 + 4, UFPW = UFW / 2 + 4;   // low-res patch 12 x 20
 
+// Work item = (2x2 output block, 4-channel quad): the low-res patch, the skip tile and the transposed skip half of the
+// fusion conv sit in shared memory, every access is a 128-bit vector of one quad, all arithmetic is packed fp32.
+// (The first version gave a thread a whole 2x2 block x 16 channels: 148 registers, 12 warps/SM, 27 % of HBM peak.)
 template <int C>
-__global__ void __launch_bounds__(128) up_fuse_kernel(const float* __restrict__ t_low, const float* __restrict__ skip,
+__global__ void __launch_bounds__(256) up_fuse_kernel(const float* __restrict__ t_low, const float* __restrict__ skip,
                                                        float* __restrict__ y, PriorW w, int H, int W) {
   constexpr int PS = C + 4;                       // padded pixel stride: conflict-free 128-bit reads
+  constexpr int Q = C / 4;                        // channel quads
   extern __shared__ __align__(16) float smem[];
-  float* sP = smem;                               // [UFPH*UFPW][PS]
-  float* sFu = sP + UFPH * UFPW * PS;             // [C][C]  right (skip) half of the fusion conv
-  float* sFb = sFu + C * C;                       // [C]
+  float* sP = smem;                               // [UFPH*UFPW][PS]   low-res patch (borders replicated)
+  float* sS = sP + UFPH * UFPW * PS;              // [UFH*UFW][PS]     skip tile
+  float* sWt = sS + UFH * UFW * PS;               // [C][C]  Wt[k][o] = right (skip) half of the fusion conv
+  float* sFb = sWt + C * C;                       // [C]
   const int tid = threadIdx.x;
   const int lh = H / 2, lw = W / 2;
   const int n = blockIdx.z;
   const int Y0 = blockIdx.y * UFH, X0 = blockIdx.x * UFW;
-  const int py0 = Y0 / 2 - 2, px0 = X0 / 2 - 2;   // low-res origin of the patch (replicated borders)
-  for (int i = tid; i < C * C; i += 128) sFu[i] = __ldg(w.fuse_w + (i / C) * 2 * C + C + (i % C));
-  for (int i = tid; i < C; i += 128) sFb[i] = __ldg(w.fuse_b + i);
-  for (int i = tid; i < UFPH * UFPW * (C / 4); i += 128) {
-    const int pix = i / (C / 4), c4 = i - pix * (C / 4);
+  const int py0 = Y0 / 2 - 2, px0 = X0 / 2 - 2;   // low-res origin of the patch
+  for (int i = tid; i < C * C; i += 256) sWt[i] = __ldg(w.fuse_w + (i % C) * 2 * C + C + (i / C));
+  for (int i = tid; i < C; i += 256) sFb[i] = __ldg(w.fuse_b + i);
+  for (int i = tid; i < UFPH * UFPW * Q; i += 256) {
+    const int pix = i / Q, c4 = i - pix * Q;
     const int pr = pix / UFPW, pc = pix - pr * UFPW;
     const int gy = clampi(py0 + pr, 0, lh - 1), gx = clampi(px0 + pc, 0, lw - 1);
     *reinterpret_cast<float4*>(sP + pix * PS + 4 * c4) =
         __ldg(reinterpret_cast<const float4*>(t_low + (((size_t)n * lh + gy) * lw + gx) * C) + c4);
   }
+  for (int i = tid; i < UFH * UFW * Q; i += 256) {
+    const int pix = i / Q, c4 = i - pix * Q;
+    const int oy = Y0 + pix / UFW, ox = X0 + pix % UFW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (oy < H && ox < W) v = __ldg(reinterpret_cast<const float4*>(skip + (((size_t)n * H + oy) * W + ox) * C) + c4);
+    *reinterpret_cast<float4*>(sS + pix * PS + 4 * c4) = v;
+  }
   __syncthreads();
-  const int by = tid >> 4, bx = tid & 15;         // 2x2 block: low-res cell (Y0/2 + by, X0/2 + bx)
   // x2 taps: even dst 2q -> src q-2..q+1 (t=.75), odd dst 2q+1 -> src q-1..q+2 (t=.25); patch rows/cols by+r, bx+c
   // hold src q-2+r: even uses r = 0..3, odd uses r = 1..4
   const float te[4] = {-0.03515625f, 0.26171875f, 0.87890625f, -0.10546875f};
   const float to[4] = {-0.10546875f, 0.87890625f, 0.26171875f, -0.03515625f};
+  struct F4 { float2 a, b; };                     // one quad on the packed pipe
+  auto fma4 = [](float s, const float4& t, F4& acc) {
+    const float2 s2 = make_float2(s, s);
+    acc.a = __ffma2_rn(s2, make_float2(t.x, t.y), acc.a);
+    acc.b = __ffma2_rn(s2, make_float2(t.z, t.w), acc.b);
+  };
+  auto fma4f = [](float s, const F4& t, F4& acc) {
+    const float2 s2 = make_float2(s, s);
+    acc.a = __ffma2_rn(s2, t.a, acc.a);
+    acc.b = __ffma2_rn(s2, t.b, acc.b);
+  };
 #pragma unroll 1
-  for (int c0 = 0; c0 < C; c0 += 16) {
-    float acc[2][2][16];
+  for (int item = tid; item < (UFH / 2) * (UFW / 2) * Q; item += 256) {
+    const int blk = item / Q, oq = item - blk * Q;
+    const int by = blk >> 4, bx = blk & 15;       // 2x2 block: low-res cell (Y0/2 + by, X0/2 + bx)
+    F4 acc[2][2];
+    {
+      const float4 b4 = *reinterpret_cast<const float4*>(sFb + 4 * oq);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[0][0][i] = acc[0][1][i] = acc[1][0][i] = acc[1][1][i] = 0.f;
+      for (int ey = 0; ey < 2; ++ey)
+#pragma unroll
+        for (int ex = 0; ex < 2; ++ex) { acc[ey][ex].a = make_float2(b4.x, b4.y); acc[ey][ex].b = make_float2(b4.z, b4.w); }
+    }
+    // skip half of the fusion conv: 4 outputs x C inputs for the four pixels of the block
+#pragma unroll 1
+    for (int k4 = 0; k4 < Q; ++k4) {
+      float4 wq[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wq[j] = *reinterpret_cast<const float4*>(sWt + (4 * k4 + j) * C + 4 * oq);
+#pragma unroll
+      for (int ey = 0; ey < 2; ++ey)
+#pragma unroll
+        for (int ex = 0; ex < 2; ++ex) {
+          const float4 sk = *reinterpret_cast<const float4*>(sS + ((2 * by + ey) * UFW + 2 * bx + ex) * PS + 4 * k4);
+          fma4(sk.x, wq[0], acc[ey][ex]);
+          fma4(sk.y, wq[1], acc[ey][ex]);
+          fma4(sk.z, wq[2], acc[ey][ex]);
+          fma4(sk.w, wq[3], acc[ey][ex]);
+        }
+    }
+    // bicubic x2 of the low-res map, separable inside the 5x5 neighbourhood the four pixels share
 #pragma unroll
     for (int r = 0; r < 5; ++r) {
-      float rs_e[16], rs_o[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) rs_e[i] = rs_o[i] = 0.f;
+      F4 rs_e, rs_o;
+      rs_e.a = rs_e.b = rs_o.a = rs_o.b = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
-        const float4* src = reinterpret_cast<const float4*>(sP + ((by + r) * UFPW + bx + c) * PS + c0);
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 t = src[i4];
-          const float tv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (c < 4) rs_e[4 * i4 + k] = fmaf(te[c < 4 ? c : 0], tv[k], rs_e[4 * i4 + k]);
-            if (c >= 1) rs_o[4 * i4 + k] = fmaf(to[c >= 1 ? c - 1 : 0], tv[k], rs_o[4 * i4 + k]);
-          }
-        }
+        const float4 t = *reinterpret_cast<const float4*>(sP + ((by + r) * UFPW + bx + c) * PS + 4 * oq);
+        if (c < 4) fma4(te[c < 4 ? c : 0], t, rs_e);
+        if (c >= 1) fma4(to[c >= 1 ? c - 1 : 0], t, rs_o);
       }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (r < 4) {
-          acc[0][0][i] = fmaf(te[r < 4 ? r : 0], rs_e[i], acc[0][0][i]);
-          acc[0][1][i] = fmaf(te[r < 4 ? r : 0], rs_o[i], acc[0][1][i]);
-        }
-        if (r >= 1) {
-          acc[1][0][i] = fmaf(to[r >= 1 ? r - 1 : 0], rs_e[i], acc[1][0][i]);
-          acc[1][1][i] = fmaf(to[r >= 1 ? r - 1 : 0], rs_o[i], acc[1][1][i]);
-        }
+      if (r < 4) {
+        fma4f(te[r < 4 ? r : 0], rs_e, acc[0][0]);
+        fma4f(te[r < 4 ? r : 0], rs_o, acc[0][1]);
+      }
+      if (r >= 1) {
+        fma4f(to[r >= 1 ? r - 1 : 0], rs_e, acc[1][0]);
+        fma4f(to[r >= 1 ? r - 1 : 0], rs_o, acc[1][1]);
       }
     }
 #pragma unroll
@@ -303,31 +338,8 @@ __global__ void __launch_bounds__(128) up_fuse_kernel(const float* __restrict__ 
       for (int ex = 0; ex < 2; ++ex) {
         const int oy = Y0 + 2 * by + ey, ox = X0 + 2 * bx + ex;
         if (oy >= H || ox >= W) continue;
-        const size_t p = ((size_t)n * H + oy) * W + ox;
-        float sk[C];
-        load_vec<C>(sk, skip + p * C);
-#pragma unroll
-        for (int o = 0; o < 16; o += 4) {
-          float2 a[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) a[j] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int k4 = 0; k4 < C / 4; ++k4) {
-            const float2 va = make_float2(sk[4 * k4], sk[4 * k4 + 1]), vb = make_float2(sk[4 * k4 + 2], sk[4 * k4 + 3]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 w4 = *reinterpret_cast<const float4*>(sFu + (c0 + o + j) * C + 4 * k4);
-              a[j] = __ffma2_rn(make_float2(w4.x, w4.y), va, a[j]);
-              a[j] = __ffma2_rn(make_float2(w4.z, w4.w), vb, a[j]);
-            }
-          }
-          float up[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) up[j] = ey ? (ex ? acc[1][1][o + j] : acc[1][0][o + j]) : (ex ? acc[0][1][o + j] : acc[0][0][o + j]);
-          *reinterpret_cast<float4*>(y + p * C + c0 + o) =
-              make_float4((up[0] + (a[0].x + a[0].y)) + sFb[c0 + o], (up[1] + (a[1].x + a[1].y)) + sFb[c0 + o + 1],
-                          (up[2] + (a[2].x + a[2].y)) + sFb[c0 + o + 2], (up[3] + (a[3].x + a[3].y)) + sFb[c0 + o + 3]);
-        }
+        *reinterpret_cast<float4*>(y + (((size_t)n * H + oy) * W + ox) * C + 4 * oq) =
+            make_float4(acc[ey][ex].a.x, acc[ey][ex].a.y, acc[ey][ex].b.x, acc[ey][ex].b.y);
       }
   }
 }
@@ -339,12 +351,16 @@ cudaError_t launch_up_fuse(const PriorW& w, int C, const float* low, const float
   dim3 grid((W + UFW - 1) / UFW, (H + UFH - 1) / UFH, N);
   if (C == 16) {
     low_conv2_kernel<16><<<g0, 128, (size_t)(3 * 16 * 16 + 16) * sizeof(float), s>>>(low, t_low, w, low_px);
-    size_t smem = (size_t)(UFPH * UFPW * (16 + 4) + 16 * 16 + 16) * sizeof(float);
-    up_fuse_kernel<16><<<grid, 128, smem, s>>>(t_low, skip, y, w, H, W);
+    size_t smem = (size_t)((UFPH * UFPW + UFH * UFW) * (16 + 4) + 16 * 16 + 16) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(up_fuse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    up_fuse_kernel<16><<<grid, 256, smem, s>>>(t_low, skip, y, w, H, W);
   } else if (C == 32) {
     low_conv2_kernel<32><<<g0, 128, (size_t)(3 * 32 * 32 + 32) * sizeof(float), s>>>(low, t_low, w, low_px);
-    size_t smem = (size_t)(UFPH * UFPW * (32 + 4) + 32 * 32 + 32) * sizeof(float);
-    up_fuse_kernel<32><<<grid, 128, smem, s>>>(t_low, skip, y, w, H, W);
+    size_t smem = (size_t)((UFPH * UFPW + UFH * UFW) * (32 + 4) + 32 * 32 + 32) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(up_fuse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    up_fuse_kernel<32><<<grid, 256, smem, s>>>(t_low, skip, y, w, H, W);
   } else {
     return cudaErrorInvalidValue;
   }
