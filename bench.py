@@ -103,7 +103,7 @@ def run_reference(args):
         return 0
     bands, h, _, desc = WORKLOADS[args.workload]
     threads = cpu_threads()
-    batch = 2
+    batch = 8
     t0 = time.perf_counter()
     value, times = time_cpu_reference(bands, h, batch, args.steps, max(1, min(args.warmup, 2)), threads)
     ms_step = 1e3 * statistics.median(times)
@@ -286,9 +286,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             threads = cpu_threads()
             t0 = time.perf_counter()
-            v, times = time_cpu_reference(bands, h, 2, 3, 1, threads)
+            v, times = time_cpu_reference(bands, h, 8, 5, 1, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"3 forwards of 2 pairs of the same workload shape (oracle port, torch CPU fp32, "
+                                    "sample": f"5 forwards of 8 pairs of the same workload shape (oracle port, torch CPU fp32, "
                                               f"both priors), median; {time.perf_counter() - t0:.1f}s"}
         if world == 1 and args.other_workloads and not args.no_e2e:
             line["other_workloads"] = other_workload(args, dev)

@@ -531,10 +531,18 @@ static cudaError_t ffn_tc_t(const BlockW& w, const float* x, float* y, int N, in
   }
   const int per_sm = (C == 16) ? 2 : 1;
   const int nws = (W + kStripW - 1) / kStripW;
-  // taller bands amortise the two halo rows (66/64 vs 34/32 vs 18/16) but need about one full wave of groups
-  int band_rows = 64;
-  while (band_rows > 8 && (band_rows > H || (N * ((H + band_rows - 1) / band_rows) * nws + 3) / 4 < (9 * sm_count * per_sm) / 10))
-    band_rows >>= 1;
+  // taller bands amortise the two halo rows (130/128, 66/64, 34/32 ...) but leave fewer groups to spread over the
+  // resident CTAs: pick the height with the best product of halo efficiency and last-wave fill
+  int band_rows = 8;
+  double best = 0.0;
+  for (int r = 128; r >= 8; r >>= 1) {
+    if (r > H) continue;
+    const long long g = ((long long)N * ((H + r - 1) / r) * nws + 3) / 4;
+    const long long cap = (long long)sm_count * per_sm;
+    const long long waves = (g + cap - 1) / cap;
+    const double score = ((double)r / (r + 2)) * ((double)g / (double)(waves * cap));
+    if (score > best * 1.005) { best = score; band_rows = r; }
+  }
   const int nbands = (H + band_rows - 1) / band_rows;
   const int units = N * nbands * nws;
   const int groups = (units + 3) / 4;

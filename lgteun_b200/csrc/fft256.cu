@@ -88,7 +88,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 // ---- column pass at H = 256 ---------------------------------------------------------------------------------------------
 // CTA = Q adjacent complex lanes (kx*C2 + ch) of one image; thread = (lane, low index); 16 * Q threads.
 template <int Q>
-__global__ void __launch_bounds__(16 * Q) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
+__global__ void __launch_bounds__(16 * Q, 3) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
                                                              int lanes_per_row) {
   using namespace f256;
   constexpr int H = 256;
