@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   constexpr int TILES = RW * 2;                           // 128-pixel tiles per CTA, two in flight (warps 0-3 / 4-7)
   constexpr uint32_t TCOLS = (2 * C < 32) ? 32 : 2 * C;   // TMEM columns: two accumulators of C columns
   __shared__ float2 tw[256];
-  __shared__ uint64_t mbar;
+  __shared__ uint64_t mbar[2];                            // one MMA-completion barrier per tile in flight
   __shared__ uint32_t tmem_slot;
   extern __shared__ __align__(16) float2 smf[];
   float2* X = smf;                                        // [16][kRowPad]
@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   const size_t row0 = (size_t)blockIdx.x * RW;
   tw[tid] = g_tw256[tid];
   if (tid == 0) {
-    mbar_init(&mbar, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
@@ -355,29 +356,29 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
         *reinterpret_cast<uint4*>(a_lo + ((C2 / 8 + kc) * 128 + trow) * 8) = lo4;
       }
     }
+    // the two tiles in flight (warps 0-3 / 4-7) run free of each other: a 128-thread named barrier publishes a tile's A
+    // operand, its own thread issues the MMAs and its own mbarrier reports completion
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+    if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+    if ((tid & 127) == 0) {
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc(C);
+      const uint32_t ab = smem_u32(a_hi);
 #pragma unroll
-      for (int tt = 0; tt < 2; ++tt) {
-        const uint32_t ab = smem_u32(ah + tt * (2 * 128 * C));
-#pragma unroll
-        for (int ks = 0; ks < C / 16; ++ks) {
-          const uint64_t dah = umma_desc(ab + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t dal = umma_desc(ab + 128 * C * 2 + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t dbh = umma_desc(smem_u32(wh) + ks * 2 * C * 16, C * 16, 128);
-          const uint64_t dbl = umma_desc(smem_u32(wl) + ks * 2 * C * 16, C * 16, 128);
-          umma_f16(tmem + tt * C, dah, dbh, idesc, ks > 0);
-          umma_f16(tmem + tt * C, dah, dbl, idesc, 1);
-          umma_f16(tmem + tt * C, dal, dbh, idesc, 1);
-        }
+      for (int ks = 0; ks < C / 16; ++ks) {
+        const uint64_t dah = umma_desc(ab + ks * 2 * 128 * 16, 128 * 16, 128);
+        const uint64_t dal = umma_desc(ab + 128 * C * 2 + ks * 2 * 128 * 16, 128 * 16, 128);
+        const uint64_t dbh = umma_desc(smem_u32(wh) + ks * 2 * C * 16, C * 16, 128);
+        const uint64_t dbl = umma_desc(smem_u32(wl) + ks * 2 * C * 16, C * 16, 128);
+        umma_f16(tmem + t * C, dah, dbh, idesc, ks > 0);
+        umma_f16(tmem + t * C, dah, dbl, idesc, 1);
+        umma_f16(tmem + t * C, dal, dbh, idesc, 1);
       }
-      umma_commit(&mbar);
+      umma_commit(&mbar[t]);
     }
-    mbar_wait(&mbar, phase);
+    mbar_wait(&mbar[t], phase);
     phase ^= 1;
     tc_fence_after();
     const float* xr = xres + pix * C;
