@@ -226,14 +226,16 @@ __global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __res
   fft16<-1>(v);
 #pragma unroll
   for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[lo * k1]);
-  __syncthreads();                                        // all inputs are in registers: the buffer becomes the exchange
+  // A sequence lives in one half-warp and in its own 272-slot region of the buffer: the hand-offs between the two
+  // radix-16 passes only need warp-level synchronisation
+  __syncwarp();                                           // all inputs are in registers: the buffer becomes the exchange
 #pragma unroll
   for (int k1 = 0; k1 < 16; ++k1) E[seq * 272 + k1 * 17 + lo] = v[k1];
-  __syncthreads();
+  __syncwarp();
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) v[n2] = E[seq * 272 + lo * 17 + n2];
   fft16<-1>(v);                                           // v[k2] = Z[lo + 16 k2]
-  __syncthreads();
+  __syncwarp();
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) X[seq * kRowPad + lo + 16 * k2] = v[k2];       // natural order, unpadded
   __syncthreads();
@@ -311,14 +313,14 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   fft16<+1>(v);
 #pragma unroll
   for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[lo * j1]);
-  __syncthreads();
+  __syncwarp();                                           // a sequence = one half-warp + its own region: warp-level hand-offs
 #pragma unroll
   for (int j1 = 0; j1 < 16; ++j1) E[seq * 272 + j1 * 17 + lo] = v[j1];
-  __syncthreads();
+  __syncwarp();
 #pragma unroll
   for (int m2 = 0; m2 < 16; ++m2) v[m2] = E[seq * 272 + lo * 17 + m2];
   fft16<+1>(v);                                           // v[j2] = (xa + i xb)[lo + 16 j2], unnormalised
-  __syncthreads();
+  __syncwarp();
 #pragma unroll
   for (int j2 = 0; j2 < 16; ++j2)
     X[seq * kRowPad + lo + 16 * j2] = make_float2(fabsf(v[j2].x * scale), fabsf(v[j2].y * scale));
