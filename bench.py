@@ -332,7 +332,7 @@ def roofline_ffn(handle, bands, batch, H, dev, stream, peaks, args):
     peak = peaks["bf16_tflops_sustained"]
     traffic = None                      # dram__bytes_read + write per launch from the committed ncu --set full capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_final_ffn_tc_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_final2_ffn_tc_traffic.json")) as f:
             t = json.load(f)
         if t["bands"] == bands and t["pairs"] == n and t["H"] == H:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
