@@ -33,8 +33,9 @@ UNIT = "pairs/s"
 WORKLOADS = {  # name: (bands, h, default per-GPU batch, description)
     "gf2": (4, 64, 512, "BASELINE configs[2]: GF-2 shape PAN 256x256 + LrMS 64x64x4, K=2 stages"),
     "wv3": (8, 64, 64, "BASELINE configs[1]: WV-3 shape PAN 256x256 + LrMS 64x64x8, K=2 stages"),
+    "tile": (8, 256, 4, "BASELINE configs[3]: scene tile PAN 1024x1024 + LrMS 256x256x8, K=2 stages"),
 }
-FLOPS_PER_PAIR = {"gf2": 10_890_657_792, "wv3": 39_732_936_704}      # BASELINE.md §2 (as executed, 2xMAC)
+FLOPS_PER_PAIR = {"gf2": 10_890_657_792, "wv3": 39_732_936_704, "tile": 635_725_021_184}   # SURVEY §8d (as executed, 2xMAC)
 
 
 def log(*a):
