@@ -52,10 +52,14 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {     // a * con
 }
 
 // ---- natural-order Stockham FFT of NF sequences of length L held in shared memory ----------------------
-// a, b: ping-pong buffers [NF][L]; tw[j] = e^{-2 pi i j / L}.  SIGN = -1 forward, +1 inverse (unnormalised).
+// a, b: ping-pong buffers [NF][LS], LS = L + 2 (kSeqPad): the pad keeps 128-bit alignment and moves consecutive sequences
+// four banks apart, so the per-frequency gathers across sequences (pack / split phases) are conflict-free.
+// tw[j] = e^{-2 pi i j / L}.  SIGN = -1 forward, +1 inverse (unnormalised).
 // Returns the buffer holding the result.  All threads of the CTA must call it.
+constexpr int kSeqPad = 2;
 template <int SIGN>
 __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int NF, int tid, int nthreads) {
+  const int LS = L + kSeqPad;
   for (int Ns = 1; Ns < L;) {
     const int rem = L / Ns;
     if ((rem & 3) == 0) {
@@ -64,7 +68,7 @@ __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int N
       for (int id = tid; id < NF * q; id += nthreads) {
         const int f = id / q, j = id - f * q;
         const int k = j & (Ns - 1);
-        const float2* src = a + f * L + j;
+        const float2* src = a + f * LS + j;
         float2 v0 = src[0], v1 = src[q], v2 = src[2 * q], v3 = src[3 * q];
         if (k) {
           float2 w1 = tw[k * tws], w2 = tw[2 * k * tws], w3 = tw[3 * k * tws];
@@ -75,7 +79,7 @@ __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int N
         float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
         float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
         float2 jd = (SIGN < 0) ? make_float2(d13.y, -d13.x) : make_float2(-d13.y, d13.x);   // (-/+ i) * d13
-        float2* dst = b + f * L + (j - k) * 4 + k;
+        float2* dst = b + f * LS + (j - k) * 4 + k;
         dst[0] = make_float2(s02.x + s13.x, s02.y + s13.y);
         dst[Ns] = make_float2(d02.x + jd.x, d02.y + jd.y);
         dst[2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
@@ -88,13 +92,13 @@ __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int N
       for (int id = tid; id < NF * q; id += nthreads) {
         const int f = id / q, j = id - f * q;
         const int k = j & (Ns - 1);
-        const float2* src = a + f * L + j;
+        const float2* src = a + f * LS + j;
         float2 v0 = src[0], v1 = src[q];
         if (k) {
           float2 w1 = tw[k * tws];
           v1 = (SIGN < 0) ? cmul(v1, w1) : cmul_conj(v1, w1);
         }
-        float2* dst = b + f * L + (j - k) * 2 + k;
+        float2* dst = b + f * LS + (j - k) * 2 + k;
         dst[0] = make_float2(v0.x + v1.x, v0.y + v1.y);
         dst[Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
       }
@@ -126,14 +130,15 @@ __device__ __forceinline__ float2* stockham_ct(float2* a, float2* b, const float
     constexpr int q = L / R;                       // butterflies per sequence
     constexpr int tws = L / (Ns * R);
     constexpr int ITEMS = NF * q;
+    constexpr int LS = L + kSeqPad;
 #pragma unroll
     for (int base = 0; base < ITEMS; base += NT) {
       const int id = base + tid;
       if (ITEMS % NT == 0 || id < ITEMS) {
         const int f = id / q, j = id % q;
         const int k = j & (Ns - 1);
-        const float2* src = a + f * L + j;
-        float2* dst = b + f * L + (j - k) * R + k;
+        const float2* src = a + f * LS + j;
+        float2* dst = b + f * LS + (j - k) * R + k;
         if constexpr (R == 4) {
           float2 v0 = src[0], v1 = src[q], v2 = src[2 * q], v3 = src[3 * q];
           if constexpr (Ns > 1) {
@@ -166,8 +171,10 @@ __device__ __forceinline__ float2* stockham_ct(float2* a, float2* b, const float
 constexpr int kFftThreads = 256;
 
 // ---- pass 1: rows forward ----------------------------------------------------------------------------
-template <int C2, bool PRE_LN, int WCT, int ROWS>
-__global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
+// NT threads per CTA: 256 on the compile-time fast paths; long rows (W >= 512) hold one row of 64-128 KB per CTA, i.e.
+// one CTA per SM, and use 512 / 1024 threads so that the SM still has 16 / 32 resident warps
+template <int C2, bool PRE_LN, int WCT, int ROWS, int NT = kFftThreads>
+__global__ void __launch_bounds__(NT) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
                                                                    BlockW w, int Wrt) {
   const int W = WCT ? WCT : Wrt;                          // WCT != 0: compile-time row length (fast path)
   constexpr int NF1 = C2 / 2;                             // complex sequences per image row (two real channels each)
@@ -175,12 +182,13 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* 
   constexpr int CIN = PRE_LN ? 2 * C2 : C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);       // [W]
-  float2* bufA = tw + W;                                  // [NF][W]
-  float2* bufB = bufA + NF * W;
+  const int LS = W + kSeqPad;                             // padded sequence stride
+  float2* bufA = tw + W;                                  // [NF][LS]
+  float2* bufB = bufA + NF * LS;
   const int tid = threadIdx.x;
   const size_t row0 = (size_t)blockIdx.x * ROWS;          // n*H + y of the first row
-  for (int j = tid; j < W; j += kFftThreads) tw[j] = g_tw[j * (kTwN / W)];
-  for (int p = tid; p < ROWS * W; p += kFftThreads) {
+  for (int j = tid; j < W; j += NT) tw[j] = g_tw[j * (kTwN / W)];
+  for (int p = tid; p < ROWS * W; p += NT) {
     const int rl = p / W, px = p - rl * W;
     const float* src = x + ((row0 + rl) * W + px) * CIN;
     float g[C2];
@@ -202,19 +210,19 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_fwd_kernel(const float* 
       load_vec<C2>(g, src);
     }
 #pragma unroll
-    for (int f = 0; f < NF1; ++f) bufA[(rl * NF1 + f) * W + px] = make_float2(g[2 * f], g[2 * f + 1]);
+    for (int f = 0; f < NF1; ++f) bufA[(rl * NF1 + f) * LS + px] = make_float2(g[2 * f], g[2 * f + 1]);
   }
   __syncthreads();
   const float2* res;
-  if constexpr (WCT != 0) res = stockham_ct<WCT, NF, -1, kFftThreads, 1>(bufA, bufB, tw, tid);
-  else res = stockham<-1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
+  if constexpr (WCT != 0) res = stockham_ct<WCT, NF, -1, NT, 1>(bufA, bufB, tw, tid);
+  else res = stockham<-1>(bufA, bufB, tw, W, NF, tid, NT);
   // split the packed transform: channel a = 2f (real part), b = 2f+1 (imag part)
   const int Wf = W / 2 + 1;
   float4* out = reinterpret_cast<float4*>(spec + row0 * Wf * C2);      // ROWS rows are contiguous in the spectrum
-  for (int id = tid; id < ROWS * Wf * NF1; id += kFftThreads) {
+  for (int id = tid; id < ROWS * Wf * NF1; id += NT) {
     const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
     const int k = rem / NF1, f = rl * NF1 + (rem - k * NF1);
-    float2 z = res[f * W + k], zm = res[f * W + ((W - k) & (W - 1))];
+    float2 z = res[f * LS + k], zm = res[f * LS + ((W - k) & (W - 1))];
     float4 o;
     o.x = 0.5f * (z.x + zm.x);        // Xa = (Z[k] + conj(Z[W-k])) / 2
     o.y = 0.5f * (z.y - zm.y);
@@ -341,8 +349,8 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
 }
 
 // ---- pass 3: rows inverse (+ proj + residual) ------------------------------------------------------------
-template <int C2, bool PROJ, int WCT, int ROWS>
-__global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2* __restrict__ spec,
+template <int C2, bool PROJ, int WCT, int ROWS, int NT = kFftThreads>
+__global__ void __launch_bounds__(NT) fft_rows_inv_kernel(const float2* __restrict__ spec,
                                                                    const float* __restrict__ local,
                                                                    const float* __restrict__ xres, float* __restrict__ y,
                                                                    BlockW w, int Wrt, float scale) {
@@ -352,41 +360,42 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_inv_kernel(const float2*
   constexpr int C = 2 * C2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tw = reinterpret_cast<float2*>(smem_raw);       // [W]
-  float2* bufA = tw + W;                                  // [NF][W]
-  float2* bufB = bufA + NF * W;
-  float* sW = reinterpret_cast<float*>(bufB + NF * W);    // [C][C] proj weight (PROJ only)
+  const int LS = W + kSeqPad;                             // padded sequence stride
+  float2* bufA = tw + W;                                  // [NF][LS]
+  float2* bufB = bufA + NF * LS;
+  float* sW = reinterpret_cast<float*>(bufB + NF * LS);    // [C][C] proj weight (PROJ only)
   float* sBias = sW + C * C;                              // [C]
   const int tid = threadIdx.x;
   const size_t row0 = (size_t)blockIdx.x * ROWS;
   const int Wf = W / 2 + 1;
-  for (int j = tid; j < W; j += kFftThreads) tw[j] = g_tw[j * (kTwN / W)];
+  for (int j = tid; j < W; j += NT) tw[j] = g_tw[j * (kTwN / W)];
   if constexpr (PROJ) {
-    for (int i = tid; i < C * C; i += kFftThreads) sW[i] = __ldg(w.proj_w + i);
-    for (int i = tid; i < C; i += kFftThreads) sBias[i] = __ldg(w.proj_b + i);
+    for (int i = tid; i < C * C; i += NT) sW[i] = __ldg(w.proj_w + i);
+    for (int i = tid; i < C; i += NT) sBias[i] = __ldg(w.proj_b + i);
   }
   const float4* in = reinterpret_cast<const float4*>(spec + row0 * Wf * C2);
-  for (int id = tid; id < ROWS * Wf * NF1; id += kFftThreads) {
+  for (int id = tid; id < ROWS * Wf * NF1; id += NT) {
     const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
     const int k = rem / NF1, f = rl * NF1 + (rem - k * NF1);
     float4 v = __ldg(in + id);                            // (Xa.re, Xa.im, Xb.re, Xb.im)
     if (k == 0 || k == W / 2) {                           // C2R ignores Im of the DC and Nyquist bins
-      bufA[f * W + k] = make_float2(v.x, v.z);
+      bufA[f * LS + k] = make_float2(v.x, v.z);
     } else {
-      bufA[f * W + k] = make_float2(v.x - v.w, v.y + v.z);          // Xa + i Xb
-      bufA[f * W + W - k] = make_float2(v.x + v.w, v.z - v.y);      // conj(Xa) + i conj(Xb)
+      bufA[f * LS + k] = make_float2(v.x - v.w, v.y + v.z);          // Xa + i Xb
+      bufA[f * LS + W - k] = make_float2(v.x + v.w, v.z - v.y);      // conj(Xa) + i conj(Xb)
     }
   }
   __syncthreads();
   const float2* res;
-  if constexpr (WCT != 0) res = stockham_ct<WCT, NF, +1, kFftThreads, 1>(bufA, bufB, tw, tid);
-  else res = stockham<+1>(bufA, bufB, tw, W, NF, tid, kFftThreads);
-  for (int p = tid; p < ROWS * W; p += kFftThreads) {
+  if constexpr (WCT != 0) res = stockham_ct<WCT, NF, +1, NT, 1>(bufA, bufB, tw, tid);
+  else res = stockham<+1>(bufA, bufB, tw, W, NF, tid, NT);
+  for (int p = tid; p < ROWS * W; p += NT) {
     const int rl = p / W, px = p - rl * W;
     const size_t row = row0 + rl;
     float g[C2];
 #pragma unroll
     for (int f = 0; f < NF1; ++f) {
-      float2 z = res[(rl * NF1 + f) * W + px];
+      float2 z = res[(rl * NF1 + f) * LS + px];
       g[2 * f] = fabsf(z.x * scale);
       g[2 * f + 1] = fabsf(z.y * scale);
     }
@@ -433,12 +442,12 @@ static bool pow2_in_range(int v) { return v >= 8 && v <= kTwN && (v & (v - 1)) =
 // rows per CTA on the fast path: 16 complex sequences per CTA (C2=8: 4 rows, C2=16: 2 rows, C2=32: 1 row)
 template <int C2> constexpr int fast_rows() { return (16 / (C2 / 2)) > 0 ? 16 / (C2 / 2) : 1; }
 
-template <int C2, bool PRE_LN, int WCT, int ROWS>
+template <int C2, bool PRE_LN, int WCT, int ROWS, int NT = kFftThreads>
 static cudaError_t rows_fwd_launch(const BlockW& w, const float* x, float* spec, int N, int H, int W, cudaStream_t s) {
-  size_t smem = (size_t)(W + 2 * ROWS * (C2 / 2) * W) * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = (size_t)(W + 2 * ROWS * (C2 / 2) * (W + kSeqPad)) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS><<<N * H / ROWS, kFftThreads, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
+  fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS, NT><<<N * H / ROWS, NT, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
   return cudaGetLastError();
 }
 template <int C2>
@@ -446,6 +455,8 @@ static cudaError_t rows_fwd_t(const BlockW& w, const float* x, float* spec, int 
   if (pre_ln) {
     if (W == 256 && H % fast_rows<C2>() == 0) return rows_fwd_launch<C2, true, 256, fast_rows<C2>()>(w, x, spec, N, H, W, s);
     if (W == 128 && H % fast_rows<C2>() == 0) return rows_fwd_launch<C2, true, 128, fast_rows<C2>()>(w, x, spec, N, H, W, s);
+    if (W >= 1024) return rows_fwd_launch<C2, true, 0, 1, 1024>(w, x, spec, N, H, W, s);
+    if (W >= 512) return rows_fwd_launch<C2, true, 0, 1, 512>(w, x, spec, N, H, W, s);
     return rows_fwd_launch<C2, true, 0, 1>(w, x, spec, N, H, W, s);
   }
   return rows_fwd_launch<C2, false, 0, 1>(w, x, spec, N, H, W, s);
@@ -497,12 +508,12 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
   // measured: several rows per CTA do not pay here (the proj weights + 64 KB of buffers cut residency: 89 vs 67 us per
   // 16 pairs), so the inverse pass keeps one row per CTA
   const int fr = (proj && (W == 256 || W == 128) && fast_rows<C2>() >= 2 && H % 2 == 0) ? 2 : 1;
-  size_t smem = (size_t)(W + 2 * fr * (C2 / 2) * W) * sizeof(float2) + (proj ? (size_t)(C * C + C) * sizeof(float) : 0);
+  size_t smem = (size_t)(W + 2 * fr * (C2 / 2) * (W + kSeqPad)) * sizeof(float2) + (proj ? (size_t)(C * C + C) * sizeof(float) : 0);
   const float scale = 1.0f / ((float)H * (float)W);
-  auto go = [&](auto kern) -> cudaError_t {
+  auto go = [&](auto kern, int nt = kFftThreads) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<N * H / fr, kFftThreads, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w, W, scale);
+    kern<<<N * H / fr, nt, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w, W, scale);
     return cudaGetLastError();
   };
   if (proj) {
@@ -510,6 +521,8 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
     if (W == 128 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 128, 2>);
     if (W == 256) return go(fft_rows_inv_kernel<C2, true, 256, 1>);
     if (W == 128) return go(fft_rows_inv_kernel<C2, true, 128, 1>);
+    if (W >= 1024) return go(fft_rows_inv_kernel<C2, true, 0, 1, 1024>, 1024);
+    if (W >= 512) return go(fft_rows_inv_kernel<C2, true, 0, 1, 512>, 512);
     return go(fft_rows_inv_kernel<C2, true, 0, 1>);
   }
   return go(fft_rows_inv_kernel<C2, false, 0, 1>);
