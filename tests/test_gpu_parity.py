@@ -399,6 +399,31 @@ def test_module_dropin(abi):
         net(g["ms"].cuda().requires_grad_(True), g["pan"].cuda())
 
 
+@pytest.mark.parametrize("bands,stage", [(4, 1), (4, 3), (8, 5)])
+def test_other_stage_counts(abi, O, bands, stage):
+    """The constructor's `stage` argument (reference default 5, config 2 — models/unlg_former.py:22, configs/
+    unlg_former.py:92-94): the module's own default initialisation, K data steps, the last prior — against the oracle,
+    with and without the discarded priors."""
+    import lgteun_b200
+    from types import SimpleNamespace
+    torch.manual_seed(100 + stage)
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=stage)
+    with torch.no_grad():
+        for i, e in enumerate(net.eta):
+            e.fill_(0.05 + 0.03 * i)                            # distinct step sizes per stage
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    ms, pan = torch.rand(2, bands, 16, 16, generator=g), torch.rand(2, 1, 64, 64, generator=g)
+    ref = O.forward(sd, ms, pan)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(ms.cuda(), pan.cuda())
+        net.skip_dead_priors = False
+        out_all = net(ms.cuda(), pan.cuda())
+    assert _maxdiff(out, ref) <= E2E_TOL
+    assert torch.equal(out, out_all)
+
+
 def test_error_behaviour(abi, h4):
     with pytest.raises(ValueError):
         h4.forward(0, 0, 0, 1, 16, 16)                           # NULL pointers
