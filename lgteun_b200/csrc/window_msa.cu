@@ -102,32 +102,43 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
     slot_sync();
     const int widx = wbase + slot;
     const bool active = widx < w_end;               // warp-uniform
-    // 2) q/k/v of this lane's two tokens for this warp's head
+    // 2) q/k/v of this lane's two tokens for this warp's head: every weight row (128-bit broadcasts) feeds both tokens,
+    //    dot products on the packed fp32 pipe with independent accumulators
     if (active) {
-#pragma unroll 1
-      for (int r = 0; r < 2; ++r) {
-        const int tok = lane + 32 * r;
-        float2 xv[C2 / 2];
+      float2 xv[2][C2 / 2];
 #pragma unroll
-        for (int k = 0; k < C2 / 2; ++k) xv[k] = make_float2(sm.xs[slot][2 * k][tok], sm.xs[slot][2 * k + 1][tok]);
-        // one output channel = one weight row [C2] read as 128-bit broadcasts, dot product on the packed fp32 pipe
-        auto dot = [&](int o) {
-          const float4* wr = reinterpret_cast<const float4*>(&sm.wqkv[o * C2]);
-          float2 acc = make_float2(0.f, 0.f);
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int k4 = 0; k4 < C2 / 4; ++k4) {
-            const float4 w4 = wr[k4];
-            acc = __ffma2_rn(make_float2(w4.x, w4.y), xv[2 * k4], acc);
-            acc = __ffma2_rn(make_float2(w4.z, w4.w), xv[2 * k4 + 1], acc);
-          }
-          return (acc.x + acc.y) + sm.bqkv[o];
-        };
-#pragma unroll 2
-        for (int j = 0; j < D; ++j) {
-          sm.qs[slot][head][tok][j] = dot(head * D + j) * scale;
-          sm.ks[slot][head][j][tok] = dot(C2 + head * D + j);
-          sm.vs[slot][head][tok][j] = dot(2 * C2 + head * D + j);
+        for (int k = 0; k < C2 / 2; ++k)
+          xv[r][k] = make_float2(sm.xs[slot][2 * k][lane + 32 * r], sm.xs[slot][2 * k + 1][lane + 32 * r]);
+      auto dot2 = [&](int o, float& d0, float& d1) {
+        const float4* wr = reinterpret_cast<const float4*>(&sm.wqkv[o * C2]);
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+#pragma unroll
+        for (int k4 = 0; k4 < C2 / 4; ++k4) {
+          const float4 w4 = wr[k4];
+          const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
+          a0 = __ffma2_rn(wa, xv[0][2 * k4], a0);
+          a1 = __ffma2_rn(wa, xv[1][2 * k4], a1);
+          a0 = __ffma2_rn(wb, xv[0][2 * k4 + 1], a0);
+          a1 = __ffma2_rn(wb, xv[1][2 * k4 + 1], a1);
         }
+        const float bias = sm.bqkv[o];
+        d0 = (a0.x + a0.y) + bias;
+        d1 = (a1.x + a1.y) + bias;
+      };
+#pragma unroll 4
+      for (int j = 0; j < D; ++j) {
+        float q0, q1, k0, k1, v0, v1;
+        dot2(head * D + j, q0, q1);
+        dot2(C2 + head * D + j, k0, k1);
+        dot2(2 * C2 + head * D + j, v0, v1);
+        sm.qs[slot][head][lane][j] = q0 * scale;
+        sm.qs[slot][head][lane + 32][j] = q1 * scale;
+        sm.ks[slot][head][j][lane] = k0;
+        sm.ks[slot][head][j][lane + 32] = k1;
+        sm.vs[slot][head][lane][j] = v0;
+        sm.vs[slot][head][lane + 32][j] = v1;
       }
     }
     __syncwarp();                                   // K / V of a (window, head) are produced and consumed by one warp
