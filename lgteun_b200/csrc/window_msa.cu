@@ -27,6 +27,7 @@ struct MsaSmem {
   alignas(16) float pos_t[kHeads * 64 * 64];        // [h][j/4][i][j%4], pre-scaled by log2(e)
   alignas(16) float wqkv[3 * C2 * C2];              // [3*C2][C2]
   float bqkv[3 * C2];
+  float lnw[C2], lnb[C2];                           // LayerNorm affine of the local half
   float xs[kWinPerIter][C2][64 + 1];                // LN'd local half, channel-major (conflict-free per-token reads)
   alignas(16) float ks[kWinPerIter][kHeads][D][64]; // channel-major: four keys per 128-bit broadcast
   alignas(16) float vs[kWinPerIter][kHeads][64][D];
@@ -45,8 +46,27 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
   for (int i = tid; i < kHeads * 64 * 64; i += kMsaThreads) sm.pos_t[i] = __ldg(w.pos_t + i);
   for (int i = tid; i < 3 * C2 * C2; i += kMsaThreads) sm.wqkv[i] = __ldg(w.qkv_w + i);
   for (int i = tid; i < 3 * C2; i += kMsaThreads) sm.bqkv[i] = __ldg(w.qkv_b + i);
+  if (PRE_LN)
+    for (int i = tid; i < C2; i += kMsaThreads) { sm.lnw[i] = __ldg(w.ln1_w + i); sm.lnb[i] = __ldg(w.ln1_b + i); }
 
+  // window coordinates: shifts when the window grid is a power of two in both directions (every forward shape), integer
+  // divisions otherwise (the per-operator entry point accepts any multiple of 8)
   const int nwx = W / kWin, nwy = H / kWin;
+  const bool grid_pow2 = ((nwx & (nwx - 1)) | (nwy & (nwy - 1))) == 0;
+  const int lg_nwx = 31 - __clz(nwx), lg_nwy = 31 - __clz(nwy);
+  auto window_of = [&](int widx, int& wx, int& wy, int& n) {
+    if (grid_pow2) {
+      wx = widx & (nwx - 1);
+      const int t = widx >> lg_nwx;
+      wy = t & (nwy - 1);
+      n = t >> lg_nwy;
+    } else {
+      wx = widx % nwx;
+      const int t = widx / nwx;
+      wy = t % nwy;
+      n = t / nwy;
+    }
+  };
   const int lane = tid & 31, warp = tid >> 5;
   const int slot = warp >> 1, head = warp & 1;      // attention phase: warp = (window slot, head)
   const int lslot = tid >> 6, ltok = tid & 63;      // load phase: thread = (window slot, token)
@@ -73,7 +93,8 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
     {
       const int widx = wbase + lslot;
       if (widx < w_end) {
-        const int wx = widx % nwx, t = widx / nwx, wy = t % nwy, n = t / nwy;
+        int wx, wy, n;
+        window_of(widx, wx, wy, n);
         const int py = wy * kWin + (ltok >> 3), px = wx * kWin + (ltok & 7);
         const float* src = x + (((size_t)n * H + py) * W + px) * CIN;
         if constexpr (PRE_LN) {
@@ -90,7 +111,7 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
           float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
 #pragma unroll
           for (int i = 0; i < C2; ++i)
-            sm.xs[lslot][i][ltok] = (v[i] - mean) * rstd * __ldg(w.ln1_w + i) + __ldg(w.ln1_b + i);
+            sm.xs[lslot][i][ltok] = (v[i] - mean) * rstd * sm.lnw[i] + sm.lnb[i];
         } else {
           float v[C2];
           load_vec<C2>(v, src);
@@ -227,7 +248,8 @@ window_msa_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW w, 
           }
         }
       }
-      const int wx = widx % nwx, t = widx / nwx, wy = t % nwy, n = t / nwy;
+      int wx, wy, n;
+      window_of(widx, wx, wy, n);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int tok = lane + 32 * r;
