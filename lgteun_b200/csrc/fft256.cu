@@ -291,15 +291,29 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   for (int i = tid; i < C; i += 256) sBias[i] = __ldg(w.proj_b + i);
   // phase 0: Hermitian rebuild of the packed spectra (C2R ignores Im of the DC and Nyquist bins)
   const float4* in = reinterpret_cast<const float4*>(spec + row0 * Wf * C2);
-  for (int id = tid; id < RW * Wf * NF1; id += 256) {
-    const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
-    const int k = rem / NF1, s = rl * NF1 + (rem - k * NF1);
-    const float4 v = __ldg(in + id);                      // (Xa.re, Xa.im, Xb.re, Xb.im)
-    if (k == 0 || k == W / 2) {
-      X[s * kRowPad + padded(k)] = make_float2(v.x, v.z);
-    } else {
-      X[s * kRowPad + padded(k)] = make_float2(v.x - v.w, v.y + v.z);           // Xa + i Xb
-      X[s * kRowPad + padded(W - k)] = make_float2(v.x + v.w, v.z - v.y);       // conj(Xa) + i conj(Xb)
+  {
+    // all of this thread's spectrum loads are issued before the first one is consumed (the loop form waited a full HBM
+    // round trip per iteration: 18 % of the kernel's stall samples)
+    constexpr int TOTAL = RW * Wf * NF1, ITERS = (TOTAL + 255) / 256;
+    float4 vb[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int id = tid + 256 * i;
+      vb[i] = (id < TOTAL) ? __ldg(in + id) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int id = tid + 256 * i;
+      if (id >= TOTAL) break;
+      const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
+      const int k = rem / NF1, s = rl * NF1 + (rem - k * NF1);
+      const float4 v = vb[i];                             // (Xa.re, Xa.im, Xb.re, Xb.im)
+      if (k == 0 || k == W / 2) {
+        X[s * kRowPad + padded(k)] = make_float2(v.x, v.z);
+      } else {
+        X[s * kRowPad + padded(k)] = make_float2(v.x - v.w, v.y + v.z);           // Xa + i Xb
+        X[s * kRowPad + padded(W - k)] = make_float2(v.x + v.w, v.z - v.y);       // conj(Xa) + i conj(Xb)
+      }
     }
   }
   tc_fence_before();
