@@ -170,8 +170,19 @@ class Pansharpening(nn.Module):
         return state
 
     # -- runtime ---------------------------------------------------------------------------------------------
-    def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+    def _weight_items(self):
+        """(state_dict key, tensor) of every parameter.  Also valid inside an ``nn.DataParallel`` replica (the reference
+        wraps the module when more than one GPU is visible, models/base/base_model.py:90-96): a replica's ``_parameters``
+        are empty and its submodules hold the broadcast copies as plain attributes (``_former_parameters``,
+        torch/nn/parallel/replicate.py), so ``parameters()`` / ``state_dict()`` cannot be used there."""
+        for prefix, m in self.named_modules():
+            former = getattr(m, "_former_parameters", None) or {}
+            for k in list(m._parameters.keys()) + [k for k in former if k not in m._parameters]:
+                t = m._parameters.get(k)
+                if t is None:
+                    t = former.get(k)
+                if t is not None:
+                    yield (prefix + "." if prefix else "") + k, t
 
     def _runtime(self, device: torch.device):
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -179,10 +190,11 @@ class Pansharpening(nn.Module):
         if rt is None:
             rt = {"handle": _abi.Handle(idx, self.in_channels, self.stage), "sig": None}
             self._rt[idx] = rt
-        sig = self._signature()
-        if rt["sig"] != sig:                 # load_state_dict / optimizer step / .to(): refresh the packed copy
+        items = list(self._weight_items())
+        sig = tuple((t.data_ptr(), t._version) for _, t in items)
+        if rt["sig"] != sig:                 # load_state_dict / optimizer step / .to() / a new replica: refresh the packed copy
             tensors = {}
-            for name, p in self.state_dict(keep_vars=True).items():
+            for name, p in items:
                 t = p.detach()
                 if t.device.type != "cuda" or t.device.index != idx:
                     raise RuntimeError(f"parameter {name} lives on {t.device}, inputs on cuda:{idx}; call .cuda() first")
@@ -204,7 +216,7 @@ class Pansharpening(nn.Module):
         if ms.dtype != torch.float32 or pan.dtype != torch.float32:
             raise TypeError("ms and pan must be float32")
         if torch.is_grad_enabled() and (ms.requires_grad or pan.requires_grad or
-                                        any(p.requires_grad for p in self.parameters())):
+                                        any(t.requires_grad for _, t in self._weight_items())):
             raise NotImplementedError("the backward of the fused forward is not built yet (SURVEY.md §8f rank 1): "
                                       "call under torch.no_grad() / after requires_grad_(False)")
         with torch.cuda.device(ms.device):

@@ -424,6 +424,26 @@ def test_other_stage_counts(abi, O, bands, stage):
     assert torch.equal(out, out_all)
 
 
+def test_dataparallel_wrapping(abi):
+    """`nn.DataParallel(core_module)` as models/base/base_model.py:90-96 builds it on a multi-GPU box: one replica and one
+    C-ABI handle per device, same result as the single-device forward (needs two visible GPUs)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import lgteun_b200
+    from types import SimpleNamespace
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=4), None, stage=2)
+    net.load_state_dict(load_weights(4))
+    g = load_case("gf2_batch")
+    ms, pan = g["ms"].cuda(), g["pan"].cuda()
+    dp = torch.nn.DataParallel(net).cuda().eval()
+    with torch.no_grad():
+        for _ in range(2):                                     # second call: handles and graphs are reused
+            out = dp(ms, pan)
+            assert _maxdiff(out, g["out"]) <= E2E_TOL
+        single = net(ms, pan)
+    assert torch.equal(out.cpu(), single.cpu())
+
+
 def test_error_behaviour(abi, h4):
     with pytest.raises(ValueError):
         h4.forward(0, 0, 0, 1, 16, 16)                           # NULL pointers

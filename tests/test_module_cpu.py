@@ -87,3 +87,41 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_weight_collection_inside_a_dataparallel_replica():
+    """The reference wraps the module in nn.DataParallel when several GPUs are visible (models/base/base_model.py:90-96).
+    A replica has empty `_parameters` and carries the broadcast copies as plain attributes; the weight table handed to the
+    C ABI must still be complete there.  The replica is built here the way torch/nn/parallel/replicate.py builds it,
+    without the CUDA broadcast."""
+    from collections import OrderedDict
+    from types import SimpleNamespace
+    import torch
+    import lgteun_b200
+
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=4), None, stage=2)
+    modules = list(net.modules())
+    index = {m: i for i, m in enumerate(modules)}
+    copies = []
+    for m in modules:
+        rep = m._replicate_for_data_parallel()
+        rep._former_parameters = OrderedDict()
+        copies.append(rep)
+    for i, m in enumerate(modules):
+        rep = copies[i]
+        for key, child in m._modules.items():
+            rep._modules[key] = None if child is None else copies[index[child]]
+        for key, p in m._parameters.items():
+            if p is None:
+                rep._parameters[key] = None
+                continue
+            t = p.detach().clone()
+            setattr(rep, key, t)
+            rep._former_parameters[key] = t
+    replica = copies[0]
+    assert list(replica.parameters()) == [] and len(replica.state_dict()) == 0       # why parameters() cannot be used
+    got = dict(replica._weight_items())
+    want = net.state_dict()
+    assert list(got) == list(want) and sorted(got) == sorted(lgteun_b200.expected_state_dict_keys(4, 2))
+    assert all(torch.equal(got[k], want[k]) for k in want)
+    assert [k for k, _ in net._weight_items()] == list(want)
