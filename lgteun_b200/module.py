@@ -215,6 +215,10 @@ class Pansharpening(nn.Module):
             raise RuntimeError("lgteun_b200.Pansharpening runs on CUDA (sm_100a) tensors only; there is no CPU path")
         if ms.dtype != torch.float32 or pan.dtype != torch.float32:
             raise TypeError("ms and pan must be float32")
+        if self.training:
+            raise NotImplementedError("training-mode forward is not built: the reference applies Dropout(0.1) after the mixer "
+                                      "projection in train() mode (models/common/LGT.py:198,216); call .eval() as the "
+                                      "reference's test loop does (models/base/base_model.py:277-278)")
         if torch.is_grad_enabled() and (ms.requires_grad or pan.requires_grad or
                                         any(t.requires_grad for _, t in self._weight_items())):
             raise NotImplementedError("the backward of the fused forward is not built yet (SURVEY.md §8f rank 1): "

@@ -397,6 +397,10 @@ def test_module_dropin(abi):
             net(torch.rand(1, 4, 12, 12).cuda(), torch.rand(1, 1, 48, 48).cuda())   # PAN 48: not a power of two
     with pytest.raises(NotImplementedError):                        # grad mode: the backward is a later row
         net(g["ms"].cuda().requires_grad_(True), g["pan"].cuda())
+    net.train()
+    with torch.no_grad(), pytest.raises(NotImplementedError):       # train(): the reference's Dropout(0.1) is active
+        net(g["ms"].cuda(), g["pan"].cuda())
+    net.eval()
 
 
 @pytest.mark.parametrize("bands,stage", [(4, 1), (4, 3), (8, 5)])
