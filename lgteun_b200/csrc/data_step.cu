@@ -55,7 +55,53 @@ __global__ void __launch_bounds__(256) bicubic_kernel(const float* __restrict__ 
   y[((size_t)blockIdx.z * oh + oy) * ow + ox] = acc;
 }
 
+// x4 (the Z0 initialisation, unlg_former.py:53): the four outputs 4i .. 4i+3 of one row read the five sources i-2 .. i+2
+// (phases t = .625, .875 from i-1 and t = .125, .375 from i), so one thread produces them from 4 x 5 loads and stores one
+// 128-bit vector.  Same weights and the same fma order as the generic kernel: bit-identical results, ~5x fewer
+// instructions (the generic form was issue-bound at 77 %).
+__global__ void __launch_bounds__(256) bicubic_x4_kernel(const float* __restrict__ x, float* __restrict__ y, int h, int w) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);    // source column
+  const int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (i >= w || oy >= 4 * h) return;
+  const float* xp = x + (size_t)blockIdx.z * h * w;
+  const float sy = 0.25f * (oy + 0.5f) - 0.5f, fy = floorf(sy);
+  float wy[4];
+  cubic_weights(sy - fy, wy);
+  const int iy = (int)fy;
+  float wx[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float sx = 0.25f * ((float)(4 * i + p) + 0.5f) - 0.5f;
+    cubic_weights(sx - floorf(sx), wx[p]);
+  }
+  int cx[5];
+#pragma unroll
+  for (int b = 0; b < 5; ++b) cx[b] = clampi(i - 2 + b, 0, w - 1);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float* row = xp + (size_t)clampi(iy - 1 + a, 0, h - 1) * w;
+    float v[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) v[b] = __ldg(row + cx[b]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int o = (p < 2) ? 0 : 1;                      // outputs 0,1 start at source i-2, outputs 2,3 at i-1
+      float r = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) r = fmaf(wx[p][b], v[o + b], r);
+      acc[p] = fmaf(wy[a], r, acc[p]);
+    }
+  }
+  *reinterpret_cast<float4*>(y + ((size_t)blockIdx.z * 4 * h + oy) * 4 * w + 4 * i) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 cudaError_t launch_bicubic(const float* x, float* y, int planes, int h, int w, int num, int den, cudaStream_t s) {
+  if (num == 4 && den == 1) {
+    dim3 grid((w + 31) / 32, (4 * h + 7) / 8, planes);
+    bicubic_x4_kernel<<<grid, 256, 0, s>>>(x, y, h, w);
+    return cudaGetLastError();
+  }
   int oh = h * num / den, ow = w * num / den;
   dim3 grid((ow + 31) / 32, (oh + 7) / 8, planes);
   bicubic_kernel<<<grid, 256, 0, s>>>(x, y, h, w, oh, ow, num, den);
