@@ -42,6 +42,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line, the JSON result.  Libraries print there too (NCCL's version banner under torchrun), so
+# file descriptor 1 is pointed at stderr for the whole run and the result is written to the saved descriptor.
+_RESULT_FD = None
+
+
+def claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -119,7 +141,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -187,8 +209,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout: keep stdout for the one JSON line the driver parses
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import lgteun_b200
@@ -303,7 +323,7 @@ def run_ours(args):
                 ms_live = timed(step_live, 3, 3)
                 line["live_prior_only"] = {"value": batch * 3 / (ms_live * 1e-3), "unit": UNIT,
                                            "note": "prior_module[0] skipped: the reference discards its output"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -394,6 +414,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=128, help="pairs per H2D/compute/D2H pipeline chunk of the e2e leg")
     ap.add_argument("--other-workloads", action="store_true", default=True)
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
