@@ -83,40 +83,67 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = o[i];
 }
+// 8-point FFT in registers, natural order in and out: two radix-4 on the even / odd samples, W8 twiddles, radix-2
+template <int SIGN>
+__device__ __forceinline__ void fft8(float2* v) {
+  constexpr float R = 0.70710678118654752f;
+  float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  radix4<SIGN>(e0, e1, e2, e3);
+  radix4<SIGN>(o0, o1, o2, o3);
+  o1 = ctw<SIGN>(o1, make_float2(R, -R));                 // W8^1
+  o2 = rot<SIGN>(o2);                                     // W8^2 = -i
+  o3 = ctw<SIGN>(o3, make_float2(-R, -R));                // W8^3
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+// M-point FFT on v[0..M), M in {8, 16}
+template <int M, int SIGN>
+__device__ __forceinline__ void fft_m(float2* v) {
+  if constexpr (M == 16) fft16<SIGN>(*reinterpret_cast<float2(*)[16]>(v));
+  else fft8<SIGN>(v);
+}
 }  // namespace f256
 
-// ---- column pass at H = 256 ---------------------------------------------------------------------------------------------
-// CTA = Q adjacent complex lanes (kx*C2 + ch) of one image; thread = (lane, low index); 16 * Q threads.
-template <int Q>
-__global__ void __launch_bounds__(16 * Q, 3) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
-                                                             int lanes_per_row) {
+// ---- column pass at H = 16 M (M = 16: 256, M = 8: 128) --------------------------------------------------------------------
+// CTA = Q adjacent complex lanes (kx*C2 + ch) of one image; thread = (lane, low index); M * Q threads.
+// H = 16 M is split as n = M n1 + n2: pass A is a 16-point FFT over n1 (one per thread, n2 = thread), twiddle W_H^{n2 k1},
+// exchange, pass B an M-point FFT over n2 for each k1 (16/M of them per thread), leaving X[k1 + 16 k2] in registers.
+// The inverse consumes exactly that distribution (m = m2 + 16 m1 with m2 = k1, m1 = k2): M-point over m1, twiddle,
+// exchange, 16-point over m2, so no reordering is needed between the two transforms.
+template <int Q, int M>
+__global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
+                                                                int lanes_per_row) {
   using namespace f256;
-  constexpr int H = 256;
+  constexpr int H = 16 * M, KPT = 16 / M, TS = 16 / M;    // k1 values per thread in pass B; twiddle-table stride
   __shared__ float2 tw[256];
-  extern __shared__ __align__(16) float2 ex[];            // exchange buffer [16][16][Q]
+  extern __shared__ __align__(16) float2 ex[];            // exchange buffer [16][M][Q]
   const int tid = threadIdx.x;
-  const int l = tid % Q, lo = tid / Q;                    // lane within the CTA, low index (n2 / k1 / m2 / j1)
+  const int l = tid % Q, lo = tid / Q;                    // lane within the CTA, low index (n2 / j1)
   const int l0 = blockIdx.x * Q;
   const bool live = l0 + l < lanes_per_row;
   float2* base = spec + (size_t)blockIdx.y * H * lanes_per_row + l0 + l;
-  for (int j = tid; j < 256; j += 16 * Q) tw[j] = g_tw256[j];
+  for (int j = tid; j < 256; j += M * Q) tw[j] = g_tw256[j];
 
-  // load rows y = 16 n1 + lo
+  // load rows y = M n1 + lo
   float2 v[16];
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1)
-    v[n1] = live ? base[(size_t)(16 * n1 + lo) * lanes_per_row] : make_float2(0.f, 0.f);
+    v[n1] = live ? base[(size_t)(M * n1 + lo) * lanes_per_row] : make_float2(0.f, 0.f);
   __syncthreads();                                        // twiddle table staged
-  // forward pass A over n1, twiddle W256^{lo k1}, exchange, pass B over n2
   fft16<-1>(v);
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[lo * k1]);
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[TS * lo * k1]);
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) ex[(k1 * 16 + lo) * Q + l] = v[k1];
+  for (int k1 = 0; k1 < 16; ++k1) ex[(k1 * M + lo) * Q + l] = v[k1];
   __syncthreads();
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) v[n2] = ex[(lo * 16 + n2) * Q + l];
-  fft16<-1>(v);                                           // v[k2] = X[ky = lo + 16 k2]
+  for (int kk = 0; kk < KPT; ++kk) {
+#pragma unroll
+    for (int n2 = 0; n2 < M; ++n2) v[kk * M + n2] = ex[((lo + M * kk) * M + n2) * Q + l];
+    fft_m<M, -1>(v + kk * M);                             // v[kk*M + k2] = X[ky = (lo + M kk) + 16 k2]
+  }
 
   // amplitude / phase mixing (LGT.py:168-177)
   {
@@ -126,9 +153,11 @@ __global__ void __launch_bounds__(16 * Q, 3) fft_cols256_kernel(float2* __restri
     const float pw = live ? __ldg(w.pha_w + ch) : 0.f, pb = live ? __ldg(w.pha_b + ch) : 0.f;
     const bool real_col = (kx == 0 || kx == W / 2);
 #pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) {
-      float2 z = v[k2];
-      if (real_col && lo == 0 && (k2 == 0 || k2 == 8)) z.y = 0.0f;     // ky in {0, 128}: exactly-real bins get +0.0 (F7)
+    for (int i = 0; i < 16; ++i) {
+      const int kk = i / M, k2 = i % M;
+      float2 z = v[i];
+      // ky in {0, H/2} <=> k1 = 0 and k2 in {0, M/2}: exactly-real bins get +0.0 (F7)
+      if (real_col && lo == 0 && kk == 0 && (k2 == 0 || k2 == M / 2)) z.y = 0.0f;
       float amp = sqrtf(fmaf(z.x, z.x, z.y * z.y));
       float pha = atan2f(z.y, z.x);
       amp = amp * aw + ab;
@@ -137,35 +166,47 @@ __global__ void __launch_bounds__(16 * Q, 3) fft_cols256_kernel(float2* __restri
       float re = amp * cs + 1e-8f;
       const float im = amp * sn + 1e-8f;
       re = re + 1e-8f;                                    // complex(real, imag) + 1e-8 adds to the real part
-      v[k2] = make_float2(re, im);
+      v[i] = make_float2(re, im);
     }
   }
-  // inverse: input index m = 16 m1 + m2 with m2 = lo (thread), m1 = k2 (register): same distribution as the forward input
-  fft16<+1>(v);
-#pragma unroll
-  for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[lo * j1]);
+  // inverse, pass A: M-point over m1 = k2 for each m2 = k1 held by this thread, twiddle conj W_H^{j1 m2}
   __syncthreads();                                        // everyone has consumed the first exchange
 #pragma unroll
-  for (int j1 = 0; j1 < 16; ++j1) ex[(j1 * 16 + lo) * Q + l] = v[j1];
+  for (int kk = 0; kk < KPT; ++kk) {
+    const int k1 = lo + M * kk;
+    fft_m<M, +1>(v + kk * M);
+#pragma unroll
+    for (int j1 = 1; j1 < M; ++j1) v[kk * M + j1] = ctw<+1>(v[kk * M + j1], tw[TS * k1 * j1]);
+#pragma unroll
+    for (int j1 = 0; j1 < M; ++j1) ex[(j1 * 16 + k1) * Q + l] = v[kk * M + j1];
+  }
   __syncthreads();
+  // pass B: 16-point over m2 for j1 = lo
 #pragma unroll
   for (int m2 = 0; m2 < 16; ++m2) v[m2] = ex[(lo * 16 + m2) * Q + l];
-  fft16<+1>(v);                                           // v[j2] = x[y = lo + 16 j2]  (unnormalised)
+  fft16<+1>(v);                                           // v[j2] = x[y = lo + M j2]  (unnormalised)
   if (live) {
 #pragma unroll
-    for (int j2 = 0; j2 < 16; ++j2) base[(size_t)(lo + 16 * j2) * lanes_per_row] = v[j2];
+    for (int j2 = 0; j2 < 16; ++j2) base[(size_t)(lo + M * j2) * lanes_per_row] = v[j2];
   }
 }
 
-cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s) {
-  constexpr int Q = 16;
+template <int M>
+static cudaError_t cols_reg_t(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s) {
+  constexpr int Q = 256 / M;
   const int lanes = (W / 2 + 1) * c2;
-  const size_t smem = (size_t)256 * Q * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(fft_cols256_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)16 * M * Q * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_cols256_kernel<Q, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((lanes + Q - 1) / Q, N);
-  fft_cols256_kernel<Q><<<grid, 16 * Q, smem, s>>>(reinterpret_cast<float2*>(spec), w, W, c2, lanes);
+  fft_cols256_kernel<Q, M><<<grid, M * Q, smem, s>>>(reinterpret_cast<float2*>(spec), w, W, c2, lanes);
   return cudaGetLastError();
+}
+cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s) {
+  return cols_reg_t<16>(w, c2, spec, N, W, s);
+}
+cudaError_t launch_fft_cols128(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s) {
+  return cols_reg_t<8>(w, c2, spec, N, W, s);
 }
 
 }  // namespace lg

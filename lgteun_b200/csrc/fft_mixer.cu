@@ -493,6 +493,7 @@ static cudaError_t cols_t(const BlockW& w, int c2, float* spec, int N, int H, in
 cudaError_t launch_fft_cols(const BlockW& w, int c, float* spec, int N, int H, int W, cudaStream_t s) {
   if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
   const int c2 = c / 2;
+  if (H == 128 && !stockham_only()) return launch_fft_cols128(w, c2, spec, N, W, s);
   if (H == 128) return cols_t<64, 128>(w, c2, spec, N, H, W, s);
   if (H < 128) return cols_t<64, 0>(w, c2, spec, N, H, W, s);
   if (H == 256 && !stockham_only()) return launch_fft_cols256(w, c2, spec, N, W, s);
