@@ -85,6 +85,7 @@ cudaError_t fft256_init_tables(cudaStream_t s);
 cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s);
 cudaError_t launch_fft_cols128(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s);   // H = 128
 cudaError_t launch_fft_rows_fwd256(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s);
+cudaError_t launch_fft_rows_fwd128(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s);   // W = 128
 cudaError_t launch_fft_rows_inv256(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
                                    int N, int H, cudaStream_t s);
 // ffn.cu

@@ -213,31 +213,36 @@ cudaError_t launch_fft_cols128(const BlockW& w, int c2, float* spec, int N, int 
 
 namespace lg {
 
-// ---- row passes at W = 256 ----------------------------------------------------------------------------------------------
-// A CTA owns 16 complex sequences (two real channels each) = 32/C2 consecutive image rows; thread = (sequence, low index).
-constexpr int kRowPad = 272;                              // 256 + one pad slot per 16: conflict-free stride-16 register loads
-__device__ __forceinline__ int padded(int i) { return i + (i >> 4); }
+// ---- row passes at W = 16 M (M = 16: 256, M = 8: 128) ----------------------------------------------------------------------
+// A CTA owns 256 / M complex sequences (two real channels each) = 512 / (M C2) consecutive image rows; thread =
+// (sequence, low index), M threads per sequence.  Same two-pass split as the column kernel (n = M n1 + n2).
+// A sequence occupies 16 (M + 1) slots: inputs are stored with one pad slot per M samples (conflict-free stride-M reads),
+// the exchange between the passes is [k1][M + 1], the result comes back in natural order — all in the same storage.
+constexpr int kRowPad = 272;                              // M = 16
+template <int M> __device__ __forceinline__ int padded_m(int i) { return i + i / M; }
+__device__ __forceinline__ int padded(int i) { return padded_m<16>(i); }
 
-template <int C2, bool PRE_LN>
+template <int C2, bool PRE_LN, int M>
 __global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __restrict__ x, float2* __restrict__ spec,
                                                                BlockW w) {
   using namespace f256;
-  constexpr int W = 256, Wf = 129;
+  constexpr int W = 16 * M, Wf = W / 2 + 1, RP = 16 * (M + 1), KPT = 16 / M, TS = 16 / M;
   constexpr int NF1 = C2 / 2;                             // sequences per image row
-  constexpr int RW = 16 / NF1;                            // image rows per CTA
+  constexpr int RW = (256 / M) / NF1;                     // image rows per CTA
+  static_assert(RW >= 1, "a CTA holds at least one image row");
   constexpr int CIN = PRE_LN ? 2 * C2 : C2;
   __shared__ float2 tw[256];
   extern __shared__ __align__(16) float2 smf[];
-  float2* X = smf;                                        // [16][kRowPad]  input sequences, later the natural-order spectrum
-  float2* E = smf;                                        // [16][16*17]    exchange between the two radix-16 passes: the SAME
-                                                          // storage (35 KB per CTA instead of 70: twice the resident CTAs)
+  float2* X = smf;                                        // [256/M][RP]  input sequences, later the natural-order spectrum
+  float2* E = smf;                                        // exchange between the two passes: the SAME storage (35 KB per
+                                                          // CTA instead of 70: twice the resident CTAs)
   const int tid = threadIdx.x;
   const size_t row0 = (size_t)blockIdx.x * RW;
   tw[tid] = g_tw256[tid];
   // phase 0: LayerNorm, pack channel pairs (2f, 2f+1) of the global half as complex samples
 #pragma unroll
-  for (int i = 0; i < RW; ++i) {
-    const int p = tid + 256 * i, rl = p >> 8, px = p & 255;
+  for (int i = 0; i < RW * W / 256; ++i) {
+    const int p = tid + 256 * i, rl = p / W, px = p % W;
     const float* src = x + ((row0 + rl) * W + px) * CIN;
     float g[C2];
     if constexpr (PRE_LN) {
@@ -257,35 +262,40 @@ __global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __res
       load_vec<C2>(g, src);
     }
 #pragma unroll
-    for (int f = 0; f < NF1; ++f) X[(rl * NF1 + f) * kRowPad + padded(px)] = make_float2(g[2 * f], g[2 * f + 1]);
+    for (int f = 0; f < NF1; ++f) X[(rl * NF1 + f) * RP + padded_m<M>(px)] = make_float2(g[2 * f], g[2 * f + 1]);
   }
   __syncthreads();
-  const int seq = tid >> 4, lo = tid & 15;
+  const int seq = tid / M, lo = tid % M;
   float2 v[16];
 #pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[seq * kRowPad + 17 * n1 + lo];       // padded(16 n1 + lo)
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[seq * RP + (M + 1) * n1 + lo];       // padded(M n1 + lo)
   fft16<-1>(v);
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[lo * k1]);
-  // A sequence lives in one half-warp and in its own 272-slot region of the buffer: the hand-offs between the two
-  // radix-16 passes only need warp-level synchronisation
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[TS * lo * k1]);
+  // A sequence lives in M lanes of one warp and in its own region of the buffer: the hand-offs between the two passes
+  // only need warp-level synchronisation
   __syncwarp();                                           // all inputs are in registers: the buffer becomes the exchange
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) E[seq * 272 + k1 * 17 + lo] = v[k1];
+  for (int k1 = 0; k1 < 16; ++k1) E[seq * RP + k1 * (M + 1) + lo] = v[k1];
   __syncwarp();
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) v[n2] = E[seq * 272 + lo * 17 + n2];
-  fft16<-1>(v);                                           // v[k2] = Z[lo + 16 k2]
+  for (int kk = 0; kk < KPT; ++kk) {
+#pragma unroll
+    for (int n2 = 0; n2 < M; ++n2) v[kk * M + n2] = E[seq * RP + (lo + M * kk) * (M + 1) + n2];
+    fft_m<M, -1>(v + kk * M);                             // v[kk*M + k2] = Z[(lo + M kk) + 16 k2]
+  }
   __syncwarp();
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) X[seq * kRowPad + lo + 16 * k2] = v[k2];       // natural order, unpadded
+  for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+    for (int k2 = 0; k2 < M; ++k2) X[seq * RP + (lo + M * kk) + 16 * k2] = v[kk * M + k2];     // natural order, unpadded
   __syncthreads();
   // split the packed transforms: channel a = 2f (real input), b = 2f+1 (imaginary input)
   float4* out = reinterpret_cast<float4*>(spec + row0 * Wf * C2);
   for (int id = tid; id < RW * Wf * NF1; id += 256) {
     const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
     const int k = rem / NF1, s = rl * NF1 + (rem - k * NF1);
-    const float2 z = X[s * kRowPad + k], zm = X[s * kRowPad + ((W - k) & (W - 1))];
+    const float2 z = X[s * RP + k], zm = X[s * RP + ((W - k) & (W - 1))];
     float4 o;
     o.x = 0.5f * (z.x + zm.x);        // Xa = (Z[k] + conj(Z[W-k])) / 2
     o.y = 0.5f * (z.y - zm.y);
@@ -458,13 +468,14 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int C2>
+template <int C2, int M>
 static cudaError_t rows256_fwd_t(const BlockW& w, const float* x, float* spec, int N, int H, cudaStream_t s) {
-  constexpr int RW = 16 / (C2 / 2);
-  const size_t smem = (size_t)(16 * kRowPad) * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd256_kernel<C2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int RW = (256 / M) / (C2 / 2);
+  if (H % RW) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(256 / M) * 16 * (M + 1) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd256_kernel<C2, true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  fft_rows_fwd256_kernel<C2, true><<<N * H / RW, 256, smem, s>>>(x, reinterpret_cast<float2*>(spec), w);
+  fft_rows_fwd256_kernel<C2, true, M><<<N * H / RW, 256, smem, s>>>(x, reinterpret_cast<float2*>(spec), w);
   return cudaGetLastError();
 }
 template <int C2>
@@ -482,9 +493,18 @@ static cudaError_t rows256_inv_t(const BlockW& w, const float* spec, const float
 // W == 256, LayerNorm prologue; H must be a multiple of 32 / C2 rows
 cudaError_t launch_fft_rows_fwd256(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s) {
   switch (c) {
-    case 16: return rows256_fwd_t<8>(w, x, spec, N, H, s);
-    case 32: return rows256_fwd_t<16>(w, x, spec, N, H, s);
-    case 64: return rows256_fwd_t<32>(w, x, spec, N, H, s);
+    case 16: return rows256_fwd_t<8, 16>(w, x, spec, N, H, s);
+    case 32: return rows256_fwd_t<16, 16>(w, x, spec, N, H, s);
+    case 64: return rows256_fwd_t<32, 16>(w, x, spec, N, H, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+// W == 128
+cudaError_t launch_fft_rows_fwd128(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s) {
+  switch (c) {
+    case 16: return rows256_fwd_t<8, 8>(w, x, spec, N, H, s);
+    case 32: return rows256_fwd_t<16, 8>(w, x, spec, N, H, s);
+    case 64: return rows256_fwd_t<32, 8>(w, x, spec, N, H, s);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -471,6 +471,7 @@ cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* s
                                 cudaStream_t s) {
   if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
   if (W == 256 && pre_ln && H % 4 == 0 && !stockham_only()) return launch_fft_rows_fwd256(w, c, x, spec, N, H, s);
+  if (W == 128 && pre_ln && H % 8 == 0 && !stockham_only()) return launch_fft_rows_fwd128(w, c, x, spec, N, H, s);
   switch (c) {
     case 16: return rows_fwd_t<8>(w, x, spec, pre_ln, N, H, W, s);
     case 32: return rows_fwd_t<16>(w, x, spec, pre_ln, N, H, W, s);
