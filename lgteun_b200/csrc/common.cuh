@@ -88,6 +88,8 @@ cudaError_t launch_fft_rows_fwd256(const BlockW& w, int c, const float* x, float
 cudaError_t launch_fft_rows_fwd128(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s);   // W = 128
 cudaError_t launch_fft_rows_inv256(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
                                    int N, int H, cudaStream_t s);
+cudaError_t launch_fft_rows_inv128(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
+                                   int N, int H, cudaStream_t s);   // W = 128
 // ffn.cu
 size_t ffn_hidden_floats(int N, int H, int W, int c);
 cudaError_t launch_ffn(const BlockW& w, int c, const float* x, float* hidden, float* y, int N, int H, int W,

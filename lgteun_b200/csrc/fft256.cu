@@ -218,9 +218,7 @@ namespace lg {
 // (sequence, low index), M threads per sequence.  Same two-pass split as the column kernel (n = M n1 + n2).
 // A sequence occupies 16 (M + 1) slots: inputs are stored with one pad slot per M samples (conflict-free stride-M reads),
 // the exchange between the passes is [k1][M + 1], the result comes back in natural order — all in the same storage.
-constexpr int kRowPad = 272;                              // M = 16
 template <int M> __device__ __forceinline__ int padded_m(int i) { return i + i / M; }
-__device__ __forceinline__ int padded(int i) { return padded_m<16>(i); }
 
 template <int C2, bool PRE_LN, int M>
 __global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __restrict__ x, float2* __restrict__ spec,
@@ -309,23 +307,24 @@ __global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __res
 // tensor cores (split-fp16 3xMMA, see tc_ptx.cuh): a 128-pixel tile of the concatenated map is written to shared memory
 // as the A operand, the accumulator comes back from TMEM for the bias + residual epilogue.  (The CUDA-core matvec this
 // replaces was 60 % of the kernel and stalled on shared-memory latency.)
-template <int C2>
+template <int C2, int M>
 __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __restrict__ spec, const float* __restrict__ local,
                                                                const float* __restrict__ xres, float* __restrict__ y,
                                                                BlockW w, float scale) {
   using namespace f256;
   using namespace tc;
-  constexpr int W = 256, Wf = 129;
-  constexpr int NF1 = C2 / 2, RW = 16 / NF1, C = 2 * C2;
-  constexpr int TILES = RW * 2;                           // 128-pixel tiles per CTA, two in flight (warps 0-3 / 4-7)
+  constexpr int W = 16 * M, Wf = W / 2 + 1, RP = 16 * (M + 1), NSEQ = 256 / M, KPT = 16 / M, TS = 16 / M;
+  constexpr int NF1 = C2 / 2, RW = NSEQ / NF1, C = 2 * C2;
+  static_assert(RW >= 1 && (RW * W) % 256 == 0, "a CTA holds whole rows and an even number of 128-pixel tiles");
+  constexpr int TILES = RW * W / 128;                     // 128-pixel tiles per CTA, two in flight (warps 0-3 / 4-7)
   constexpr uint32_t TCOLS = (2 * C < 32) ? 32 : 2 * C;   // TMEM columns: two accumulators of C columns
   __shared__ float2 tw[256];
   __shared__ uint64_t mbar[2];                            // one MMA-completion barrier per tile in flight
   __shared__ uint32_t tmem_slot;
   extern __shared__ __align__(16) float2 smf[];
-  float2* X = smf;                                        // [16][kRowPad]
-  float2* E = smf;                                        // [16][272] exchange, same storage
-  __half* wh = reinterpret_cast<__half*>(smf + 16 * kRowPad);   // proj weight hi [C/8][C][8], then lo
+  float2* X = smf;                                        // [NSEQ][RP]
+  float2* E = smf;                                        // exchange, same storage
+  __half* wh = reinterpret_cast<__half*>(smf + NSEQ * RP);      // proj weight hi [C/8][C][8], then lo
   __half* wl = wh + C * C;
   __half* ah = wl + C * C;                                // A operand: [2 tiles][hi | lo][C/8][128][8]
   float* sBias = reinterpret_cast<float*>(ah + 2 * 2 * 128 * C);
@@ -360,10 +359,10 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
       const int k = rem / NF1, s = rl * NF1 + (rem - k * NF1);
       const float4 v = vb[i];                             // (Xa.re, Xa.im, Xb.re, Xb.im)
       if (k == 0 || k == W / 2) {
-        X[s * kRowPad + padded(k)] = make_float2(v.x, v.z);
+        X[s * RP + padded_m<M>(k)] = make_float2(v.x, v.z);
       } else {
-        X[s * kRowPad + padded(k)] = make_float2(v.x - v.w, v.y + v.z);           // Xa + i Xb
-        X[s * kRowPad + padded(W - k)] = make_float2(v.x + v.w, v.z - v.y);       // conj(Xa) + i conj(Xb)
+        X[s * RP + padded_m<M>(k)] = make_float2(v.x - v.w, v.y + v.z);           // Xa + i Xb
+        X[s * RP + padded_m<M>(W - k)] = make_float2(v.x + v.w, v.z - v.y);       // conj(Xa) + i conj(Xb)
       }
     }
   }
@@ -371,24 +370,29 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const int seq = tid >> 4, lo = tid & 15;
+  const int seq = tid / M, lo = tid % M;
   float2 v[16];
 #pragma unroll
-  for (int m1 = 0; m1 < 16; ++m1) v[m1] = X[seq * kRowPad + 17 * m1 + lo];
+  for (int m1 = 0; m1 < 16; ++m1) v[m1] = X[seq * RP + (M + 1) * m1 + lo];
   fft16<+1>(v);
 #pragma unroll
-  for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[lo * j1]);
-  __syncwarp();                                           // a sequence = one half-warp + its own region: warp-level hand-offs
+  for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[TS * lo * j1]);
+  __syncwarp();                                           // a sequence = M lanes of one warp + its own region: warp-level hand-offs
 #pragma unroll
-  for (int j1 = 0; j1 < 16; ++j1) E[seq * 272 + j1 * 17 + lo] = v[j1];
+  for (int j1 = 0; j1 < 16; ++j1) E[seq * RP + j1 * (M + 1) + lo] = v[j1];
   __syncwarp();
 #pragma unroll
-  for (int m2 = 0; m2 < 16; ++m2) v[m2] = E[seq * 272 + lo * 17 + m2];
-  fft16<+1>(v);                                           // v[j2] = (xa + i xb)[lo + 16 j2], unnormalised
+  for (int kk = 0; kk < KPT; ++kk) {
+#pragma unroll
+    for (int m2 = 0; m2 < M; ++m2) v[kk * M + m2] = E[seq * RP + (lo + M * kk) * (M + 1) + m2];
+    fft_m<M, +1>(v + kk * M);                             // v[kk*M + j2] = (xa + i xb)[(lo + M kk) + 16 j2], unnormalised
+  }
   __syncwarp();
 #pragma unroll
-  for (int j2 = 0; j2 < 16; ++j2)
-    X[seq * kRowPad + lo + 16 * j2] = make_float2(fabsf(v[j2].x * scale), fabsf(v[j2].y * scale));
+  for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+    for (int j2 = 0; j2 < M; ++j2)
+      X[seq * RP + (lo + M * kk) + 16 * j2] = make_float2(fabsf(v[kk * M + j2].x * scale), fabsf(v[kk * M + j2].y * scale));
   __syncthreads();
   // phase 3: concat(local, global) -> proj 1x1 (tensor cores) -> + bias + residual
   const int t = warp >> 2;                                // which of the two tiles in flight
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
   uint32_t phase = 0;
 #pragma unroll 1
   for (int round = 0; round < TILES / 2; ++round) {
-    const int p = (round * 2 + t) * 128 + trow, rl = p >> 8, px = p & 255;
+    const int p = (round * 2 + t) * 128 + trow, rl = p / W, px = p % W;
     const size_t pix = (row0 + rl) * W + px;
     {
       const float4* lsrc = reinterpret_cast<const float4*>(local + pix * C2);
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
       for (int kc = 0; kc < C2 / 8; ++kc) {               // global half: channels [C2, C), pairs (2f, 2f+1) per sequence
         float2 q[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) q[i] = X[(rl * NF1 + 4 * kc + i) * kRowPad + px];
+        for (int i = 0; i < 4; ++i) q[i] = X[(rl * NF1 + 4 * kc + i) * RP + px];
         uint4 hi, lo4;
         split8(q, hi, lo4);
         *reinterpret_cast<uint4*>(a_hi + ((C2 / 8 + kc) * 128 + trow) * 8) = hi;
@@ -478,15 +482,16 @@ static cudaError_t rows256_fwd_t(const BlockW& w, const float* x, float* spec, i
   fft_rows_fwd256_kernel<C2, true, M><<<N * H / RW, 256, smem, s>>>(x, reinterpret_cast<float2*>(spec), w);
   return cudaGetLastError();
 }
-template <int C2>
+template <int C2, int M>
 static cudaError_t rows256_inv_t(const BlockW& w, const float* spec, const float* local, const float* xres, float* y, int N,
                                  int H, cudaStream_t s) {
-  constexpr int RW = 16 / (C2 / 2), C = 2 * C2;
-  const size_t smem = (size_t)(16 * kRowPad) * sizeof(float2) + (size_t)(2 * C * C + 2 * 2 * 128 * C) * 2 + (size_t)C * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(fft_rows_inv256_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int RW = (256 / M) / (C2 / 2), C = 2 * C2;
+  if (H % RW) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(256 / M) * 16 * (M + 1) * sizeof(float2) + (size_t)(2 * C * C + 2 * 2 * 128 * C) * 2 + (size_t)C * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_inv256_kernel<C2, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  fft_rows_inv256_kernel<C2><<<N * H / RW, 256, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
-                                                           1.0f / ((float)H * 256.0f));
+  fft_rows_inv256_kernel<C2, M><<<N * H / RW, 256, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
+                                                              1.0f / ((float)H * (float)(16 * M)));
   return cudaGetLastError();
 }
 
@@ -511,9 +516,19 @@ cudaError_t launch_fft_rows_fwd128(const BlockW& w, int c, const float* x, float
 cudaError_t launch_fft_rows_inv256(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
                                    int N, int H, cudaStream_t s) {
   switch (c) {
-    case 16: return rows256_inv_t<8>(w, spec, local, xres, y, N, H, s);
-    case 32: return rows256_inv_t<16>(w, spec, local, xres, y, N, H, s);
-    case 64: return rows256_inv_t<32>(w, spec, local, xres, y, N, H, s);
+    case 16: return rows256_inv_t<8, 16>(w, spec, local, xres, y, N, H, s);
+    case 32: return rows256_inv_t<16, 16>(w, spec, local, xres, y, N, H, s);
+    case 64: return rows256_inv_t<32, 16>(w, spec, local, xres, y, N, H, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+// W == 128
+cudaError_t launch_fft_rows_inv128(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
+                                   int N, int H, cudaStream_t s) {
+  switch (c) {
+    case 16: return rows256_inv_t<8, 8>(w, spec, local, xres, y, N, H, s);
+    case 32: return rows256_inv_t<16, 8>(w, spec, local, xres, y, N, H, s);
+    case 64: return rows256_inv_t<32, 8>(w, spec, local, xres, y, N, H, s);
     default: return cudaErrorInvalidValue;
   }
 }

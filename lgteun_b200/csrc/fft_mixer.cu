@@ -534,6 +534,7 @@ cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const
                                 int proj, int N, int H, int W, cudaStream_t s) {
   if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
   if (W == 256 && proj && H % 4 == 0 && !stockham_only()) return launch_fft_rows_inv256(w, c, spec, local, xres, y, N, H, s);
+  if (W == 128 && proj && H % 8 == 0 && !stockham_only()) return launch_fft_rows_inv128(w, c, spec, local, xres, y, N, H, s);
   switch (c) {
     case 16: return rows_inv_t<8>(w, spec, local, xres, y, proj, N, H, W, s);
     case 32: return rows_inv_t<16>(w, spec, local, xres, y, proj, N, H, W, s);
