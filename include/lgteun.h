@@ -140,6 +140,53 @@ int lgteun_op_normalize(lgteun_t* ctx, const float* raw, float* out, int64_t n, 
 int lgteun_op_to_nhwc(lgteun_t* ctx, const float* nchw, float* nhwc, int N, int C, int H, int W, float scale,
                       void* stream);
 
+/* ---- training step (BASELINE.json configs[4]) ----------------------------------------------------
+ * UnlgFormer.train_iter (models/unlg_former.py:87-113): output = G(lr, pan) in train() mode, rec_loss = nn.L1Loss
+ * (models/base/losses.py:19-40) * loss_cfg.rec_loss.w, zero_grad / backward / Adam.step (base_model.py:116-131).
+ *
+ * Parameters and gradients live in ONE flat fp32 device buffer each, laid out as the handle's weight table:
+ * weight i occupies [lgteun_weight_offset(i), +lgteun_weight_numel(i)) of lgteun_flat_numel() floats (offsets are
+ * 16-byte aligned; padding floats are never read and get zero gradient).  Data-parallel training all-reduces the flat
+ * gradient once per step.  As in the reference only prior_module[K-1] reaches the output
+ * (unlg_former.py:63-67): the other priors are not executed and their gradient is zero (torch: .grad is None). */
+int64_t lgteun_flat_numel(const lgteun_t* ctx);
+int64_t lgteun_weight_offset(const lgteun_t* ctx, int i);
+
+/* Bytes of the activation tape + backward scratch for one step of this size (allocated lazily by train_forward). */
+int64_t lgteun_train_workspace_bytes(lgteun_t* ctx, int N, int h, int w);
+
+/* Pansharpening.forward in train() mode (models/unlg_former.py:50-67 with nn.Dropout(dropout_p) after the mixer
+ * projection, LGT.py:198,216; dropout_p = 0 gives the eval-mode function).  Reads the weights from flat_param (NOT from
+ * lgteun_load_weights' snapshot) and records the activations the backward needs inside the handle.  The keep mask of
+ * LGB block `layer` (0,1 encoder; 2 bottleneck; 3,4 decoder) is a counter-based hash of (seed, layer, NHWC element
+ * index); lgteun_dropout_mask returns the same mask (values 0 or 1/(1-p)) for parity tests. */
+int lgteun_train_forward(lgteun_t* ctx, const float* flat_param, const float* ms, const float* pan, float* out,
+                         int N, int h, int w, float dropout_p, uint64_t seed, void* stream);
+
+/* loss.backward() for the tape of the last lgteun_train_forward: dout [N,B,4h,4w] is dLoss/dOutput; flat_grad
+ * (lgteun_flat_numel floats) is OVERWRITTEN with dLoss/dParameters (zero_grad + backward).  flat_param, ms and pan of the
+ * forward must still be valid and unchanged.  One backward per forward. */
+int lgteun_train_backward(lgteun_t* ctx, const float* dout, float* flat_grad, void* stream);
+
+/* Kernels launched by the last train_forward + train_backward pair. */
+int lgteun_train_launches(const lgteun_t* ctx);
+
+/* ReconstructionLoss('l1') (models/base/losses.py:29,39) times `weight`: loss_dev[0] = weight * mean|out - gt|;
+ * dout (may be NULL) = its gradient wrt out.  n = element count. */
+int lgteun_l1_loss(lgteun_t* ctx, const float* out, const float* gt, int64_t n, float weight, float* loss_dev,
+                   float* dout, void* stream);
+
+/* torch.optim.Adam.step (base_model.py:121-122; no weight decay / amsgrad) fused over a flat buffer: grad is multiplied
+ * by grad_scale first (1/world_size after a summing all-reduce); step counts from 1. */
+int lgteun_adam_step(lgteun_t* ctx, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+int lgteun_dropout_mask(lgteun_t* ctx, uint64_t seed, int layer, float p, float* mask_out, int64_t n, void* stream);
+
+/* Replay a recorded step: masks = five device pointers (NHWC [N,H,W,c] of each LGB block in execution order, values 0 or
+ * 1/(1-p)) used by the following train_forward / train_backward pairs instead of the generated masks; NULL switches back. */
+int lgteun_train_set_masks(lgteun_t* ctx, const float* const* masks);
+
 #ifdef __cplusplus
 }
 #endif

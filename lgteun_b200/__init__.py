@@ -5,6 +5,7 @@ Public surface (mirrors the reference's hot-path interface, models/unlg_former.p
     install(...)                        plug it behind the reference's MODELS registry / UnlgFormer runner
     shard_range / forward_sharded       batch sharding for one-process-per-GPU inference
     forward_scene / plan_tiles          overlap-tile driver for scenes larger than one tile
+    Trainer / FlatParameters            the training step (train-mode forward, L1, backward, all-reduce, Adam)
 The compute lives in lgteun_b200/csrc (CUDA) behind the C ABI of include/lgteun.h."""
 from . import _abi
 from .module import Pansharpening, expected_state_dict_keys, param_count
@@ -12,6 +13,7 @@ from .register import install
 from .hostio import HostPipeline
 from .sharding import forward_sharded, shard_range
 from .scene import forward_scene, plan_tiles
+from .train import FlatParameters, Trainer
 
-__all__ = ["Pansharpening", "install", "shard_range", "forward_sharded", "forward_scene", "plan_tiles", "HostPipeline", "expected_state_dict_keys", "param_count", "_abi"]
+__all__ = ["Pansharpening", "install", "shard_range", "forward_sharded", "forward_scene", "plan_tiles", "HostPipeline", "Trainer", "FlatParameters", "expected_state_dict_keys", "param_count", "_abi"]
 __version__ = "0.1.0"

@@ -39,6 +39,18 @@ SIGNATURES = {
     "lgteun_op_metrics": (c_int, [c_void_p, _F, _F, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_void_p]),
     "lgteun_op_normalize": (c_int, [c_void_p, _F, _F, c_int64, ctypes.c_float, c_void_p]),
     "lgteun_op_to_nhwc": (c_int, [c_void_p, _F, _F, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p]),
+    # training step
+    "lgteun_flat_numel": (c_int64, [c_void_p]),
+    "lgteun_weight_offset": (c_int64, [c_void_p, c_int]),
+    "lgteun_train_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int]),
+    "lgteun_train_forward": (c_int, [c_void_p, _F, _F, _F, _F, c_int, c_int, c_int, ctypes.c_float, ctypes.c_uint64, c_void_p]),
+    "lgteun_train_backward": (c_int, [c_void_p, _F, _F, c_void_p]),
+    "lgteun_train_launches": (c_int, [c_void_p]),
+    "lgteun_l1_loss": (c_int, [c_void_p, _F, _F, c_int64, ctypes.c_float, _F, _F, c_void_p]),
+    "lgteun_adam_step": (c_int, [c_void_p, _F, _F, _F, _F, c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                 ctypes.c_float, c_int, ctypes.c_float, c_void_p]),
+    "lgteun_dropout_mask": (c_int, [c_void_p, ctypes.c_uint64, c_int, ctypes.c_float, _F, c_int64, c_void_p]),
+    "lgteun_train_set_masks": (c_int, [c_void_p, POINTER(c_void_p)]),
 }
 
 _lib = None
@@ -118,6 +130,43 @@ class Handle:
 
     def workspace_bytes(self, N, h, w):
         return lib().lgteun_workspace_bytes(self._p, N, h, w)
+
+    # -- training step -----------------------------------------------------------------------------------------
+    def flat_numel(self):
+        return lib().lgteun_flat_numel(self._p)
+
+    def flat_layout(self):
+        """[(state_dict key, offset in floats, numel)] of the flat parameter / gradient buffers."""
+        n = lib().lgteun_num_weights(self._p)
+        return [(lib().lgteun_weight_name(self._p, i).decode(), lib().lgteun_weight_offset(self._p, i),
+                 lib().lgteun_weight_numel(self._p, i)) for i in range(n)]
+
+    def train_forward(self, flat_param_ptr, ms_ptr, pan_ptr, out_ptr, N, h, w, dropout_p=0.1, seed=0, stream=0):
+        check(lib().lgteun_train_forward(self._p, flat_param_ptr, ms_ptr, pan_ptr, out_ptr, N, h, w, dropout_p, seed,
+                                         c_void_p(stream)))
+
+    def train_backward(self, dout_ptr, flat_grad_ptr, stream=0):
+        check(lib().lgteun_train_backward(self._p, dout_ptr, flat_grad_ptr, c_void_p(stream)))
+
+    def train_launches(self):
+        return lib().lgteun_train_launches(self._p)
+
+    def l1_loss(self, out_ptr, gt_ptr, n, weight, loss_ptr, dout_ptr, stream=0):
+        check(lib().lgteun_l1_loss(self._p, out_ptr, gt_ptr, n, weight, loss_ptr, dout_ptr, c_void_p(stream)))
+
+    def adam_step(self, p_ptr, g_ptr, m_ptr, v_ptr, n, lr, beta1, beta2, eps, step, grad_scale=1.0, stream=0):
+        check(lib().lgteun_adam_step(self._p, p_ptr, g_ptr, m_ptr, v_ptr, n, lr, beta1, beta2, eps, step, grad_scale,
+                                     c_void_p(stream)))
+
+    def dropout_mask(self, seed, layer, p, out_ptr, n, stream=0):
+        check(lib().lgteun_dropout_mask(self._p, seed, layer, p, out_ptr, n, c_void_p(stream)))
+
+    def set_masks(self, ptrs):
+        if ptrs is None:
+            check(lib().lgteun_train_set_masks(self._p, None))
+        else:
+            arr = (c_void_p * 5)(*ptrs)
+            check(lib().lgteun_train_set_masks(self._p, arr))
 
     def op(self, name, *args, stream=0):
         check(getattr(lib(), "lgteun_op_" + name)(self._p, *args, c_void_p(stream)))

@@ -9,81 +9,19 @@
 #include <string>
 #include <vector>
 
-#include "../../include/lgteun.h"
-#include "common.cuh"
+#include "ctx.cuh"
 
 using namespace lg;
 
-namespace {
+using namespace lgctx;
 
-thread_local std::string g_err;
-
-int fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
+namespace lgctx {
+std::string& err_slot() {
+  thread_local std::string e;
+  return e;
 }
-int fail_cuda(cudaError_t e, const char* what) {
-  g_err = std::string(what) + ": " + cudaGetErrorString(e);
-  return LGTEUN_ECUDA;
-}
-#define CK(call)                                         \
-  do {                                                   \
-    cudaError_t e_ = (call);                             \
-    if (e_ != cudaSuccess) return fail_cuda(e_, #call);  \
-  } while (0)
-
-struct WeightSlot {
-  std::string name;
-  int64_t numel;
-  const float** slot;   // where the arena pointer is published
-  size_t offset;        // floats from the arena base
-};
-
-struct Derived {        // arena regions computed from loaded tensors
-  const float* const* src;
-  const float** dst;
-  int rows, cols;       // transpose [rows][cols] -> [cols][rows]; rows == 0: pos_emb transpose; rows == -1: FFN fp16 pack
-  size_t offset;
-  const BlockW* blk;    // FFN pack only: the block whose f0/f1/f2 weights are packed, cols = channels
-};
-
-struct Workspace {      // bump-allocated views for one problem size
-  float *ms, *pan, *out;          // staging copies of the caller's tensors (graph replays use fixed addresses)
-  float *zA, *zB, *resid;
-  float *X0, *X1, *X2;            // full-res NHWC maps
-  float *L0, *L1;                 // half-res NHWC maps (2C channels)
-  float *loc, *spec, *hidden;
-};
-
-struct GraphEntry {
-  int N, h, w, flags;
-  cudaGraph_t graph;              // kept alive: the copy-node handles below belong to it
-  cudaGraphExec_t exec;
-  cudaGraphNode_t n_ms, n_pan, n_out;
-  const float *ms, *pan;
-  float* out;
-  int launches;
-};
-
-}  // namespace
-
-struct lgteun_ctx {
-  int device, B, C, K;
-  DataW dw;
-  PriorW prior[kMaxStages];
-  std::vector<WeightSlot> slots;
-  std::vector<Derived> derived;
-  float* arena = nullptr;
-  size_t arena_floats = 0;
-  bool loaded = false;
-  float* ws_base = nullptr;
-  size_t ws_bytes = 0;
-  std::vector<GraphEntry> graphs;
-  cudaStream_t cap_stream = nullptr;   // capture never runs on the caller's stream (it may be the legacy stream)
-  double* metric_acc = nullptr;        // scratch of lgteun_op_metrics
-  size_t metric_acc_doubles = 0;
-  int last_launches = 0;
-};
+}  // namespace lgctx
+#define g_err (lgctx::err_slot())
 
 namespace {
 
@@ -127,19 +65,19 @@ void add_block(lgteun_ctx* c, const std::string& p, BlockW* b, int ch) {
 void build_table(lgteun_ctx* c) {
   const int B = c->B, C = c->C;
   const char* dn[4] = {"D.1", "D.3", "DT.1", "DT.3"};
-  const float** dwp[4] = {&c->dw.d1_w, &c->dw.d3_w, &c->dw.dt1_w, &c->dw.dt3_w};
-  const float** dbp[4] = {&c->dw.d1_b, &c->dw.d3_b, &c->dw.dt1_b, &c->dw.dt3_b};
+  const float** dwp[4] = {&c->wv.dw.d1_w, &c->wv.dw.d3_w, &c->wv.dw.dt1_w, &c->wv.dw.dt3_w};
+  const float** dbp[4] = {&c->wv.dw.d1_b, &c->wv.dw.d3_b, &c->wv.dw.dt1_b, &c->wv.dw.dt3_b};
   for (int i = 0; i < 4; ++i) {
     add_slot(c, std::string(dn[i]) + ".weight", B * 9, dwp[i]);
     add_slot(c, std::string(dn[i]) + ".bias", B, dbp[i]);
   }
-  add_slot(c, "R.weight", B, &c->dw.r_w);
-  add_slot(c, "R.bias", 1, &c->dw.r_b);
-  add_slot(c, "RT.weight", B, &c->dw.rt_w);
-  add_slot(c, "RT.bias", B, &c->dw.rt_b);
-  for (int i = 0; i < c->K; ++i) add_slot(c, "eta." + std::to_string(i), 1, &c->dw.eta[i]);
+  add_slot(c, "R.weight", B, &c->wv.dw.r_w);
+  add_slot(c, "R.bias", 1, &c->wv.dw.r_b);
+  add_slot(c, "RT.weight", B, &c->wv.dw.rt_w);
+  add_slot(c, "RT.bias", B, &c->wv.dw.rt_b);
+  for (int i = 0; i < c->K; ++i) add_slot(c, "eta." + std::to_string(i), 1, &c->wv.dw.eta[i]);
   for (int i = 0; i < c->K; ++i) {
-    PriorW* p = &c->prior[i];
+    PriorW* p = &c->wv.prior[i];
     const std::string pre = "prior_module." + std::to_string(i);
     add_slot(c, pre + ".patch_embed.proj.0.weight", B, &p->pe_dw_w);
     add_slot(c, pre + ".patch_embed.proj.0.bias", B, &p->pe_dw_b);
@@ -162,6 +100,7 @@ void build_table(lgteun_ctx* c) {
   }
   size_t off = 0;
   for (auto& s : c->slots) { s.offset = off; off += align4((size_t)s.numel); }
+  c->flat_floats = off;
   for (auto& d : c->derived) {
     d.offset = off;
     size_t floats = d.rows > 0 ? (size_t)d.rows * d.cols : d.rows == 0 ? 2 * 64 * 64
@@ -313,7 +252,7 @@ void run_block(Launcher& L, const BlockW& b, int ch, float* a, float* t, const W
 // LGT.forward (LGT.py:314-344)
 void run_prior(Launcher& L, const lgteun_ctx* c, int i, const float* zin, float* zout, const Workspace& ws, int N, int H,
                int W, cudaStream_t s) {
-  const PriorW& p = c->prior[i];
+  const PriorW& p = c->wv.prior[i];
   const int C = c->C;
   LG_L(L, 0, launch_patch_embed(p, c->B, zin, ws.X0, N, H, W, s));
   for (int j = 0; j < 2; ++j) run_block(L, p.enc[j], C, ws.X0, ws.X1, ws, N, H, W, s);       // skip = X0
@@ -333,7 +272,7 @@ cudaError_t run_forward(const lgteun_ctx* c, const float* ms, const float* pan, 
   LG_L(L, 0, launch_bicubic(ms, ws.zA, N * c->B, h, w, 4, 1, s));
   float *za = ws.zA, *zb = ws.zB;
   for (int i = 0; i < c->K; ++i) {
-    LG_L(L, 0, launch_data_step(c->dw, i, c->B, za, ms, pan, ws.resid, zb, N, h, w, s), 2);
+    LG_L(L, 0, launch_data_step(c->wv.dw, i, c->B, za, ms, pan, ws.resid, zb, N, h, w, s), 2);
     float* t = za; za = zb; zb = t;
     const bool last = (i == c->K - 1);
     // the reference discards the priors of stages 0..K-2 (unlg_former.py:63-67); run them only on request
@@ -368,8 +307,8 @@ int lgteun_create(int device, int bands, int stages, lgteun_t** out) {
                                    std::to_string(prop.major) + std::to_string(prop.minor));
   lgteun_ctx* c = new lgteun_ctx();
   c->device = device; c->B = bands; c->C = 4 * bands; c->K = stages;
-  memset(&c->dw, 0, sizeof(c->dw));
-  memset(c->prior, 0, sizeof(c->prior));
+  memset(&c->wv.dw, 0, sizeof(c->wv.dw));
+  memset(c->wv.prior, 0, sizeof(c->wv.prior));
   build_table(c);
   cudaError_t e = cudaMalloc(&c->arena, c->arena_floats * sizeof(float));
   if (e != cudaSuccess) { delete c; return fail_cuda(e, "cudaMalloc(weight arena)"); }
@@ -386,6 +325,7 @@ void lgteun_destroy(lgteun_t* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   drop_graphs(c);
+  lgctx::train_destroy(c);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->metric_acc) cudaFree(c->metric_acc);
   if (c->ws_base) cudaFree(c->ws_base);
@@ -584,7 +524,7 @@ int lgteun_forward_host(lgteun_t* c, const float* ms_host, const float* pan_host
 // ---- per-operator entry points ----------------------------------------------------------------------------
 static const BlockW* pick_block(const lgteun_ctx* c, int prior, int lgb, int block, int* ch) {
   if (prior < 0 || prior >= c->K) return nullptr;
-  const PriorW& p = c->prior[prior];
+  const PriorW& p = c->wv.prior[prior];
   if (lgb == 0 && block >= 0 && block < 2) { *ch = c->C; return &p.enc[block]; }
   if (lgb == 1 && block == 0) { *ch = 2 * c->C; return &p.bott[0]; }
   if (lgb == 2 && block >= 0 && block < 2) { *ch = c->C; return &p.dec[block]; }
@@ -625,14 +565,14 @@ int lgteun_op_data_step(lgteun_t* c, int stage, const float* z_in, const float* 
   Workspace ws;
   rc = ensure_ws(c, N, h, w, &ws);
   if (rc) return rc;
-  CK(launch_data_step(c->dw, stage, c->B, z_in, ms, pan, ws.resid, z_out, N, h, w, s));
+  CK(launch_data_step(c->wv.dw, stage, c->B, z_in, ms, pan, ws.resid, z_out, N, h, w, s));
   return 0;
 }
 
 int lgteun_op_patch_embed(lgteun_t* c, int prior, const float* x, float* y, int N, int H, int W, void* stream) {
   OP_PROLOGUE
   if (prior < 0 || prior >= c->K || N <= 0 || H <= 0 || W <= 0) return fail(LGTEUN_EINVAL, "bad argument");
-  CK(launch_patch_embed(c->prior[prior], c->B, x, y, N, H, W, s));
+  CK(launch_patch_embed(c->wv.prior[prior], c->B, x, y, N, H, W, s));
   return 0;
 }
 

@@ -162,12 +162,35 @@ class Pansharpening(nn.Module):
         self.eta = nn.ParameterList([nn.Parameter(torch.tensor(0.1)) for _ in range(self.stage)])   # :40
         self.prior_module = nn.ModuleList([_lgt(b) for _ in range(self.stage)])              # :42-48
         self._rt: Dict[int, dict] = {}      # device index -> {"handle", "sig"}; runtime only, never pickled
+        self._flat = None                   # train.FlatParameters once a training-mode forward has run
+        self.dropout_p = 0.1                # nn.Dropout(0.1) after the mixer projection (LGT.py:198)
+        self._train_calls = 0
 
     # -- pickling / replication: runtime handles are per process ------------------------------------------
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_rt"] = {}
+        state["_flat"] = None
         return state
+
+    def _invalidate_runtime(self):
+        """Parameters were changed behind autograd's back (fused optimizer step): re-snapshot on the next eval forward."""
+        for rt in self._rt.values():
+            rt["sig"] = None
+
+    def _flat_parameters(self):
+        """The flat parameter / gradient buffers of the training step (created on first use; rebuilt if the parameters
+        were moved, e.g. by .to() or a fresh load of the module)."""
+        from .train import FlatParameters
+        flat = self._flat
+        if flat is not None:
+            base = flat.param.data_ptr()
+            params = dict(self.named_parameters())
+            if not all(params[k].data_ptr() == base + 4 * off for k, off, _ in flat.layout):
+                flat = None
+        if flat is None:
+            flat = self._flat = FlatParameters(self)
+        return flat
 
     # -- runtime ---------------------------------------------------------------------------------------------
     def _weight_items(self):
@@ -215,14 +238,23 @@ class Pansharpening(nn.Module):
             raise RuntimeError("lgteun_b200.Pansharpening runs on CUDA (sm_100a) tensors only; there is no CPU path")
         if ms.dtype != torch.float32 or pan.dtype != torch.float32:
             raise TypeError("ms and pan must be float32")
-        if self.training:
-            raise NotImplementedError("training-mode forward is not built: the reference applies Dropout(0.1) after the mixer "
-                                      "projection in train() mode (models/common/LGT.py:198,216); call .eval() as the "
-                                      "reference's test loop does (models/base/base_model.py:277-278)")
-        if torch.is_grad_enabled() and (ms.requires_grad or pan.requires_grad or
-                                        any(t.requires_grad for _, t in self._weight_items())):
-            raise NotImplementedError("the backward of the fused forward is not built yet (SURVEY.md §8f rank 1): "
-                                      "call under torch.no_grad() / after requires_grad_(False)")
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for _, t in self._weight_items())
+        if self.training or needs_grad:
+            # train_iter path (models/unlg_former.py:94): Dropout(0.1) is active in train() mode (LGT.py:198,216) and the
+            # output carries the autograd graph of the hand-written backward (train.cu)
+            if ms.requires_grad or pan.requires_grad:
+                raise NotImplementedError("gradients with respect to ms / pan are not computed (the reference never needs them)")
+            if not self._parameters and not any(True for _ in self.parameters()):
+                raise NotImplementedError("training inside nn.DataParallel replicas is not supported: use lgteun_b200.Trainer "
+                                          "with one process per GPU (torch.distributed)")
+            from .train import autograd_forward
+            self._train_calls += 1
+            p = self.dropout_p if self.training else 0.0
+            seed = (torch.initial_seed() + self._train_calls) & 0x7FFFFFFFFFFFFFFF
+            if not needs_grad:
+                with torch.no_grad():
+                    return autograd_forward(self, ms, pan, p, seed)
+            return autograd_forward(self, ms, pan, p, seed)
         with torch.cuda.device(ms.device):
             handle = self._runtime(ms.device)
             ms_c, pan_c = ms.contiguous(), pan.contiguous()

@@ -139,13 +139,15 @@ def global_mixer(sd: SD, p: str, x: Tensor) -> Tensor:
     return out.permute(0, 2, 3, 1)
 
 
-def lg_mixer(sd: SD, p: str, x: Tensor) -> Tensor:
-    """LGMixer (eval mode: dropout is the identity), LGT.py:200-219."""
+def lg_mixer(sd: SD, p: str, x: Tensor, mask: Optional[Tensor] = None) -> Tensor:
+    """LGMixer, LGT.py:200-219.  ``mask`` (NHWC, values 0 or 1/(1-p)) is the train-mode nn.Dropout(0.1) of LGT.py:198,216
+    applied to the projection output; None = eval mode (identity)."""
     c = x.shape[-1]
     x1 = local_mixer(sd, p + ".local_mixer", x[..., : c // 2].contiguous())
     x2 = global_mixer(sd, p + ".global_mixer", x[..., c // 2:].contiguous())
     out = torch.cat((x1, x2), dim=-1).permute(0, 3, 1, 2)
-    return pconv(sd, p + ".proj", out).permute(0, 2, 3, 1)
+    out = pconv(sd, p + ".proj", out).permute(0, 2, 3, 1)
+    return out if mask is None else out * mask
 
 
 def feed_forward(sd: SD, p: str, x: Tensor) -> Tensor:
@@ -159,29 +161,31 @@ def feed_forward(sd: SD, p: str, x: Tensor) -> Tensor:
     return t.permute(0, 2, 3, 1)
 
 
-def lgb_block(sd: SD, p: str, x: Tensor) -> Tensor:
+def lgb_block(sd: SD, p: str, x: Tensor, mask: Optional[Tensor] = None) -> Tensor:
     """One (mixer, ffn) pair with pre-norm + residual, LGT.py:231-247, :45-61."""
-    x = lg_mixer(sd, p + ".0.fn.fn", layer_norm(sd, p + ".0.fn.norm", x)) + x
+    x = lg_mixer(sd, p + ".0.fn.fn", layer_norm(sd, p + ".0.fn.norm", x), mask) + x
     x = feed_forward(sd, p + ".1.fn.fn", layer_norm(sd, p + ".1.fn.norm", x)) + x
     return x
 
 
-def lgb(sd: SD, p: str, x: Tensor, num_blocks: int) -> Tensor:
+def lgb(sd: SD, p: str, x: Tensor, num_blocks: int, masks: Optional[List[Tensor]] = None) -> Tensor:
     """LGB: num_blocks blocks, NHWC in, NCHW out (LGT.py:240-248)."""
     for j in range(num_blocks):
-        x = lgb_block(sd, f"{p}.blocks.{j}", x)
+        x = lgb_block(sd, f"{p}.blocks.{j}", x, None if masks is None else masks[j])
     return x.permute(0, 3, 1, 2)
 
 
-def lgt(sd: SD, p: str, x: Tensor) -> Tensor:
-    """LGT U-Net with num_block=[2,1] (unlg_former.py:47-48), LGT.py:314-344."""
+def lgt(sd: SD, p: str, x: Tensor, masks: Optional[List[Tensor]] = None) -> Tensor:
+    """LGT U-Net with num_block=[2,1] (unlg_former.py:47-48), LGT.py:314-344.  ``masks``: the five dropout masks of the
+    blocks in execution order (encoder 0, 1; bottleneck; decoder 0, 1), None = eval mode."""
+    m = (lambda a, b: None) if masks is None else (lambda a, b: masks[a:b])
     fea = patch_embed(sd, p + ".patch_embed", x)
-    skip = lgb(sd, p + ".encoder_layers.0.0", fea, 2)                                    # LGT.py:326-327
+    skip = lgb(sd, p + ".encoder_layers.0.0", fea, 2, m(0, 2))                           # LGT.py:326-327
     fea = pconv(sd, p + ".encoder_layers.0.1.1", bicubic(skip, 0.5)).permute(0, 2, 3, 1)  # LGT.py:328-329
-    fea = lgb(sd, p + ".bottleneck", fea, 1)                                             # LGT.py:332
+    fea = lgb(sd, p + ".bottleneck", fea, 1, m(2, 3))                                    # LGT.py:332
     fea = pconv(sd, p + ".decoder_layers.0.0.1", bicubic(fea, 2))                        # LGT.py:336
     fea = pconv(sd, p + ".decoder_layers.0.1", torch.cat([fea, skip], dim=1))            # LGT.py:337-338
-    fea = lgb(sd, p + ".decoder_layers.0.2", fea.permute(0, 2, 3, 1), 2)                 # LGT.py:339
+    fea = lgb(sd, p + ".decoder_layers.0.2", fea.permute(0, 2, 3, 1), 2, m(3, 5))        # LGT.py:339
     return pconv(sd, p + ".tail.1", bicubic(fea, 1)) + x                                 # LGT.py:342
 
 
@@ -209,6 +213,37 @@ def forward(sd: SD, ms: Tensor, pan: Tensor, stages: Optional[int] = None,
             if i == K - 1 or not skip_dead_priors:
                 out = lgt(sd, f"prior_module.{i}", z)                   # unlg_former.py:63
         return out
+
+
+def forward_train(sd: SD, ms: Tensor, pan: Tensor, masks: Optional[List[Tensor]] = None) -> Tensor:
+    """Pansharpening.forward with autograd enabled and the live prior's dropout masks given explicitly (train() mode,
+    unlg_former.py:50-67 + LGT.py:198,216).  Dead priors are skipped: their outputs never reach the loss, so torch leaves
+    their parameters' .grad at None (unlg_former.py:63-67)."""
+    K = num_stages(sd)
+    z = bicubic(ms, 4)
+    for i in range(K):
+        z = data_step(sd, z, ms, pan, i)
+    return lgt(sd, f"prior_module.{K - 1}", z, masks)
+
+
+def train_step_grads(sd: SD, ms: Tensor, pan: Tensor, gt: Tensor, masks: Optional[List[Tensor]] = None,
+                     loss_weight: float = 1.0):
+    """One UnlgFormer.train_iter up to loss.backward() (models/unlg_former.py:87-110): nn.L1Loss(out, gt) * w
+    (models/base/losses.py:29,39; configs/unlg_former.py:88-90).  Returns (out, loss, {key: grad or None})."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    out = forward_train(leaf, ms, pan, masks)
+    loss = F.l1_loss(out, gt) * loss_weight
+    loss.backward()
+    return out.detach(), loss.detach(), {k: v.grad for k, v in leaf.items()}
+
+
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, b1: float = 0.9, b2: float = 0.999,
+              eps: float = 1e-8):
+    """torch.optim.Adam single-tensor update (base_model.py:121-122: Adam(betas=(0.9, 0.999), lr)), no weight decay."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    denom = v.sqrt() / math.sqrt(1 - b2 ** step) + eps
+    return p - (lr / (1 - b1 ** step)) * m / denom, m, v
 
 
 # --------------------------------------------------------------------------------------------
