@@ -330,6 +330,158 @@ def run_ours(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# training step (BASELINE configs[4])
+# ----------------------------------------------------------------------------------------------------------------
+TRAIN_WORKLOADS = {  # name: (bands, h, per-GPU batch, description)
+    "train": (8, 32, 4, "BASELINE configs[4]: training step fwd+bwd+Adam, WV-2 shape x8 bands, PAN 128x128 + LrMS 32x32x8 "
+                        "(reference train patches), batch 4 per GPU (configs/unlg_former.py:48), K=2 stages"),
+    "train256": (8, 64, 4, "BASELINE configs[4] at the eval shape: training step, 8 bands, PAN 256x256 + LrMS 64x64x8, "
+                           "batch 4 per GPU, K=2 stages"),
+}
+
+
+def run_train(args):
+    """pairs/s of UnlgFormer.train_iter (models/unlg_former.py:87-113): train-mode forward, L1 loss, backward, gradient
+    all-reduce over NCCL (N > 1), Adam — lgteun_b200.Trainer.step.  `value`: batches resident in HBM; `e2e`: every step
+    copies ms / pan / gt from pinned host memory and reads the loss back."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import lgteun_b200
+    from lgteun_b200.sharding import max_over_ranks
+
+    bands, h, default_batch, desc = TRAIN_WORKLOADS[args.workload]
+    batch = args.batch or default_batch
+    H = 4 * h
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=2)
+    net.load_state_dict(golden_weights(bands))
+    net = net.to(dev).train()
+    trainer = lgteun_b200.Trainer(net, lr=1.5e-3, betas=(0.9, 0.999), dropout_p=0.1, seed=19971118)
+    gen = torch.Generator().manual_seed(100 + rank)
+    nbuf = 4                                                # rotate a few batches (a fresh batch every step)
+    host = [(torch.rand(batch, bands, h, h, generator=gen).pin_memory(), torch.rand(batch, 1, H, H, generator=gen).pin_memory(),
+             torch.rand(batch, bands, H, H, generator=gen).pin_memory()) for _ in range(nbuf)]
+    devb = [tuple(t.to(dev) for t in hb) for hb in host]
+    stage = tuple(torch.empty_like(t) for t in devb[0])
+    loss_h = torch.zeros(1).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    it = {"i": 0}
+
+    def step_resident():
+        ms, pan, gt = devb[it["i"] % nbuf]
+        it["i"] += 1
+        trainer.step(ms, pan, gt)
+
+    def step_e2e():
+        hb = host[it["i"] % nbuf]
+        it["i"] += 1
+        for d, s in zip(stage, hb):
+            d.copy_(s, non_blocking=True)
+        loss = trainer.step(*stage)
+        loss_h.copy_(loss, non_blocking=True)
+        stream.synchronize()                                # train_iter reads loss.item() every step (unlg_former.py:104-106)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    if not torch.isfinite(trainer.loss).all() or not torch.isfinite(trainer.flat.param).all():
+        raise RuntimeError("non-finite loss / parameters after the timed steps")
+    value = batch * world * args.steps / (ms_total * 1e-3)
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = timed(step_e2e, e2e_steps, 3) if not args.no_e2e else float("nan")
+    launches = trainer.handle.train_launches() + 2          # + L1 loss + Adam
+    line = {
+        "metric": "LGTEUN train step (fwd+bwd+Adam) pairs/sec", "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": batch, "global_batch": batch * world,
+                   "parallelism": f"data parallel x{world}: one NCCL all-reduce of the flat fp32 gradient "
+                                  f"({trainer.flat.grad.numel()} floats) per step" if world > 1 else "single GPU",
+                   "optimizer": "Adam lr=1.5e-3 betas=(0.9,0.999) (configs/unlg_former.py:82-84), dropout 0.1, L1 loss",
+                   "l2": "activation tape per step exceeds the 126 MB L2" if batch * H * H >= 4 * 128 * 128 else "fits L2",
+                   "weights": "reference default init, seed 19971118 (tests/golden)"},
+        "e2e": {"value": batch * world * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(t.numel() for t in host[0]) * 4), "d2h_bytes_per_step": 4,
+                "api": "lgteun_b200.Trainer.step on staged pinned host batches, loss read back every step", "steps": e2e_steps},
+        "gpu_launches": int(launches * args.steps), "clocks": clocks,
+        "loss_after": float(trainer.loss.item()), "train_tape_bytes": int(trainer.handle.train_workspace_bytes(batch, h, h)),
+    }
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_train_reference(args):
+    """CPU arm of the training workloads: the oracle port's train step (torch autograd + torch.optim.Adam over the oracle
+    restatement) on the host cores, a bounded sample (steps of one batch)."""
+    import torch
+    claim_stdout()
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import lgteun_oracle as O
+    bands, h, default_batch, desc = TRAIN_WORKLOADS[args.workload]
+    batch = args.batch or default_batch
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
+    sd = {k: v.clone().requires_grad_(True) for k, v in golden_weights(bands).items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1.5e-3)
+    gen = torch.Generator().manual_seed(100)
+    ms, pan, gt = torch.rand(batch, bands, h, h, generator=gen), torch.rand(batch, 1, 4 * h, 4 * h, generator=gen), \
+        torch.rand(batch, bands, 4 * h, 4 * h, generator=gen)
+    C, H = 4 * bands, 4 * h
+    times = []
+    steps = max(1, min(args.steps, 5))
+    for i in range(max(1, min(args.warmup, 1)) + steps):
+        t0 = time.perf_counter()
+        masks = [(torch.rand(batch, hh, hh, cc, generator=gen) >= 0.1).float() / 0.9
+                 for hh, cc in [(H, C), (H, C), (H // 2, 2 * C), (H, C), (H, C)]]
+        loss = torch.nn.functional.l1_loss(O.forward_train(sd, ms, pan, masks), gt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    t = sorted(times[-steps:])[steps // 2]
+    v = batch / t
+    emit({"metric": "LGTEUN train step (fwd+bwd+Adam) pairs/sec", "value": v, "unit": UNIT, "n_gpus": 0, "steps": steps,
+          "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic", "impl": "reference",
+          "config": {"workload": desc, "batch_per_gpu": batch, "parallelism": f"cpu x{threads} threads"},
+          "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                           "sample": f"{steps} train steps of one batch of {batch} (oracle port: torch CPU autograd + Adam), median"},
+          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return 0
+
+
 def roofline_ffn(handle, bands, batch, H, dev, stream, peaks, args):
     """The dominant kernel: residual(pre_norm(feed_forward)) of a full-resolution block (c = 4*bands at HxH), timed
     on its own with CUDA events on the launch stream right after the timed steps (same shapes, same buffers).
@@ -404,7 +556,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gf2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="gf2", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--skip-dead-priors", action="store_true",
                     help="skip prior_module[0..K-2] whose output the reference discards (identical result)")
@@ -416,6 +568,10 @@ def main():
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload in TRAIN_WORKLOADS:
+        if args.impl == "reference":
+            return run_train_reference(args)
+        return run_train(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

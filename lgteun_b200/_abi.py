@@ -148,6 +148,9 @@ class Handle:
     def train_backward(self, dout_ptr, flat_grad_ptr, stream=0):
         check(lib().lgteun_train_backward(self._p, dout_ptr, flat_grad_ptr, c_void_p(stream)))
 
+    def train_workspace_bytes(self, N, h, w):
+        return lib().lgteun_train_workspace_bytes(self._p, N, h, w)
+
     def train_launches(self):
         return lib().lgteun_train_launches(self._p)
 

