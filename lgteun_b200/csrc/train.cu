@@ -98,33 +98,28 @@ void optin_smem(K kernel, size_t bytes) {
 void pw(Run& R, int act, TV x, int Cin, const float* W, int wso, int wsi, const float* b, TV y, int Cout, size_t NP,
         const TV* add = nullptr, const TV* gate = nullptr) {
   if (R.dry) return;
-  const size_t smem = 64 * (size_t)(Cin + 1) * sizeof(float);
   const TV none{nullptr, 0, 0, 0, 0};
-  if (act) {
-    optin_smem(k_pw<1>, smem);
-    k_pw<1><<<blocks(NP, 64), 256, smem, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, add ? *add : none, add != nullptr,
-                                                gate ? *gate : none, gate != nullptr);
+  const TV a = add ? *add : none, g = gate ? *gate : none;
+  const int ua = add != nullptr, ug = gate != nullptr;
+  if (Cout <= 32) {
+    dim3 grid(blocks(NP, 256), (Cout + 15) / 16);
+    if (act) k_pw<1, 16><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
+    else k_pw<0, 16><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
   } else {
-    optin_smem(k_pw<0>, smem);
-    k_pw<0><<<blocks(NP, 64), 256, smem, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, add ? *add : none, add != nullptr,
-                                                gate ? *gate : none, gate != nullptr);
+    dim3 grid(blocks(NP, 64), (Cout + 63) / 64);
+    if (act) k_pw<1, 64><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
+    else k_pw<0, 64><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
   }
   R.check();
 }
 void pw_wgrad(Run& R, int act, TV x, int Cin, TV dy, int Cout, const float* dW, int wso, int wsi, const float* db, size_t NP) {
   if (R.dry) return;
-  const size_t smem = 32 * (size_t)(Cin + Cout + 2) * sizeof(float);
-  const unsigned chunks = (unsigned)((Cin * Cout + 4095) / 4096);
-  size_t tiles = (NP + 31) / 32;
-  unsigned gx = (unsigned)std::min<size_t>(tiles, std::max<unsigned>(1, 148 * 4 / chunks));
-  dim3 grid(gx, chunks);
-  if (act) {
-    optin_smem(k_pw_wgrad<1>, smem);
-    k_pw_wgrad<1><<<grid, 256, smem, R.s>>>(x, Cin, dy, Cout, const_cast<float*>(dW), wso, wsi, const_cast<float*>(db), NP);
-  } else {
-    optin_smem(k_pw_wgrad<0>, smem);
-    k_pw_wgrad<0><<<grid, 256, smem, R.s>>>(x, Cin, dy, Cout, const_cast<float*>(dW), wso, wsi, const_cast<float*>(db), NP);
-  }
+  const int ci_tiles = (Cin + 63) / 64, co_tiles = (Cout + 63) / 64;
+  const size_t tiles = (NP + 31) / 32;
+  const unsigned gx = (unsigned)std::min<size_t>(tiles, std::max(1, 148 * 4 / (ci_tiles * co_tiles)));
+  dim3 grid(gx, ci_tiles * co_tiles);
+  if (act) k_pw_wgrad<1><<<grid, 256, 0, R.s>>>(x, Cin, dy, Cout, const_cast<float*>(dW), wso, wsi, const_cast<float*>(db), NP, ci_tiles);
+  else k_pw_wgrad<0><<<grid, 256, 0, R.s>>>(x, Cin, dy, Cout, const_cast<float*>(dW), wso, wsi, const_cast<float*>(db), NP, ci_tiles);
   R.check();
 }
 void ln_fwd(Run& R, TV x, int C, const float* g, const float* b, TV y, size_t NP) {
@@ -172,12 +167,12 @@ void attn_fwd(Run& R, int D, const float* qkv, const float* pos, TV out, int N, 
 void attn_bwd(Run& R, int D, const float* qkv, const float* pos, TV dout, float* dqkv, const float* dpos, int N, int H, int W) {
   if (R.dry) return;
   const int nwin = N * (H / 8) * (W / 8);
-  dim3 grid(std::min(nwin, 148 * 2), 2);
-  const size_t smem = (4 * 64 * D + 3 * 64 * 65) * sizeof(float);
+  const unsigned grid = (unsigned)std::min(nwin, 148 * 4);
+  const size_t smem = 2 * (4 * 64 * D + 3 * 64 + 64 * 64) * sizeof(float);
   float* dp = const_cast<float*>(dpos);
-  if (D == 4) { optin_smem(k_attn_bwd<4>, smem); k_attn_bwd<4><<<grid, 64, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
-  else if (D == 8) { optin_smem(k_attn_bwd<8>, smem); k_attn_bwd<8><<<grid, 64, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
-  else { optin_smem(k_attn_bwd<16>, smem); k_attn_bwd<16><<<grid, 64, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
+  if (D == 4) { optin_smem(k_attn_bwd<4>, smem); k_attn_bwd<4><<<grid, 128, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
+  else if (D == 8) { optin_smem(k_attn_bwd<8>, smem); k_attn_bwd<8><<<grid, 128, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
+  else { optin_smem(k_attn_bwd<16>, smem); k_attn_bwd<16><<<grid, 128, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
   R.check();
 }
 int fft_cpb(int L, int c2) {    // channels of one line per block: at most 8192 complex points (64 KB) of shared memory

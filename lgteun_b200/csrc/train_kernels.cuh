@@ -33,118 +33,133 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // ---- pointwise (1x1) convolution:  y[p,co] = sum_ci W[co*wso + ci*wsi] * f(x[p,ci]) + b[co]  (+ add[p,co]) (* gelu'(gate)) -------
 // Forward of bmu.point_conv (basic_module_unformer_v2.py:13-14) with (wso, wsi) = (Cin, 1); its data gradient with the
 // transposed strides (1, Cout_fwd).  ACT = 1 applies the exact GELU to x while staging it (the conv-FFN's activations,
-// LGT.py:97,99, are never stored).
-template <int ACT>
+// LGT.py:97,99, are never stored).  Shared-memory tiled fp32 GEMM: a block owns TPX pixels x TCO output channels
+// (TPX * TCO = 4096), a thread 4 x 4 of them; K (input channels) is streamed in chunks of 32.
+template <int ACT, int TCO>
 __global__ void __launch_bounds__(256) k_pw(TV x, int Cin, const float* __restrict__ W, int wso, int wsi,
                                             const float* __restrict__ b, TV y, int Cout, size_t NP, TV add, int use_add,
                                             TV gate, int use_gate) {
-  extern __shared__ float sm[];
-  constexpr int TPX = 64;
+  constexpr int TPX = 4096 / TCO, KC = 32, NTX = TCO / 4;
+  __shared__ float xs[TPX][KC + 1];
+  __shared__ float ws[KC][TCO + 1];
+  const int tx = threadIdx.x % NTX, ty = threadIdx.x / NTX;
   const size_t p0 = (size_t)blockIdx.x * TPX;
-  const int ldx = Cin + 1;
-  for (int i = threadIdx.x; i < TPX * Cin; i += 256) {
-    int px, ci;
-    if (x.nchw) { px = i % TPX; ci = i / TPX; } else { px = i / Cin; ci = i - px * Cin; }
-    const size_t gp = p0 + px;
-    float v = 0.f;
-    if (gp < NP) { v = x.p[tv_at(x, gp, ci)]; if (ACT) v = gelu_exact(v); }
-    sm[px * ldx + ci] = v;
+  const int co0 = blockIdx.y * TCO;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < Cin; k0 += KC) {
+    for (int i = threadIdx.x; i < TPX * KC; i += 256) {
+      int px, k;
+      if (x.nchw) { px = i % TPX; k = i / TPX; } else { k = i % KC; px = i / KC; }
+      const size_t gp = p0 + px;
+      float v = 0.f;
+      if (gp < NP && k0 + k < Cin) { v = x.p[tv_at(x, gp, k0 + k)]; if (ACT) v = gelu_exact(v); }
+      xs[px][k] = v;
+    }
+    for (int i = threadIdx.x; i < TCO * KC; i += 256) {
+      int co, k;
+      if (wsi == 1) { k = i % KC; co = i / KC; } else { co = i % TCO; k = i / TCO; }
+      ws[k][co] = (co0 + co < Cout && k0 + k < Cin) ? __ldg(W + (size_t)(co0 + co) * wso + (size_t)(k0 + k) * wsi) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < KC; ++k) {
+      float xv[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = xs[ty * 4 + i][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  const int px = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  const size_t gp = p0 + px;
-  const float* xr = sm + px * ldx;
-  for (int co0 = grp * 4; co0 < Cout; co0 += 16) {
-    float acc[4];
-    const float* wr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t gp = p0 + ty * 4 + i;
+    if (gp >= NP) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int co = min(co0 + j, Cout - 1);
-      acc[j] = b ? b[co] : 0.f;
-      wr[j] = W + (size_t)co * wso;
-    }
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float xv = xr[ci];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, __ldg(wr[j] + (size_t)ci * wsi), acc[j]);
-    }
-    if (gp < NP) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int co = co0 + j;
-        if (co < Cout) {
-          float v = acc[j];
-          if (use_gate) v *= gelu_grad(gate.p[tv_at(gate, gp, co)]);
-          if (use_add) v += add.p[tv_at(add, gp, co)];
-          y.p[tv_at(y, gp, co)] = v;
-        }
-      }
+      const int co = co0 + tx * 4 + j;
+      if (co >= Cout) continue;
+      float v = acc[i][j] + (b ? b[co] : 0.f);
+      if (use_gate) v *= gelu_grad(gate.p[tv_at(gate, gp, co)]);
+      if (use_add) v += add.p[tv_at(add, gp, co)];
+      y.p[tv_at(y, gp, co)] = v;
     }
   }
 }
 
 // weight / bias gradient of the same conv:  dW[co*wso + ci*wsi] += sum_p dy[p,co] * f(x[p,ci]);  db[co] += sum_p dy[p,co].
-// grid = (pixel-tile groups, ceil(Cin*Cout / 4096)); every thread owns up to 16 (co, ci) pairs in registers over all the
-// tiles of its block and issues one atomicAdd per pair at the end.
+// Split-K GEMM (K = pixels): blockIdx.y selects a 64 x 64 (co, ci) tile, blockIdx.x a pixel range; a thread accumulates
+// 4 x 4 entries in registers over its block's range and issues one atomicAdd per entry.
 template <int ACT>
 __global__ void __launch_bounds__(256) k_pw_wgrad(TV x, int Cin, TV dy, int Cout, float* __restrict__ dW, int wso, int wsi,
-                                                  float* __restrict__ db, size_t NP) {
-  extern __shared__ float sm[];
-  constexpr int TPX = 32;
-  const int ldx = Cin + 1, ldy = Cout + 1;
-  float* xs = sm;
-  float* dys = sm + TPX * ldx;
-  const int pairs = Cin * Cout, chunk0 = blockIdx.y * 4096;
-  int pco[16], pci[16];
-  float acc[16];
+                                                  float* __restrict__ db, size_t NP, int ci_tiles) {
+  constexpr int TP = 32;
+  __shared__ __align__(16) float xs[TP][64];
+  __shared__ __align__(16) float dys[TP][64];
+  const int ci0 = (blockIdx.y % ci_tiles) * 64, co0 = (blockIdx.y / ci_tiles) * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int pair = chunk0 + j * 256 + threadIdx.x;
-    acc[j] = 0.f;
-    if (pair < pairs) { pco[j] = pair / Cin; pci[j] = pair - pco[j] * Cin; } else { pco[j] = -1; pci[j] = 0; }
-  }
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float bacc = 0.f;
-  const bool do_bias = db && blockIdx.y == 0 && threadIdx.x < Cout;
-  const size_t tiles = (NP + TPX - 1) / TPX;
+  const bool do_bias = db && ci0 == 0 && threadIdx.x < 64 && co0 + threadIdx.x < Cout;
+  const size_t tiles = (NP + TP - 1) / TP;
   for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const size_t p0 = t * TPX;
-    for (int i = threadIdx.x; i < TPX * Cin; i += 256) {
-      int px, ci;
-      if (x.nchw) { px = i % TPX; ci = i / TPX; } else { px = i / Cin; ci = i - px * Cin; }
+    const size_t p0 = t * TP;
+    for (int i = threadIdx.x; i < TP * 64; i += 256) {
+      int px, c;
+      if (x.nchw) { px = i % TP; c = i / TP; } else { c = i & 63; px = i >> 6; }
       const size_t gp = p0 + px;
       float v = 0.f;
-      if (gp < NP) { v = x.p[tv_at(x, gp, ci)]; if (ACT) v = gelu_exact(v); }
-      xs[px * ldx + ci] = v;
+      if (gp < NP && ci0 + c < Cin) { v = x.p[tv_at(x, gp, ci0 + c)]; if (ACT) v = gelu_exact(v); }
+      xs[px][c] = v;
     }
-    for (int i = threadIdx.x; i < TPX * Cout; i += 256) {
-      int px, co;
-      if (dy.nchw) { px = i % TPX; co = i / TPX; } else { px = i / Cout; co = i - px * Cout; }
+    for (int i = threadIdx.x; i < TP * 64; i += 256) {
+      int px, c;
+      if (dy.nchw) { px = i % TP; c = i / TP; } else { c = i & 63; px = i >> 6; }
       const size_t gp = p0 + px;
-      dys[px * ldy + co] = gp < NP ? dy.p[tv_at(dy, gp, co)] : 0.f;
+      dys[px][c] = (gp < NP && co0 + c < Cout) ? dy.p[tv_at(dy, gp, co0 + c)] : 0.f;
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (pco[j] >= 0) {
-        const float* a = dys + pco[j];
-        const float* bb = xs + pci[j];
-        float s = 0.f;
 #pragma unroll 8
-        for (int p = 0; p < TPX; ++p) s = fmaf(a[p * ldy], bb[p * ldx], s);
-        acc[j] += s;
-      }
+    for (int p = 0; p < TP; ++p) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[p][tx * 4]);
+      const float4 dv = *reinterpret_cast<const float4*>(&dys[p][ty * 4]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(da[i], xa[j], acc[i][j]);
     }
     if (do_bias) {
-      float s = 0.f;
-      for (int p = 0; p < TPX; ++p) s += dys[p * ldy + threadIdx.x];
-      bacc += s;
+      float sacc = 0.f;
+#pragma unroll 8
+      for (int p = 0; p < TP; ++p) sacc += dys[p][threadIdx.x];
+      bacc += sacc;
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    if (pco[j] >= 0) atomicAdd(dW + (size_t)pco[j] * wso + (size_t)pci[j] * wsi, acc[j]);
-  if (do_bias) atomicAdd(db + threadIdx.x, bacc);
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + tx * 4 + j;
+      if (ci < Cin) atomicAdd(dW + (size_t)co * wso + (size_t)ci * wsi, acc[i][j]);
+    }
+  }
+  if (do_bias) atomicAdd(db + co0 + threadIdx.x, bacc);
 }
 
 // ---- LayerNorm over channels (LGT.py:54-61; biased variance, eps 1e-5), one thread per pixel -------------------------------------
@@ -366,92 +381,95 @@ __global__ void __launch_bounds__(64) k_attn_fwd(const float* __restrict__ qkv, 
   for (int d = 0; d < D; ++d) out.p[gp * out.ld + head * D + d] = o[d] * inv;
 }
 
-// backward: recomputes the probabilities; dqkv is written exactly once per element, dpos accumulates over windows in shared
-// memory (the block loops over windows) and is flushed with one atomicAdd per entry.
+// backward: a 128-thread block handles both heads of a window and loops over windows.  Phase 1 (thread = query token) gets
+// the row statistics (max, 1/sum, delta = sum_j P dP) and dq; phase 2 (thread = key token) recomputes P and dS column-wise
+// for dk, dv and the positional-bias gradient, which accumulates over the block's windows in shared memory and is flushed
+// with one atomicAdd per entry.  dqkv is written exactly once per element.
 template <int D>
-__global__ void __launch_bounds__(64) k_attn_bwd(const float* __restrict__ qkv, const float* __restrict__ pos, TV dout,
-                                                 float* __restrict__ dqkv, float* __restrict__ dpos, int N, int H, int W) {
+__global__ void __launch_bounds__(128) k_attn_bwd(const float* __restrict__ qkv, const float* __restrict__ pos, TV dout,
+                                                  float* __restrict__ dqkv, float* __restrict__ dpos, int N, int H, int W) {
   extern __shared__ float sm[];
-  float* qs = sm;                 // [64][D]  unscaled q
+  const int head = threadIdx.x >> 6, i = threadIdx.x & 63;
+  float* base = sm + head * (4 * 64 * D + 3 * 64 + 64 * 64);
+  float* qs = base;               // [64][D]  scaled q
   float* ks = qs + 64 * D;
   float* vs = ks + 64 * D;
   float* dos = vs + 64 * D;
-  float* Ps = dos + 64 * D;       // [64][65]
-  float* dSs = Ps + 64 * 65;
-  float* dps = dSs + 64 * 65;
+  float* st = dos + 64 * D;       // [3][64]  row max, 1 / row sum, delta
+  float* dps = st + 3 * 64;       // [64][64] dpos accumulator, [query][key]
   const int nwx = W / 8, nwin = (H / 8) * nwx, c2 = 2 * D, ld = 3 * c2;
-  const int head = blockIdx.y, i = threadIdx.x;
   const float scale = rsqrtf((float)D);
-  const float* pr = pos + ((size_t)head * 64 + i) * 64;
-  for (int j = 0; j < 64; ++j) dps[i * 65 + j] = 0.f;
+  const float* ph = pos + (size_t)head * 64 * 64;
+  for (int j = 0; j < 64; ++j) dps[j * 64 + i] = 0.f;
   for (int g = blockIdx.x; g < N * nwin; g += gridDim.x) {
     const int win = g % nwin, n = g / nwin;
     const size_t gp = ((size_t)n * H + (win / nwx) * 8 + i / 8) * W + (win % nwx) * 8 + i % 8;
     const float* row = qkv + gp * ld + head * D;
-    float q[D], dO[D];
-    __syncthreads();              // previous window's phase 2 is done with the shared tiles
+    float q[D], kk[D], vv[D], dO[D];
+    __syncthreads();              // the previous window's phase 2 is done with the shared tiles
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       q[d] = row[d] * scale;
-      qs[i * D + d] = row[d];
-      ks[i * D + d] = row[c2 + d];
-      vs[i * D + d] = row[2 * c2 + d];
+      kk[d] = row[c2 + d];
+      vv[d] = row[2 * c2 + d];
       dO[d] = dout.p[gp * dout.ld + head * D + d];
+      qs[i * D + d] = q[d];
+      ks[i * D + d] = kk[d];
+      vs[i * D + d] = vv[d];
       dos[i * D + d] = dO[d];
     }
     __syncthreads();
-    float s[64], mx = -INFINITY;
-#pragma unroll
+    // phase 1: query row i — online softmax statistics, then a second sweep for dq (scores are recomputed, not stored)
+    float mx = -INFINITY, sum = 0.f, dsum = 0.f;
+    const float* pr = ph + i * 64;
+#pragma unroll 4
     for (int j = 0; j < 64; ++j) {
-      float a = 0.f;
+      float a = pr[j], dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < D; ++d) a = fmaf(q[d], ks[j * D + d], a);
-      s[j] = a + pr[j];
-      mx = fmaxf(mx, s[j]);
+      for (int d = 0; d < D; ++d) { a = fmaf(q[d], ks[j * D + d], a); dp = fmaf(dO[d], vs[j * D + d], dp); }
+      const float mn = fmaxf(mx, a), r = __expf(mx - mn), e = __expf(a - mn);
+      sum = fmaf(sum, r, e);
+      dsum = fmaf(dsum, r, e * dp);
+      mx = mn;
     }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
-    const float inv = 1.f / sum;
-    float delta = 0.f;
-    float dp[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) {
-      s[j] *= inv;
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) a = fmaf(dO[d], vs[j * D + d], a);
-      dp[j] = a;
-      delta = fmaf(s[j], a, delta);
-    }
+    const float inv = 1.f / sum, delta = dsum * inv;
     float dq[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) dq[d] = 0.f;
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < 64; ++j) {
-      const float ds = s[j] * (dp[j] - delta);
-      Ps[i * 65 + j] = s[j];
-      dSs[i * 65 + j] = ds;
-      dps[i * 65 + j] += ds;
+      float a = pr[j], dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { a = fmaf(q[d], ks[j * D + d], a); dp = fmaf(dO[d], vs[j * D + d], dp); }
+      const float ds = __expf(a - mx) * inv * (dp - delta);
 #pragma unroll
       for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, ks[j * D + d], dq[d]);
     }
+    st[i] = mx;
+    st[64 + i] = inv;
+    st[128 + i] = delta;
     __syncthreads();
-    // phase 2: thread = key token
+    // phase 2: key column i
     float dk[D], dv[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+#pragma unroll 4
     for (int r = 0; r < 64; ++r) {
-      const float ds = dSs[r * 65 + i], p = Ps[r * 65 + i];
+      float a = ph[r * 64 + i], dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { a = fmaf(qs[r * D + d], kk[d], a); dp = fmaf(dos[r * D + d], vv[d], dp); }
+      const float p = __expf(a - st[r]) * st[64 + r];
+      const float ds = p * (dp - st[128 + r]);
+      dps[r * 64 + i] += ds;
 #pragma unroll
       for (int d = 0; d < D; ++d) { dk[d] = fmaf(ds, qs[r * D + d], dk[d]); dv[d] = fmaf(p, dos[r * D + d], dv[d]); }
     }
     float* orow = dqkv + gp * ld + head * D;
 #pragma unroll
-    for (int d = 0; d < D; ++d) { orow[d] = dq[d] * scale; orow[c2 + d] = dk[d] * scale; orow[2 * c2 + d] = dv[d]; }
+    for (int d = 0; d < D; ++d) { orow[d] = dq[d] * scale; orow[c2 + d] = dk[d]; orow[2 * c2 + d] = dv[d]; }
   }
-  float* dpr = dpos + ((size_t)head * 64 + i) * 64;
-  for (int j = 0; j < 64; ++j) atomicAdd(dpr + j, dps[i * 65 + j]);
+  float* dph = dpos + (size_t)head * 64 * 64;
+  for (int r = 0; r < 64; ++r) atomicAdd(dph + r * 64 + i, dps[r * 64 + i]);
 }
 
 // ---- FFT passes of the global mixer (LGT.py:162-180) and their adjoints ---------------------------------------------------------
