@@ -102,6 +102,12 @@ cudaError_t launch_ffn_tc(const BlockW& w, int c, const float* x, float* y, int 
 // pwgemm_tc.cu — conv-FFN of the widest level (c = 64) as tcgen05 pixel-GEMMs; buf_a / buf_b: N*H*W*256 floats each
 cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, float* buf_b, float* y, int N, int H, int W,
                                cudaStream_t s);
+// training-step GEMMs on the same tcgen05 kernel (train.cu): Y[P,N] = f(s X[P,K]) . W^T / s (+ bias) (+ resid | * gelu'(gate));
+// pro: 0 plain, 2 GELU on X; epi: 0 bias (may be NULL), 2 bias + resid, 3 gate; wpack from launch_pack_umma_f16_strided
+bool train_pwgemm_supported(int K, int N);
+cudaError_t launch_train_pwgemm(int K, int N, int pro, int epi, const float* X, float* Y, const void* wpack, const float* bias,
+                                const float* aux, long long px, const float* scale_dev, cudaStream_t s);
+cudaError_t launch_pack_umma_f16_strided(const float* w, int wso, int wsi, void* pack /*N*K floats*/, int N, int K, cudaStream_t s);
 // metrics.cu — PSNR / SAM / ERGAS per image in fp64 (acc: N*(2+2B) doubles scratch, out: N*3 doubles)
 cudaError_t launch_metrics(const float* pred, const float* gt, double* acc, double* out, int N, int B, int H, int W,
                            float max_value, cudaStream_t s);

@@ -23,8 +23,13 @@ namespace lg {
 
 namespace pw = tc;
 
-enum { PRO_PLAIN = 0, PRO_LN = 1 };
-enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2 };
+enum { PRO_PLAIN = 0, PRO_LN = 1, PRO_GELU = 2 };          // PRO_GELU: A = GELU(x) (the conv-FFN's activations are recomputed, not stored)
+enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_GATE = 3 };   // EPI_GATE: out = acc * gelu'(gate) (training backward)
+
+// d/dx of the exact (erf) GELU: Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_grad_exact(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
 constexpr int kNS = 64;                 // output channels per weight slice
 constexpr int kPwThreads = 256;
 
@@ -33,10 +38,14 @@ template <int K, int N, int PRO, int EPI>
 __global__ void __launch_bounds__(kPwThreads, 1)
 pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __half* __restrict__ wpack,
                  const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                 const float* __restrict__ resid, long long total_px, int num_tiles) {
+                 const float* __restrict__ resid, long long total_px, int num_tiles, const float* __restrict__ scale_dev) {
   using namespace pw;
-  static_assert(K % 16 == 0 && N % kNS == 0 && N <= 256, "tile shape");
+  constexpr int kNS = N < lg::kNS ? N : lg::kNS;                                // narrow outputs (N = 16, 32) are one slice
+  static_assert(K % 16 == 0 && N % kNS == 0 && N % 16 == 0 && N <= 256, "tile shape");
   constexpr int KC = K / 8;
+  // training backward: the A operand (a gradient, ~1e-7) is multiplied by a power of two before the fp16 hi/lo split and
+  // the accumulator divided by it, so that it sits in fp16's normal range like the O(1) activations of the forward
+  const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
@@ -48,14 +57,14 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;                                     // TMEM lane quarter / column half
   const int row = q * 32 + lane;
-  constexpr uint32_t TCOLS = (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  constexpr uint32_t TCOLS = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
 
   if (tid == 0) {
     mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  for (int i = tid; i < N; i += kPwThreads) sbias[i] = __ldg(bias + i);
+  for (int i = tid; i < N; i += kPwThreads) sbias[i] = bias ? __ldg(bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -105,6 +114,12 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
             v[2] = make_float2((v[2].x - mean) * rstd * g1.x + b1.x, (v[2].y - mean) * rstd * g1.y + b1.y);
             v[3] = make_float2((v[3].x - mean) * rstd * g1.z + b1.z, (v[3].y - mean) * rstd * g1.w + b1.w);
           }
+          if constexpr (PRO == PRO_GELU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = gelu_pair(v[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = make_float2(v[i].x * a_scale, v[i].y * a_scale);
         } else {
           v[0] = v[1] = v[2] = v[3] = make_float2(0.f, 0.f);
         }
@@ -155,15 +170,17 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
     // ---- epilogue: this thread owns columns [half*N/2, (half+1)*N/2) of its pixel ----------------------------------
     {
       float* dst = Out + p * N;
-      const float* res = (EPI == EPI_BIAS_RESID) ? resid + p * N : nullptr;
+      const float* res = (EPI == EPI_BIAS_RESID || EPI == EPI_GATE) ? resid + p * N : nullptr;
 #pragma unroll 2
       for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 8) {
         float2 v[4];
         tmem_ld8(lane_addr + c0, v);
         tmem_ld_wait();
         const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 4);
-        v[0] = __fadd2_rn(v[0], make_float2(b0.x, b0.y)); v[1] = __fadd2_rn(v[1], make_float2(b0.z, b0.w));
-        v[2] = __fadd2_rn(v[2], make_float2(b1.x, b1.y)); v[3] = __fadd2_rn(v[3], make_float2(b1.z, b1.w));
+        v[0] = __ffma2_rn(v[0], make_float2(inv_scale, inv_scale), make_float2(b0.x, b0.y));
+        v[1] = __ffma2_rn(v[1], make_float2(inv_scale, inv_scale), make_float2(b0.z, b0.w));
+        v[2] = __ffma2_rn(v[2], make_float2(inv_scale, inv_scale), make_float2(b1.x, b1.y));
+        v[3] = __ffma2_rn(v[3], make_float2(inv_scale, inv_scale), make_float2(b1.z, b1.w));
         if constexpr (EPI == EPI_BIAS_GELU) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) v[i] = gelu_pair(v[i]);
@@ -173,6 +190,13 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
             const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
             v[0] = __fadd2_rn(v[0], make_float2(r0.x, r0.y)); v[1] = __fadd2_rn(v[1], make_float2(r0.z, r0.w));
             v[2] = __fadd2_rn(v[2], make_float2(r1.x, r1.y)); v[3] = __fadd2_rn(v[3], make_float2(r1.z, r1.w));
+          }
+          if constexpr (EPI == EPI_GATE) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+            v[0] = make_float2(v[0].x * gelu_grad_exact(r0.x), v[0].y * gelu_grad_exact(r0.y));
+            v[1] = make_float2(v[1].x * gelu_grad_exact(r0.z), v[1].y * gelu_grad_exact(r0.w));
+            v[2] = make_float2(v[2].x * gelu_grad_exact(r1.x), v[2].y * gelu_grad_exact(r1.y));
+            v[3] = make_float2(v[3].x * gelu_grad_exact(r1.z), v[3].y * gelu_grad_exact(r1.w));
           }
           *reinterpret_cast<float4*>(dst + c0) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
           *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
@@ -229,7 +253,8 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
 
 template <int K, int N, int PRO, int EPI>
 static cudaError_t pwgemm_launch(const float* A, float* Out, const void* wpack, const float* bias, const float* ln_g,
-                                 const float* ln_b, const float* resid, long long total_px, cudaStream_t s) {
+                                 const float* ln_b, const float* resid, long long total_px, cudaStream_t s,
+                                 const float* scale_dev = nullptr) {
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
@@ -237,12 +262,56 @@ static cudaError_t pwgemm_launch(const float* A, float* Out, const void* wpack, 
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
   const int tiles = (int)((total_px + 127) / 128);
-  const size_t smem = 16 + (size_t)N * 4 + (size_t)(2 * 128 * K + 2 * kNS * K) * 2 + 128;
+  constexpr int NS = N < kNS ? N : kNS;
+  const size_t smem = 16 + (size_t)N * 4 + (size_t)(2 * 128 * K + 2 * NS * K) * 2 + 128;
   cudaError_t e = cudaFuncSetAttribute(pwgemm_tc_kernel<K, N, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int grid = tiles < sm_count ? tiles : sm_count;
   pwgemm_tc_kernel<K, N, PRO, EPI><<<grid, kPwThreads, smem, s>>>(A, Out, reinterpret_cast<const __half*>(wpack), bias, ln_g,
-                                                                  ln_b, resid, total_px, tiles);
+                                                                  ln_b, resid, total_px, tiles, scale_dev);
+  return cudaGetLastError();
+}
+
+// ---- training step (train.cu): the conv-FFN's 1x1 convs and their data gradients on the same kernel -------------------------
+//   Y[P,N] = f(s X[P,K]) . W^T / s (+ bias) (+ resid | * gelu'(gate)),  wpack = split-fp16 pack of W[N][K]
+//   pro: 0 plain, 2 GELU on X;  epi: 0 bias, 2 bias + resid, 3 gate (aux = resid / gate tensor [P,N])
+template <int K, int N>
+static cudaError_t train_pw_dispatch(int pro, int epi, const float* X, float* Y, const void* wpack, const float* bias,
+                                     const float* aux, long long px, const float* scale_dev, cudaStream_t s) {
+  if (pro == PRO_PLAIN && epi == EPI_BIAS) return pwgemm_launch<K, N, PRO_PLAIN, EPI_BIAS>(X, Y, wpack, bias, nullptr, nullptr, nullptr, px, s, scale_dev);
+  if (pro == PRO_GELU && epi == EPI_BIAS) return pwgemm_launch<K, N, PRO_GELU, EPI_BIAS>(X, Y, wpack, bias, nullptr, nullptr, nullptr, px, s, scale_dev);
+  if (pro == PRO_GELU && epi == EPI_BIAS_RESID) return pwgemm_launch<K, N, PRO_GELU, EPI_BIAS_RESID>(X, Y, wpack, bias, nullptr, nullptr, aux, px, s, scale_dev);
+  if (pro == PRO_PLAIN && epi == EPI_GATE) return pwgemm_launch<K, N, PRO_PLAIN, EPI_GATE>(X, Y, wpack, bias, nullptr, nullptr, aux, px, s, scale_dev);
+  return cudaErrorInvalidValue;
+}
+bool train_pwgemm_supported(int K, int N) {
+  const int c = K < N ? K : N, c4 = K < N ? N : K;
+  return (c == 16 || c == 32 || c == 64) && (c4 == 4 * c || (K == N && (K == 64 || K == 128 || K == 256)));
+}
+cudaError_t launch_train_pwgemm(int K, int N, int pro, int epi, const float* X, float* Y, const void* wpack, const float* bias,
+                                const float* aux, long long px, const float* scale_dev, cudaStream_t s) {
+#define LG_TPW(KK, NN) if (K == KK && N == NN) return train_pw_dispatch<KK, NN>(pro, epi, X, Y, wpack, bias, aux, px, scale_dev, s)
+  LG_TPW(16, 64); LG_TPW(32, 128); LG_TPW(64, 256);      // c -> 4c
+  LG_TPW(64, 64); LG_TPW(128, 128); LG_TPW(256, 256);    // 4c -> 4c
+  LG_TPW(64, 16); LG_TPW(128, 32); LG_TPW(256, 64);      // 4c -> c
+#undef LG_TPW
+  return cudaErrorInvalidValue;
+}
+// W[n*wso + k*wsi] (fp32, any strides: transposed views are free) -> hi | lo fp16 in the UMMA layout [K/8][N][8]
+__global__ void pack_umma_f16_strided_kernel(const float* __restrict__ w, int wso, int wsi, __half* __restrict__ hi,
+                                             __half* __restrict__ lo, int N, int K) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx - n * K;
+  const float v = w[(size_t)n * wso + (size_t)k * wsi];
+  const __half h = __float2half_rn(v);
+  const size_t o = ((size_t)(k >> 3) * N + n) * 8 + (k & 7);
+  hi[o] = h;
+  lo[o] = __float2half_rn(v - __half2float(h));
+}
+cudaError_t launch_pack_umma_f16_strided(const float* w, int wso, int wsi, void* pack, int N, int K, cudaStream_t s) {
+  __half* hi = reinterpret_cast<__half*>(pack);
+  pack_umma_f16_strided_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(w, wso, wsi, hi, hi + (size_t)N * K, N, K);
   return cudaGetLastError();
 }
 

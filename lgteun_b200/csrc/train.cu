@@ -7,6 +7,7 @@
 // As in the reference only the last prior is live (unlg_former.py:63-67): priors 0..K-2 are not executed and their
 // parameters receive no gradient (torch leaves their .grad at None; here the flat gradient is zero there).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -46,6 +47,7 @@ struct TrainState {
   size_t fwd_end = 0;           // arena offset where the backward's scratch starts
   const float* flat_param = nullptr;
   const float *ms = nullptr, *pan = nullptr;
+  float* gscale = nullptr;      // device scalar: power of two that brings max|dLoss/dOut| to [0.5, 1) (tensor-core backward GEMMs)
   DataTape data[kMaxStages];
   PriorTape prior;
   int launches_fwd = 0, launches_bwd = 0;
@@ -122,32 +124,72 @@ void pw_wgrad(Run& R, int act, TV x, int Cin, TV dy, int Cout, const float* dW, 
   else k_pw_wgrad<0><<<grid, 256, 0, R.s>>>(x, Cin, dy, Cout, const_cast<float*>(dW), wso, wsi, const_cast<float*>(db), NP, ci_tiles);
   R.check();
 }
+// The conv-FFN's three 1x1 convs and their data gradients run on the tcgen05 pixel-GEMM of pwgemm_tc.cu (split-fp16 operands,
+// fp32 TMEM accumulation) when the channel counts fit it; LGTEUN_TRAIN_GEMM=simt keeps them on the CUDA-core GEMM (A/B runs).
+bool use_tc_gemm(int K, int N) {
+  static const bool simt = [] { const char* e = getenv("LGTEUN_TRAIN_GEMM"); return e && std::string(e) == "simt"; }();
+  return !simt && train_pwgemm_supported(K, N);
+}
+// Y[NP,N] = f(X[NP,K]) . W^T (+ bias) (+ aux | * gelu'(aux)); W[n*wso + k*wsi] is re-packed every step (the weights move)
+void tc_pw(Run& R, int K, int N, int pro, int epi, const float* X, float* Y, const float* W, int wso, int wsi, const float* bias,
+           const float* aux, size_t NP, const float* scale) {
+  float* pack = R.take((size_t)N * K);
+  if (R.dry) return;
+  cudaError_t e = launch_pack_umma_f16_strided(W, wso, wsi, pack, N, K, R.s);
+  ++R.launches;
+  if (e == cudaSuccess) { e = launch_train_pwgemm(K, N, pro, epi, X, Y, pack, bias, aux, (long long)NP, scale, R.s); ++R.launches; }
+  if (R.err == cudaSuccess) R.err = e;
+}
+bool ln_fast(TV a, TV b, int C, size_t NP) {
+  return !a.nchw && !b.nchw && a.ld == C && b.ld == C && (C == 16 || C == 32 || C == 64) && NP % 2 == 0;
+}
 void ln_fwd(Run& R, TV x, int C, const float* g, const float* b, TV y, size_t NP) {
   if (R.dry) return;
-  k_ln_fwd<<<blocks(NP), 256, 0, R.s>>>(x, C, g, b, y, NP);
+  const unsigned gw = (unsigned)std::min<size_t>(148 * 8, (NP + 63) / 64);
+  if (ln_fast(x, y, C, NP)) {
+    if (C == 16) k_ln_warp<16, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
+    else if (C == 32) k_ln_warp<32, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
+    else k_ln_warp<64, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
+  } else {
+    k_ln_fwd<<<blocks(NP), 256, 0, R.s>>>(x, C, g, b, y, NP);
+  }
   R.check();
 }
 void ln_bwd(Run& R, TV x, int C, const float* g, TV dy, TV dx, int accumulate, const float* dg, const float* db, size_t NP) {
   if (R.dry) return;
-  k_ln_bwd<<<blocks(NP), 256, 2 * C * sizeof(float), R.s>>>(x, C, g, dy, dx, accumulate, const_cast<float*>(dg),
-                                                            const_cast<float*>(db), NP);
+  float *pg = const_cast<float*>(dg), *pb = const_cast<float*>(db);
+  const unsigned gw = (unsigned)std::min<size_t>(148 * 8, (NP + 63) / 64);
+  if (ln_fast(x, dy, C, NP) && !dx.nchw && dx.ld == C) {
+    if (C == 16) k_ln_warp<16, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
+    else if (C == 32) k_ln_warp<32, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
+    else k_ln_warp<64, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
+  } else {
+    k_ln_bwd<<<blocks(NP), 256, 2 * C * sizeof(float), R.s>>>(x, C, g, dy, dx, accumulate, pg, pb, NP);
+  }
   R.check();
 }
 void dwconv(Run& R, int K, TV x, const float* w, const float* b, TV y, int N, int H, int W, int C, int flip,
             const TV* add = nullptr, float add_scale = 1.f) {
   if (R.dry) return;
   const TV none{nullptr, 0, 0, 0, 0};
+  const int lh = ilog2(H), lw = ilog2(W), lc = ilog2(C);
+  if (K == 3 && !add && !x.nchw && !y.nchw && x.ld == C && y.ld == C && C >= 4) {
+    k_dw3_v4<<<blocks((size_t)N * H * W * C / 4), 256, 10 * C * sizeof(float), R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
+    R.check();
+    return;
+  }
   const unsigned g = blocks((size_t)N * H * W * C);
-  if (K == 3) k_dw<3><<<g, 256, 0, R.s>>>(x, w, b, y, N, H, W, C, flip, add ? *add : none, add_scale, add != nullptr);
-  else k_dw<1><<<g, 256, 0, R.s>>>(x, w, b, y, N, H, W, C, flip, add ? *add : none, add_scale, add != nullptr);
+  if (K == 3) k_dw<3><<<g, 256, 0, R.s>>>(x, w, b, y, N, lh, lw, lc, flip, add ? *add : none, add_scale, add != nullptr);
+  else k_dw<1><<<g, 256, 0, R.s>>>(x, w, b, y, N, lh, lw, lc, flip, add ? *add : none, add_scale, add != nullptr);
   R.check();
 }
 void dw_wgrad(Run& R, int K, TV x, TV dy, const float* dw, const float* db, int N, int H, int W, int C) {
   if (R.dry) return;
   const size_t NP = (size_t)N * H * W;
-  const unsigned g = (unsigned)std::min<size_t>(148 * 4, (NP + 256 / C - 1) / (256 / C));
-  if (K == 3) k_dw_wgrad<3><<<g, 256, C * 10 * sizeof(float), R.s>>>(x, dy, const_cast<float*>(dw), const_cast<float*>(db), N, H, W, C);
-  else k_dw_wgrad<1><<<g, 256, C * 2 * sizeof(float), R.s>>>(x, dy, const_cast<float*>(dw), const_cast<float*>(db), N, H, W, C);
+  const int lh = ilog2(H), lw = ilog2(W), lc = ilog2(C);
+  const unsigned g = (unsigned)std::min<size_t>(148 * 8, (NP + 256 / C - 1) / (256 / C));
+  if (K == 3) k_dw_wgrad<3><<<g, 256, C * 10 * sizeof(float), R.s>>>(x, dy, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
+  else k_dw_wgrad<1><<<g, 256, C * 2 * sizeof(float), R.s>>>(x, dy, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
   R.check();
 }
 // bicubic resize of [N,Hi,Wi,C] to [N,Ho,Wo,C]; adjoint: scatter-add of y (gradient) into x
@@ -244,15 +286,19 @@ float* fwd_block(Run& R, const Step& S, const BlockW& w, int ch, BlockTape& t, f
   // conv-FFN (LGT.py:95-109); the GELUs are applied while staging the next conv's input
   t.A2 = R.take(NP * ch);
   ln_fwd(R, nhwc(t.Xmid, ch), ch, w.ln2_w, w.ln2_b, nhwc(t.A2, ch), NP);
+  const bool tc = use_tc_gemm(ch, c4);
   t.h1 = R.take(NP * c4);
-  pw(R, 0, nhwc(t.A2, ch), ch, w.f0_w, ch, 1, w.f0_b, nhwc(t.h1, c4), c4, NP);
+  if (tc) tc_pw(R, ch, c4, 0, 0, t.A2, t.h1, w.f0_w, ch, 1, w.f0_b, nullptr, NP, nullptr);
+  else pw(R, 0, nhwc(t.A2, ch), ch, w.f0_w, ch, 1, w.f0_b, nhwc(t.h1, c4), c4, NP);
   t.h2 = R.take(NP * c4);
-  pw(R, 1, nhwc(t.h1, c4), c4, w.f1_w, c4, 1, w.f1_b, nhwc(t.h2, c4), c4, NP);
+  if (tc) tc_pw(R, c4, c4, 2, 0, t.h1, t.h2, w.f1_w, c4, 1, w.f1_b, nullptr, NP, nullptr);
+  else pw(R, 1, nhwc(t.h1, c4), c4, w.f1_w, c4, 1, w.f1_b, nhwc(t.h2, c4), c4, NP);
   t.h3 = R.take(NP * c4);
   dwconv(R, 3, nhwc(t.h2, c4), w.dw_w, w.dw_b, nhwc(t.h3, c4), N, H, W, c4, 0);
   t.Xout = R.take(NP * ch);
   const TV res = nhwc(t.Xmid, ch);
-  pw(R, 1, nhwc(t.h3, c4), c4, w.f2_w, c4, 1, w.f2_b, nhwc(t.Xout, ch), ch, NP, &res);
+  if (tc) tc_pw(R, c4, ch, 2, 2, t.h3, t.Xout, w.f2_w, c4, 1, w.f2_b, t.Xmid, NP, nullptr);
+  else pw(R, 1, nhwc(t.h3, c4), c4, w.f2_w, c4, 1, w.f2_b, nhwc(t.Xout, ch), ch, NP, &res);
   return t.Xout;
 }
 
@@ -264,19 +310,24 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
   const TV gx = nhwc(gX, ch);
   // FFN
   pw_wgrad(R, 1, nhwc(t.h3, c4), c4, gx, ch, g.f2_w, c4, 1, g.f2_b, NP);
+  const bool tc = use_tc_gemm(ch, c4);
+  const float* gs = S.T->gscale;
   float* dh3 = R.take(NP * c4);
   const TV gate3 = nhwc(t.h3, c4);
-  pw(R, 0, gx, ch, w.f2_w, 1, c4, nullptr, nhwc(dh3, c4), c4, NP, nullptr, &gate3);
+  if (tc) tc_pw(R, ch, c4, 0, 3, gX, dh3, w.f2_w, 1, c4, nullptr, t.h3, NP, gs);
+  else pw(R, 0, gx, ch, w.f2_w, 1, c4, nullptr, nhwc(dh3, c4), c4, NP, nullptr, &gate3);
   dw_wgrad(R, 3, nhwc(t.h2, c4), nhwc(dh3, c4), g.dw_w, g.dw_b, N, H, W, c4);
   float* dh2 = R.take(NP * c4);
   dwconv(R, 3, nhwc(dh3, c4), w.dw_w, nullptr, nhwc(dh2, c4), N, H, W, c4, 1);
   pw_wgrad(R, 1, nhwc(t.h1, c4), c4, nhwc(dh2, c4), c4, g.f1_w, c4, 1, g.f1_b, NP);
   float* dh1 = R.take(NP * c4);
   const TV gate1 = nhwc(t.h1, c4);
-  pw(R, 0, nhwc(dh2, c4), c4, w.f1_w, 1, c4, nullptr, nhwc(dh1, c4), c4, NP, nullptr, &gate1);
+  if (tc) tc_pw(R, c4, c4, 0, 3, dh2, dh1, w.f1_w, 1, c4, nullptr, t.h1, NP, gs);
+  else pw(R, 0, nhwc(dh2, c4), c4, w.f1_w, 1, c4, nullptr, nhwc(dh1, c4), c4, NP, nullptr, &gate1);
   pw_wgrad(R, 0, nhwc(t.A2, ch), ch, nhwc(dh1, c4), c4, g.f0_w, ch, 1, g.f0_b, NP);
   float* dA2 = R.take(NP * ch);
-  pw(R, 0, nhwc(dh1, c4), c4, w.f0_w, 1, ch, nullptr, nhwc(dA2, ch), ch, NP);
+  if (tc) tc_pw(R, c4, ch, 0, 0, dh1, dA2, w.f0_w, 1, ch, nullptr, nullptr, NP, gs);
+  else pw(R, 0, nhwc(dh1, c4), c4, w.f0_w, 1, ch, nullptr, nhwc(dA2, ch), ch, NP);
   ln_bwd(R, nhwc(t.Xmid, ch), ch, w.ln2_w, nhwc(dA2, ch), gx, 1, g.ln2_w, g.ln2_b, NP);
   // mixer: gX is now the gradient of Xmid = Xin + drop(proj(cat))
   float* dpr = gX;
@@ -470,6 +521,15 @@ void run_fwd(Run& R, const Step& S, const float* ms, const float* pan, float* ou
 void run_bwd(Run& R, const Step& S, const float* dout, int h, int w) {
   const int N = S.N, B = S.c->B, K = S.c->K, H = 4 * h, W = 4 * w;
   float* gZ = R.take((size_t)N * B * H * W);
+  S.T->gscale = R.take(64);
+  if (!R.dry) {
+    R.zero(S.T->gscale, 64);
+    k_absmax<<<(unsigned)std::min<size_t>(148 * 4, ((size_t)N * B * H * W + 255) / 256), 256, 0, R.s>>>(
+        dout, (size_t)N * B * H * W, reinterpret_cast<unsigned*>(S.T->gscale + 1));
+    R.check();
+    k_pow2_scale<<<1, 1, 0, R.s>>>(reinterpret_cast<const unsigned*>(S.T->gscale + 1), S.T->gscale);
+    R.check();
+  }
   bwd_prior(R, S, S.w->prior[K - 1], S.g->prior[K - 1], S.T->prior, dout, gZ, H, W);
   for (int i = K - 1; i >= 0; --i) bwd_data(R, S, S.w->dw, S.g->dw, i, S.T->data[i], gZ, h, w);
 }

@@ -11,21 +11,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace lgtrain {
 
 struct TV {
   float* p;
   int ld;     // NHWC: floats per pixel
   int nchw;   // 1: p[((n*C + k)*P + pix)]
-  int C, P;   // NCHW only: channels, pixels per image
+  int C, lp;  // NCHW only: channels, log2(pixels per image) (image sizes are powers of two)
 };
 __host__ __device__ __forceinline__ size_t tv_at(const TV& t, size_t gp, int k) {
-  return t.nchw ? ((gp / t.P) * t.C + k) * (size_t)t.P + gp % t.P : gp * (size_t)t.ld + k;
+  return t.nchw ? ((((gp >> t.lp) * t.C + k) << t.lp) + (gp & (((size_t)1 << t.lp) - 1))) : gp * (size_t)t.ld + k;
 }
 inline TV nhwc(const float* p, int ld) { return TV{const_cast<float*>(p), ld, 0, 0, 0}; }
-inline TV nchw(const float* p, int C, int P) { return TV{const_cast<float*>(p), 0, 1, C, P}; }
+inline TV nchw(const float* p, int C, int P) {
+  int lp = 0;
+  while ((1 << lp) < P) ++lp;
+  return TV{const_cast<float*>(p), 0, 1, C, lp};
+}
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// exact-form (erf) GELU, 4.8e-7 absolute (common.cuh: one ex2 instead of erff; the inference kernels use the same form)
+__device__ __forceinline__ float gelu_exact(float x) { return lg::gelu_fast(x); }
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
@@ -221,18 +228,88 @@ __global__ void __launch_bounds__(256) k_ln_bwd(TV x, int C, const float* __rest
   for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(dgamma + i, sm[i]); atomicAdd(dbeta + i, sm[C + i]); }
 }
 
+// NHWC-contiguous LayerNorm with lanes = channels (C in {16, 32, 64}): coalesced loads, statistics by warp shuffles,
+// gamma / beta gradients accumulate per lane in registers over all the pixels a warp visits.  NP % (32 / min(C, 32)) == 0.
+template <int C, int BWD>
+__global__ void __launch_bounds__(256) k_ln_warp(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                                 const float* __restrict__ dy, float* __restrict__ out, int accumulate,
+                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, size_t NP) {
+  constexpr int GROUP = C < 32 ? C : 32, VPL = C / GROUP, PPW = 32 / GROUP;
+  __shared__ float red[2 * C];
+  if (BWD) {
+    for (int i = threadIdx.x; i < 2 * C; i += 256) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, cl = lane % GROUP, sub = lane / GROUP;
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * 8;
+  float gam[VPL], bet[VPL], ag[VPL], ab[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) { gam[t] = g[cl + 32 * t]; bet[t] = BWD ? 0.f : b[cl + 32 * t]; ag[t] = 0.f; ab[t] = 0.f; }
+  for (size_t gp = warp * PPW + sub; gp < NP; gp += nwarps * PPW) {
+    float v[VPL], s = 0.f;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) { v[t] = x[gp * C + cl + 32 * t]; s += v[t]; }
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float var = 0.f;
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) { v[t] -= mean; var = fmaf(v[t], v[t], var); }
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.f / sqrtf(var * (1.f / C) + 1e-5f);
+    if (!BWD) {
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) out[gp * C + cl + 32 * t] = v[t] * rstd * gam[t] + bet[t];
+    } else {
+      float d[VPL], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        v[t] *= rstd;
+        d[t] = dy[gp * C + cl + 32 * t];
+        const float gg = d[t] * gam[t];
+        m1 += gg;
+        m2 = fmaf(gg, v[t], m2);
+        ag[t] = fmaf(d[t], v[t], ag[t]);
+        ab[t] += d[t];
+      }
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1) {
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+      }
+      m1 *= (1.f / C);
+      m2 *= (1.f / C);
+#pragma unroll
+      for (int t = 0; t < VPL; ++t) {
+        float r = rstd * (d[t] * gam[t] - m1 - v[t] * m2);
+        const size_t o = gp * C + cl + 32 * t;
+        if (accumulate) r += out[o];
+        out[o] = r;
+      }
+    }
+  }
+  if (BWD) {
+#pragma unroll
+    for (int t = 0; t < VPL; ++t) { atomicAdd(red + cl + 32 * t, ag[t]); atomicAdd(red + C + cl + 32 * t, ab[t]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(dgamma + i, red[i]); atomicAdd(dbeta + i, red[C + i]); }
+  }
+}
+
 // ---- depthwise KxK convolution with zero padding (bmu.dep_conv, basic_module_unformer_v2.py:17-18), K in {1, 3} ---------------
-// flip = 1 uses the point-reflected taps: the data gradient of the same conv.
+// flip = 1 uses the point-reflected taps: the data gradient of the same conv.  H, W, C are powers of two (lh, lw, lc).
 template <int K>
 __global__ void __launch_bounds__(256) k_dw(TV x, const float* __restrict__ w, const float* __restrict__ b, TV y, int N,
-                                            int H, int W, int C, int flip, TV add, float add_scale, int use_add) {
-  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, P = (size_t)H * W, total = (size_t)N * P * C;
+                                            int lh, int lw, int lc, int flip, TV add, float add_scale, int use_add) {
+  const int H = 1 << lh, W = 1 << lw, C = 1 << lc;
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, total = (size_t)N << (lh + lw + lc);
   if (idx >= total) return;
   int k;
   size_t gp;
-  if (y.nchw) { const size_t pix = idx % P, r = idx / P; k = (int)(r % C); gp = (r / C) * P + pix; }
-  else { k = (int)(idx % C); gp = idx / C; }
-  const int xx = (int)(gp % W), yy = (int)((gp / W) % H);
+  if (y.nchw) { const size_t r = idx >> (lh + lw); k = (int)(r & (C - 1)); gp = ((r >> lc) << (lh + lw)) + (idx & (((size_t)1 << (lh + lw)) - 1)); }
+  else { k = (int)(idx & (C - 1)); gp = idx >> lc; }
+  const int xx = (int)(gp & (W - 1)), yy = (int)((gp >> lw) & (H - 1));
   float acc = b ? b[k] : 0.f;
 #pragma unroll
   for (int dy = 0; dy < K; ++dy)
@@ -246,22 +323,53 @@ __global__ void __launch_bounds__(256) k_dw(TV x, const float* __restrict__ w, c
   if (use_add) acc = fmaf(add_scale, add.p[tv_at(add, gp, k)], acc);
   y.p[tv_at(y, gp, k)] = acc;
 }
+// 3x3, NHWC contiguous in and out (ld == C, C % 4 == 0): four channels per thread, taps staged in shared memory as [tap][C]
+__global__ void __launch_bounds__(256) k_dw3_v4(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                float* __restrict__ y, int N, int lh, int lw, int lc, int flip) {
+  extern __shared__ __align__(16) float wsm[];   // [10][C]: 9 taps + bias
+  const int H = 1 << lh, W = 1 << lw, C = 1 << lc;
+  for (int i = threadIdx.x; i < 10 * C; i += 256) {
+    const int t = i >> lc, k = i & (C - 1);
+    wsm[i] = t < 9 ? w[k * 9 + (flip ? 8 - t : t)] : (b ? b[k] : 0.f);
+  }
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, total = (size_t)N << (lh + lw + lc - 2);
+  if (idx >= total) return;
+  const int k = (int)(idx & (C / 4 - 1)) * 4;
+  const size_t gp = idx >> (lc - 2);
+  const int xx = (int)(gp & (W - 1)), yy = (int)((gp >> lw) & (H - 1));
+  float4 acc = *reinterpret_cast<const float4*>(wsm + 9 * C + k);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int sy = yy + dy - 1, sx = xx + dx - 1;
+      if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+      const float4 wv = *reinterpret_cast<const float4*>(wsm + (dy * 3 + dx) * C + k);
+      const float4 xv = *reinterpret_cast<const float4*>(x + ((gp + (size_t)(dy - 1) * W + (dx - 1)) << lc) + k);
+      acc.x = fmaf(wv.x, xv.x, acc.x); acc.y = fmaf(wv.y, xv.y, acc.y);
+      acc.z = fmaf(wv.z, xv.z, acc.z); acc.w = fmaf(wv.w, xv.w, acc.w);
+    }
+  *reinterpret_cast<float4*>(y + (gp << lc) + k) = acc;
+}
 
-// dw[k][tap] += sum dy[p] * x[p + tap];  db[k] += sum dy[p].  blockDim = 256, C divides 256; thread = (pixel slot, channel).
+// dw[k][tap] += sum dy[p] * x[p + tap];  db[k] += sum dy[p].  blockDim = 256, C (a power of two) divides 256;
+// thread = (pixel slot, channel).
 template <int K>
-__global__ void __launch_bounds__(256) k_dw_wgrad(TV x, TV dy, float* __restrict__ dw, float* __restrict__ db, int N, int H,
-                                                  int W, int C) {
+__global__ void __launch_bounds__(256) k_dw_wgrad(TV x, TV dy, float* __restrict__ dw, float* __restrict__ db, int N, int lh,
+                                                  int lw, int lc) {
   extern __shared__ float sm[];   // [C][K*K+1]
   constexpr int T = K * K;
+  const int H = 1 << lh, W = 1 << lw, C = 1 << lc;
   for (int i = threadIdx.x; i < C * (T + 1); i += 256) sm[i] = 0.f;
   __syncthreads();
-  const int k = threadIdx.x % C, ppb = 256 / C;
-  const size_t NP = (size_t)N * H * W;
+  const int k = threadIdx.x & (C - 1), ppb = 256 >> lc;
+  const size_t NP = (size_t)N << (lh + lw);
   float acc[T], bacc = 0.f;
 #pragma unroll
   for (int i = 0; i < T; ++i) acc[i] = 0.f;
-  for (size_t gp = (size_t)blockIdx.x * ppb + threadIdx.x / C; gp < NP; gp += (size_t)gridDim.x * ppb) {
-    const int xx = (int)(gp % W), yy = (int)((gp / W) % H);
+  for (size_t gp = (size_t)blockIdx.x * ppb + (threadIdx.x >> lc); gp < NP; gp += (size_t)gridDim.x * ppb) {
+    const int xx = (int)(gp & (W - 1)), yy = (int)((gp >> lw) & (H - 1));
     const float g = dy.p[tv_at(dy, gp, k)];
     bacc += g;
 #pragma unroll
@@ -731,6 +839,19 @@ __global__ void __launch_bounds__(256) k_data_update_bwd(float* __restrict__ gz,
     atomicAdd(drtb + threadIdx.x, red[1 + B + threadIdx.x]);
     atomicAdd(drw + threadIdx.x, red[1 + 2 * B + threadIdx.x]);
   }
+}
+
+// max |x| as the bit pattern of a non-negative float (monotone as unsigned), then the power of two 2^-ceil(log2 max)
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(out, __float_as_uint(m));
+}
+__global__ void k_pow2_scale(const unsigned* __restrict__ maxbits, float* __restrict__ scale) {
+  const float m = __uint_as_float(*maxbits);
+  *scale = m > 0.f ? exp2f(-ceilf(log2f(m))) : 1.f;
 }
 
 // ---- loss and optimiser ------------------------------------------------------------------------------------------------------------
