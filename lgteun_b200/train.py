@@ -68,6 +68,18 @@ class FlatParameters:
             p.grad = views[key] if self.is_live(key) else None
 
 
+def allreduce_gradients(flat_grad: torch.Tensor, group=None) -> float:
+    """The one collective of data-parallel training: SUM all-reduce of the flat gradient over the ranks, in place.
+    Returns the factor the optimiser applies afterwards (1 / world size): every rank's loss is a mean over ITS batch
+    (nn.L1Loss, models/base/losses.py:29), so the mean over the global batch is the average of the rank gradients."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
 class Trainer:
     """The fused training step of ``UnlgFormer.train_iter`` for one process / one GPU; with an initialised
     ``torch.distributed`` process group (NCCL) the flat gradient is averaged over the ranks before the Adam update, i.e.
@@ -124,14 +136,13 @@ class Trainer:
     def step(self, ms: torch.Tensor, pan: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
         """One train_iter: returns the (local) loss as a 1-element CUDA tensor (no host sync)."""
         _, loss = self.forward_backward(ms, pan, gt)
-        if self.world > 1:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.group)
+        gscale = allreduce_gradients(self.flat.grad, self.group)
         lr = self.lr()
         self.steps += 1
         with torch.cuda.device(self.flat.device):
             self.handle.adam_step(self.flat.param.data_ptr(), self.flat.grad.data_ptr(), self.exp_avg.data_ptr(),
                                   self.exp_avg_sq.data_ptr(), self.flat.param.numel(), lr, self.betas[0], self.betas[1], self.eps,
-                                  self.steps, 1.0 / self.world, torch.cuda.current_stream().cuda_stream)
+                                  self.steps, gscale, torch.cuda.current_stream().cuda_stream)
         self.module._invalidate_runtime()      # the eval-mode handle keeps a packed snapshot of the weights: refresh on next use
         return loss
 

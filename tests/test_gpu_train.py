@@ -200,3 +200,16 @@ def test_module_train_iter_and_trainer(abi, O):
         else:
             ok = g.abs() > 0.05 * max(g.abs().max().item(), 1e-30)      # see the note on Adam's first step above
             assert ((v.cpu() - after[k]).abs()[ok] <= 2e-5).all(), k
+
+
+def test_data_parallel_trainer_two_gpus(abi):
+    """NCCL path: one process per GPU under torchrun (tests/ddp_train_check.py).  Needs two visible GPUs."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ddp_train_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DDP_OK 2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
