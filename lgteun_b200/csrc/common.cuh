@@ -108,6 +108,10 @@ bool train_pwgemm_supported(int K, int N);
 cudaError_t launch_train_pwgemm(int K, int N, int pro, int epi, const float* X, float* Y, const void* wpack, const float* bias,
                                 const float* aux, long long px, const float* scale_dev, cudaStream_t s);
 cudaError_t launch_pack_umma_f16_strided(const float* w, int wso, int wsi, void* pack /*N*K floats*/, int N, int K, cudaStream_t s);
+// weight gradient of a 1x1 conv on tcgen05 (K = pixels): dW[co*wso + ci*wsi] += sum_p dY[p,co] f(X[p,ci]), db[co] += sum_p dY[p,co]
+bool train_pwgrad_supported(int Cin, int Cout);
+cudaError_t launch_train_pwgrad(int Cin, int Cout, int act, const float* X, int ldx, const float* dY, int ldy, float* dW, int wso,
+                                int wsi, float* db, long long px, const float* scale_dev, cudaStream_t s);
 // metrics.cu — PSNR / SAM / ERGAS per image in fp64 (acc: N*(2+2B) doubles scratch, out: N*3 doubles)
 cudaError_t launch_metrics(const float* pred, const float* gt, double* acc, double* out, int N, int B, int H, int W,
                            float max_value, cudaStream_t s);

@@ -315,6 +315,169 @@ cudaError_t launch_pack_umma_f16_strided(const float* w, int wso, int wsi, void*
   return cudaGetLastError();
 }
 
+
+// ---- weight gradient of a 1x1 conv on the tensor cores (training backward) -------------------------------------------------------
+//   dW[co*wso + ci*wsi] += sum_p dY[p,co] * f(X[p,ci]);   db[co] += sum_p dY[p,co]          (K of the GEMM = pixels)
+// A CTA walks 128-pixel tiles: both operands are transposed while they are staged — a thread loads 8 consecutive pixels of
+// one channel and writes them as one 16-byte K-run of the core-matrix layout — so that A = dY^T [co][pixel] (128 rows, rows
+// >= Cout stay zero) and B = f(X)^T [ci][pixel] are K-major; every tile adds 8 x (hi*hi + hi*lo + lo*hi) MMAs into the same
+// [128 x NCI] fp32 TMEM accumulator, which is read once at the end and added to dW with atomics (the CTAs split the pixels).
+// dY is a gradient (~1e-7): it is multiplied by the step's power-of-two scale before the fp16 split, dW divided by it.
+template <int NCI, int ACT>
+__global__ void __launch_bounds__(kPwThreads, 1)
+pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy, int Cout, float* __restrict__ dW,
+                 int wso, int wsi, float* __restrict__ db, long long total_px, int num_tiles, const float* __restrict__ scale_dev) {
+  using namespace pw;
+  static_assert(NCI % 16 == 0 && NCI <= 256, "tile shape");
+  constexpr int KC = 16;                                                        // 128 pixels per tile = 16 K-chunks of 8
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
+  __half* ah = reinterpret_cast<__half*>(smem_raw + 16);                        // [KC][128][8]
+  __half* al = ah + 128 * 128;
+  __half* bh = al + 128 * 128;                                                  // [KC][NCI][8]
+  __half* bl = bh + NCI * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int co0 = blockIdx.y * 128;
+  const int mrows = Cout - co0 < 128 ? Cout - co0 : 128;                        // a power of two >= 16
+  constexpr uint32_t TCOLS = (NCI <= 32) ? 32 : (NCI <= 64) ? 64 : (NCI <= 128 ? 128 : 256);
+  const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
+
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+  for (int i = tid; i < 128 * 128 * 2 / 8; i += kPwThreads) reinterpret_cast<uint4*>(ah)[i] = make_uint4(0, 0, 0, 0);   // ah and al
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t a_h = smem_u32(ah), a_l = smem_u32(al), b_h = smem_u32(bh), b_l = smem_u32(bl);
+  uint32_t phase = 0;
+  float bsum = 0.f;
+  bool first = true;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const long long p0 = (long long)tile * 128;
+    for (int item = tid; item < KC * mrows; item += kPwThreads) {              // 256 % mrows == 0: a thread keeps its channel
+      const int co = item & (mrows - 1), g = item / mrows;
+      float2 v[4];
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long p = p0 + g * 8 + j;
+        t[j] = p < total_px ? __ldg(dY + p * ldy + co0 + co) : 0.f;
+        bsum += t[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = make_float2(t[2 * j] * a_scale, t[2 * j + 1] * a_scale);
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(ah + (g * 128 + co) * 8) = hi;
+      *reinterpret_cast<uint4*>(al + (g * 128 + co) * 8) = lo;
+    }
+    for (int item = tid; item < KC * NCI; item += kPwThreads) {
+      const int ci = item % NCI, g = item / NCI;
+      float2 v[4];
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long p = p0 + g * 8 + j;
+        t[j] = p < total_px ? __ldg(X + p * ldx + ci) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = make_float2(t[2 * j], t[2 * j + 1]);
+        if constexpr (ACT == 1) v[j] = gelu_pair(v[j]);
+      }
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      *reinterpret_cast<uint4*>(bh + (g * NCI + ci) * 8) = hi;
+      *reinterpret_cast<uint4*>(bl + (g * NCI + ci) * 8) = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc(NCI);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t dah = umma_desc(a_h + ks * 2 * 128 * 16, 128 * 16, 128);
+        const uint64_t dal = umma_desc(a_l + ks * 2 * 128 * 16, 128 * 16, 128);
+        const uint64_t dbh = umma_desc(b_h + ks * 2 * NCI * 16, NCI * 16, 128);
+        const uint64_t dbl = umma_desc(b_l + ks * 2 * NCI * 16, NCI * 16, 128);
+        umma_f16(tmem, dah, dbh, idesc, !(first && ks == 0));
+        umma_f16(tmem, dah, dbl, idesc, 1);
+        umma_f16(tmem, dal, dbh, idesc, 1);
+      }
+      umma_commit(mbar);
+    }
+    first = false;
+    mbar_wait(mbar, phase);                        // the operand tiles may be overwritten
+    phase ^= 1;
+  }
+  tc_fence_after();
+  if (!first) {
+    const int row = q * 32 + lane;                 // output channel co0 + row
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = half * (NCI / 2); c0 < (half + 1) * (NCI / 2); c0 += 8) {
+      float2 v[4];
+      tmem_ld8(lane_addr + c0, v);
+      tmem_ld_wait();
+      if (row < mrows) {
+        float* dst = dW + (size_t)(co0 + row) * wso;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          atomicAdd(dst + (size_t)(c0 + 2 * j) * wsi, v[j].x * inv_scale);
+          atomicAdd(dst + (size_t)(c0 + 2 * j + 1) * wsi, v[j].y * inv_scale);
+        }
+      }
+    }
+    if (db && tid < KC * mrows) atomicAdd(db + co0 + (tid & (mrows - 1)), bsum);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+template <int NCI>
+static cudaError_t pwgrad_launch(int act, const float* X, int ldx, const float* dY, int ldy, int Cout, float* dW, int wso, int wsi,
+                                 float* db, long long px, const float* scale_dev, cudaStream_t s) {
+  const int tiles = (int)((px + 127) / 128);
+  const size_t smem = 16 + (size_t)(2 * 128 * 128 + 2 * NCI * 128) * 2 + 128;
+  const dim3 grid(tiles < 148 ? tiles : 148, (Cout + 127) / 128);
+  cudaError_t e;
+  if (act) {
+    e = cudaFuncSetAttribute(pwgrad_tc_kernel<NCI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pwgrad_tc_kernel<NCI, 1><<<grid, kPwThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, tiles, scale_dev);
+  } else {
+    e = cudaFuncSetAttribute(pwgrad_tc_kernel<NCI, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pwgrad_tc_kernel<NCI, 0><<<grid, kPwThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, tiles, scale_dev);
+  }
+  return cudaGetLastError();
+}
+bool train_pwgrad_supported(int Cin, int Cout) {
+  auto p2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  return p2(Cin) && Cin >= 16 && Cin <= 256 && p2(Cout) && Cout >= 16 && Cout <= 256;
+}
+cudaError_t launch_train_pwgrad(int Cin, int Cout, int act, const float* X, int ldx, const float* dY, int ldy, float* dW, int wso,
+                                int wsi, float* db, long long px, const float* scale_dev, cudaStream_t s) {
+  switch (Cin) {
+    case 16: return pwgrad_launch<16>(act, X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, scale_dev, s);
+    case 32: return pwgrad_launch<32>(act, X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, scale_dev, s);
+    case 64: return pwgrad_launch<64>(act, X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, scale_dev, s);
+    case 128: return pwgrad_launch<128>(act, X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, scale_dev, s);
+    case 256: return pwgrad_launch<256>(act, X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, scale_dev, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
 // conv-FFN of a c = 64 block.  scratch: two buffers of N*H*W*256 floats (h1 / act, hidden).
 cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, float* buf_b, float* y, int N, int H, int W,
                                cudaStream_t s) {

@@ -114,8 +114,20 @@ void pw(Run& R, int act, TV x, int Cin, const float* W, int wso, int wsi, const 
   }
   R.check();
 }
-void pw_wgrad(Run& R, int act, TV x, int Cin, TV dy, int Cout, const float* dW, int wso, int wsi, const float* db, size_t NP) {
+bool use_tc_wgrad(int Cin, int Cout) {
+  static const bool simt = [] { const char* e = getenv("LGTEUN_TRAIN_GEMM"); return e && std::string(e) == "simt"; }();
+  return !simt && train_pwgrad_supported(Cin, Cout);
+}
+void pw_wgrad(Run& R, int act, TV x, int Cin, TV dy, int Cout, const float* dW, int wso, int wsi, const float* db, size_t NP,
+              const float* gscale = nullptr) {
   if (R.dry) return;
+  if (gscale && !x.nchw && !dy.nchw && use_tc_wgrad(Cin, Cout)) {
+    cudaError_t e = launch_train_pwgrad(Cin, Cout, act, x.p, x.ld, dy.p, dy.ld, const_cast<float*>(dW), wso, wsi,
+                                        const_cast<float*>(db), (long long)NP, gscale, R.s);
+    ++R.launches;
+    if (R.err == cudaSuccess) R.err = e;
+    return;
+  }
   const int ci_tiles = (Cin + 63) / 64, co_tiles = (Cout + 63) / 64;
   const size_t tiles = (NP + 31) / 32;
   const unsigned gx = (unsigned)std::min<size_t>(tiles, std::max(1, 148 * 4 / (ci_tiles * co_tiles)));
@@ -309,7 +321,7 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
   const size_t NP = (size_t)N * H * W, SP = (size_t)N * H * Wh * c2 * 2;
   const TV gx = nhwc(gX, ch);
   // FFN
-  pw_wgrad(R, 1, nhwc(t.h3, c4), c4, gx, ch, g.f2_w, c4, 1, g.f2_b, NP);
+  pw_wgrad(R, 1, nhwc(t.h3, c4), c4, gx, ch, g.f2_w, c4, 1, g.f2_b, NP, S.T->gscale);
   const bool tc = use_tc_gemm(ch, c4);
   const float* gs = S.T->gscale;
   float* dh3 = R.take(NP * c4);
@@ -319,12 +331,12 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
   dw_wgrad(R, 3, nhwc(t.h2, c4), nhwc(dh3, c4), g.dw_w, g.dw_b, N, H, W, c4);
   float* dh2 = R.take(NP * c4);
   dwconv(R, 3, nhwc(dh3, c4), w.dw_w, nullptr, nhwc(dh2, c4), N, H, W, c4, 1);
-  pw_wgrad(R, 1, nhwc(t.h1, c4), c4, nhwc(dh2, c4), c4, g.f1_w, c4, 1, g.f1_b, NP);
+  pw_wgrad(R, 1, nhwc(t.h1, c4), c4, nhwc(dh2, c4), c4, g.f1_w, c4, 1, g.f1_b, NP, S.T->gscale);
   float* dh1 = R.take(NP * c4);
   const TV gate1 = nhwc(t.h1, c4);
   if (tc) tc_pw(R, c4, c4, 0, 3, dh2, dh1, w.f1_w, 1, c4, nullptr, t.h1, NP, gs);
   else pw(R, 0, nhwc(dh2, c4), c4, w.f1_w, 1, c4, nullptr, nhwc(dh1, c4), c4, NP, nullptr, &gate1);
-  pw_wgrad(R, 0, nhwc(t.A2, ch), ch, nhwc(dh1, c4), c4, g.f0_w, ch, 1, g.f0_b, NP);
+  pw_wgrad(R, 0, nhwc(t.A2, ch), ch, nhwc(dh1, c4), c4, g.f0_w, ch, 1, g.f0_b, NP, S.T->gscale);
   float* dA2 = R.take(NP * ch);
   if (tc) tc_pw(R, c4, ch, 0, 0, dh1, dA2, w.f0_w, 1, ch, nullptr, nullptr, NP, gs);
   else pw(R, 0, nhwc(dh1, c4), c4, w.f0_w, 1, ch, nullptr, nhwc(dA2, ch), ch, NP);
@@ -339,7 +351,7 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
       R.check();
     }
   }
-  pw_wgrad(R, 0, nhwc(t.cat, ch), ch, nhwc(dpr, ch), ch, g.proj_w, ch, 1, g.proj_b, NP);
+  pw_wgrad(R, 0, nhwc(t.cat, ch), ch, nhwc(dpr, ch), ch, g.proj_w, ch, 1, g.proj_b, NP, S.T->gscale);
   float* dcat = R.take(NP * ch);
   pw(R, 0, nhwc(dpr, ch), ch, w.proj_w, 1, ch, nullptr, nhwc(dcat, ch), ch, NP);
   float* dA = R.take(NP * ch);
@@ -413,20 +425,20 @@ void bwd_prior(Run& R, const Step& S, const PriorW& w, const PriorW& g, const Pr
   pw(R, 0, nchw(dout, B, P), B, w.tail_w, 1, C, nullptr, nhwc(gX, C), C, NP);
   for (int j = 1; j >= 0; --j) bwd_block(R, S, w.dec[j], g.dec[j], C, t.dec[j], gX, H, W, 3 + j);
   const float* skip = t.enc[1].Xout;
-  pw_wgrad(R, 0, nhwc(t.u1, C), C, nhwc(gX, C), C, g.fuse_w, 2 * C, 1, g.fuse_b, NP);
-  pw_wgrad(R, 0, nhwc(skip, C), C, nhwc(gX, C), C, g.fuse_w + C, 2 * C, 1, nullptr, NP);
+  pw_wgrad(R, 0, nhwc(t.u1, C), C, nhwc(gX, C), C, g.fuse_w, 2 * C, 1, g.fuse_b, NP, S.T->gscale);
+  pw_wgrad(R, 0, nhwc(skip, C), C, nhwc(gX, C), C, g.fuse_w + C, 2 * C, 1, nullptr, NP, S.T->gscale);
   float* du1 = R.take(NP * C);
   pw(R, 0, nhwc(gX, C), C, w.fuse_w, 1, 2 * C, nullptr, nhwc(du1, C), C, NP);
   float* gSkip = R.take(NP * C);
   pw(R, 0, nhwc(gX, C), C, w.fuse_w + C, 1, 2 * C, nullptr, nhwc(gSkip, C), C, NP);
-  pw_wgrad(R, 0, nhwc(t.u0, 2 * C), 2 * C, nhwc(du1, C), C, g.up_w, 2 * C, 1, g.up_b, NP);
+  pw_wgrad(R, 0, nhwc(t.u0, 2 * C), 2 * C, nhwc(du1, C), C, g.up_w, 2 * C, 1, g.up_b, NP, S.T->gscale);
   float* du0 = R.take(NP * 2 * C);
   pw(R, 0, nhwc(du1, C), C, w.up_w, 1, 2 * C, nullptr, nhwc(du0, 2 * C), 2 * C, NP);
   float* gL = R.take(NP2 * 2 * C);
   R.zero(gL, NP2 * 2 * C);
   resize(R, nhwc(gL, 2 * C), H2, W2, nhwc(du0, 2 * C), H, W, 2 * C, N, 1);
   bwd_block(R, S, w.bott[0], g.bott[0], 2 * C, t.bott, gL, H2, W2, 2);
-  pw_wgrad(R, 0, nhwc(t.d0, C), C, nhwc(gL, 2 * C), 2 * C, g.down_w, C, 1, g.down_b, NP2);
+  pw_wgrad(R, 0, nhwc(t.d0, C), C, nhwc(gL, 2 * C), 2 * C, g.down_w, C, 1, g.down_b, NP2, S.T->gscale);
   float* dd0 = R.take(NP2 * C);
   pw(R, 0, nhwc(gL, 2 * C), 2 * C, w.down_w, 1, C, nullptr, nhwc(dd0, C), C, NP2);
   resize(R, nhwc(gSkip, C), H, W, nhwc(dd0, C), H2, W2, C, N, 1);
