@@ -199,6 +199,13 @@ void dw_wgrad(Run& R, int K, TV x, TV dy, const float* dw, const float* db, int 
   if (R.dry) return;
   const size_t NP = (size_t)N * H * W;
   const int lh = ilog2(H), lw = ilog2(W), lc = ilog2(C);
+  if (K == 3 && !x.nchw && !dy.nchw && x.ld == C && dy.ld == C && C >= 4 && C <= 1024 && W >= 8) {
+    const size_t per_block = (size_t)(1024 / C) * 8;   // pixels one block visits per sweep
+    const unsigned gv = (unsigned)std::min<size_t>(148 * 8, (NP + per_block - 1) / per_block);
+    k_dw3_wgrad_v4<<<gv, 256, C * 10 * sizeof(float), R.s>>>(x.p, dy.p, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
+    R.check();
+    return;
+  }
   const unsigned g = (unsigned)std::min<size_t>(148 * 8, (NP + 256 / C - 1) / (256 / C));
   if (K == 3) k_dw_wgrad<3><<<g, 256, C * 10 * sizeof(float), R.s>>>(x, dy, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
   else k_dw_wgrad<1><<<g, 256, C * 2 * sizeof(float), R.s>>>(x, dy, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);

@@ -392,6 +392,71 @@ __global__ void __launch_bounds__(256) k_dw_wgrad(TV x, TV dy, float* __restrict
   }
 }
 
+// The conv-FFN's depthwise 3x3 (LGT.py:101, NHWC with ld == C, W >= 8): thread = (8-pixel row segment, channel quad); a
+// 3x3 window of float4 slides along the row, so a pixel costs three x loads and one dy load of 128 bits for four channels.
+__device__ __forceinline__ void fma4(float4& a, const float4 g, const float4 v) {
+  a.x = fmaf(g.x, v.x, a.x); a.y = fmaf(g.y, v.y, a.y); a.z = fmaf(g.z, v.z, a.z); a.w = fmaf(g.w, v.w, a.w);
+}
+__global__ void __launch_bounds__(256) k_dw3_wgrad_v4(const float* __restrict__ x, const float* __restrict__ dy,
+                                                      float* __restrict__ dw, float* __restrict__ db, int N, int lh, int lw,
+                                                      int lc) {
+  extern __shared__ float sm[];   // [C][10]
+  const int H = 1 << lh, W = 1 << lw, C = 1 << lc, lq = lc - 2, CQ = 1 << lq;
+  for (int i = threadIdx.x; i < C * 10; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const int q = threadIdx.x & (CQ - 1), slot = threadIdx.x >> lq, slots = 256 >> lq, lseg = lw - 3;
+  const size_t nseg = (size_t)N << (lh + lseg);
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(dy);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[9], bacc = zero;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = zero;
+  for (size_t s = (size_t)blockIdx.x * slots + slot; s < nseg; s += (size_t)gridDim.x * slots) {
+    const int x0 = (int)(s & (((size_t)1 << lseg) - 1)) << 3, yy = (int)((s >> lseg) & (H - 1));
+    const size_t row = (s >> lseg) << lw;        // pixel index of (n, yy, 0)
+    const bool up = yy > 0, dn = yy + 1 < H;
+    float4 wa[3], wb[3], wc[3];
+    auto column = [&](int xx, float4 (&c)[3]) {
+      const bool in = xx >= 0 && xx < W;
+      const size_t p = ((row + xx) << lq) + q;
+      c[0] = (in && up) ? __ldg(x4 + p - ((size_t)W << lq)) : zero;
+      c[1] = in ? __ldg(x4 + p) : zero;
+      c[2] = (in && dn) ? __ldg(x4 + p + ((size_t)W << lq)) : zero;
+    };
+    column(x0 - 1, wa);
+    column(x0, wb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int xx = x0 + i;
+      column(xx + 1, wc);
+      const float4 g = __ldg(g4 + ((row + xx) << lq) + q);
+      bacc.x += g.x; bacc.y += g.y; bacc.z += g.z; bacc.w += g.w;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        fma4(acc[r * 3 + 0], g, wa[r]);
+        fma4(acc[r * 3 + 1], g, wb[r]);
+        fma4(acc[r * 3 + 2], g, wc[r]);
+        wa[r] = wb[r];
+        wb[r] = wc[r];
+      }
+    }
+  }
+  float* mine = sm + (q << 2) * 10;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    atomicAdd(mine + i, acc[i].x); atomicAdd(mine + 10 + i, acc[i].y);
+    atomicAdd(mine + 20 + i, acc[i].z); atomicAdd(mine + 30 + i, acc[i].w);
+  }
+  atomicAdd(mine + 9, bacc.x); atomicAdd(mine + 19, bacc.y); atomicAdd(mine + 29, bacc.z); atomicAdd(mine + 39, bacc.w);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 10; i += 256) {
+    const int kk = i / 10, t = i % 10;
+    if (t < 9) atomicAdd(dw + kk * 9 + t, sm[i]);
+    else if (db) atomicAdd(db + kk, sm[i]);
+  }
+}
+
 // ---- bicubic resize (bmu.sampling_ / sampling_unit_, basic_module_unformer_v2.py:21-34): Keys A = -0.75,
 // src = (dst + .5) * rscale - .5, tap indices clamped.  adjoint = 1 scatters y (a gradient) into x with atomics. ----------------
 __device__ __forceinline__ void cubic_coef(float t, float (&c)[4]) {
