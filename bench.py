@@ -550,13 +550,145 @@ def other_workload(args, dev):
     return {name: {"workload": desc, "batch": batch, "pairs_per_s": batch / (t * 1e-3), "ms_per_step": t}}
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# companion operators: SFIIN.Freprocess models/SFIIN.py:210-236, PanFormer WindowAttention
+# models/common/modules.py:341-422
+# ----------------------------------------------------------------------------------------------------------------
+def companion_spec(name, batch):
+    """(metric, description, module, inputs, oracle closure, roofline dict without the measured fields, launches per step)"""
+    import torch
+    import lgteun_b200
+    g = torch.Generator().manual_seed(0)
+    torch.manual_seed(19971118)
+    if name == "freprocess":
+        C, H, W = 8, 256, 256                                   # SFIIN builds Freprocess(8), models/SFIIN.py:321,247
+        batch = batch or 64
+        net = lgteun_b200.Freprocess(C)
+        inputs = (torch.rand(batch, C, H, W, generator=g), torch.rand(batch, C, H, W, generator=g))
+
+        def oracle(sd, xs):
+            from oracle import companions_oracle as CO
+            return CO.freprocess_forward(sd, *xs)
+        alg = 3 * batch * C * H * W * 4
+        roof = {"bound": "hbm", "kernel": "whole operator (7 launches: pre conv, 4 FFT passes, fusion, post conv)",
+                "work": alg, "unit": "GB/s", "algorithmic_bytes": alg}
+        return ("SFIIN.Freprocess fwd feature-map pairs/sec",
+                f"SFIIN.Freprocess(channels={C}) forward on two [{batch},{C},{H},{W}] feature maps (SURVEY 8f rank 4)",
+                net, inputs, oracle, roof, 7)
+    dim, heads, hd, n = 64, 4, 16, 64                           # PanFormer: n_feats 64, 4 heads of 16, window 4 (panformer.py:22)
+    batch = batch or 128
+    net = lgteun_b200.WindowAttention(dim=dim, heads=heads, head_dim=hd, shifted=True, window_size=4, relative_pos_embedding=True,
+                                      cross_attn=True)
+    inputs = (torch.randn(batch, n, n, dim, generator=g), torch.randn(batch, n, n, dim, generator=g))
+
+    def oracle(sd, xs):
+        from oracle import companions_oracle as CO
+        return CO.window_attention_forward(sd, xs[0], xs[1], heads, hd, 4, True, True)
+    inner = heads * hd
+    flops = batch * n * n * (2 * dim * 3 * inner + 2 * inner * dim + 4 * 16 * inner)
+    roof = {"bound": "tensor", "kernel": "win_attn_kernel<16> (q/kv projections + shifted cross window attention + to_out, one launch)",
+            "work": flops, "unit": "TFLOP/s", "algorithmic_bytes": 3 * batch * n * n * dim * 4,
+            "note": "fp32 on CUDA cores in this round (36.9 kFLOP per token against 768 B: far above the HBM ridge)"}
+    return ("PanFormer WindowAttention fwd feature maps/sec",
+            f"PanFormer WindowAttention(dim {dim}, {heads}x{hd}, window 4, shifted, cross) forward on [{batch},{n},{n},{dim}] maps "
+            f"(SURVEY 8f rank 4)", net, inputs, oracle, roof, 1)
+
+
+def run_companion(args):
+    """value = operator calls' items / s, device-resident; e2e through the module with pinned host tensors."""
+    import torch
+    threads = cpu_threads()
+    metric, desc, net, inputs, oracle, roof, launches = companion_spec(args.workload, args.batch)
+    batch = inputs[0].shape[0]
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        torch.set_num_threads(threads)
+        nb = 8
+        xs = tuple(t[:nb] for t in inputs)
+        times = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            oracle(sd, xs)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        v = nb / statistics.median(times)
+        emit({"impl": "reference", "metric": metric, "value": v, "unit": "items/s", "n_gpus": args.gpus, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": desc + f"; CPU sample: batch {nb} per step", "parallelism": f"cpu x{threads} threads"},
+              "cpu_baseline": {"value": v, "unit": "items/s", "cores": threads, "kind": "port",
+                               "sample": f"{args.steps} forwards of {nb} items (oracle/companions_oracle.py, torch CPU fp32), median"},
+              "e2e": {"value": v, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return 0
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise RuntimeError("the companion workloads are single-GPU operator benches")
+    dev = torch.device("cuda", 0)
+    net = net.to(dev).eval()
+    ind = tuple(t.to(dev) for t in inputs)
+    sampler = ClockSampler(0)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            net(*ind)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            net(*ind)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_step = e0.elapsed_time(e1) / args.steps
+        # end to end: pinned host tensors in, pinned host tensor out, every step
+        inh = tuple(t.pin_memory() for t in inputs)
+        oh = torch.empty_like(inputs[0]).pin_memory()
+        net(*(t.to(dev, non_blocking=True) for t in inh))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oh.copy_(net(*(t.to(dev, non_blocking=True) for t in inh)), non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    peaks = load_peaks()
+    peak = peaks["hbm_gbs"] if roof["bound"] == "hbm" else peaks["bf16_tflops"]
+    achieved = roof.pop("work") / (ms_step * 1e-3) / (1e9 if roof["bound"] == "hbm" else 1e12)
+    roof.update(achieved=achieved, peak=peak, frac=achieved / peak, traffic=None,
+                peak_source=f"{peaks['source']} " + ("copy bandwidth" if roof["bound"] == "hbm" else "bf16 dense burst"))
+    line = {"metric": metric, "value": batch / (ms_step * 1e-3), "unit": "items/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": batch, "parallelism": "single GPU",
+                       "l2": "inputs and output of one step exceed the 126 MB L2", "weights": "torch default init, seed 19971118"},
+            "e2e": {"value": batch / e2e_s, "unit": "items/s", "h2d_bytes_per_step": sum(t.numel() for t in inputs) * 4,
+                    "d2h_bytes_per_step": inputs[0].numel() * 4, "api": f"lgteun_b200.{type(net).__name__}.forward on pinned host tensors"},
+            "gpu_launches": launches * args.steps, "clocks": clocks, "roofline": roof}
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(threads)
+        xs = tuple(t[:8] for t in inputs)
+        ts = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            ref = oracle(sd, xs)
+            ts.append(time.perf_counter() - t0)
+        with torch.no_grad():
+            err = (net(*(t[:8] for t in ind)).cpu() - ref).abs().max().item()
+        line["cpu_baseline"] = {"value": 8 / statistics.median(ts[1:]), "unit": "items/s", "cores": threads, "kind": "port",
+                                "sample": "3 forwards of 8 items (oracle port, torch CPU fp32), median"}
+        line["max_abs_delta_vs_oracle"] = err
+    emit(line)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gf2", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
+    ap.add_argument("--workload", default="gf2", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + ["freprocess", "winattn"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--skip-dead-priors", action="store_true",
                     help="skip prior_module[0..K-2] whose output the reference discards (identical result)")
@@ -568,6 +700,8 @@ def main():
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload in ("freprocess", "winattn"):
+        return run_companion(args)
     if args.workload in TRAIN_WORKLOADS:
         if args.impl == "reference":
             return run_train_reference(args)

@@ -187,6 +187,33 @@ int lgteun_dropout_mask(lgteun_t* ctx, uint64_t seed, int layer, float p, float*
  * 1/(1-p)) used by the following train_forward / train_backward pairs instead of the generated masks; NULL switches back. */
 int lgteun_train_set_masks(lgteun_t* ctx, const float* const* masks);
 
+/* ---- companion operators -----------------------------------------------------------------------
+ * SFIIN.Freprocess.forward(msf, panf) (models/SFIIN.py:210-236), the FFT amplitude / phase fusion of a network the
+ * reference repository ships beside LGTEUN: rfft2 of the two pre-convolved maps, amp_fuse / pha_fuse perceptrons per
+ * spectrum bin, |irfft2|, post conv.  msf, panf, out: NCHW [N,C,H,W] device tensors; C in {4, 8, 16} (SFIIN: 8), H and W
+ * powers of two in [8, 1024].  weights = 14 device pointers in state_dict order: pre1.weight, pre1.bias, pre2.weight,
+ * pre2.bias, amp_fuse.0.weight [C,2C,1,1], amp_fuse.0.bias, amp_fuse.2.weight, amp_fuse.2.bias, pha_fuse.0.weight,
+ * pha_fuse.0.bias, pha_fuse.2.weight, pha_fuse.2.bias, post.weight, post.bias.  No handle: the operator keeps no state;
+ * the caller provides `workspace` (device memory of at least lgteun_op_freprocess_workspace_bytes bytes). */
+int64_t lgteun_op_freprocess_workspace_bytes(int N, int C, int H, int W);
+int lgteun_op_freprocess(int device, const float* msf, const float* panf, float* out, int N, int C, int H, int W,
+                         const float* const* weights, float* workspace, int64_t workspace_bytes, void* stream);
+
+/* PanFormer's WindowAttention.forward(x, y=None) (models/common/modules.py:341-422; built by SwinBlock :425-455 with
+ * dim 64, 4 heads of 16, window 4: models/panformer.py:22): optional cyclic shift, bias-free q/k/v projections (self
+ * attention: y = NULL, w_q = to_qkv.weight, w_kv = to_qkv.weight + heads*head_dim*dim; cross attention: q from y with
+ * to_q.weight, k/v from x with to_kv.weight), window attention with the relative position table [2ws-1, 2ws-1]
+ * (relative_pos_embedding != 0) or a dense [ws^2, ws^2] bias, the two -inf masks [ws^2, ws^2] on the last window row /
+ * column of a shifted block, to_out (weight [dim, heads*head_dim], bias), shift back.  x, y, out: [b, n_h, n_w, dim]
+ * device tensors (channels last, as the reference passes them); scale = head_dim ** -0.5.
+ * window_size must be 4, head_dim in {8, 16, 32}, dim % 4 == 0, dim and heads*head_dim <= 128 with the
+ * projection weights (4 * dim * heads*head_dim floats) resident in shared memory (PanFormer's 64 x 64: 93 KB of 227 KB). */
+int lgteun_op_window_attention(int device, const float* x, const float* y, float* out, int b, int n_h, int n_w, int dim, int heads,
+                               int head_dim, int window_size, int shifted, int relative_pos_embedding, float scale,
+                               const float* w_q, const float* w_kv, const float* w_out, const float* b_out,
+                               const float* pos_embedding, const float* upper_lower_mask, const float* left_right_mask,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

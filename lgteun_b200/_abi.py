@@ -51,6 +51,11 @@ SIGNATURES = {
                                  ctypes.c_float, c_int, ctypes.c_float, c_void_p]),
     "lgteun_dropout_mask": (c_int, [c_void_p, ctypes.c_uint64, c_int, ctypes.c_float, _F, c_int64, c_void_p]),
     "lgteun_train_set_masks": (c_int, [c_void_p, POINTER(c_void_p)]),
+    # companion operators
+    "lgteun_op_freprocess_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "lgteun_op_freprocess": (c_int, [c_int, _F, _F, _F, c_int, c_int, c_int, c_int, POINTER(c_void_p), _F, c_int64, c_void_p]),
+    "lgteun_op_window_attention": (c_int, [c_int, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                           ctypes.c_float, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
 }
 
 _lib = None

@@ -584,6 +584,23 @@ size_t plan_bytes(lgteun_ctx* c, TrainState* T, int N, int h, int w) {
 
 }  // namespace
 
+// The generic power-of-two FFT passes, exported for the companion operators of companion_ops.cu.
+namespace lgctx {
+cudaError_t launch_fft_rows(cudaStream_t s, int mode, const float* xin, int ldx, float* spec, float* xout, int ldo, float* xabs,
+                            int ldabs, int N, int H, int W, int c2, float scale, int weight2) {
+  Run R{nullptr};
+  R.s = s;
+  fft_rows(R, mode, xin, ldx, nullptr, spec, xout, ldo, xabs, ldabs, N, H, W, c2, scale, weight2);
+  return R.err;
+}
+cudaError_t launch_fft_cols(cudaStream_t s, float* spec, int N, int H, int W, int c2, int dir, int fixreal) {
+  Run R{nullptr};
+  R.s = s;
+  fft_cols(R, spec, N, H, W, c2, dir, fixreal);
+  return R.err;
+}
+}  // namespace lgctx
+
 extern "C" {
 
 int64_t lgteun_flat_numel(const lgteun_t* c) { return c ? (int64_t)c->flat_floats : -1; }

@@ -656,18 +656,41 @@ __device__ __forceinline__ void fft_twiddles(float2* tw, int L, int dir) {
     tw[k] = make_float2(c, dir < 0 ? -s : s);
   }
 }
-// in-place transform of nch lines stored bit-reversed at buf[ch*ls + i]; ends with a __syncthreads()
+// in-place transform of nch lines stored bit-reversed at buf[ch*ls + i]; ends with a __syncthreads().
+// Two radix-2 levels per sweep (a thread carries four points through levels s and s + 1 in registers): the same butterflies
+// and twiddles as the plain radix-2 schedule, hence the same bits, with half the barriers and shared-memory round trips.
 __device__ __forceinline__ void fft_pow2(float2* buf, const float2* tw, int L, int logL, int nch, int ls) {
   __syncthreads();
-  for (int s = 1; s <= logL; ++s) {
-    const int half = 1 << (s - 1), tstep = L >> s;
+  int s = 1;
+  if (logL & 1) {
     for (int b = threadIdx.x; b < nch * (L / 2); b += blockDim.x) {
       const int ch = b / (L / 2), j = b - ch * (L / 2);
-      const int pos = j & (half - 1), i0 = ((j >> (s - 1)) << s) + pos, i1 = i0 + half;
       float2* base = buf + ch * ls;
-      const float2 a = base[i0], t = cmul(tw[pos * tstep], base[i1]);
-      base[i0] = make_float2(a.x + t.x, a.y + t.y);
-      base[i1] = make_float2(a.x - t.x, a.y - t.y);
+      const float2 a = base[2 * j], t = base[2 * j + 1];          // level 1: twiddle 1
+      base[2 * j] = make_float2(a.x + t.x, a.y + t.y);
+      base[2 * j + 1] = make_float2(a.x - t.x, a.y - t.y);
+    }
+    __syncthreads();
+    s = 2;
+  }
+  for (; s < logL; s += 2) {
+    const int half = 1 << (s - 1), t1 = L >> s, t2 = L >> (s + 1);
+    for (int b = threadIdx.x; b < nch * (L / 4); b += blockDim.x) {
+      const int ch = b / (L / 4), j = b - ch * (L / 4);
+      const int pos = j & (half - 1), i0 = ((j >> (s - 1)) << (s + 1)) + pos;
+      float2* base = buf + ch * ls;
+      const float2 x0 = base[i0], x1 = base[i0 + half], x2 = base[i0 + 2 * half], x3 = base[i0 + 3 * half];
+      const float2 w1 = tw[pos * t1], wa = tw[pos * t2], wb = tw[(pos + half) * t2];
+      float2 t = cmul(w1, x1);
+      const float2 y0 = make_float2(x0.x + t.x, x0.y + t.y), y1 = make_float2(x0.x - t.x, x0.y - t.y);
+      t = cmul(w1, x3);
+      const float2 y2 = make_float2(x2.x + t.x, x2.y + t.y), y3 = make_float2(x2.x - t.x, x2.y - t.y);
+      t = cmul(wa, y2);
+      base[i0] = make_float2(y0.x + t.x, y0.y + t.y);
+      base[i0 + 2 * half] = make_float2(y0.x - t.x, y0.y - t.y);
+      t = cmul(wb, y3);
+      base[i0 + half] = make_float2(y1.x + t.x, y1.y + t.y);
+      base[i0 + 3 * half] = make_float2(y1.x - t.x, y1.y - t.y);
     }
     __syncthreads();
   }
