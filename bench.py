@@ -570,11 +570,11 @@ def companion_spec(name, batch):
             from oracle import companions_oracle as CO
             return CO.freprocess_forward(sd, *xs)
         alg = 3 * batch * C * H * W * 4
-        roof = {"bound": "hbm", "kernel": "whole operator (7 launches: pre conv, 4 FFT passes, fusion, post conv)",
+        roof = {"bound": "hbm", "kernel": "whole operator (3 launches: pre convs + row rFFT, column FFT + fusion + inverse column FFT, inverse row FFT + post conv)",
                 "work": alg, "unit": "GB/s", "algorithmic_bytes": alg}
         return ("SFIIN.Freprocess fwd feature-map pairs/sec",
                 f"SFIIN.Freprocess(channels={C}) forward on two [{batch},{C},{H},{W}] feature maps (SURVEY 8f rank 4)",
-                net, inputs, oracle, roof, 7)
+                net, inputs, oracle, roof, 3)
     dim, heads, hd, n = 64, 4, 16, 64                           # PanFormer: n_feats 64, 4 heads of 16, window 4 (panformer.py:22)
     batch = batch or 128
     net = lgteun_b200.WindowAttention(dim=dim, heads=heads, head_dim=hd, shifted=True, window_size=4, relative_pos_embedding=True,

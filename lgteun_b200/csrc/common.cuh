@@ -85,6 +85,15 @@ cudaError_t fft256_init_tables(cudaStream_t s);
 cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s);
 cudaError_t launch_fft_cols128(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s);   // H = 128
 cudaError_t launch_fft_rows_fwd256(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s);
+// plain register-resident passes (no LayerNorm / mixing / projection) for the companion operator of companion_ops.cu
+cudaError_t launch_fft_cols_plain(int H, int c2, float* spec, int N, int W, int dir, cudaStream_t s);                 // H in {128, 256}
+// forward columns + amp/pha fusion + inverse columns of Freprocess in one launch; cudaErrorNotSupported if (H, C) is not built.
+// fuse_w = {amp_fuse.0.weight, .0.bias, amp_fuse.2.weight, .2.bias, pha_fuse.0.weight, .0.bias, pha_fuse.2.weight, .2.bias}
+cudaError_t launch_fre_cols_fused(int H, int C, const float* S, float* G, const float* const* fuse_w, int N, int W, cudaStream_t s);
+cudaError_t launch_fft_rows_fwd_pre(int W, int C, const float* msf, const float* panf, const float* const* pre_w, float* spec, int N,
+                                    int H, cudaStream_t s);
+cudaError_t launch_fft_rows_inv_post(int W, int C, const float* spec, const float* post_w, const float* post_b, float* y_nchw, int N,
+                                     int H, cudaStream_t s);
 cudaError_t launch_fft_rows_fwd128(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s);   // W = 128
 cudaError_t launch_fft_rows_inv256(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
                                    int N, int H, cudaStream_t s);

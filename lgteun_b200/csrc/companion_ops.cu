@@ -8,14 +8,19 @@
 //     out  = post(|irfft2(complex(amp cos pha + 1e-8, amp sin pha + 1e-8) + 1e-8, s=(H, W))|)           :232-236
 //
 // Layout: the two pre-convolved maps are written NHWC side by side ([N,H,W,2C]: ms channels, then pan channels), so ONE
-// real-to-complex transform (row pass + column pass of the global mixer, train_kernels.cuh) produces both spectra
-// S[n][ky][kx][2C]; the fusion kernel reads a bin's 2C complex values once, runs both two-layer perceptrons in registers
-// with the weights in shared memory and writes the C fused complex values; the inverse passes end in |.| and the post
-// conv writes NCHW.  The spectra are the only intermediates in HBM (the reference materialises 14).
+// real-to-complex transform produces both spectra S[n][ky][kx][2C]; the fusion kernel reads a bin's 2C complex values once,
+// runs both two-layer perceptrons in registers with the weights in shared memory and writes the C fused complex values; the
+// inverse row pass ends in |.|, the post conv and the NCHW store.  At 128 / 256 points the transforms are the register-
+// resident radix-16 passes of the global mixer (fft256.cu: plain forward rows, forward-only / inverse-only columns, inverse
+// rows fused with `post`), at other power-of-two sizes the shared-memory passes of train_kernels.cuh.  At 128 / 256 points
+// the operator is three launches — pre convs + row rFFT, column FFT + fusion + inverse column FFT, inverse row FFT + |.| +
+// post conv — and the two spectra are the only intermediates in HBM (the reference materialises 14 tensors).
 // The four purely real bins get an exact +0.0 imaginary part before angle() (what rfft2 delivers).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 
 #include "ctx.cuh"
@@ -169,19 +174,47 @@ cudaError_t run_freprocess(const float* msf, const float* panf, float* out, int 
   float* pre = ws;                                   // [N,H,W,2C]; reused for the |irfft2| map [N,H,W,C]
   float* S = pre + align64(NP * 2 * C);              // complex [N,H,Wh,2C]
   float* G = S + align64(nbins * 2 * C * 2);         // complex [N,H,Wh,C]
-  fre_pre_kernel<C><<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(msf, panf, w.pre1_w, w.pre1_b, w.pre2_w, w.pre2_b, pre, HW, NP);
-  cudaError_t e = cudaGetLastError();
+  const bool fast_w = (W == 128 || W == 256), fast_h = (H == 128 || H == 256);   // register-resident passes of fft256.cu
+  cudaError_t e;
+  if (fast_w) {                                           // pre1 / pre2 convs as the prologue of the row transform
+    const float* pre_w[4] = {w.pre1_w, w.pre1_b, w.pre2_w, w.pre2_b};
+    e = lg::launch_fft_rows_fwd_pre(W, C, msf, panf, pre_w, S, N, H, s);
+  } else {
+    fre_pre_kernel<C><<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(msf, panf, w.pre1_w, w.pre1_b, w.pre2_w, w.pre2_b, pre, HW, NP);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    e = lgctx::launch_fft_rows(s, 0, pre, 2 * C, S, nullptr, 0, nullptr, 0, N, H, W, 2 * C, 1.f, 0);
+  }
   if (e != cudaSuccess) return e;
-  if ((e = lgctx::launch_fft_rows(s, 0, pre, 2 * C, S, nullptr, 0, nullptr, 0, N, H, W, 2 * C, 1.f, 0)) != cudaSuccess) return e;
-  if ((e = lgctx::launch_fft_cols(s, S, N, H, W, 2 * C, -1, 1)) != cudaSuccess) return e;
-  fre_fuse_kernel<C><<<(unsigned)((nbins + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float2*>(S), reinterpret_cast<float2*>(G),
-                                                                    nbins, w.a0w, w.a0b, w.a2w, w.a2b, w.p0w, w.p0b, w.p2w, w.p2b);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if ((e = lgctx::launch_fft_cols(s, G, N, H, W, C, +1, 0)) != cudaSuccess) return e;
+  // column stage: one fused kernel (forward FFT, amp / pha fusion, inverse FFT) where it is built, else three passes
+  static const bool unfused = [] { const char* v = getenv("LGTEUN_FRE_UNFUSED"); return v && v[0] == '1'; }();   // A/B aid
+  const float* fuse_w[8] = {w.a0w, w.a0b, w.a2w, w.a2b, w.p0w, w.p0b, w.p2w, w.p2b};
+  e = (fast_h && !unfused) ? lg::launch_fre_cols_fused(H, C, S, G, fuse_w, N, W, s) : cudaErrorNotSupported;
+  if (e == cudaErrorNotSupported) {
+    e = fast_h ? lg::launch_fft_cols_plain(H, 2 * C, S, N, W, -1, s) : lgctx::launch_fft_cols(s, S, N, H, W, 2 * C, -1, 1);
+    if (e != cudaSuccess) return e;
+    fre_fuse_kernel<C><<<(unsigned)((nbins + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float2*>(S), reinterpret_cast<float2*>(G),
+                                                                      nbins, w.a0w, w.a0b, w.a2w, w.a2b, w.p0w, w.p0b, w.p2w, w.p2b);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    e = fast_h ? lg::launch_fft_cols_plain(H, C, G, N, W, +1, s) : lgctx::launch_fft_cols(s, G, N, H, W, C, +1, 0);
+  }
+  if (e != cudaSuccess) return e;
+  if (fast_w) return lg::launch_fft_rows_inv_post(W, C, G, w.post_w, w.post_b, out, N, H, s);   // C2R + |.| + post conv + NCHW
   if ((e = lgctx::launch_fft_rows(s, 1, nullptr, 0, G, pre, C, pre, C, N, H, W, C, 1.f / ((float)H * (float)W), 1)) != cudaSuccess)
     return e;
   fre_post_kernel<C><<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(pre, w.post_w, w.post_b, out, HW, NP);
   return cudaGetLastError();
+}
+
+// the register-resident passes read their twiddles from a per-device table that lgteun_create() fills; this operator has no handle
+cudaError_t ensure_tables(int device, cudaStream_t s) {
+  static std::mutex mu;
+  static bool done[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+  if (done[device]) return cudaSuccess;
+  cudaError_t e = lg::fft256_init_tables(s);
+  if (e == cudaSuccess) done[device] = true;
+  return e;
 }
 
 }  // namespace lgcomp
@@ -210,7 +243,8 @@ int lgteun_op_freprocess(int device, const float* msf, const float* panf, float*
   const lgcomp::FreW w{weights[0], weights[1], weights[2],  weights[3],  weights[4],  weights[5],  weights[6],
                        weights[7], weights[8], weights[9], weights[10], weights[11], weights[12], weights[13]};
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e;
+  cudaError_t e = lgcomp::ensure_tables(device, s);
+  if (e != cudaSuccess) return fail_cuda(e, "Freprocess: twiddle tables");
   if (C == 4) e = lgcomp::run_freprocess<4>(msf, panf, out, N, H, W, w, workspace, s);
   else if (C == 8) e = lgcomp::run_freprocess<8>(msf, panf, out, N, H, W, w, workspace, s);
   else e = lgcomp::run_freprocess<16>(msf, panf, out, N, H, W, w, workspace, s);

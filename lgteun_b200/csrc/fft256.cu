@@ -112,7 +112,9 @@ __device__ __forceinline__ void fft_m(float2* v) {
 // exchange, pass B an M-point FFT over n2 for each k1 (16/M of them per thread), leaving X[k1 + 16 k2] in registers.
 // The inverse consumes exactly that distribution (m = m2 + 16 m1 with m2 = k1, m1 = k2): M-point over m1, twiddle,
 // exchange, 16-point over m2, so no reordering is needed between the two transforms.
-template <int Q, int M>
+// MODE 0: forward + mixing + inverse (the global mixer).  MODE 1: forward only, MODE 2: unnormalised inverse only — the plain
+// column transforms of the companion operator SFIIN.Freprocess (companion_ops.cu), which mixes channels between the two.
+template <int Q, int M, int MODE = 0>
 __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
                                                                 int lanes_per_row) {
   using namespace f256;
@@ -126,8 +128,14 @@ __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restric
   float2* base = spec + (size_t)blockIdx.y * H * lanes_per_row + l0 + l;
   for (int j = tid; j < 256; j += M * Q) tw[j] = g_tw256[j];
 
-  // load rows y = M n1 + lo
   float2 v[16];
+  if constexpr (MODE == 2) {                              // the spectrum in the distribution the inverse consumes
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      v[i] = live ? base[(size_t)((lo + M * (i / M)) + 16 * (i % M)) * lanes_per_row] : make_float2(0.f, 0.f);
+    __syncthreads();                                      // twiddle table staged
+  } else {
+  // load rows y = M n1 + lo
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1)
     v[n1] = live ? base[(size_t)(M * n1 + lo) * lanes_per_row] : make_float2(0.f, 0.f);
@@ -144,9 +152,18 @@ __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restric
     for (int n2 = 0; n2 < M; ++n2) v[kk * M + n2] = ex[((lo + M * kk) * M + n2) * Q + l];
     fft_m<M, -1>(v + kk * M);                             // v[kk*M + k2] = X[ky = (lo + M kk) + 16 k2]
   }
-
+  }
+  if constexpr (MODE == 1) {
+    const bool real_col = ((l0 + l) / C2 == 0 || (l0 + l) / C2 == W / 2);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int kk = i / M, k2 = i % M;
+      if (real_col && lo == 0 && kk == 0 && (k2 == 0 || k2 == M / 2)) v[i].y = 0.0f;      // exactly-real bins (F7)
+      if (live) base[(size_t)((lo + M * kk) + 16 * k2) * lanes_per_row] = v[i];
+    }
+  } else {
   // amplitude / phase mixing (LGT.py:168-177)
-  {
+  if constexpr (MODE == 0) {
     const int lane = l0 + l;
     const int kx = lane / C2, ch = lane - kx * C2;
     const float aw = live ? __ldg(w.amp_w + ch) : 0.f, ab = live ? __ldg(w.amp_b + ch) : 0.f;
@@ -170,7 +187,7 @@ __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restric
     }
   }
   // inverse, pass A: M-point over m1 = k2 for each m2 = k1 held by this thread, twiddle conj W_H^{j1 m2}
-  __syncthreads();                                        // everyone has consumed the first exchange
+  if constexpr (MODE == 0) __syncthreads();               // everyone has consumed the first exchange
 #pragma unroll
   for (int kk = 0; kk < KPT; ++kk) {
     const int k1 = lo + M * kk;
@@ -189,6 +206,7 @@ __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restric
 #pragma unroll
     for (int j2 = 0; j2 < 16; ++j2) base[(size_t)(lo + M * j2) * lanes_per_row] = v[j2];
   }
+  }   // MODE != 1
 }
 
 template <int M>
@@ -220,48 +238,17 @@ namespace lg {
 // the exchange between the passes is [k1][M + 1], the result comes back in natural order — all in the same storage.
 template <int M> __device__ __forceinline__ int padded_m(int i) { return i + i / M; }
 
-template <int C2, bool PRE_LN, int M>
-__global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __restrict__ x, float2* __restrict__ spec,
-                                                               BlockW w) {
+// The transform itself: X holds 256 / M packed complex sequences ([seq][RP], one pad slot per M samples); runs the two
+// register passes, splits the packed transforms and writes spec rows [row0, row0 + RW).  Starts with the barrier that
+// publishes X.
+template <int C2, int M>
+__device__ __forceinline__ void rows_fwd_transform(float2* X, const float2* tw, float2* __restrict__ spec, size_t row0) {
   using namespace f256;
   constexpr int W = 16 * M, Wf = W / 2 + 1, RP = 16 * (M + 1), KPT = 16 / M, TS = 16 / M;
-  constexpr int NF1 = C2 / 2;                             // sequences per image row
-  constexpr int RW = (256 / M) / NF1;                     // image rows per CTA
-  static_assert(RW >= 1, "a CTA holds at least one image row");
-  constexpr int CIN = PRE_LN ? 2 * C2 : C2;
-  __shared__ float2 tw[256];
-  extern __shared__ __align__(16) float2 smf[];
-  float2* X = smf;                                        // [256/M][RP]  input sequences, later the natural-order spectrum
-  float2* E = smf;                                        // exchange between the two passes: the SAME storage (35 KB per
+  constexpr int NF1 = C2 / 2, RW = (256 / M) / NF1;
+  float2* E = X;                                          // exchange between the two passes: the SAME storage (35 KB per
                                                           // CTA instead of 70: twice the resident CTAs)
   const int tid = threadIdx.x;
-  const size_t row0 = (size_t)blockIdx.x * RW;
-  tw[tid] = g_tw256[tid];
-  // phase 0: LayerNorm, pack channel pairs (2f, 2f+1) of the global half as complex samples
-#pragma unroll
-  for (int i = 0; i < RW * W / 256; ++i) {
-    const int p = tid + 256 * i, rl = p / W, px = p % W;
-    const float* src = x + ((row0 + rl) * W + px) * CIN;
-    float g[C2];
-    if constexpr (PRE_LN) {
-      float v[CIN];
-      load_vec<CIN>(v, src);
-      float mean = 0.f;
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) mean += v[c];
-      mean *= (1.0f / CIN);
-      float var = 0.f;
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) { float d = v[c] - mean; var = fmaf(d, d, var); }
-      const float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
-#pragma unroll
-      for (int c = 0; c < C2; ++c) g[c] = (v[C2 + c] - mean) * rstd * __ldg(w.ln1_w + C2 + c) + __ldg(w.ln1_b + C2 + c);
-    } else {
-      load_vec<C2>(g, src);
-    }
-#pragma unroll
-    for (int f = 0; f < NF1; ++f) X[(rl * NF1 + f) * RP + padded_m<M>(px)] = make_float2(g[2 * f], g[2 * f + 1]);
-  }
   __syncthreads();
   const int seq = tid / M, lo = tid % M;
   float2 v[16];
@@ -301,6 +288,97 @@ __global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __res
     o.w = 0.5f * (zm.x - z.x);
     out[id] = o;
   }
+}
+
+template <int C2, bool PRE_LN, int M>
+__global__ void __launch_bounds__(256) fft_rows_fwd256_kernel(const float* __restrict__ x, float2* __restrict__ spec,
+                                                               BlockW w) {
+  using namespace f256;
+  constexpr int W = 16 * M, RP = 16 * (M + 1);
+  constexpr int NF1 = C2 / 2;                             // sequences per image row
+  constexpr int RW = (256 / M) / NF1;                     // image rows per CTA
+  static_assert(RW >= 1, "a CTA holds at least one image row");
+  constexpr int CIN = PRE_LN ? 2 * C2 : C2;
+  __shared__ float2 tw[256];
+  extern __shared__ __align__(16) float2 smf[];
+  float2* X = smf;                                        // [256/M][RP]  input sequences, later the natural-order spectrum
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * RW;
+  tw[tid] = g_tw256[tid];
+  // phase 0: LayerNorm, pack channel pairs (2f, 2f+1) of the global half as complex samples
+#pragma unroll
+  for (int i = 0; i < RW * W / 256; ++i) {
+    const int p = tid + 256 * i, rl = p / W, px = p % W;
+    const float* src = x + ((row0 + rl) * W + px) * CIN;
+    float g[C2];
+    if constexpr (PRE_LN) {
+      float v[CIN];
+      load_vec<CIN>(v, src);
+      float mean = 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) mean += v[c];
+      mean *= (1.0f / CIN);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) { float d = v[c] - mean; var = fmaf(d, d, var); }
+      const float rstd = 1.0f / sqrtf(var * (1.0f / CIN) + kLnEps);
+#pragma unroll
+      for (int c = 0; c < C2; ++c) g[c] = (v[C2 + c] - mean) * rstd * __ldg(w.ln1_w + C2 + c) + __ldg(w.ln1_b + C2 + c);
+    } else {
+      load_vec<C2>(g, src);
+    }
+#pragma unroll
+    for (int f = 0; f < NF1; ++f) X[(rl * NF1 + f) * RP + padded_m<M>(px)] = make_float2(g[2 * f], g[2 * f + 1]);
+  }
+  rows_fwd_transform<C2, M>(X, tw, spec, row0);
+}
+
+// Forward row pass of Freprocess with its `pre1` / `pre2` 1x1 convs as the prologue (models/SFIIN.py:213-214,223-224): reads
+// the two NCHW inputs, writes the spectrum of cat(pre1(msf) + 1e-8, pre2(panf) + 1e-8) — the pre-convolved map never
+// exists in HBM.  C2 = 2 C channels per pixel.
+template <int C2, int M>
+__global__ void __launch_bounds__(256) fft_rows_fwd_pre_kernel(const float* __restrict__ msf, const float* __restrict__ panf,
+                                                                const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                const float* __restrict__ w2, const float* __restrict__ b2,
+                                                                float2* __restrict__ spec, int H) {
+  using namespace f256;
+  constexpr int W = 16 * M, RP = 16 * (M + 1), C = C2 / 2, NF1 = C2 / 2, RW = (256 / M) / NF1;
+  static_assert(RW >= 1, "a CTA holds at least one image row");
+  __shared__ float2 tw[256];
+  __shared__ __align__(16) float sw[2][C][C];
+  __shared__ float sb[2][C];
+  extern __shared__ __align__(16) float2 smf[];
+  float2* X = smf;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * RW;
+  tw[tid] = g_tw256[tid];
+  for (int i = tid; i < 2 * C * C; i += 256) sw[i / (C * C)][(i / C) % C][i % C] = __ldg((i < C * C ? w1 : w2) + i % (C * C));
+  if (tid < 2 * C) sb[tid / C][tid % C] = __ldg((tid < C ? b1 : b2) + tid % C);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RW * W / 256; ++i) {
+    const int p = tid + 256 * i, rl = p / W, px = p % W;
+    const size_t grow = row0 + rl, n = grow / H, yy = grow - n * H;
+    const size_t off = ((n * C) * (size_t)H + yy) * W + px;           // channel 0 of this pixel in an NCHW tensor
+    float g[C2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const float* src = (t ? panf : msf) + off;
+      float xin[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) xin[k] = __ldg(src + (size_t)k * H * W);
+#pragma unroll
+      for (int co = 0; co < C; ++co) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) a = fmaf(sw[t][co][k], xin[k], a);
+        g[t * C + co] = (a + sb[t][co]) + 1e-8f;
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < NF1; ++f) X[(rl * NF1 + f) * RP + padded_m<M>(px)] = make_float2(g[2 * f], g[2 * f + 1]);
+  }
+  rows_fwd_transform<C2, M>(X, tw, spec, row0);
 }
 
 // Inverse row pass + the rest of LGMixer: y = proj(cat(local, |irfft|)) + xres.  The c x c projection runs on the
@@ -493,6 +571,332 @@ static cudaError_t rows256_inv_t(const BlockW& w, const float* spec, const float
   fft_rows_inv256_kernel<C2, M><<<N * H / RW, 256, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
                                                               1.0f / ((float)H * (float)(16 * M)));
   return cudaGetLastError();
+}
+
+// ---- plain passes for the companion operator SFIIN.Freprocess (companion_ops.cu) -----------------------
+template <int M, int MODE>
+static cudaError_t cols_plain_t(int c2, float* spec, int N, int W, cudaStream_t s) {
+  constexpr int Q = 256 / M;
+  const int lanes = (W / 2 + 1) * c2;
+  const size_t smem = (size_t)16 * M * Q * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_cols256_kernel<Q, M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((lanes + Q - 1) / Q, N);
+  fft_cols256_kernel<Q, M, MODE><<<grid, M * Q, smem, s>>>(reinterpret_cast<float2*>(spec), BlockW{}, W, c2, lanes);
+  return cudaGetLastError();
+}
+// in-place column FFT of spec[n][H][W/2+1][c2] for H in {128, 256}: dir < 0 forward (the four real bins get +0.0 imaginary
+// parts), dir > 0 unnormalised inverse
+cudaError_t launch_fft_cols_plain(int H, int c2, float* spec, int N, int W, int dir, cudaStream_t s) {
+  if (H == 256) return dir < 0 ? cols_plain_t<16, 1>(c2, spec, N, W, s) : cols_plain_t<16, 2>(c2, spec, N, W, s);
+  if (H == 128) return dir < 0 ? cols_plain_t<8, 1>(c2, spec, N, W, s) : cols_plain_t<8, 2>(c2, spec, N, W, s);
+  return cudaErrorInvalidValue;
+}
+// The whole column stage of Freprocess in one kernel (models/SFIIN.py:223-234 between the row transforms): forward FFT
+// along H of the 2C-channel spectrum S[n][ky][kx][2C], amp_fuse / pha_fuse per bin, inverse FFT along H of the C fused
+// channels into G[n][ky][kx][C].  A CTA owns KX = Q / 2C adjacent kx (Q = 256 / M lanes, all 2C channels of a bin inside the
+// CTA); the forward transform is the two-pass register scheme of fft_cols256_kernel, the spectrum then goes through shared
+// memory ([ky][Q + 1], one pad slot per row) so that one thread sees the 2C channels of a bin, the fused C channels come back
+// the same way and the threads of the first Q / 2 lanes run the inverse transform.
+struct FreFuseW {
+  const float *a0w, *a0b, *a2w, *a2b, *p0w, *p0b, *p2w, *p2b;
+};
+template <int C, int M>
+__global__ void __launch_bounds__(256) fre_cols_fused_kernel(const float2* __restrict__ S, float2* __restrict__ G, FreFuseW fw,
+                                                             int W) {
+  using namespace f256;
+  constexpr int H = 16 * M, Q = 256 / M, C2 = 2 * C, KX = Q / C2, KPT = 16 / M, TS = 16 / M, QP = Q + 1;
+  static_assert(KX >= 1, "all 2C channels of a bin live in one CTA");
+  __shared__ float2 tw[256];
+  __shared__ __align__(16) float w0[2][C][C2];           // 16-byte rows: the broadcast weight reads become LDS.128
+  __shared__ __align__(16) float w2[2][C][C];
+  __shared__ float bb[2][2][C];
+  extern __shared__ __align__(16) float2 ex[];            // [H][Q + 1]; the first H * Q slots double as the pass exchange
+  const int tid = threadIdx.x;
+  const int l = tid % Q, lo = tid / Q;
+  const int Wh = W / 2 + 1, kx0 = blockIdx.x * KX;
+  const bool live = kx0 + l / C2 < Wh;
+  const size_t in_row = (size_t)Wh * C2, out_row = (size_t)Wh * C;
+  const float2* base = S + (size_t)blockIdx.y * H * in_row + (size_t)kx0 * C2 + l;
+  tw[tid] = g_tw256[tid];
+  for (int i = tid; i < 2 * C * C2; i += 256) {
+    const int t = i / (C * C2), r = i % (C * C2);
+    w0[t][r / C2][r % C2] = __ldg((t ? fw.p0w : fw.a0w) + r);
+  }
+  for (int i = tid; i < 2 * C * C; i += 256) {
+    const int t = i / (C * C), r = i % (C * C);
+    w2[t][r / C][r % C] = __ldg((t ? fw.p2w : fw.a2w) + r);
+  }
+  for (int i = tid; i < 4 * C; i += 256) {
+    const int t = i / (2 * C), ly = (i / C) & 1, k = i % C;
+    bb[t][ly][k] = __ldg((t ? (ly ? fw.p2b : fw.p0b) : (ly ? fw.a2b : fw.a0b)) + k);
+  }
+  float2 v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = live ? __ldg(base + (size_t)(M * n1 + lo) * in_row) : make_float2(0.f, 0.f);
+  __syncthreads();                                        // tables staged
+  fft16<-1>(v);
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) v[k1] = ctw<-1>(v[k1], tw[TS * lo * k1]);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) ex[(k1 * M + lo) * Q + l] = v[k1];
+  __syncthreads();
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk) {
+#pragma unroll
+    for (int n2 = 0; n2 < M; ++n2) v[kk * M + n2] = ex[((lo + M * kk) * M + n2) * Q + l];
+    fft_m<M, -1>(v + kk * M);                             // v[kk*M + k2] = X[ky = (lo + M kk) + 16 k2]
+  }
+  __syncthreads();                                        // everyone has consumed the pass exchange
+  {
+    const int kx = kx0 + l / C2;
+    const bool real_col = (kx == 0 || kx == W / 2);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int kk = i / M, k2 = i % M;
+      if (real_col && lo == 0 && kk == 0 && (k2 == 0 || k2 == M / 2)) v[i].y = 0.0f;      // exactly-real bins (F7)
+      ex[((lo + M * kk) + 16 * k2) * QP + l] = v[i];
+    }
+  }
+  __syncthreads();
+  // amp_fuse / pha_fuse: thread = bin (ky, kx); the C fused values overwrite the first C slots of the bin's own 2C inputs
+  for (int b = tid; b < H * KX; b += 256) {
+    const int ky = b / KX, kxi = b % KX;
+    float2* bin = ex + ky * QP + kxi * C2;
+    float in[2][C2];
+#pragma unroll
+    for (int c = 0; c < C2; ++c) {
+      const float2 z = bin[c];
+      in[0][c] = sqrtf(z.x * z.x + z.y * z.y);
+      in[1][c] = atan2f(z.y, z.x);
+    }
+    float out[2][C];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float hdn[C];
+#pragma unroll
+      for (int co = 0; co < C; ++co) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < C2; ++k) a = fmaf(w0[t][co][k], in[t][k], a);
+        a += bb[t][0][co];
+        hdn[co] = a > 0.f ? a : 0.1f * a;                 // LeakyReLU(0.1)
+      }
+#pragma unroll
+      for (int co = 0; co < C; ++co) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) a = fmaf(w2[t][co][k], hdn[k], a);
+        out[t][co] = a + bb[t][1][co];
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < C; ++co) {
+      float sn, cs;
+      sincosf(out[1][co], &sn, &cs);
+      bin[co] = make_float2((out[0][co] * cs + 1e-8f) + 1e-8f, out[0][co] * sn + 1e-8f);
+    }
+  }
+  __syncthreads();
+  // inverse along H for the Q / 2 fused lanes (kx, co)
+  const bool inv = l < Q / 2;
+  const int kxi = l / C, co = l % C;
+  const bool live_o = inv && (kx0 + kxi < Wh);
+  if (inv) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ex[((lo + M * (i / M)) + 16 * (i % M)) * QP + kxi * C2 + co];
+  }
+  __syncthreads();                                        // the bin buffer becomes the pass exchange again
+  if (inv) {
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk) {
+      const int k1 = lo + M * kk;
+      fft_m<M, +1>(v + kk * M);
+#pragma unroll
+      for (int j1 = 1; j1 < M; ++j1) v[kk * M + j1] = ctw<+1>(v[kk * M + j1], tw[TS * k1 * j1]);
+#pragma unroll
+      for (int j1 = 0; j1 < M; ++j1) ex[(j1 * 16 + k1) * Q + l] = v[kk * M + j1];
+    }
+  }
+  __syncthreads();
+  if (inv) {
+#pragma unroll
+    for (int m2 = 0; m2 < 16; ++m2) v[m2] = ex[(lo * 16 + m2) * Q + l];
+    fft16<+1>(v);                                         // v[j2] = x[y = lo + M j2]  (unnormalised)
+    if (live_o) {
+      float2* dst = G + (size_t)blockIdx.y * H * out_row + (size_t)(kx0 + kxi) * C + co;
+#pragma unroll
+      for (int j2 = 0; j2 < 16; ++j2) dst[(size_t)(lo + M * j2) * out_row] = v[j2];
+    }
+  }
+}
+template <int C, int M>
+static cudaError_t fre_cols_fused_t(const float* S, float* G, const FreFuseW& fw, int N, int W, cudaStream_t s) {
+  constexpr int Q = 256 / M, KX = Q / (2 * C), H = 16 * M;
+  const size_t smem = (size_t)H * (Q + 1) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fre_cols_fused_kernel<C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((W / 2 + 1 + KX - 1) / KX, N);
+  fre_cols_fused_kernel<C, M><<<grid, 256, smem, s>>>(reinterpret_cast<const float2*>(S), reinterpret_cast<float2*>(G), fw, W);
+  return cudaGetLastError();
+}
+// returns cudaErrorNotSupported when (H, C) has no fused instantiation (the caller then runs the three separate passes)
+cudaError_t launch_fre_cols_fused(int H, int C, const float* S, float* G, const float* const* fuse_w, int N, int W, cudaStream_t s) {
+  const FreFuseW fw{fuse_w[0], fuse_w[1], fuse_w[2], fuse_w[3], fuse_w[4], fuse_w[5], fuse_w[6], fuse_w[7]};
+  if (H == 256) {
+    if (C == 4) return fre_cols_fused_t<4, 16>(S, G, fw, N, W, s);
+    if (C == 8) return fre_cols_fused_t<8, 16>(S, G, fw, N, W, s);
+  } else if (H == 128) {
+    if (C == 4) return fre_cols_fused_t<4, 8>(S, G, fw, N, W, s);
+    if (C == 8) return fre_cols_fused_t<8, 8>(S, G, fw, N, W, s);
+    if (C == 16) return fre_cols_fused_t<16, 8>(S, G, fw, N, W, s);
+  }
+  return cudaErrorNotSupported;
+}
+
+template <int C2, int M>
+static cudaError_t rows_fwd_pre_t(const float* msf, const float* panf, const float* const* pre_w, float* spec, int N, int H,
+                                  cudaStream_t s) {
+  constexpr int RW = (256 / M) / (C2 / 2);
+  if (H % RW) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(256 / M) * 16 * (M + 1) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_pre_kernel<C2, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_rows_fwd_pre_kernel<C2, M><<<N * H / RW, 256, smem, s>>>(msf, panf, pre_w[0], pre_w[1], pre_w[2], pre_w[3],
+                                                               reinterpret_cast<float2*>(spec), H);
+  return cudaGetLastError();
+}
+// pre1 / pre2 convs + row rFFT of Freprocess: NCHW msf, panf [N][C][H][W] -> spec[N][H][W/2+1][2C];
+// pre_w = {pre1.weight, pre1.bias, pre2.weight, pre2.bias}; W in {128, 256}, C in {4, 8, 16}
+cudaError_t launch_fft_rows_fwd_pre(int W, int C, const float* msf, const float* panf, const float* const* pre_w, float* spec, int N,
+                                    int H, cudaStream_t s) {
+  if (W == 256) {
+    if (C == 4) return rows_fwd_pre_t<8, 16>(msf, panf, pre_w, spec, N, H, s);
+    if (C == 8) return rows_fwd_pre_t<16, 16>(msf, panf, pre_w, spec, N, H, s);
+    if (C == 16) return rows_fwd_pre_t<32, 16>(msf, panf, pre_w, spec, N, H, s);
+  } else if (W == 128) {
+    if (C == 4) return rows_fwd_pre_t<8, 8>(msf, panf, pre_w, spec, N, H, s);
+    if (C == 8) return rows_fwd_pre_t<16, 8>(msf, panf, pre_w, spec, N, H, s);
+    if (C == 16) return rows_fwd_pre_t<32, 8>(msf, panf, pre_w, spec, N, H, s);
+  }
+  return cudaErrorInvalidValue;
+}
+// Inverse row pass of Freprocess (models/SFIIN.py:235-236): C2R of spec[N][H][W/2+1][C] (the same register transform as
+// fft_rows_inv256_kernel), |.| * scale, then the `post` 1x1 conv C -> C and the NCHW store — the |irfft2| map stays in
+// shared memory.
+template <int C, int M>
+__global__ void __launch_bounds__(256) fft_rows_inv_post_kernel(const float2* __restrict__ spec, const float* __restrict__ pw,
+                                                                 const float* __restrict__ pb, float* __restrict__ y, int H,
+                                                                 float scale) {
+  using namespace f256;
+  constexpr int W = 16 * M, Wf = W / 2 + 1, RP = 16 * (M + 1), NSEQ = 256 / M, KPT = 16 / M, TS = 16 / M;
+  constexpr int NF1 = C / 2, RW = NSEQ / NF1;
+  static_assert(RW >= 1, "a CTA holds at least one image row");
+  __shared__ float2 tw[256];
+  __shared__ __align__(16) float sw[C][C];
+  __shared__ float sb[C];
+  extern __shared__ __align__(16) float2 smf[];
+  float2* X = smf;                                        // [NSEQ][RP]
+  float2* E = smf;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * RW;
+  tw[tid] = g_tw256[tid];
+  for (int i = tid; i < C * C; i += 256) sw[i / C][i % C] = __ldg(pw + i);
+  if (tid < C) sb[tid] = __ldg(pb + tid);
+  const float4* in = reinterpret_cast<const float4*>(spec + row0 * Wf * C);
+  {
+    constexpr int TOTAL = RW * Wf * NF1, ITERS = (TOTAL + 255) / 256;
+    float4 vb[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int id = tid + 256 * i;
+      vb[i] = (id < TOTAL) ? __ldg(in + id) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int id = tid + 256 * i;
+      if (id >= TOTAL) break;
+      const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
+      const int k = rem / NF1, sq = rl * NF1 + (rem - k * NF1);
+      const float4 v = vb[i];                             // (Xa.re, Xa.im, Xb.re, Xb.im)
+      if (k == 0 || k == W / 2) {
+        X[sq * RP + padded_m<M>(k)] = make_float2(v.x, v.z);
+      } else {
+        X[sq * RP + padded_m<M>(k)] = make_float2(v.x - v.w, v.y + v.z);          // Xa + i Xb
+        X[sq * RP + padded_m<M>(W - k)] = make_float2(v.x + v.w, v.z - v.y);      // conj(Xa) + i conj(Xb)
+      }
+    }
+  }
+  __syncthreads();
+  const int seq = tid / M, lo = tid % M;
+  float2 v[16];
+#pragma unroll
+  for (int m1 = 0; m1 < 16; ++m1) v[m1] = X[seq * RP + (M + 1) * m1 + lo];
+  fft16<+1>(v);
+#pragma unroll
+  for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[TS * lo * j1]);
+  __syncwarp();
+#pragma unroll
+  for (int j1 = 0; j1 < 16; ++j1) E[seq * RP + j1 * (M + 1) + lo] = v[j1];
+  __syncwarp();
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk) {
+#pragma unroll
+    for (int m2 = 0; m2 < M; ++m2) v[kk * M + m2] = E[seq * RP + (lo + M * kk) * (M + 1) + m2];
+    fft_m<M, +1>(v + kk * M);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+    for (int j2 = 0; j2 < M; ++j2)
+      X[seq * RP + (lo + M * kk) + 16 * j2] = make_float2(fabsf(v[kk * M + j2].x * scale), fabsf(v[kk * M + j2].y * scale));
+  __syncthreads();
+  // post conv, thread = pixel; NCHW planes are written with consecutive threads on consecutive pixels
+#pragma unroll
+  for (int i = 0; i < RW * W / 256; ++i) {
+    const int p = tid + 256 * i, rl = p / W, px = p % W;
+    const size_t grow = row0 + rl, n = grow / H, yy = grow - n * H;
+    float g[C];
+#pragma unroll
+    for (int f = 0; f < NF1; ++f) {
+      const float2 t = X[(rl * NF1 + f) * RP + px];
+      g[2 * f] = t.x;
+      g[2 * f + 1] = t.y;
+    }
+    float* dst = y + ((n * C) * (size_t)H + yy) * W + px;
+#pragma unroll
+    for (int co = 0; co < C; ++co) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) a = fmaf(sw[co][k], g[k], a);
+      dst[(size_t)co * H * W] = a + sb[co];
+    }
+  }
+}
+template <int C, int M>
+static cudaError_t rows_inv_post_t(const float* spec, const float* pw, const float* pb, float* y, int N, int H, cudaStream_t s) {
+  constexpr int RW = (256 / M) / (C / 2);
+  if (H % RW) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(256 / M) * 16 * (M + 1) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_inv_post_kernel<C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_rows_inv_post_kernel<C, M><<<N * H / RW, 256, smem, s>>>(reinterpret_cast<const float2*>(spec), pw, pb, y, H,
+                                                               1.0f / ((float)H * (float)(16 * M)));
+  return cudaGetLastError();
+}
+cudaError_t launch_fft_rows_inv_post(int W, int C, const float* spec, const float* post_w, const float* post_b, float* y_nchw, int N,
+                                     int H, cudaStream_t s) {
+  if (W == 256) {
+    if (C == 4) return rows_inv_post_t<4, 16>(spec, post_w, post_b, y_nchw, N, H, s);
+    if (C == 8) return rows_inv_post_t<8, 16>(spec, post_w, post_b, y_nchw, N, H, s);
+    if (C == 16) return rows_inv_post_t<16, 16>(spec, post_w, post_b, y_nchw, N, H, s);
+  } else if (W == 128) {
+    if (C == 4) return rows_inv_post_t<4, 8>(spec, post_w, post_b, y_nchw, N, H, s);
+    if (C == 8) return rows_inv_post_t<8, 8>(spec, post_w, post_b, y_nchw, N, H, s);
+    if (C == 16) return rows_inv_post_t<16, 8>(spec, post_w, post_b, y_nchw, N, H, s);
+  }
+  return cudaErrorInvalidValue;
 }
 
 // W == 256, LayerNorm prologue; H must be a multiple of 32 / C2 rows

@@ -42,7 +42,8 @@ def test_freprocess_matches_recorded_reference(lib, case):
     assert err <= _tol(ref)
 
 
-@pytest.mark.parametrize("channels,n,h,w", [(8, 3, 128, 128), (4, 2, 8, 16), (16, 1, 64, 32), (8, 1, 256, 256)])
+@pytest.mark.parametrize("channels,n,h,w", [(8, 3, 128, 128), (4, 2, 8, 16), (16, 1, 64, 32), (8, 1, 256, 256), (8, 2, 256, 64),
+                                               (4, 1, 32, 128), (16, 1, 128, 256), (4, 2, 256, 128), (16, 1, 256, 128), (8, 2, 128, 256)])
 def test_freprocess_matches_oracle(lib, channels, n, h, w):
     from oracle import companions_oracle as CO
     torch.manual_seed(100 + channels + h)

@@ -395,12 +395,20 @@ def test_module_dropin(abi):
             net(g["ms"], g["pan"])                                  # CPU tensors: no fallback
         with pytest.raises(ValueError):
             net(torch.rand(1, 4, 12, 12).cuda(), torch.rand(1, 1, 48, 48).cuda())   # PAN 48: not a power of two
-    with pytest.raises(NotImplementedError):                        # grad mode: the backward is a later row
+    with pytest.raises(NotImplementedError):                        # gradients w.r.t. ms / pan: the reference never needs them
         net(g["ms"].cuda().requires_grad_(True), g["pan"].cuda())
+    # train() mode runs the training forward (tests/test_gpu_train.py): the reference's Dropout(0.1) is active (LGT.py:198,216),
+    # so the result differs from eval; with the dropout switched off it is the eval result
     net.train()
-    with torch.no_grad(), pytest.raises(NotImplementedError):       # train(): the reference's Dropout(0.1) is active
-        net(g["ms"].cuda(), g["pan"].cuda())
+    with torch.no_grad():
+        out_drop = net(g["ms"].cuda(), g["pan"].cuda())
+        net.dropout_p = 0.0
+        out_nodrop = net(g["ms"].cuda(), g["pan"].cuda())
+    net.dropout_p = 0.1
     net.eval()
+    assert out_drop.shape == out2.shape and torch.isfinite(out_drop).all()
+    assert _maxdiff(out_drop, g["out"] + 0.25) > E2E_TOL
+    assert _maxdiff(out_nodrop, g["out"] + 0.25) <= E2E_TOL
 
 
 @pytest.mark.parametrize("bands,stage", [(4, 1), (4, 3), (8, 5)])
