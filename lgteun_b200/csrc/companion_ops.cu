@@ -401,8 +401,194 @@ __global__ void __launch_bounds__(128) win_attn_kernel(WinAttnArgs a) {
   }
 }
 
+// PanFormer's own configuration (dim 64, 4 heads of 16: models/panformer.py:22) as a register-tiled kernel.  The projections are
+// 4 tokens x 6 (q/k/v) resp. 4 tokens x 2 (to_out) outputs per thread: a thread's columns are o = lane + 32 i, stored side by
+// side in the k-major weight copy, so the weights arrive as conflict-free 64-bit loads and the tokens as warp-uniform 128-bit
+// loads (12 + 4..8 shared-memory loads per 96 FMAs instead of 20 per 64).  The attention runs on all 128 threads: two threads per
+// (head, query) row take eight keys each and merge max / sum / output with one shuffle exchange.
+__device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+__global__ void __launch_bounds__(128, 2) win_attn_pf_kernel(WinAttnArgs a) {
+  constexpr int DIM = 64, NH = 4, HD = 16, INNER = NH * HD, N3 = 3 * INNER, QS = N3 + 4, CPT = N3 / 32, DPT = DIM / 32;
+  extern __shared__ __align__(16) float sm[];
+  float* wt = sm;                         // [DIM][N3]     (q | k | v)^T, columns permuted: slot lane * CPT + i holds o = lane + 32 i
+  float* wo = wt + DIM * N3;              // [INNER][DIM]  to_out.weight^T, slot lane * DPT + i holds c = lane + 32 i
+  float* bo = wo + INNER * DIM;           // [DIM]
+  float* pos = bo + DIM;                  // [T][T]
+  float* ul = pos + T * T;
+  float* lr = ul + T * T;
+  float* xs = lr + T * T;                 // [T][DIM]
+  float* ys = xs + T * DIM;
+  float* qkv = ys + T * DIM;              // [T][QS]  (row stride padded: the per-query loads of the attention spread over banks)
+  float* ao = qkv + T * QS;               // [T][INNER]
+  const int tid = threadIdx.x, lane = tid & 31, tg = tid >> 5;
+  for (int i = tid; i < N3 * DIM; i += 128) {
+    const int o = i / DIM, k = i - o * DIM;
+    wt[k * N3 + (o & 31) * CPT + (o >> 5)] = o < INNER ? __ldg(a.wq + i) : __ldg(a.wkv + i - INNER * DIM);
+  }
+  for (int i = tid; i < DIM * INNER; i += 128) {
+    const int c = i / INNER, k = i - c * INNER;
+    wo[k * DIM + (c & 31) * DPT + (c >> 5)] = __ldg(a.wout + i);
+  }
+  for (int i = tid; i < DIM; i += 128) bo[i] = __ldg(a.bout + i);
+  for (int i = tid; i < T * T; i += 128) {
+    const int qi = i / T, kj = i % T;
+    pos[i] = a.relative ? __ldg(a.pos + ((kj / WS - qi / WS) + WS - 1) * (2 * WS - 1) + (kj % WS - qi % WS) + WS - 1)
+                        : __ldg(a.pos + i);
+    ul[i] = a.shifted ? __ldg(a.ul_mask + i) : 0.f;
+    lr[i] = a.shifted ? __ldg(a.lr_mask + i) : 0.f;
+  }
+  const int nw_h = a.n_h / WS, nw_w = a.n_w / WS, nwin = a.b * nw_h * nw_w, d = a.shifted ? WS / 2 : 0;
+  const bool cross = a.y != nullptr;
+  for (int g = blockIdx.x; g < nwin; g += gridDim.x) {
+    const int n = g / (nw_h * nw_w), wy = (g / nw_w) % nw_h, wx = g % nw_w;
+    __syncthreads();                      // weights staged / previous window done with the tiles
+    for (int i = tid; i < T * (DIM / 4); i += 128) {
+      const int t = i / (DIM / 4), c = i - t * (DIM / 4);
+      const int py = (wy * WS + t / WS + d) % a.n_h, px = (wx * WS + t % WS + d) % a.n_w;
+      const size_t src = (((size_t)n * a.n_h + py) * a.n_w + px) * DIM;
+      reinterpret_cast<float4*>(xs + t * DIM)[c] = __ldg(reinterpret_cast<const float4*>(a.x + src) + c);
+      if (cross) reinterpret_cast<float4*>(ys + t * DIM)[c] = __ldg(reinterpret_cast<const float4*>(a.y + src) + c);
+    }
+    __syncthreads();
+    {   // q / k / v projections: tokens 4 tg .. 4 tg + 3, columns lane + 32 i (i < 2: q, from y in a cross block)
+      const float* qsrc = cross ? ys : xs;
+      float acc[4][CPT];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) acc[t][i] = 0.f;
+#pragma unroll 2
+      for (int k = 0; k < DIM; k += 4) {
+        float4 xv[4], qv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          xv[t] = *reinterpret_cast<const float4*>(xs + (tg * 4 + t) * DIM + k);
+          qv[t] = *reinterpret_cast<const float4*>(qsrc + (tg * 4 + t) * DIM + k);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float* wr = wt + (k + kk) * N3 + lane * CPT;
+          const float2 w01 = *reinterpret_cast<const float2*>(wr), w23 = *reinterpret_cast<const float2*>(wr + 2),
+                       w45 = *reinterpret_cast<const float2*>(wr + 4);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float xin = f4c(xv[t], kk), qin = f4c(qv[t], kk);
+            acc[t][0] = fmaf(qin, w01.x, acc[t][0]);
+            acc[t][1] = fmaf(qin, w01.y, acc[t][1]);
+            acc[t][2] = fmaf(xin, w23.x, acc[t][2]);
+            acc[t][3] = fmaf(xin, w23.y, acc[t][3]);
+            acc[t][4] = fmaf(xin, w45.x, acc[t][4]);
+            acc[t][5] = fmaf(xin, w45.y, acc[t][5]);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) qkv[(tg * 4 + t) * QS + lane + 32 * i] = acc[t][i];
+    }
+    __syncthreads();
+    {   // attention: row = (head, query) = tid / 2, this thread's eight keys = half * 8 ..
+      const int r = tid >> 1, half = tid & 1, h = r >> 4, qi = r & 15;
+      float q[HD], sc[8];
+#pragma unroll
+      for (int e = 0; e < HD; e += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(qkv + qi * QS + h * HD + e);
+        q[e] = t4.x; q[e + 1] = t4.y; q[e + 2] = t4.z; q[e + 3] = t4.w;
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = half * 8 + jj;
+        const float* kr = qkv + j * QS + INNER + h * HD;
+        float dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < HD; e += 4) {
+          const float4 k4 = *reinterpret_cast<const float4*>(kr + e);
+          dot = fmaf(q[e], k4.x, dot);
+          dot = fmaf(q[e + 1], k4.y, dot);
+          dot = fmaf(q[e + 2], k4.z, dot);
+          dot = fmaf(q[e + 3], k4.w, dot);
+        }
+        float v = dot * a.scale + pos[qi * T + j];
+        if (wy == nw_h - 1) v += ul[qi * T + j];
+        if (wx == nw_w - 1) v += lr[qi * T + j];
+        sc[jj] = v;
+        mx = fmaxf(mx, v);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));      // the row's diagonal key is never masked: mx is finite
+      float sum = 0.f, o[HD];
+#pragma unroll
+      for (int e = 0; e < HD; ++e) o[e] = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float p = expf(sc[jj] - mx);
+        sum += p;
+        const float* vr = qkv + (half * 8 + jj) * QS + 2 * INNER + h * HD;
+#pragma unroll
+        for (int e = 0; e < HD; e += 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(vr + e);
+          o[e] = fmaf(p, v4.x, o[e]);
+          o[e + 1] = fmaf(p, v4.y, o[e + 1]);
+          o[e + 2] = fmaf(p, v4.z, o[e + 2]);
+          o[e + 3] = fmaf(p, v4.w, o[e + 3]);
+        }
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+#pragma unroll
+      for (int e = 0; e < HD; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 1);
+      const float inv = 1.f / sum;
+      float* dst = ao + qi * INNER + h * HD + half * (HD / 2);
+#pragma unroll
+      for (int e = 0; e < HD / 2; ++e) dst[e] = (half ? o[HD / 2 + e] : o[e]) * inv;
+    }
+    __syncthreads();
+    {   // to_out + store at the un-shifted pixel: tokens 4 tg .. 4 tg + 3, channels lane + 32 i
+      float acc[4][DPT];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) acc[t][i] = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < INNER; k += 4) {
+        float4 av[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) av[t] = *reinterpret_cast<const float4*>(ao + (tg * 4 + t) * INNER + k);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float2 w = *reinterpret_cast<const float2*>(wo + (k + kk) * DIM + lane * DPT);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float ain = f4c(av[t], kk);
+            acc[t][0] = fmaf(ain, w.x, acc[t][0]);
+            acc[t][1] = fmaf(ain, w.y, acc[t][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int tok = tg * 4 + t;
+        const int py = (wy * WS + tok / WS + d) % a.n_h, px = (wx * WS + tok % WS + d) % a.n_w;
+        float* dst = a.out + (((size_t)n * a.n_h + py) * a.n_w + px) * DIM;
+        dst[lane] = acc[t][0] + bo[lane];
+        dst[lane + 32] = acc[t][1] + bo[lane + 32];
+      }
+    }
+  }
+}
+
 inline size_t win_attn_smem(int dim, int inner) {
   return (size_t)(dim * 3 * inner + inner * dim + dim + 3 * T * T + 2 * T * dim + T * 3 * inner + T * inner) * sizeof(float);
+}
+
+cudaError_t launch_win_attn_pf(const WinAttnArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)(64 * 192 + 64 * 64 + 64 + 3 * T * T + 2 * T * 64 + T * 196 + T * 64) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(win_attn_pf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int nwin = a.b * (a.n_h / WS) * (a.n_w / WS);
+  win_attn_pf_kernel<<<(unsigned)std::min(nwin, 148 * 2), 128, smem, s>>>(a);
+  return cudaGetLastError();
 }
 
 template <int HD>
@@ -438,7 +624,9 @@ int lgteun_op_window_attention(int device, const float* x, const float* y, float
   lgcomp::WinAttnArgs a{x, y, w_q, w_kv, w_out, b_out, pos_embedding, upper_lower_mask, left_right_mask, out, b, n_h, n_w, dim,
                         heads, shifted != 0, relative_pos_embedding != 0, scale};
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = head_dim == 8 ? lgcomp::launch_win_attn<8>(a, s)
+  static const bool generic_only = [] { const char* v = getenv("LGTEUN_WINATTN_GENERIC"); return v && v[0] == '1'; }();   // A/B aid
+  cudaError_t e = (dim == 64 && heads == 4 && head_dim == 16 && !generic_only) ? lgcomp::launch_win_attn_pf(a, s)
+                  : head_dim == 8 ? lgcomp::launch_win_attn<8>(a, s)
                   : head_dim == 16 ? lgcomp::launch_win_attn<16>(a, s) : lgcomp::launch_win_attn<32>(a, s);
   if (e != cudaSuccess) return fail_cuda(e, "WindowAttention");
   return 0;
