@@ -39,6 +39,11 @@ class Freprocess(nn.Module):
         self.post = _conv1x1(channels, channels)
         self._ws = None
 
+    def __getstate__(self):                  # the runner pickles module objects (models/base/base_model.py:362-368)
+        state = self.__dict__.copy()
+        state["_ws"] = None                  # scratch memory is not part of the model
+        return state
+
     def forward(self, msf, panf):
         if msf.shape != panf.shape or msf.dim() != 4 or msf.shape[1] != self.channels:
             raise ValueError(f"Freprocess: expected two [N,{self.channels},H,W] tensors, got {tuple(msf.shape)} and "

@@ -404,46 +404,52 @@ __global__ void __launch_bounds__(128) win_attn_kernel(WinAttnArgs a) {
 // PanFormer's own configuration (dim 64, 4 heads of 16: models/panformer.py:22) as a register-tiled kernel.  The projections are
 // 4 tokens x 6 (q/k/v) resp. 4 tokens x 2 (to_out) outputs per thread: a thread's columns are o = lane + 32 i, stored side by
 // side in the k-major weight copy, so the weights arrive as conflict-free 64-bit loads and the tokens as warp-uniform 128-bit
-// loads (12 + 4..8 shared-memory loads per 96 FMAs instead of 20 per 64).  The attention runs on all 128 threads: two threads per
-// (head, query) row take eight keys each and merge max / sum / output with one shuffle exchange.
+// loads (12 + 4..8 shared-memory loads per 96 FMAs instead of 20 per 64).  The attention runs on all threads: two threads per
+// (head, query) row take eight keys each and merge max / sum / output with one shuffle exchange.  A CTA of 256 threads works on
+// two windows at a time that share the 64 KB of weights (16 warps per SM at two CTAs).
 __device__ __forceinline__ float f4c(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
-__global__ void __launch_bounds__(128, 2) win_attn_pf_kernel(WinAttnArgs a) {
+__global__ void __launch_bounds__(256, 2) win_attn_pf_kernel(WinAttnArgs a) {
   constexpr int DIM = 64, NH = 4, HD = 16, INNER = NH * HD, N3 = 3 * INNER, QS = N3 + 4, CPT = N3 / 32, DPT = DIM / 32;
+  constexpr int PS = T + 1, AS = INNER + 4;          // padded row strides of the bias / mask tables and of the attention output
+  constexpr int SLOT = 2 * T * DIM + T * QS;        // per-window tiles: x, y (later the attention output), q/k/v
   extern __shared__ __align__(16) float sm[];
   float* wt = sm;                         // [DIM][N3]     (q | k | v)^T, columns permuted: slot lane * CPT + i holds o = lane + 32 i
   float* wo = wt + DIM * N3;              // [INNER][DIM]  to_out.weight^T, slot lane * DPT + i holds c = lane + 32 i
   float* bo = wo + INNER * DIM;           // [DIM]
-  float* pos = bo + DIM;                  // [T][T]
-  float* ul = pos + T * T;
-  float* lr = ul + T * T;
-  float* xs = lr + T * T;                 // [T][DIM]
+  float* pos = bo + DIM;                  // [T][PS]
+  float* ul = pos + T * PS;
+  float* lr = ul + T * PS;
+  // A CTA works on two windows at a time (threads 0-127 / 128-255) that share the weights: 16 warps per SM instead of 8
+  const int tid = threadIdx.x, slot = tid >> 7, lane = tid & 31, tg = (tid >> 5) & 3, t7 = tid & 127;
+  float* xs = lr + T * PS + slot * SLOT;  // [T][DIM]
   float* ys = xs + T * DIM;
   float* qkv = ys + T * DIM;              // [T][QS]  (row stride padded: the per-query loads of the attention spread over banks)
-  float* ao = qkv + T * QS;               // [T][INNER]
-  const int tid = threadIdx.x, lane = tid & 31, tg = tid >> 5;
-  for (int i = tid; i < N3 * DIM; i += 128) {
+  float* ao = xs;                         // [T][AS]  the attention output reuses the token tiles (dead after the projections)
+  for (int i = tid; i < N3 * DIM; i += 256) {
     const int o = i / DIM, k = i - o * DIM;
     wt[k * N3 + (o & 31) * CPT + (o >> 5)] = o < INNER ? __ldg(a.wq + i) : __ldg(a.wkv + i - INNER * DIM);
   }
-  for (int i = tid; i < DIM * INNER; i += 128) {
+  for (int i = tid; i < DIM * INNER; i += 256) {
     const int c = i / INNER, k = i - c * INNER;
     wo[k * DIM + (c & 31) * DPT + (c >> 5)] = __ldg(a.wout + i);
   }
-  for (int i = tid; i < DIM; i += 128) bo[i] = __ldg(a.bout + i);
-  for (int i = tid; i < T * T; i += 128) {
-    const int qi = i / T, kj = i % T;
-    pos[i] = a.relative ? __ldg(a.pos + ((kj / WS - qi / WS) + WS - 1) * (2 * WS - 1) + (kj % WS - qi % WS) + WS - 1)
+  for (int i = tid; i < DIM; i += 256) bo[i] = __ldg(a.bout + i);
+  for (int i = tid; i < T * T; i += 256) {
+    const int qi = i / T, kj = i % T, ps = qi * PS + kj;
+    pos[ps] = a.relative ? __ldg(a.pos + ((kj / WS - qi / WS) + WS - 1) * (2 * WS - 1) + (kj % WS - qi % WS) + WS - 1)
                         : __ldg(a.pos + i);
-    ul[i] = a.shifted ? __ldg(a.ul_mask + i) : 0.f;
-    lr[i] = a.shifted ? __ldg(a.lr_mask + i) : 0.f;
+    ul[ps] = a.shifted ? __ldg(a.ul_mask + i) : 0.f;
+    lr[ps] = a.shifted ? __ldg(a.lr_mask + i) : 0.f;
   }
   const int nw_h = a.n_h / WS, nw_w = a.n_w / WS, nwin = a.b * nw_h * nw_w, d = a.shifted ? WS / 2 : 0;
   const bool cross = a.y != nullptr;
-  for (int g = blockIdx.x; g < nwin; g += gridDim.x) {
+  for (int g0 = blockIdx.x * 2; g0 < nwin; g0 += gridDim.x * 2) {
+    const int g = g0 + slot;
+    const bool active = g < nwin;         // uniform over the four warps of a slot; every thread still meets the barriers
     const int n = g / (nw_h * nw_w), wy = (g / nw_w) % nw_h, wx = g % nw_w;
-    __syncthreads();                      // weights staged / previous window done with the tiles
-    for (int i = tid; i < T * (DIM / 4); i += 128) {
+    __syncthreads();                      // weights staged / previous windows done with the tiles
+    for (int i = t7; active && i < T * (DIM / 4); i += 128) {
       const int t = i / (DIM / 4), c = i - t * (DIM / 4);
       const int py = (wy * WS + t / WS + d) % a.n_h, px = (wx * WS + t % WS + d) % a.n_w;
       const size_t src = (((size_t)n * a.n_h + py) * a.n_w + px) * DIM;
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(128, 2) win_attn_pf_kernel(WinAttnArgs a) {
       if (cross) reinterpret_cast<float4*>(ys + t * DIM)[c] = __ldg(reinterpret_cast<const float4*>(a.y + src) + c);
     }
     __syncthreads();
-    {   // q / k / v projections: tokens 4 tg .. 4 tg + 3, columns lane + 32 i (i < 2: q, from y in a cross block)
+    if (active) {   // q / k / v projections: tokens 4 tg .. 4 tg + 3, columns lane + 32 i (i < 2: q, from y in a cross block)
       const float* qsrc = cross ? ys : xs;
       float acc[4][CPT];
 #pragma unroll
@@ -489,8 +495,8 @@ __global__ void __launch_bounds__(128, 2) win_attn_pf_kernel(WinAttnArgs a) {
         for (int i = 0; i < CPT; ++i) qkv[(tg * 4 + t) * QS + lane + 32 * i] = acc[t][i];
     }
     __syncthreads();
-    {   // attention: row = (head, query) = tid / 2, this thread's eight keys = half * 8 ..
-      const int r = tid >> 1, half = tid & 1, h = r >> 4, qi = r & 15;
+    if (active) {   // attention: row = (head, query) = t7 / 2, this thread's eight keys = half * 8 ..
+      const int r = t7 >> 1, half = t7 & 1, h = r >> 4, qi = r & 15;
       float q[HD], sc[8];
 #pragma unroll
       for (int e = 0; e < HD; e += 4) {
@@ -511,9 +517,9 @@ __global__ void __launch_bounds__(128, 2) win_attn_pf_kernel(WinAttnArgs a) {
           dot = fmaf(q[e + 2], k4.z, dot);
           dot = fmaf(q[e + 3], k4.w, dot);
         }
-        float v = dot * a.scale + pos[qi * T + j];
-        if (wy == nw_h - 1) v += ul[qi * T + j];
-        if (wx == nw_w - 1) v += lr[qi * T + j];
+        float v = dot * a.scale + pos[qi * PS + j];
+        if (wy == nw_h - 1) v += ul[qi * PS + j];
+        if (wx == nw_w - 1) v += lr[qi * PS + j];
         sc[jj] = v;
         mx = fmaxf(mx, v);
       }
@@ -539,12 +545,16 @@ __global__ void __launch_bounds__(128, 2) win_attn_pf_kernel(WinAttnArgs a) {
 #pragma unroll
       for (int e = 0; e < HD; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 1);
       const float inv = 1.f / sum;
-      float* dst = ao + qi * INNER + h * HD + half * (HD / 2);
 #pragma unroll
-      for (int e = 0; e < HD / 2; ++e) dst[e] = (half ? o[HD / 2 + e] : o[e]) * inv;
+      for (int e = 0; e < HD; ++e) o[e] *= inv;
+      // ao aliases the token tiles: every thread is past the projections (barrier above), and q/k/v, which the other rows
+      // still read, live in their own region
+      float* dst = ao + qi * AS + h * HD + half * (HD / 2);
+#pragma unroll
+      for (int e = 0; e < HD / 2; ++e) dst[e] = half ? o[HD / 2 + e] : o[e];
     }
     __syncthreads();
-    {   // to_out + store at the un-shifted pixel: tokens 4 tg .. 4 tg + 3, channels lane + 32 i
+    if (active) {   // to_out + store at the un-shifted pixel: tokens 4 tg .. 4 tg + 3, channels lane + 32 i
       float acc[4][DPT];
 #pragma unroll
       for (int t = 0; t < 4; ++t)
@@ -554,7 +564,7 @@ __global__ void __launch_bounds__(128, 2) win_attn_pf_kernel(WinAttnArgs a) {
       for (int k = 0; k < INNER; k += 4) {
         float4 av[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) av[t] = *reinterpret_cast<const float4*>(ao + (tg * 4 + t) * INNER + k);
+        for (int t = 0; t < 4; ++t) av[t] = *reinterpret_cast<const float4*>(ao + (tg * 4 + t) * AS + k);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const float2 w = *reinterpret_cast<const float2*>(wo + (k + kk) * DIM + lane * DPT);
@@ -583,11 +593,11 @@ inline size_t win_attn_smem(int dim, int inner) {
 }
 
 cudaError_t launch_win_attn_pf(const WinAttnArgs& a, cudaStream_t s) {
-  const size_t smem = (size_t)(64 * 192 + 64 * 64 + 64 + 3 * T * T + 2 * T * 64 + T * 196 + T * 64) * sizeof(float);
+  const size_t smem = (size_t)(64 * 192 + 64 * 64 + 64 + 3 * T * (T + 1) + 2 * (2 * T * 64 + T * 196)) * sizeof(float);   // 110.5 KB
   cudaError_t e = cudaFuncSetAttribute(win_attn_pf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int nwin = a.b * (a.n_h / WS) * (a.n_w / WS);
-  win_attn_pf_kernel<<<(unsigned)std::min(nwin, 148 * 2), 128, smem, s>>>(a);
+  win_attn_pf_kernel<<<(unsigned)std::min((nwin + 1) / 2, 148 * 2), 256, smem, s>>>(a);
   return cudaGetLastError();
 }
 
