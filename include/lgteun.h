@@ -194,7 +194,8 @@ int lgteun_train_set_masks(lgteun_t* ctx, const float* const* masks);
  * powers of two in [8, 1024].  weights = 14 device pointers in state_dict order: pre1.weight, pre1.bias, pre2.weight,
  * pre2.bias, amp_fuse.0.weight [C,2C,1,1], amp_fuse.0.bias, amp_fuse.2.weight, amp_fuse.2.bias, pha_fuse.0.weight,
  * pha_fuse.0.bias, pha_fuse.2.weight, pha_fuse.2.bias, post.weight, post.bias.  No handle: the operator keeps no state;
- * the caller provides `workspace` (device memory of at least lgteun_op_freprocess_workspace_bytes bytes). */
+ * the caller provides `workspace` (device memory of at least lgteun_op_freprocess_workspace_bytes bytes).  The first call on a
+ * device fills a twiddle table and synchronises `stream` once: make one call before capturing the operator into a CUDA graph. */
 int64_t lgteun_op_freprocess_workspace_bytes(int N, int C, int H, int W);
 int lgteun_op_freprocess(int device, const float* msf, const float* panf, float* out, int N, int C, int H, int W,
                          const float* const* weights, float* workspace, int64_t workspace_bytes, void* stream);
