@@ -103,10 +103,14 @@ void pw(Run& R, int act, TV x, int Cin, const float* W, int wso, int wsi, const 
   const TV none{nullptr, 0, 0, 0, 0};
   const TV a = add ? *add : none, g = gate ? *gate : none;
   const int ua = add != nullptr, ug = gate != nullptr;
-  if (Cout <= 32) {
-    dim3 grid(blocks(NP, 256), (Cout + 15) / 16);
+  if (Cout <= 16) {
+    dim3 grid(blocks(NP, 256), 1);
     if (act) k_pw<1, 16><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
     else k_pw<0, 16><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
+  } else if (Cout <= 32) {              // one block covers all output channels: x is read once
+    dim3 grid(blocks(NP, 128), 1);
+    if (act) k_pw<1, 32><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
+    else k_pw<0, 32><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
   } else {
     dim3 grid(blocks(NP, 64), (Cout + 63) / 64);
     if (act) k_pw<1, 64><<<grid, 256, 0, R.s>>>(x, Cin, W, wso, wsi, b, y, Cout, NP, a, ua, g, ug);
