@@ -218,6 +218,13 @@ void dw_wgrad(Run& R, int K, TV x, TV dy, const float* dw, const float* db, int 
 // bicubic resize of [N,Hi,Wi,C] to [N,Ho,Wo,C]; adjoint: scatter-add of y (gradient) into x
 void resize(Run& R, TV x, int Hi, int Wi, TV y, int Ho, int Wo, int C, int N, int adjoint) {
   if (R.dry) return;
+  if (!x.nchw && !y.nchw && x.ld == C && y.ld == C && C % 4 == 0) {
+    k_resize_v4<<<blocks((size_t)N * Ho * Wo * (C / 4)), 256, 0, R.s>>>(reinterpret_cast<const float4*>(x.p), Hi, Wi,
+                                                                      reinterpret_cast<float4*>(y.p), Ho, Wo, C / 4, N,
+                                                                      (float)Hi / (float)Ho, adjoint);
+    R.check();
+    return;
+  }
   k_resize<<<blocks((size_t)N * Ho * Wo * C), 256, 0, R.s>>>(x, Hi, Wi, y, Ho, Wo, C, N, (float)Hi / (float)Ho, adjoint);
   R.check();
 }

@@ -512,6 +512,56 @@ __global__ void __launch_bounds__(256) k_resize(TV x, int Hi, int Wi, TV y, int 
   }
 }
 
+// NHWC maps with ld == C, C % 4 == 0: thread = (output pixel, channel quad), 128-bit taps; the adjoint scatters with the
+// 128-bit vector atomics of sm_90+.
+__global__ void __launch_bounds__(256) k_resize_v4(const float4* __restrict__ x, int Hi, int Wi, float4* __restrict__ y, int Ho, int Wo,
+                                                   int CQ, int N, float rscale, int adjoint) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, Po = (size_t)Ho * Wo, total = (size_t)N * Po * CQ;
+  if (idx >= total) return;
+  const int q = (int)(idx % CQ);
+  const size_t gpo = idx / CQ;
+  const int ox = (int)(gpo % Wo), oy = (int)((gpo / Wo) % Ho);
+  const size_t n = gpo / Po;
+  const float sy = (oy + 0.5f) * rscale - 0.5f, sx = (ox + 0.5f) * rscale - 0.5f;
+  const float fy = floorf(sy), fx = floorf(sx);
+  float cy[4], cx[4];
+  cubic_coef(sy - fy, cy);
+  cubic_coef(sx - fx, cx);
+  const int iy = (int)fy, ix = (int)fx;
+  const size_t base = n * (size_t)Hi * Wi;
+  if (!adjoint) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), Hi - 1);
+      float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), Wi - 1);
+        const float4 v = __ldg(x + (base + (size_t)yy * Wi + xx) * CQ + q);
+        row.x = fmaf(cx[b], v.x, row.x); row.y = fmaf(cx[b], v.y, row.y);
+        row.z = fmaf(cx[b], v.z, row.z); row.w = fmaf(cx[b], v.w, row.w);
+      }
+      acc.x = fmaf(cy[a], row.x, acc.x); acc.y = fmaf(cy[a], row.y, acc.y);
+      acc.z = fmaf(cy[a], row.z, acc.z); acc.w = fmaf(cy[a], row.w, acc.w);
+    }
+    y[gpo * CQ + q] = acc;
+  } else {
+    const float4 g = y[gpo * CQ + q];
+    float4* xo = const_cast<float4*>(x);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), Hi - 1);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), Wi - 1);
+        const float c = cy[a] * cx[b];
+        atomicAdd(xo + (base + (size_t)yy * Wi + xx) * CQ + q, make_float4(c * g.x, c * g.y, c * g.z, c * g.w));
+      }
+    }
+  }
+}
+
 // ---- window multi-head self-attention (local_mixer, LGT.py:130-146; window merge :207-208) ------------------------------------------
 // qkv [NP, 6D] NHWC (q | k | v thirds, head-major inside a third), D = head dim; one 64-thread block per (window, head),
 // thread = query token i*8+j.
