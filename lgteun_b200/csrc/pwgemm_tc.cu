@@ -27,9 +27,7 @@ enum { PRO_PLAIN = 0, PRO_LN = 1, PRO_GELU = 2 };          // PRO_GELU: A = GELU
 enum { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESID = 2, EPI_GATE = 3 };   // EPI_GATE: out = acc * gelu'(gate) (training backward)
 
 // d/dx of the exact (erf) GELU: Phi(x) + x phi(x)
-__device__ __forceinline__ float gelu_grad_exact(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
+__device__ __forceinline__ float gelu_grad_exact(float x) { return gelu_grad_fast(x); }   // common.cuh: 3.3e-7 absolute
 constexpr int kNS = 64;                 // output channels per weight slice
 constexpr int kPwThreads = 256;
 

@@ -33,9 +33,7 @@ inline TV nchw(const float* p, int C, int P) {
 
 // exact-form (erf) GELU, 4.8e-7 absolute (common.cuh: one ex2 instead of erff; the inference kernels use the same form)
 __device__ __forceinline__ float gelu_exact(float x) { return lg::gelu_fast(x); }
-__device__ __forceinline__ float gelu_grad(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
+__device__ __forceinline__ float gelu_grad(float x) { return lg::gelu_grad_fast(x); }
 
 // ---- pointwise (1x1) convolution:  y[p,co] = sum_ci W[co*wso + ci*wsi] * f(x[p,ci]) + b[co]  (+ add[p,co]) (* gelu'(gate)) -------
 // Forward of bmu.point_conv (basic_module_unformer_v2.py:13-14) with (wso, wsi) = (Cin, 1); its data gradient with the
