@@ -148,3 +148,41 @@ class WindowAttention(nn.Module):
             if t is not None:
                 t.record_stream(cur)
         return out
+
+
+def swap_companions(root: nn.Module):
+    """Drop-in inside the reference's own networks: replace every ``Freprocess`` (models/SFIIN.py:210, a child of ``SpaFre``
+    :247) and every ``WindowAttention`` (models/common/modules.py:341, inside ``SwinBlock.attention_block`` :428) of ``root``
+    by the lgteun_b200 module with the same constructor arguments, weights, device and train / eval flag.  The rest of the
+    network keeps running in PyTorch; the swapped operators run under ``torch.no_grad()`` (inference).  Instances whose
+    configuration the kernels do not cover (window size other than 4, unsupported channel counts) are left alone.
+    Returns ``{"Freprocess": n, "WindowAttention": m}``."""
+    counts = {"Freprocess": 0, "WindowAttention": 0}
+    for parent in list(root.modules()):
+        for name, child in list(parent.named_children()):
+            if isinstance(child, (Freprocess, WindowAttention)):
+                continue
+            kind = type(child).__name__
+            if kind == "Freprocess" and isinstance(getattr(child, "pre1", None), nn.Conv2d):
+                channels = child.pre1.in_channels
+                if channels not in (4, 8, 16):
+                    continue
+                new = Freprocess(channels)
+            elif kind == "WindowAttention" and isinstance(getattr(child, "to_out", None), nn.Linear):
+                heads, inner, dim = int(child.heads), child.to_out.in_features, child.to_out.out_features
+                head_dim = inner // heads
+                if (int(child.window_size) != 4 or head_dim not in (8, 16, 32) or dim % 4 or dim > 128 or inner > 128
+                        or 4 * dim * inner * 4 + 32 * 1024 > 227 * 1024):
+                    continue
+                new = WindowAttention(dim=dim, heads=heads, head_dim=head_dim, shifted=bool(child.shifted), window_size=4,
+                                      relative_pos_embedding=bool(child.relative_pos_embedding), cross_attn=bool(child.cross_attn))
+            else:
+                continue
+            new.load_state_dict(child.state_dict())
+            first = next(child.parameters(), None)
+            if first is not None:
+                new.to(first.device)
+            new.train(child.training)
+            parent._modules[name] = new
+            counts[kind] += 1
+    return counts

@@ -111,3 +111,46 @@ def test_window_attention_module_mirrors_the_reference_interface(case):
         net(x, y) if cross else net(x)
     with pytest.raises(ValueError):
         net(x, None if cross else x)
+
+
+def test_swap_companions_inside_unmodified_reference_networks():
+    """lgteun_b200.swap_companions on the reference's own SpaFre (models/SFIIN.py:240-273) and SwinModule
+    (models/common/modules.py:458-505): the operators are replaced, the networks' state_dicts do not change, and the
+    reference forward now reaches the lgteun_b200 operators (which refuse CPU tensors: there is no fallback)."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference checkout not present (GPU box)")
+    import importlib.util
+    import lgteun_b200
+    spec = importlib.util.spec_from_file_location("make_golden_companions", os.path.join(GOLDEN, "make_golden_companions.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sf, md = mod.load_sfiin(), mod.load_modules()
+
+    torch.manual_seed(3)
+    spafre = sf.SpaFre(8).eval()
+    before = {k: v.clone() for k, v in spafre.state_dict().items()}
+    assert lgteun_b200.swap_companions(spafre) == {"Freprocess": 1, "WindowAttention": 0}
+    assert isinstance(spafre.fre_process, lgteun_b200.Freprocess) and not spafre.fre_process.training
+    after = spafre.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+        spafre(torch.zeros(1, 8, 16, 16), torch.zeros(1, 8, 16, 16))
+
+    swin = md.SwinModule(in_channels=64, hidden_dimension=64, layers=2, downscaling_factor=1, num_heads=4, head_dim=16,
+                         window_size=4, relative_pos_embedding=True, cross_attn=True).eval()     # models/panformer.py:51-53
+    before = {k: v.clone() for k, v in swin.state_dict().items()}
+    assert lgteun_b200.swap_companions(swin) == {"Freprocess": 0, "WindowAttention": 2}          # regular + shifted block
+    kinds = [type(m).__module__ for m in swin.modules() if type(m).__name__ == "WindowAttention"]
+    assert kinds == ["lgteun_b200.companions"] * 2
+    after = swin.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
+    assert lgteun_b200.swap_companions(swin) == {"Freprocess": 0, "WindowAttention": 0}          # idempotent
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+        swin(torch.zeros(1, 64, 8, 8), torch.zeros(1, 64, 8, 8))
+
+    big = md.WindowAttention(dim=64, heads=4, head_dim=16, shifted=False, window_size=8, relative_pos_embedding=True,
+                             cross_attn=False)
+    holder = torch.nn.Sequential(big)
+    assert lgteun_b200.swap_companions(holder) == {"Freprocess": 0, "WindowAttention": 0}        # window 8 is left alone
+    assert holder[0] is big
