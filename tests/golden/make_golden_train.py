@@ -3,8 +3,8 @@
 Runs models.unlg_former.Pansharpening in train() mode exactly as UnlgFormer.train_iter does (models/unlg_former.py:87-110):
 out = G(lr, pan); loss = nn.L1Loss()(out, gt) * 1.0; loss.backward(); Adam(lr=1.5e-3).step() (configs/unlg_former.py:82-90).
 The five nn.Dropout(0.1) masks of the live prior (LGT.py:198,216) are captured with forward hooks so that the oracle and
-the CUDA path can replay the same step.  Writes tests/golden/train_gf2.npz: inputs, masks (NHWC), output, loss, every
-gradient (absent key = .grad is None) and the parameters after the Adam step."""
+the CUDA path can replay the same step.  Writes tests/golden/train_gf2.npz (4 bands) and train_wv3.npz (8 bands): inputs, masks
+(NHWC), output, loss, every gradient (absent key = .grad is None) and the parameters after the Adam step."""
 import os
 import sys
 
@@ -16,15 +16,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import ref_import  # noqa: E402
 
 
-def main():
+def record(bands, n, h, fname, after_keys=None):
+    """after_keys: None = store every updated parameter, else only these (keeps the 8-band fixture small)."""
     torch.set_num_threads(1)
-    net = ref_import.build(4, stages=2, seed=19971118)
+    net = ref_import.build(bands, stages=2, seed=19971118)
     net.train()
     gen = torch.Generator().manual_seed(1)
-    n, h = 2, 8
-    ms = torch.rand(n, 4, h, h, generator=gen)
+    ms = torch.rand(n, bands, h, h, generator=gen)
     pan = torch.rand(n, 1, 4 * h, 4 * h, generator=gen)
-    gt = torch.rand(n, 4, 4 * h, 4 * h, generator=gen)
+    gt = torch.rand(n, bands, 4 * h, 4 * h, generator=gen)
     masks = []
     hooks = []
     prior = net.prior_module[-1]
@@ -57,10 +57,19 @@ def main():
     for k, g in grads.items():
         arrays["grad/" + k] = g.numpy()
     for k, p in net.named_parameters():
-        if k in grads:
+        if k in grads and (after_keys is None or k in after_keys):
             arrays["after/" + k] = p.detach().numpy()
-    np.savez_compressed(os.path.join(HERE, "train_gf2.npz"), **arrays)
-    print("loss", loss.item(), "live grads", len(grads), "of", len(list(net.parameters())))
+    np.savez_compressed(os.path.join(HERE, fname), **arrays)
+    print(fname, "loss", loss.item(), "live grads", len(grads), "of", len(list(net.parameters())))
+
+
+AFTER_KEYS_WV = ("eta.1", "R.weight", "prior_module.1.tail.1.weight",
+                 "prior_module.1.bottleneck.blocks.0.0.fn.fn.local_mixer.pos_emb")
+
+
+def main():
+    record(4, 2, 8, "train_gf2.npz")                      # GF-2 / WV-2 band count
+    record(8, 1, 8, "train_wv3.npz", AFTER_KEYS_WV)       # 8 bands (BASELINE configs[4]); batch 1 keeps the fixture small
 
 
 if __name__ == "__main__":
