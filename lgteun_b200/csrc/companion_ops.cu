@@ -174,7 +174,8 @@ cudaError_t run_freprocess(const float* msf, const float* panf, float* out, int 
   float* pre = ws;                                   // [N,H,W,2C]; reused for the |irfft2| map [N,H,W,C]
   float* S = pre + align64(NP * 2 * C);              // complex [N,H,Wh,2C]
   float* G = S + align64(nbins * 2 * C * 2);         // complex [N,H,Wh,C]
-  const bool fast_w = (W == 128 || W == 256), fast_h = (H == 128 || H == 256);   // register-resident passes of fft256.cu
+  // register-resident passes of fft256.cu; a CTA of the row kernels owns up to 16 whole image rows
+  const bool fast_w = (W == 128 || W == 256) && H % 16 == 0, fast_h = (H == 128 || H == 256);
   cudaError_t e;
   if (fast_w) {                                           // pre1 / pre2 convs as the prologue of the row transform
     const float* pre_w[4] = {w.pre1_w, w.pre1_b, w.pre2_w, w.pre2_b};
