@@ -168,6 +168,12 @@ int lgteun_train_forward(lgteun_t* ctx, const float* flat_param, const float* ms
  * forward must still be valid and unchanged.  One backward per forward. */
 int lgteun_train_backward(lgteun_t* ctx, const float* dout, float* flat_grad, void* stream);
 
+/* A handle keeps ONE activation tape.  lgteun_train_generation returns the serial number of the last lgteun_train_forward
+ * (0 before the first); lgteun_train_backward_of runs the backward only if the tape still is that forward's and fails with
+ * LGTEUN_ESTATE otherwise (forward A, forward B, backward A would silently mix A's dout with B's activations). */
+uint64_t lgteun_train_generation(const lgteun_t* ctx);
+int lgteun_train_backward_of(lgteun_t* ctx, uint64_t generation, const float* dout, float* flat_grad, void* stream);
+
 /* Kernels launched by the last train_forward + train_backward pair. */
 int lgteun_train_launches(const lgteun_t* ctx);
 

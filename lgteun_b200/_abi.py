@@ -45,6 +45,8 @@ SIGNATURES = {
     "lgteun_train_workspace_bytes": (c_int64, [c_void_p, c_int, c_int, c_int]),
     "lgteun_train_forward": (c_int, [c_void_p, _F, _F, _F, _F, c_int, c_int, c_int, ctypes.c_float, ctypes.c_uint64, c_void_p]),
     "lgteun_train_backward": (c_int, [c_void_p, _F, _F, c_void_p]),
+    "lgteun_train_generation": (ctypes.c_uint64, [c_void_p]),
+    "lgteun_train_backward_of": (c_int, [c_void_p, ctypes.c_uint64, _F, _F, c_void_p]),
     "lgteun_train_launches": (c_int, [c_void_p]),
     "lgteun_l1_loss": (c_int, [c_void_p, _F, _F, c_int64, ctypes.c_float, _F, _F, c_void_p]),
     "lgteun_adam_step": (c_int, [c_void_p, _F, _F, _F, _F, c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
@@ -150,8 +152,16 @@ class Handle:
         check(lib().lgteun_train_forward(self._p, flat_param_ptr, ms_ptr, pan_ptr, out_ptr, N, h, w, dropout_p, seed,
                                          c_void_p(stream)))
 
-    def train_backward(self, dout_ptr, flat_grad_ptr, stream=0):
-        check(lib().lgteun_train_backward(self._p, dout_ptr, flat_grad_ptr, c_void_p(stream)))
+    def train_backward(self, dout_ptr, flat_grad_ptr, stream=0, generation=None):
+        """Backward of the handle's tape; with ``generation`` (the value of train_generation() right after the forward) it
+        raises if another forward has overwritten that tape in the meantime."""
+        if generation is None:
+            check(lib().lgteun_train_backward(self._p, dout_ptr, flat_grad_ptr, c_void_p(stream)))
+        else:
+            check(lib().lgteun_train_backward_of(self._p, generation, dout_ptr, flat_grad_ptr, c_void_p(stream)))
+
+    def train_generation(self):
+        return lib().lgteun_train_generation(self._p)
 
     def train_workspace_bytes(self, N, h, w):
         return lib().lgteun_train_workspace_bytes(self._p, N, h, w)

@@ -41,6 +41,7 @@ struct TrainState {
   size_t cap = 0;
   // tape of the last lgteun_train_forward
   bool valid = false;
+  uint64_t generation = 0;      // bumped by every lgteun_train_forward: a backward names the forward it belongs to
   int N = 0, h = 0, w = 0;
   float p_drop = 0.f;
   uint64_t seed = 0;
@@ -666,7 +667,19 @@ int lgteun_train_forward(lgteun_t* c, const float* flat_param, const float* ms, 
   T->fwd_end = R.off;
   T->launches_fwd = R.launches;
   T->valid = true;
+  ++T->generation;
   return 0;
+}
+
+uint64_t lgteun_train_generation(const lgteun_t* c) { return (c && c->train) ? c->train->generation : 0; }
+
+int lgteun_train_backward_of(lgteun_t* c, uint64_t generation, const float* dout, float* flat_grad, void* stream) {
+  if (!c) return fail(LGTEUN_EINVAL, "NULL argument");
+  TrainState* T = c->train;
+  if (!T || !T->valid || T->generation != generation)
+    return fail(LGTEUN_ESTATE, "the activation tape belongs to another forward: a handle keeps ONE tape, so the forward of generation " +
+                                   std::to_string(generation) + " was overwritten by a later lgteun_train_forward (or already consumed)");
+  return lgteun_train_backward(c, dout, flat_grad, stream);
 }
 
 int lgteun_train_backward(lgteun_t* c, const float* dout, float* flat_grad, void* stream) {

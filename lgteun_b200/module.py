@@ -250,7 +250,10 @@ class Pansharpening(nn.Module):
             from .train import autograd_forward
             self._train_calls += 1
             p = self.dropout_p if self.training else 0.0
-            seed = (torch.initial_seed() + self._train_calls) & 0x7FFFFFFFFFFFFFFF
+            rank = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()      # data-parallel ranks must not drop the same positions
+            seed = (torch.initial_seed() + self._train_calls + 0x9E3779B1 * rank) & 0x7FFFFFFFFFFFFFFF
             if not needs_grad:
                 with torch.no_grad():
                     return autograd_forward(self, ms, pan, p, seed)
@@ -264,10 +267,13 @@ class Pansharpening(nn.Module):
                            torch.cuda.current_stream(ms.device).cuda_stream)
         return out
 
-    def evaluate(self, pred: torch.Tensor, gt: torch.Tensor, bit_depth: int = 11) -> torch.Tensor:
+    def evaluate(self, pred: torch.Tensor, gt: torch.Tensor, bit_depth: int = 11, dynamic_range: float = 2047.5) -> torch.Tensor:
         """PSNR / SAM / ERGAS per image on the device, float64 — the reduced-resolution metrics the reference's test
         loop computes per image with numpy (models/base/base_model.py:304-327, models/base/metrics.py).  pred / gt are
-        the normalised [N,B,H,W] CUDA tensors of the eval loop; returns a float64 CUDA tensor [N, 3]."""
+        the normalised [N,B,H,W] CUDA tensors of the eval loop; returns a float64 CUDA tensor [N, 3].
+        ``bit_depth`` is the de-normalisation scale 2**bit_depth - .5 (dataset/utils.py:252-263); ``dynamic_range`` is the
+        PSNR peak, which the reference keeps at the module constant 2047.5 whatever cfg.bit_depth says
+        (models/base/metrics.py:19,39)."""
         if pred.shape != gt.shape or pred.dim() != 4 or pred.shape[1] != self.in_channels:
             raise ValueError("pred and gt must both be [N,B,H,W]")
         if pred.device.type != "cuda" or gt.device != pred.device or pred.dtype != torch.float32 or gt.dtype != torch.float32:
@@ -277,8 +283,12 @@ class Pansharpening(nn.Module):
             n, _, h, w = pred.shape
             out = torch.empty((n, 3), dtype=torch.float64, device=pred.device)
             pc, gc = pred.contiguous(), gt.contiguous()
-            handle.op("metrics", pc.data_ptr(), gc.data_ptr(), out.data_ptr(), n, h, w, float(2 ** bit_depth - 0.5),
+            max_value = float(2 ** bit_depth - 0.5)
+            handle.op("metrics", pc.data_ptr(), gc.data_ptr(), out.data_ptr(), n, h, w, max_value,
                       stream=torch.cuda.current_stream(pred.device).cuda_stream)
+            if float(dynamic_range) != max_value:        # the kernel's PSNR peak is max_value: 20 log10(R'/R) moves it
+                import math
+                out[:, 0] += 20.0 * math.log10(float(dynamic_range) / max_value)
         return out
 
     def normalize(self, raw: torch.Tensor, bit_depth: int = 11) -> torch.Tensor:

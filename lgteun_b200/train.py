@@ -88,7 +88,10 @@ class Trainer:
     def __init__(self, module: Pansharpening, lr: float = 1.5e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  loss_weight: float = 1.0, dropout_p: float = 0.1, seed: int = 19971118, step_size: int = 0,
                  gamma: float = 0.85, process_group=None):
-        self.flat = FlatParameters(module)
+        # ONE flat buffer per module: the drop-in module's own train-mode forward (module._flat_parameters) must see the
+        # buffer this trainer updates, otherwise a later module(ms, pan) would re-flatten into a new buffer and the
+        # trainer would keep stepping the orphaned one
+        self.flat = module._flat_parameters()
         self.module = module
         self.handle = self.flat.handle
         self.lr0, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
@@ -100,8 +103,40 @@ class Trainer:
         self.exp_avg_sq = torch.zeros_like(self.flat.param)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        ddp = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(process_group) if ddp else 1
+        self.rank = dist.get_rank(process_group) if ddp else 0
         self._buf = {}
+        if self.world > 1:
+            self.broadcast_state()
+
+    def broadcast_state(self, src: int = 0):
+        """Make every rank start from rank ``src``'s parameters and Adam moments (what torch DDP does at construction):
+        averaged gradients applied to different weights would keep the replicas different for ever.  Call it again after
+        loading a checkpoint on one rank."""
+        if self.world > 1:
+            for t in (self.flat.param, self.exp_avg, self.exp_avg_sq):
+                dist.broadcast(t, src=src, group=self.group)
+            steps = torch.tensor([self.steps], dtype=torch.int64, device=self.flat.device)
+            dist.broadcast(steps, src=src, group=self.group)
+            self.steps = int(steps.item())
+            self.module._invalidate_runtime()
+
+    def _check_alias(self):
+        """The module's parameters must still live inside ``flat.param`` (a .to() / .cuda() / load of new Parameter objects
+        moves them out): re-flattening silently would orphan the optimiser state, so raise instead."""
+        base = self.flat.param.data_ptr()
+        params = dict(self.module.named_parameters())
+        for key, off, _ in self.flat.layout:
+            if params[key].data_ptr() != base + 4 * off:
+                raise RuntimeError(f"parameter {key} no longer aliases the trainer's flat buffer (the module was moved or its "
+                                   "parameters were replaced after Trainer was created); build a new Trainer")
+        if self.module._flat is not self.flat:
+            raise RuntimeError("the module was re-flattened after this Trainer was created; build a new Trainer")
+
+    def dropout_seed(self) -> int:
+        """Per-step, per-rank seed of the counter-based dropout masks: ranks must not drop the same positions."""
+        return (self.seed + self.steps + 0x9E3779B1 * self.rank) & 0x7FFFFFFFFFFFFFFF
 
     def lr(self) -> float:
         return self.lr0 * (self.gamma ** (self.steps // self.step_size)) if self.step_size > 0 else self.lr0
@@ -123,11 +158,12 @@ class Trainer:
             if t.device != self.flat.device or t.dtype != torch.float32:
                 raise RuntimeError("Trainer needs float32 tensors on the module's CUDA device")
         ms, pan, gt = ms.contiguous(), pan.contiguous(), gt.contiguous()
+        self._check_alias()
         with torch.cuda.device(self.flat.device):
             stream = torch.cuda.current_stream().cuda_stream
             out, dout = self._buffers(tuple(gt.shape))
             self.handle.train_forward(self.flat.param.data_ptr(), ms.data_ptr(), pan.data_ptr(), out.data_ptr(), n, h, w,
-                                      self.dropout_p, self.seed + self.steps, stream)
+                                      self.dropout_p, self.dropout_seed(), stream)
             self.handle.l1_loss(out.data_ptr(), gt.data_ptr(), out.numel(), self.loss_weight, self.loss.data_ptr(),
                                 dout.data_ptr(), stream)
             self.handle.train_backward(dout.data_ptr(), self.flat.grad.data_ptr(), stream)
@@ -160,6 +196,7 @@ class _TrainForward(torch.autograd.Function):
             flat.handle.train_forward(flat.param.data_ptr(), ms.data_ptr(), pan.data_ptr(), out.data_ptr(), n, h, w,
                                       dropout_p, seed, torch.cuda.current_stream().cuda_stream)
         ctx.flat = flat
+        ctx.generation = flat.handle.train_generation()   # a handle keeps ONE tape: backward() names the forward it belongs to
         ctx.keep = (ms, pan)                    # the tape refers to the caller's input buffers
         return out
 
@@ -168,7 +205,10 @@ class _TrainForward(torch.autograd.Function):
         flat = ctx.flat
         dout = dout.contiguous()
         with torch.cuda.device(dout.device):
-            flat.handle.train_backward(dout.data_ptr(), flat.grad.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            # raises (LGTEUN_ESTATE) if a later train-mode forward overwrote this node's tape: forward A, forward B,
+            # backward A must not combine A's dout with B's activations
+            flat.handle.train_backward(dout.data_ptr(), flat.grad.data_ptr(), torch.cuda.current_stream().cuda_stream,
+                                       generation=ctx.generation)
         g = flat.grad.clone()                   # param.grad must not alias the buffer the next backward overwrites
         shapes = {k: p.shape for k, p in flat.module.named_parameters()}
         grads = tuple(g[off:off + numel].view(shapes[key]) if flat.is_live(key) else None for key, off, numel in flat.layout)

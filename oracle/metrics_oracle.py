@@ -37,11 +37,13 @@ def ergas(fake: np.ndarray, real: np.ndarray, scale: int = 4) -> float:
     return float(100 / scale * np.sqrt((mses / (means ** 2 + _EPS)).mean()))
 
 
-def evaluate(pred_nchw: np.ndarray, gt_nchw: np.ndarray) -> np.ndarray:
-    """Mean [PSNR, SAM, ERGAS] over a batch of NCHW images normalised to [0,1)."""
+def evaluate(pred_nchw: np.ndarray, gt_nchw: np.ndarray, bit_depth: int = 11) -> np.ndarray:
+    """Mean [PSNR, SAM, ERGAS] over a batch of NCHW images normalised to [0,1): de-normalised with 2**bit_depth - .5
+    (dataset/utils.py:252-263); the PSNR peak stays the module constant 2047.5 (metrics.py:19,39)."""
     rows = []
+    scale = np.float32(2 ** bit_depth - 0.5)
     for p, g in zip(pred_nchw, gt_nchw):
-        p = np.transpose(p, (1, 2, 0)) * DYNAMIC_RANGE
-        g = np.transpose(g, (1, 2, 0)) * DYNAMIC_RANGE
+        p = np.transpose(p, (1, 2, 0)) * scale
+        g = np.transpose(g, (1, 2, 0)) * scale
         rows.append([psnr(p, g), sam(p, g), ergas(p, g)])
     return np.asarray(rows).mean(axis=0)

@@ -386,6 +386,9 @@ def test_module_dropin(abi):
         m = net.evaluate(out, g["out"].cuda()).cpu().numpy()
         assert m.shape == (out.shape[0], 3)
         assert np.allclose(m.mean(axis=0), M.evaluate(out.cpu().numpy(), g["out"].numpy()), rtol=1e-9, atol=1e-9)
+        # 10-bit data: de-normalised with 1023.5 while the PSNR peak stays the reference's constant 2047.5 (metrics.py:19,39)
+        m10 = net.evaluate(out, g["out"].cuda(), bit_depth=10).cpu().numpy()
+        assert np.allclose(m10.mean(axis=0), M.evaluate(out.cpu().numpy(), g["out"].numpy(), bit_depth=10), rtol=1e-7, atol=1e-7)
         # weight refresh after an in-place parameter update
         net.prior_module[1].tail[1].bias.add_(0.25)
         out2 = net(g["ms"].cuda(), g["pan"].cuda())

@@ -202,6 +202,61 @@ def test_module_train_iter_and_trainer(abi, O):
             assert ((v.cpu() - after[k]).abs()[ok] <= 2e-5).all(), k
 
 
+def test_trainer_and_module_share_one_flat_buffer(abi):
+    """Trainer first, module call second: the module's own train-mode forward must not re-flatten the
+    parameters into a new buffer; moving the module after Trainer creation raises instead of training an orphan."""
+    import lgteun_b200
+    from oracle.ref_import import Config
+    torch.manual_seed(3)
+    net = lgteun_b200.Pansharpening(Config(ms_chans=4), None, stage=2).cuda()
+    tr = lgteun_b200.Trainer(net, lr=1.5e-3, dropout_p=0.0)
+    assert net._flat is tr.flat
+    gen = torch.Generator().manual_seed(6)
+    ms, pan, gt = (torch.rand(1, 4, 8, 8, generator=gen).cuda(), torch.rand(1, 1, 32, 32, generator=gen).cuda(),
+                   torch.rand(1, 4, 32, 32, generator=gen).cuda())
+    net.train()
+    out = net(ms, pan)                                   # autograd path of the drop-in module
+    assert net._flat is tr.flat
+    out.sum().backward()
+    before = tr.flat.param.clone()
+    tr.step(ms, pan, gt)
+    torch.cuda.synchronize()
+    assert not torch.equal(before, tr.flat.param)
+    sd = net.state_dict()                                # state_dict reads the buffer the trainer stepped
+    key, off, numel = tr.flat.layout[0]
+    assert torch.equal(sd[key].reshape(-1), tr.flat.param[off:off + numel])
+    net.eval()
+    with torch.no_grad():
+        y1 = net(ms, pan)
+    tr.step(ms, pan, gt)
+    with torch.no_grad():
+        y2 = net(ms, pan)
+    assert not torch.equal(y1, y2)                       # the eval forward follows the trained weights
+    for p in net.parameters():                           # parameters replaced behind the trainer's back
+        p.data = p.data.clone()
+    with pytest.raises(RuntimeError):
+        tr.step(ms, pan, gt)
+
+
+def test_backward_of_an_overwritten_tape_raises(abi):
+    """One tape per handle: forward A, forward B, backward A must raise, not mix A's dout with B's tape."""
+    import lgteun_b200
+    from oracle.ref_import import Config
+    torch.manual_seed(4)
+    net = lgteun_b200.Pansharpening(Config(ms_chans=4), None, stage=2).cuda().train()
+    gen = torch.Generator().manual_seed(7)
+    ms, pan = torch.rand(1, 4, 8, 8, generator=gen).cuda(), torch.rand(1, 1, 32, 32, generator=gen).cuda()
+    a = net(ms, pan)
+    b = net(ms * 0.5, pan)
+    with pytest.raises(RuntimeError, match="tape"):
+        a.sum().backward()
+    b2 = net(ms * 0.5, pan)                              # the latest forward still works
+    b2.sum().backward()
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
+    h = abi.Handle(0, 4, 2)
+    assert h.train_generation() == 0
+
+
 def test_data_parallel_trainer_two_gpus(abi):
     """NCCL path: one process per GPU under torchrun (tests/ddp_train_check.py).  Needs two visible GPUs."""
     import subprocess
