@@ -192,6 +192,196 @@ class ClockSampler:
         return out
 
 
+
+# ----------------------------------------------------------------------------------------------------------------
+# helpers shared by the legs of our arm
+# ----------------------------------------------------------------------------------------------------------------
+def timed_region(fn, steps, warmup, dev, stream, world):
+    """W untimed calls, then exactly `steps` calls between two CUDA events on the launch stream, bracketed by a barrier +
+    synchronize on both sides; returns ms, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from lgteun_b200.sharding import max_over_ranks
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    return max_over_ranks(e0.elapsed_time(e1), dev)
+
+
+def parity_vs_oracle(net, dev, ms_h, pan_h, pairs=2):
+    """max |delta| of the product forward (through the nn.Module / C ABI / CUDA graph) against the CPU oracle on the first
+    `pairs` pairs of the TIMED inputs.  The oracle is the checker here, never the thing measured."""
+    import torch
+    from oracle import lgteun_oracle as O
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        got = net(ms_h[:pairs].to(dev), pan_h[:pairs].to(dev)).cpu()
+    ref = O.forward(sd, ms_h[:pairs], pan_h[:pairs])
+    return float((got - ref).abs().max().item())
+
+
+def gpu_eager_baseline(bands, h, dev, big_batch=64):
+    """The incumbent GPU path (models/base/base_model.py:299-302): the reference's op sequence dispatched by
+    torch eager to cuDNN / cuBLAS / cuFFT / ATen on this B200 — here the oracle restatement run on CUDA tensors (the
+    reference itself cannot travel to the GPU box), both priors executed as the reference executes them, fp32, TF32 off.
+    Also records how far torch-CUDA is from torch-CPU for the same function."""
+    import torch
+    from oracle import lgteun_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = golden_weights(bands)
+    sd_d = {k: v.to(dev) for k, v in sd.items()}
+    out = {"what": "oracle port (= the reference's torch op sequence) on CUDA: torch eager -> cuDNN/cuBLAS/cuFFT, fp32, TF32 off, "
+                   "both priors executed, inputs resident, cuda.synchronize around each forward",
+           "unit": UNIT}
+    for label, b in (("batch1", 1), ("batch_large", big_batch)):
+        while b >= 1:
+            try:
+                ms, pan = synth_inputs(b, bands, h)
+                ms, pan = ms.to(dev), pan.to(dev)
+                with torch.no_grad():
+                    for _ in range(2):
+                        O.forward(sd_d, ms, pan, skip_dead_priors=False)
+                    torch.cuda.synchronize(dev)
+                    ts = []
+                    for _ in range(5):
+                        t0 = time.perf_counter()
+                        O.forward(sd_d, ms, pan, skip_dead_priors=False)
+                        torch.cuda.synchronize(dev)
+                        ts.append(time.perf_counter() - t0)
+                out[label] = {"batch": b, "pairs_per_s": b / statistics.median(ts), "ms_per_forward": 1e3 * statistics.median(ts)}
+                break
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                if label == "batch1":
+                    break
+                b //= 2
+    ms, pan = synth_inputs(2, bands, h)
+    with torch.no_grad():
+        d = (O.forward(sd_d, ms.to(dev), pan.to(dev)).cpu() - O.forward(sd, ms, pan)).abs().max().item()
+    out["torch_cuda_vs_torch_cpu_max_abs_delta"] = float(d)
+    del sd_d
+    torch.cuda.empty_cache()
+    return out
+
+
+def forward_leg(name, batch, flags, dev, stream, world, rank, steps=5, warmup=3):
+    """Device-resident forward throughput of another workload / batch on all ranks: (total pairs/s, ms per step)."""
+    import torch
+    import lgteun_b200
+    from lgteun_b200.sharding import sum_over_ranks
+    bands, h, _, desc = WORKLOADS[name]
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=2)
+    net.load_state_dict(golden_weights(bands))
+    net = net.to(dev).eval()
+    handle = net._runtime(dev)
+    ms, pan = synth_inputs(batch, bands, h, seed=1000 + rank)
+    ms, pan = ms.to(dev), pan.to(dev)
+    out = torch.empty(batch, bands, 4 * h, 4 * h, device=dev)
+
+    def step():
+        handle.forward(ms.data_ptr(), pan.data_ptr(), out.data_ptr(), batch, h, h, flags, stream.cuda_stream)
+    t = timed_region(step, steps, warmup, dev, stream, world)
+    total = sum_over_ranks(batch, dev) * steps
+    if not torch.isfinite(out).all():
+        raise RuntimeError(f"non-finite output in the {name} leg")
+    del net, handle, ms, pan, out
+    torch.cuda.empty_cache()
+    return total / (t * 1e-3), t / steps, desc
+
+
+def train_leg(dev, stream, world, rank, peaks, steps=10, warmup=3, with_cpu=False):
+    """BASELINE configs[4] inside the same run: lgteun_b200.Trainer.step (train-mode forward, L1, backward, NCCL all-reduce
+    of the flat gradient when world > 1, Adam) on per-rank batches of 4 x 8 bands x PAN 128^2 (the reference's train patches)."""
+    import torch
+    import lgteun_b200
+    bands, h, batch, desc = TRAIN_WORKLOADS["train"]
+    H = 4 * h
+    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=2)
+    net.load_state_dict(golden_weights(bands))
+    net = net.to(dev).train()
+    trainer = lgteun_b200.Trainer(net, lr=1.5e-3, betas=(0.9, 0.999), dropout_p=0.1, seed=19971118)
+    gen = torch.Generator().manual_seed(100 + rank)
+    nbuf = 4
+    devb = [(torch.rand(batch, bands, h, h, generator=gen).to(dev), torch.rand(batch, 1, H, H, generator=gen).to(dev),
+             torch.rand(batch, bands, H, H, generator=gen).to(dev)) for _ in range(nbuf)]
+    it = {"i": 0}
+
+    def step():
+        ms, pan, gt = devb[it["i"] % nbuf]
+        it["i"] += 1
+        trainer.step(ms, pan, gt)
+    for _ in range(warmup):
+        step()
+    trainer.allreduce_events = []
+    t = timed_region(step, steps, 0, dev, stream, world)
+    ar = [a.elapsed_time(b) for a, b in trainer.allreduce_events]
+    trainer.allreduce_events = None
+    if not torch.isfinite(trainer.loss).all() or not torch.isfinite(trainer.flat.param).all():
+        raise RuntimeError("non-finite loss / parameters in the training leg")
+    ms_step = t / steps
+    # whole-step roofline: forward of the live path (data steps + prior_module[K-1]) = 0.5008 of the two-prior forward FLOPs,
+    # backward ~ 2x forward; WV-3 per-pair FLOPs scale with the pixel count (PAN 128^2 = 1/4 of PAN 256^2)
+    fwd_flops = FLOPS_PER_PAIR["wv3"] * 0.5008 * (H * H) / (256 * 256)
+    achieved = 3 * fwd_flops * batch / (ms_step * 1e-3) / 1e12
+    res = {"workload": desc, "batch_per_gpu": batch, "global_batch": batch * world, "ms_per_step": ms_step,
+           "pairs_per_s": batch * world / (ms_step * 1e-3), "steps": steps,
+           "allreduce_ms": (statistics.median(ar) if ar else None),
+           "allreduce": (f"dist.all_reduce(SUM) of the flat fp32 gradient, {trainer.flat.grad.numel()} floats, NCCL over NVLink; CUDA events "
+                         "on the launch stream around the call (includes the wait for the last backward kernel's stream hand-off)")
+           if world > 1 else "none (single GPU)",
+           "gpu_launches_per_step": int(trainer.handle.train_launches() + 2),
+           "loss_after": float(trainer.loss.item()),
+           "roofline": {"bound": "tensor", "kernel": "whole training step (no single kernel dominates: ~300 launches; pixel-GEMMs on tcgen05, "
+                        "attention / FFT / resize backward on CUDA cores)", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+                        "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "work": "3 x forward FLOPs of the live path (data steps + last prior) per pair",
+                        "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json)"}}
+    if with_cpu:
+        res["cpu_baseline"] = cpu_train_baseline(bands, h, batch)
+    del trainer, net, devb
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_train_baseline(bands, h, batch, steps=2):
+    """Oracle port's training step (torch CPU autograd + torch Adam) on the host cores: a bounded sample."""
+    import torch
+    from oracle import lgteun_oracle as O
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
+    sd = {k: v.clone().requires_grad_(True) for k, v in golden_weights(bands).items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=1.5e-3)
+    gen = torch.Generator().manual_seed(100)
+    H, C = 4 * h, 4 * bands
+    ms, pan, gt = torch.rand(batch, bands, h, h, generator=gen), torch.rand(batch, 1, H, H, generator=gen), \
+        torch.rand(batch, bands, H, H, generator=gen)
+    ts = []
+    for _ in range(1 + steps):
+        t0 = time.perf_counter()
+        masks = [(torch.rand(batch, hh, hh, cc, generator=gen) >= 0.1).float() / 0.9
+                 for hh, cc in [(H, C), (H, C), (H // 2, 2 * C), (H, C), (H, C)]]
+        loss = torch.nn.functional.l1_loss(O.forward_train(sd, ms, pan, masks), gt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts[1:])
+    return {"value": batch / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} train steps of one batch of {batch} (oracle port: torch CPU autograd + Adam), median"}
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
@@ -247,27 +437,24 @@ def run_ours(args):
         pipe(ms_h, pan_h, out_h)
 
     def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(dev)
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        return max_over_ranks(e0.elapsed_time(e1), dev)        # ms, max over ranks
+        return timed_region(fn, steps, warmup, dev, stream, world)        # ms, max over ranks
 
-    # parity spot check before timing (the number is meaningless if the result is wrong)
+    # parity check before timing (the number is meaningless if the result is wrong): the first 2 pairs of the timed inputs
+    # through the product path against the CPU oracle, on every rank's own shard
     step_resident()
     torch.cuda.synchronize(dev)
     if not torch.isfinite(out_d).all():
         raise RuntimeError("non-finite output")
+    parity = None
+    if not args.no_parity:
+        parity = parity_vs_oracle(net, dev, ms_h, pan_h, pairs=min(2, batch))
+        # the graph-replayed timed buffer must hold the same two results
+        with torch.no_grad():
+            again = net(ms_d[:min(2, batch)], pan_d[:min(2, batch)])
+        parity = max(parity, float((again - out_d[:min(2, batch)]).abs().max().item()))
+        parity = max_over_ranks(parity, dev)
+        if not parity <= 1e-3:
+            raise RuntimeError(f"parity check failed before timing: max|delta| vs oracle = {parity:.3e} > 1e-3")
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(step_resident, args.steps, args.warmup)
@@ -299,10 +486,35 @@ def run_ours(args):
                 "steps": e2e_steps},
         "gpu_launches": int(launches_per_fwd * args.steps),
         "clocks": clocks,
+        "max_abs_delta_vs_oracle": parity,
+        "parity": "first 2 pairs of every rank's timed inputs, product path (nn.Module -> C ABI -> CUDA graph) vs the CPU oracle, "
+                  "checked before timing (limit 1e-3); max over ranks",
     }
 
+    # ---- legs every rank takes part in (BASELINE configs[1], [2] as strong scaling, [4]) ------------------------------------
+    peaks = load_peaks()
+    extra = {}
+    if args.other_workloads and not args.no_e2e:
+        other = "wv3" if args.workload == "gf2" else "gf2"
+        ob = min(WORKLOADS[other][2], 64)
+        v, t, d = forward_leg(other, ob, flags, dev, stream, world, rank)
+        extra["other_workloads"] = {other: {"workload": d, "batch_per_gpu": ob, "global_batch": ob * world, "pairs_per_s": v,
+                                            "ms_per_step": t, "scaling": "weak"}}
+        gb = WORKLOADS[args.workload][2]                     # BASELINE configs[2]: ONE global batch of 512 split N ways
+        if gb % world == 0:
+            if world == 1 and batch == gb:
+                extra["strong"] = {"global_batch": gb, "batch_per_gpu": gb, "pairs_per_s": value, "ms_per_step": ms_total / args.steps,
+                                   "scaling": "strong", "note": "N = 1: the headline run itself"}
+            else:
+                v, t, _ = forward_leg(args.workload, gb // world, flags, dev, stream, world, rank)
+                extra["strong"] = {"global_batch": gb, "batch_per_gpu": gb // world, "pairs_per_s": v, "ms_per_step": t,
+                                   "scaling": "strong",
+                                   "note": "BASELINE configs[2] read literally: the global batch of 512 GF-2 pairs sharded over the ranks"}
+        if not args.no_train_leg:
+            extra["train"] = train_leg(dev, stream, world, rank, peaks, with_cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+
     if rank == 0:
-        peaks = load_peaks()
+        line.update(extra)
         line["roofline"] = roofline_ffn(handle, bands, batch, H, dev, stream, peaks, args)
         line["gflop_per_pair"] = FLOPS_PER_PAIR[args.workload] / 1e9 * (0.5008 if args.skip_dead_priors else 1.0)
         line["model_tflops"] = value * line["gflop_per_pair"] / 1e3
@@ -313,8 +525,9 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"5 forwards of 8 pairs of the same workload shape (oracle port, torch CPU fp32, "
                                               f"both priors), median; {time.perf_counter() - t0:.1f}s"}
+        if world == 1 and not args.no_gpu_eager:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(bands, h, dev)
         if world == 1 and args.other_workloads and not args.no_e2e:
-            line["other_workloads"] = other_workload(args, dev)
             if not args.skip_dead_priors:
                 # same workload with the two discarded priors skipped (bit-identical output) — reported
                 # beside the headline, never instead of it
@@ -506,48 +719,26 @@ def roofline_ffn(handle, bands, batch, H, dev, stream, peaks, args):
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     traffic = None                      # dram__bytes_read + write per launch from the committed ncu --set full capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_final2_ffn_tc_traffic.json")) as f:
-            t = json.load(f)
-        if t["bands"] == bands and t["pairs"] == n and t["H"] == H:
-            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    except Exception:
-        pass
-    return {"bound": "tensor", "kernel": f"ffn (LN+1x1+GELU+1x1+dw3x3+GELU+1x1+res), c={c}, {n}x{H}x{H} px",
+    traffic_src = None                  # (regenerated whenever ffn_tc.cu changes: the newest *_ffn_tc_traffic.json wins)
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ffn_tc_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            if t["bands"] == bands and t["pairs"] == n and t["H"] == H:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+                traffic_src = os.path.basename(path)
+                break
+        except Exception:
+            continue
+    return {"bound": "tensor", "limiter": "issue / latency of the CUDA-core epilogues (GELU x2, depthwise 3x3, fp16 hi/lo split) between "
+            "the tcgen05 GEMMs: the tensor pipe itself is mostly idle, see DESIGN.md",
+            "traffic_source": traffic_src,
+            "kernel": f"ffn (LN+1x1+GELU+1x1+dw3x3+GELU+1x1+res), c={c}, {n}x{H}x{H} px",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "algorithmic_bytes": 2 * 4 * c * n * H * H,
             "ms_per_launch": ms, "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json)",
             "note": "fp32 parity needs 3-way split operands on the tensor pipe: the reachable ceiling is peak/3"}
-
-
-def other_workload(args, dev):
-    import torch
-    import lgteun_b200
-    from lgteun_b200 import _abi
-    name = "wv3" if args.workload == "gf2" else "gf2"
-    bands, h, batch, desc = WORKLOADS[name]
-    batch = min(batch, 64)
-    net = lgteun_b200.Pansharpening(SimpleNamespace(ms_chans=bands), None, stage=2)
-    net.load_state_dict(golden_weights(bands))
-    net = net.to(dev).eval()
-    handle = net._runtime(dev)
-    ms, pan = synth_inputs(batch, bands, h)
-    ms, pan = ms.to(dev), pan.to(dev)
-    out = torch.empty(batch, bands, 4 * h, 4 * h, device=dev)
-    flags = 0 if args.skip_dead_priors else _abi.RUN_DEAD_PRIORS
-    s = torch.cuda.current_stream(dev)
-    for _ in range(3):
-        handle.forward(ms.data_ptr(), pan.data_ptr(), out.data_ptr(), batch, h, h, flags, s.cuda_stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    e0.record(s)
-    reps = 5
-    for _ in range(reps):
-        handle.forward(ms.data_ptr(), pan.data_ptr(), out.data_ptr(), batch, h, h, flags, s.cuda_stream)
-    e1.record(s)
-    torch.cuda.synchronize(dev)
-    t = e0.elapsed_time(e1) / reps
-    return {name: {"workload": desc, "batch": batch, "pairs_per_s": batch / (t * 1e-3), "ms_per_step": t}}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -697,6 +888,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
     ap.add_argument("--e2e-chunk", type=int, default=128, help="pairs per H2D/compute/D2H pipeline chunk of the e2e leg")
     ap.add_argument("--other-workloads", action="store_true", default=True)
+    ap.add_argument("--no-parity", action="store_true", help="profiling aid: skip the oracle check before timing")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager-on-CUDA incumbent baseline (N = 1 only)")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the training-step leg (BASELINE configs[4])")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -107,6 +107,7 @@ class Trainer:
         self.world = dist.get_world_size(process_group) if ddp else 1
         self.rank = dist.get_rank(process_group) if ddp else 0
         self._buf = {}
+        self.allreduce_events = None      # set to [] to collect a CUDA-event pair around every step's all-reduce
         if self.world > 1:
             self.broadcast_state()
 
@@ -172,7 +173,13 @@ class Trainer:
     def step(self, ms: torch.Tensor, pan: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
         """One train_iter: returns the (local) loss as a 1-element CUDA tensor (no host sync)."""
         _, loss = self.forward_backward(ms, pan, gt)
+        if self.allreduce_events is not None:                # measurement aid (bench.py): device time of the collective
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.flat.device))
         gscale = allreduce_gradients(self.flat.grad, self.group)
+        if self.allreduce_events is not None:
+            e1.record(torch.cuda.current_stream(self.flat.device))
+            self.allreduce_events.append((e0, e1))
         lr = self.lr()
         self.steps += 1
         with torch.cuda.device(self.flat.device):
