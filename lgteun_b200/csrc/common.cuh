@@ -56,9 +56,11 @@ struct DataW {                        // models/unlg_former.py:29-40
 
 // ---- kernel launchers (one per .cu file) ---------------------------------------------------------
 // data_step.cu
+int data_step_launches();   // 1 (fused persistent kernel) or 2 (LGTEUN_DATA_STEP=split)
+size_t data_step_scratch_floats(int N, int B, int h, int w);   // size of launch_data_step's `resid` scratch
 cudaError_t launch_bicubic(const float* x, float* y, int planes, int h, int w, int num, int den, cudaStream_t s);
 cudaError_t launch_data_step(const DataW& w, int stage, int B, const float* z_in, const float* ms, const float* pan,
-                             float* resid /*[N,B,h,w] scratch*/, float* z_out, int N, int h, int wd, cudaStream_t s);
+                             float* resid /*scratch: data_step_scratch_floats()*/, float* z_out, int N, int h, int wd, cudaStream_t s);
 // pixel_ops.cu
 cudaError_t launch_patch_embed(const PriorW& w, int B, const float* x_nchw, float* y, int N, int H, int W, cudaStream_t s);
 cudaError_t launch_down(const PriorW& w, int C, const float* x, float* y, int N, int H, int W, cudaStream_t s);

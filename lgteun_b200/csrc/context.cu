@@ -127,7 +127,7 @@ size_t ws_layout(const lgteun_ctx* c, int N, int h, int w, Workspace* out) {
   size_t off = 0;
   auto take = [&](size_t floats) { size_t o = off; off += (floats + 63) & ~(size_t)63; return o; };
   size_t o_ms = take(N * B * h * w), o_pan = take(N * P), o_out = take(N * B * P);
-  size_t o_zA = take(N * B * P), o_zB = take(N * B * P), o_res = take(N * B * h * w);
+  size_t o_zA = take(N * B * P), o_zB = take(N * B * P), o_res = take(data_step_scratch_floats(N, (int)B, h, w));
   size_t o_X0 = take(N * P * C), o_X1 = take(N * P * C), o_X2 = take(N * P * C);
   size_t o_L0 = take(N * P / 4 * 2 * C), o_L1 = take(N * P / 4 * 2 * C);
   size_t o_loc = take(N * P * C / 2);
@@ -272,7 +272,7 @@ cudaError_t run_forward(const lgteun_ctx* c, const float* ms, const float* pan, 
   LG_L(L, 0, launch_bicubic(ms, ws.zA, N * c->B, h, w, 4, 1, s));
   float *za = ws.zA, *zb = ws.zB;
   for (int i = 0; i < c->K; ++i) {
-    LG_L(L, 0, launch_data_step(c->wv.dw, i, c->B, za, ms, pan, ws.resid, zb, N, h, w, s), 2);
+    LG_L(L, 0, launch_data_step(c->wv.dw, i, c->B, za, ms, pan, ws.resid, zb, N, h, w, s), data_step_launches());
     float* t = za; za = zb; zb = t;
     const bool last = (i == c->K - 1);
     // the reference discards the priors of stages 0..K-2 (unlg_former.py:63-67); run them only on request
@@ -396,7 +396,7 @@ int lgteun_forward_launches(lgteun_t* c, int N, int h, int w, int flags) {
   // patch_embed, 5 blocks x (msa, 3 fft passes, ffn = 1 fused tcgen05 launch or 2 CUDA-core launches), down, up_fuse, tail
   const int per_prior = 1 + 4 * (4 + ffn_launches(c->C)) + (4 + ffn_launches(2 * c->C)) + 4;
   const int priors = (flags & LGTEUN_RUN_DEAD_PRIORS) ? c->K : 1;
-  return 1 + 2 * c->K + priors * per_prior;
+  return 1 + data_step_launches() * c->K + priors * per_prior;
 }
 
 static int find_copy_nodes(cudaGraph_t g, const Workspace& ws, GraphEntry* ge) {
