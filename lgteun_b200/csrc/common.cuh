@@ -73,6 +73,12 @@ cudaError_t launch_tail(const PriorW& w, int B, const float* fea, const float* x
 //  c/2 channels are used;  pre_ln = 0: x is already the [N,H,W,c/2] local half.
 cudaError_t launch_window_msa(const BlockW& w, int c, const float* x, float* y_half, int pre_ln, int N, int H, int W,
                               cudaStream_t s);
+// window_msa_tc.cu — the same operator on tcgen05 / TMEM (c = 16, 32).  variant 0 = hybrid (QKV projection and Q.K^T +
+// positional bias on the tensor pipe, softmax and P.V on the CUDA cores), 1 = all three GEMMs on the tensor pipe.
+// launch_window_msa picks per channel count (LGTEUN_MSA=simt|hybrid|tc overrides, for A/B measurement)
+bool window_msa_tc_supported(int c);
+cudaError_t launch_window_msa_tc(const BlockW& w, int c, const float* x, float* y_half, int pre_ln, int N, int H, int W,
+                                 int variant, cudaStream_t s);
 // fft_mixer.cu
 size_t spectrum_floats(int N, int H, int W, int c2);
 cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* spec, int pre_ln, int N, int H, int W,

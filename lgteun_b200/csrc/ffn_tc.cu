@@ -90,7 +90,7 @@ static_assert(sizeof(FfnTcSmem<32>) + 128 <= 227 * 1024, "c = 32: one CTA per SM
 template <int C, int G>
 __global__ void __launch_bounds__(128 * G + 32, (C == 16) ? 2 : 1)
 ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w, const __half* __restrict__ wpack,
-              int H, int W, int nws, int nbands, int band_rows, int total_units, int num_groups) {
+              int H, int W, int nws, int nbands, int band_rows, int total_units, int num_groups, int exp_mode) {
   constexpr int C4 = 4 * C;
   constexpr int NT = 128 * G;           // epilogue threads (warps 0 .. 4G-1); warp 4G only issues the MMAs
   constexpr int CH = C4 / G;            // hidden channels per thread
@@ -372,7 +372,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       float4 pr0, pr1;                                    // residual of the previous output row (stored after S_b)
       if constexpr (kOwnA3) load_residual(it - 1, pr0, pr1);
       // ---- S_b: GELU(D1) -> A2 (hi/lo fp16); D1 already holds the bias, and is exactly 0 outside the image ------------
-      mbar_wait(&sm.mbar[0], ph1);
+      if (exp_mode != 1) mbar_wait(&sm.mbar[0], ph1);
       ph1 ^= 1;
       tc_fence_after();
       {
@@ -398,7 +398,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       if constexpr (kOwnA3) {
         // the previous row's GEMM3 ran under this S_b; its accumulator sits in the slot GEMM2 of this row overwrites
         if (it >= 3) {
-          mbar_wait(&sm.mbar[2], ph3);
+          if (exp_mode != 1) mbar_wait(&sm.mbar[2], ph3);
           ph3 ^= 1;
           tc_fence_after();
           store_row(it - 1, pr0, pr1);
@@ -413,7 +413,7 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         stage_a();
         signal(&sm.ready[0]);
       }
-      mbar_wait(&sm.mbar[1], ph2);
+      if (exp_mode != 1) mbar_wait(&sm.mbar[1], ph2);
       ph2 ^= 1;
       tc_fence_after();
       if (it < 2) continue;                               // uniform over the CTA
@@ -550,8 +550,9 @@ static cudaError_t ffn_tc_t(const BlockW& w, const float* x, float* y, int N, in
   cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int grid = groups < sm_count * per_sm ? groups : sm_count * per_sm;
+  static const int exp_mode = [] { const char* e = getenv("LGTEUN_FFN_EXP"); return e ? atoi(e) : 0; }();
   ffn_tc_kernel<C, G><<<grid, 128 * G + 32, smem, s>>>(x, y, w, reinterpret_cast<const __half*>(w.ffn_pack), H, W, nws, nbands,
-                                                   band_rows, units, groups);
+                                                   band_rows, units, groups, exp_mode);
   return cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@
 // fetched from shared memory (128-bit broadcasts) feeds two queries — the kernel is bound by the shared-memory
 // instruction queue, not by math.  Softmax is computed online over blocks of 16 (d=4) or 8 keys in base 2
 // (pos_emb and the q scale are pre-multiplied by log2 e; ex2.approx), all dot products on the packed fp32 pipe.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace lg {
@@ -288,6 +289,16 @@ static cudaError_t launch_msa_t(const BlockW& w, const float* x, float* y, int p
 
 cudaError_t launch_window_msa(const BlockW& w, int c, const float* x, float* y_half, int pre_ln, int N, int H, int W,
                               cudaStream_t s) {
+  // LGTEUN_MSA: unset = the fastest measured kernel per channel count (hybrid tcgen05 kernel at c = 32, this
+  // CUDA-core kernel at c = 16 and 64); "simt" / "hybrid" / "tc" force one form wherever it is built (A/B measurement)
+  static const int mode = [] {
+    const char* e = getenv("LGTEUN_MSA");
+    return !e ? 0 : e[0] == 's' ? 1 : e[0] == 'h' ? 2 : e[0] == 't' ? 3 : 0;
+  }();
+  if (window_msa_tc_supported(c)) {
+    if (mode == 3) return launch_window_msa_tc(w, c, x, y_half, pre_ln, N, H, W, 1, s);
+    if (mode == 2 || (mode == 0 && c == 32)) return launch_window_msa_tc(w, c, x, y_half, pre_ln, N, H, W, 0, s);
+  }
   switch (c) {
     case 16: return launch_msa_t<8>(w, x, y_half, pre_ln, N, H, W, s);
     case 32: return launch_msa_t<16>(w, x, y_half, pre_ln, N, H, W, s);

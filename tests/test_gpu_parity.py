@@ -475,7 +475,45 @@ def test_error_behaviour(abi, h4):
     fresh.close()
 
 
-@pytest.mark.parametrize("env", [{"LGTEUN_FFN": "simt"}, {"LGTEUN_FFT": "stockham"}])
+def test_window_msa_variants_match_the_oracle():
+    """The three forms of the window MSA (CUDA-core kernel, hybrid tcgen05 kernel, all-tensor-core kernel: LGTEUN_MSA =
+    simt / hybrid / tc; the switch is read once per process) against the oracle at the operator tolerance, in child
+    processes: the per-operator test above only sees the default dispatch."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "from conftest import load_weights\n"
+        "from lgteun_b200 import _abi\n"
+        "from oracle import lgteun_oracle as O\n"
+        "worst = 0.0\n"
+        "for bands in (4, 8):\n"
+        "    sd = load_weights(bands)\n"
+        "    h = _abi.Handle(0, bands, 2)\n"
+        "    h.load_weights({k: v.cuda().contiguous() for k, v in sd.items()})\n"
+        "    for lgb, shape in ((0, (3, 32, 40)), (1, (2, 24, 16)), (0, (1, 8, 8))):\n"
+        "        n, H, W = shape\n"
+        "        c2 = (4 * bands * (2 if lgb == 1 else 1)) // 2\n"
+        "        x = torch.randn(n, H, W, c2, generator=torch.Generator().manual_seed(11 + lgb))\n"
+        "        y = torch.empty_like(x, device='cuda')\n"
+        "        h.op('local_mixer', 1, lgb, 0, x.cuda().data_ptr(), y.data_ptr(), n, H, W)\n"
+        "        pre = 'prior_module.1.' + ('encoder_layers.0.0', 'bottleneck')[lgb] + '.blocks.0.0.fn.fn.local_mixer'\n"
+        "        worst = max(worst, float((y.cpu() - O.local_mixer(sd, pre, x)).abs().max()))\n"
+        "print('MAXDIFF', worst)\n"
+    )
+    for mode in ("simt", "hybrid", "tc"):
+        res = subprocess.run([sys.executable, "-c", code], env={**os.environ, "LGTEUN_MSA": mode}, capture_output=True, text=True,
+                             timeout=300)
+        assert res.returncode == 0, (mode, res.stderr[-2000:])
+        diff = float(res.stdout.strip().split("MAXDIFF")[-1])
+        assert diff <= 2e-5, (mode, diff)
+
+
+@pytest.mark.parametrize("env", [{"LGTEUN_FFN": "simt"}, {"LGTEUN_FFT": "stockham"}, {"LGTEUN_MSA": "simt"}, {"LGTEUN_MSA": "hybrid"},
+                                 {"LGTEUN_MSA": "tc"}, {"LGTEUN_DATA_STEP": "split"}])
 def test_ab_switch_paths_stay_correct(env):
     """The A/B switches (CUDA-core FFN, shared-memory Stockham FFT passes) select other kernels of the SAME library for
     measurement; they are read once per process, so they are exercised in a child process against the golden output."""
