@@ -525,7 +525,6 @@ struct Smem {
   alignas(16) __half ash[2 * 128 * 8], asl[2 * 128 * 8];      // A of S [2][128 rows = (head, query)][8]
   alignas(16) __half bsh[2 * 64 * 8], bsl[2 * 64 * 8];        // B of S [2][64 keys][8]
   alignas(16) float v[64 * C2];                               // V [key][channel] fp32
-  alignas(16) float xstage[128 * 2 * C2];                     // next window's pixels, one slot per thread (cp.async, fetched under P3)
   float bqkv[3 * C2];
   float lnw[C2], lnb[C2];
 };
@@ -641,30 +640,29 @@ window_msa_qk_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW 
       }
       return ((size_t)n * H + wy * kWin + (ri >> 3)) * W + wx * kWin + (ri & 7);
     };
-    // this thread's pixel of window `widx` -> its staging slot, asynchronously (consumed by the same thread in P1)
-    float* const stage = &sm.xstage[row * CIN];
+    // optional register prefetch of the NEXT window's pixel by warps 0-1.  Measured (c = 16, 64 pairs): 404 us with it, 386 us
+    // without (the extra live registers spill at the 96-register budget that four CTAs per SM need); a cp.async staging
+    // buffer was slower as well (425 us).  Off.
+    constexpr bool kPrefetch = false;
+    float xr[CIN];
     auto fetch = [&](int widx) {
-      if (widx < total_windows) {
-        const float* src = x + pixel_of(widx) * CIN;
-        const uint32_t dst = smem_u32(stage);
-#pragma unroll
-        for (int i = 0; i < CIN / 4; ++i)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(src + 4 * i) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (kPrefetch && warp < 2 && widx < total_windows) load_vec<CIN>(xr, x + pixel_of(widx) * CIN);
     };
-    constexpr bool kPrefetch = false;      // measured: staging the next window's pixels through cp.async does not pay
-    if (kPrefetch) fetch(blockIdx.x);
+    fetch(blockIdx.x);
     for (int widx = blockIdx.x; widx < total_windows; widx += gridDim.x) {
       const size_t pix = pixel_of(widx);
       // ---- P1: token ri -> rows ri and 64 + ri of the QKV operand (warps 0-1 load / normalise, and store both copies)
       if (warp < 2) {
         float v[C2];
-        if (kPrefetch) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const float* src = kPrefetch ? stage : x + pix * CIN;
+        const float* src = x + pix * CIN;
         if constexpr (PRE_LN) {
           float a[CIN];
-          load_vec<CIN>(a, src);
+          if constexpr (kPrefetch) {
+#pragma unroll
+            for (int i = 0; i < CIN; ++i) a[i] = xr[i];
+          } else {
+            load_vec<CIN>(a, src);
+          }
           float mean = 0.f;
 #pragma unroll
           for (int i = 0; i < CIN; ++i) mean += a[i];
@@ -676,8 +674,14 @@ window_msa_qk_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW 
 #pragma unroll
           for (int i = 0; i < C2; ++i) v[i] = (a[i] - mean) * rstd * sm.lnw[i] + sm.lnb[i];
         } else {
-          load_vec<C2>(v, src);
+          if constexpr (kPrefetch) {
+#pragma unroll
+            for (int i = 0; i < C2; ++i) v[i] = xr[i];
+          } else {
+            load_vec<C2>(v, src);
+          }
         }
+        fetch(widx + (int)gridDim.x);            // the next window's pixel flies under the rest of this window
 #pragma unroll
         for (int c = 0; c < C2 / 8; ++c) {
           const float2 t8[4] = {make_float2(v[8 * c], v[8 * c + 1]), make_float2(v[8 * c + 2], v[8 * c + 3]),
@@ -691,7 +695,6 @@ window_msa_qk_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW 
         }
       }
       signal(&sm.ready_x);
-      if (kPrefetch) fetch(widx + (int)gridDim.x);            // the staging slot was consumed above: the next window's pixel flies under P2 .. P3
       // ---- P2: S accumulator = pos; q, k -> operands of the S GEMM (rows 0-63); v -> shared memory (rows 64-127)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {

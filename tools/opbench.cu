@@ -166,6 +166,7 @@ static int run_op(void* p, cudaStream_t s) {
     case 6: return lgteun_op_prior(a->ctx, 1, a->x, a->y, a->N, a->H, a->W, s);
     case 7: return lgteun_forward(a->ctx, a->x2, a->x3, a->y, a->N, a->H / 4, a->W / 4, LGTEUN_RUN_DEAD_PRIORS, s);
     case 8: return lgteun_forward(a->ctx, a->x2, a->x3, a->y, a->N, a->H / 4, a->W / 4, 0, s);
+    case 10: return lgteun_forward(a->ctx, a->x2, a->x3, a->y, a->N, a->H / 4, a->W / 4, LGTEUN_RUN_DEAD_PRIORS | LGTEUN_NO_GRAPH, s);
     case 9: return lgteun_op_patch_embed(a->ctx, 1, a->x, a->y, a->N, a->H, a->W, s);
   }
   return -1;
@@ -242,7 +243,7 @@ int main(int argc, char** argv) {
     cudaFree(x);
     cudaFree(y);
   }
-  if (want("data_step") || want("bicubic") || want("forward") || want("forward_live") || want("prior") || want("patch_embed")) {
+  if (want("data_step") || want("bicubic") || want("forward") || want("forward_nograph") || want("forward_live") || want("prior") || want("patch_embed")) {
     float* ms = dev_random((size_t)N * bands * P / 16, 0.f, 1.f, 101);
     float* pn = dev_random((size_t)N * P, 0.f, 1.f, 102);
     float* z = dev_random((size_t)N * bands * P, 0.f, 1.f, 103);
@@ -275,6 +276,11 @@ int main(int argc, char** argv) {
     if (want("forward")) {
       OpArgs a{ctx, 7, 0, N, H, W, bands, nullptr, ms, pn, y};
       Case c{"forward", (size_t)N * bands * P, 4.0 * N * P * (bands + 1.0 + bands / 16.0), y, run_op, &a};
+      timeit(c);
+    }
+    if (want("forward_nograph")) {     // direct launches; with LGTEUN_TIMING=1 the library prints per-kernel-family device times
+      OpArgs a{ctx, 10, 0, N, H, W, bands, nullptr, ms, pn, y};
+      Case c{"forward_nograph", (size_t)N * bands * P, 4.0 * N * P * (bands + 1.0 + bands / 16.0), y, run_op, &a};
       timeit(c);
     }
     if (want("forward_live")) {
