@@ -31,6 +31,7 @@ struct BlockW {                       // one LGB block: LGT.py:231-239
   const float *f2_w, *f2_b;           // net.4                      [c, 4c]
   const float *f0_wt, *f1_wt, *f2_wt; // derived: the three FFN weights transposed to [in][out] (CUDA-core path)
   const float *ffn_pack;              // derived: fp16 hi/lo of W0,W1,W2 in UMMA K-major core-matrix layout (ffn_tc.cu)
+  const float *ffn_cl_pack;           // derived: the same weights + bias K-steps in the order ffn_cl.cu copies to shared memory
   const float *proj_pack;             // derived: fp16 hi | lo of proj_w in the same layout (fft256.cu)
 };
 
@@ -116,6 +117,10 @@ size_t ffn_tc_pack_halves(int c);
 cudaError_t launch_pack_umma_f16(const float* w, void* hi, void* lo, int N, int K, cudaStream_t s);
 cudaError_t launch_pack_umma_f16_bias(const float* w, const float* bias, void* hi, void* lo, int N, int K, cudaStream_t s);  // K+8 columns
 cudaError_t launch_ffn_tc(const BlockW& w, int c, const float* x, float* y, int N, int H, int W, cudaStream_t s);
+// ffn_cl.cu — the fused FFN with hidden channels on TMEM lanes and pixels in TMEM columns (c = 16 or 32); default
+size_t ffn_cl_pack_halves(int c);
+cudaError_t launch_ffn_cl_pack(const BlockW& b, int c, void* pack, cudaStream_t s);
+cudaError_t launch_ffn_cl(const BlockW& w, int c, const float* x, float* y, int N, int H, int W, cudaStream_t s);
 // pwgemm_tc.cu — conv-FFN of the widest level (c = 64) as tcgen05 pixel-GEMMs; buf_a / buf_b: N*H*W*256 floats each
 cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, float* buf_b, float* y, int N, int H, int W,
                                cudaStream_t s);

@@ -58,6 +58,7 @@ void add_block(lgteun_ctx* c, const std::string& p, BlockW* b, int ch) {
   c->derived.push_back({&b->f1_w, &b->f1_wt, c4, c4, 0, nullptr});
   c->derived.push_back({&b->f2_w, &b->f2_wt, ch, c4, 0, nullptr});
   if (ch == 16 || ch == 32 || ch == 64) c->derived.push_back({&b->f0_w, &b->ffn_pack, -1, ch, 0, b});
+  if (ch == 16 || ch == 32) c->derived.push_back({&b->f0_w, &b->ffn_cl_pack, -3, ch, 0, b});
   c->derived.push_back({&b->proj_w, &b->proj_pack, -2, ch, 0, b});      // proj [c][c] as fp16 hi | lo
 }
 
@@ -104,7 +105,8 @@ void build_table(lgteun_ctx* c) {
   for (auto& d : c->derived) {
     d.offset = off;
     size_t floats = d.rows > 0 ? (size_t)d.rows * d.cols : d.rows == 0 ? 2 * 64 * 64
-                    : d.rows == -1 ? ffn_tc_pack_halves(d.cols) / 2 : (size_t)d.cols * d.cols;
+                    : d.rows == -1 ? ffn_tc_pack_halves(d.cols) / 2
+                    : d.rows == -3 ? ffn_cl_pack_halves(d.cols) / 2 : (size_t)d.cols * d.cols;
     off += align4(floats);
   }
   c->arena_floats = off;
@@ -226,11 +228,16 @@ bool ffn_simt() {
   static const bool simt = [] { const char* e = getenv("LGTEUN_FFN"); return e && std::string(e) == "simt"; }();
   return simt;
 }
+// LGTEUN_FFN=tc selects the pixels-on-lanes kernel of ffn_tc.cu instead of ffn_cl.cu (A/B measurement)
+bool ffn_cl() {
+  static const bool cl = [] { const char* e = getenv("LGTEUN_FFN"); return !(e && std::string(e) == "tc"); }();
+  return cl;
+}
 bool use_tc_ffn(int ch) { return !ffn_simt() && (ch == 16 || ch == 32); }
 bool use_wide_tc_ffn(int ch) { return !ffn_simt() && ch == 64; }
 int ffn_launches(int ch) { return use_tc_ffn(ch) ? 1 : use_wide_tc_ffn(ch) ? 4 : 2; }
 cudaError_t run_ffn(const BlockW& b, int ch, const float* x, float* y, float* hidden, int N, int H, int W, cudaStream_t s) {
-  if (use_tc_ffn(ch)) return launch_ffn_tc(b, ch, x, y, N, H, W, s);
+  if (use_tc_ffn(ch)) return ffn_cl() ? launch_ffn_cl(b, ch, x, y, N, H, W, s) : launch_ffn_tc(b, ch, x, y, N, H, W, s);
   if (use_wide_tc_ffn(ch)) return launch_ffn_wide_tc(b, x, hidden, hidden + (size_t)N * H * W * 256, y, N, H, W, s);
   return launch_ffn(b, ch, x, hidden, y, N, H, W, s);
 }
@@ -365,6 +372,8 @@ int lgteun_load_weights(lgteun_t* c, const char* const* names, const float* cons
     else if (d.rows == -2) {
       char* base = reinterpret_cast<char*>(dst);
       CK(launch_pack_umma_f16(*d.src, base, base + (size_t)d.cols * d.cols * 2, d.cols, d.cols, s));
+    } else if (d.rows == -3) {
+      CK(launch_ffn_cl_pack(*d.blk, d.cols, dst, s));
     } else {
       // fp16 hi/lo operands of the three FFN GEMMs: w0h | w0l | w1h | w1l | w2h | w2l (halves), see ffn_tc.cu
       const int ch = d.cols, c4 = 4 * ch;

@@ -213,28 +213,31 @@ ffn_tc_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   };
 
   if (warp == 4 * G) {
-    // ---- MMA issuer: one thread waits for the operand-ready barriers in the order the epilogue warps raise them and
-    // feeds the tensor pipe, so no epilogue warp ever carries the issue sequence on its critical path
-    if (lane == 0) {
-      uint32_t pa1 = 0, pa2 = 0, pa3 = 0;
-      for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
-        mbar_wait(&sm.ready[0], pa1); pa1 ^= 1;
+    // ---- MMA issuer: the whole warp waits for the operand-ready barriers in the order the epilogue warps raise them; one
+    // elected lane feeds the tensor pipe (under elect.sync ptxas moves the operands to uniform registers without a
+    // divergence loop), so no epilogue warp ever carries the issue sequence on its critical path
+    uint32_t pa1 = 0, pa2 = 0, pa3 = 0;
+    for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+      mbar_wait(&sm.ready[0], pa1); pa1 ^= 1;
+      tc_fence_after();
+      if (elect_one()) issue_g1();
+      __syncwarp();
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&sm.ready[1], pa2); pa2 ^= 1;
         tc_fence_after();
-        issue_g1();
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(&sm.ready[1], pa2); pa2 ^= 1;
+        if (elect_one()) issue_g2(it);
+        __syncwarp();
+        if (it + 1 < iters) {
+          mbar_wait(&sm.ready[0], pa1); pa1 ^= 1;
           tc_fence_after();
-          issue_g2(it);
-          if (it + 1 < iters) {
-            mbar_wait(&sm.ready[0], pa1); pa1 ^= 1;
-            tc_fence_after();
-            issue_g1();
-          }
-          if (it >= 2) {
-            mbar_wait(&sm.ready[2], pa3); pa3 ^= 1;
-            tc_fence_after();
-            issue_g3(it);
-          }
+          if (elect_one()) issue_g1();
+          __syncwarp();
+        }
+        if (it >= 2) {
+          mbar_wait(&sm.ready[2], pa3); pa3 ^= 1;
+          tc_fence_after();
+          if (elect_one()) issue_g3(it);
+          __syncwarp();
         }
       }
     }
