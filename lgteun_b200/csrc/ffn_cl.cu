@@ -41,7 +41,7 @@ namespace cl {
 
 constexpr int kIn = 32;              // interior pixels of a row segment (output columns per half and iteration)
 constexpr int kNPS = 40;             // stored pixel columns of every operand tile (34 used: interior + 2 halo)
-constexpr int kB1Stride = 704;       // bytes between the 8-channel chunks of the K-major GEMM1 operand (640 + 64: bank spread)
+constexpr int kB1Stride = 736;       // bytes between the 8-channel chunks of the K-major GEMM1 operand (640 + 96: bank spread)
 constexpr int kMnK = (kNPS / 8) * 128;   // bytes between 8-channel blocks of an MN-major tile (5 pixel blocks x 128 B)
 constexpr int kWarpsPerStream = 12;
 
@@ -319,18 +319,17 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     // ---- service warps 8, 9, 11: loaders; warps 8 / 9 (TMEM lane quarters 0 / 1 = D3 rows of half 0 / 1) also store the output --------
     //   c = 16 (5 pixel groups per half): warp 8: half 0 groups 0-2, warp 9: half 1 groups 0-2, warp 11: groups 3-4 of both halves
     //   c = 32 (9 pixel groups): three each
-    auto service = [&](auto LI) {
-    constexpr int li = decltype(LI)::value;
-    constexpr int NPW = (HV == 2) ? 4 : 3;           // pass slots of one loader warp per row
-    const int cq = lane % LPP;                       // 4-channel group of this lane
-    const float4 g4 = *reinterpret_cast<const float4*>(&sm.lng[4 * cq]);
-    const float4 b4 = *reinterpret_cast<const float4*>(&sm.lnb[4 * cq]);
-    // (half, pixel group) of every pass slot, compile-time per warp role; pg < 0: unused
-    constexpr int ph[4] = {HV == 2 ? (li < 2 ? li : 0) : 0, HV == 2 ? (li < 2 ? li : 0) : 0, HV == 2 ? (li < 2 ? li : 1) : 0,
-                           HV == 2 ? (li < 2 ? li : 1) : 0};
-    constexpr int pg[4] = {HV == 2 ? (li < 2 ? 0 : 3) : 3 * li, HV == 2 ? (li < 2 ? 1 : 4) : 3 * li + 1,
-                           HV == 2 ? (li < 2 ? 2 : 3) : 3 * li + 2, HV == 2 ? (li < 2 ? -1 : 4) : -1};
-    constexpr bool outw = li < HV;                   // this warp stores the output rows of half li
+    // ---- service warps 8, 9, 11: loaders (a lane owns 16 channels of ONE pixel of the row: no cross-lane reduction at c = 16, one
+    // shuffle at c = 32); warps 8 / 9 (TMEM lane quarters 0 / 1 = D3 rows of half 0 / 1) also store the output rows -------------------
+    //   c = 16: warp 8 = half 0 pixel columns 0..31, warp 9 = half 1 columns 0..31, warp 11 lanes 0..3 = columns 32, 33 of both halves
+    //   c = 32: two lanes per pixel: warp 8 = columns 0..15, warp 9 = 16..31, warp 11 lanes 0..3 = columns 32, 33
+    const int li = lw == 8 ? 0 : lw == 9 ? 1 : 2;
+    constexpr int LQ = C / 16;                       // lanes per pixel
+    const int chalf = lane % LQ;                     // 16-channel half of this lane
+    const int h = (HV == 2) ? (li < 2 ? li : (lane >> 1) & 1) : 0;
+    const int pc = li < 2 ? ((HV == 2) ? lane : li * 16 + lane / LQ) : 32 + ((HV == 2) ? (lane & 1) : lane / LQ);
+    const bool lane_on = li < 2 || lane < 4;
+    const bool outw = li < HV;                       // this warp stores the output rows of half li
     uint32_t gi = 0, j3 = 0;
     // Output cursor (warps 8 / 9): rows are stored 3 + LAG loader iterations after their own: the loaders run at most two rows
     // ahead of S_b (empty[] gate), so by then the row's GEMM3 has been issued and the wait below is short and cannot deadlock.
@@ -340,7 +339,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     bool o_col = false;
     int o_rows = 0;
     auto out_geometry = [&]() {
-      const int unit = o_grp * HV + ((HV == 2) ? li : 0);
+      const int unit = o_grp * HV + ((HV == 2) ? (li & 1) : 0);
       const bool uok = unit < total_units && o_grp < num_groups;
       const int ws = uok ? unit % nws : 0, t = uok ? unit / nws : 0;
       const int un = t / nbands, uy0 = (t % nbands) * band_rows, ux0 = ws * kIn;
@@ -395,97 +394,79 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         out_geometry();
       }
     };
-    // shared-memory store addresses of every pass slot for buffer 0 (buffer 1: + a constant); pass slots 0,1 belong to half
-    // ph[0], slots 2,3 to half ph[NPW - 1]
-    uint32_t sa_x[NPW], sa_f1[NPW], sa_f2[NPW];
-#pragma unroll
-    for (int p = 0; p < NPW; ++p) {
-      const int pc = (pg[p] < 0 ? 0 : pg[p]) * PPP + lane / LPP;
-      sa_x[p] = smem_u32(&st.b1h[0][ph[p]][(cq >> 1) * kB1Stride + pc * 16 + (cq & 1) * 8]);
-      sa_f1[p] = smem_u32(&st.b1f[0][ph[p]][pc * 16]);
-      sa_f2[p] = smem_u32(&st.a2f[0][ph[p]][(pc >> 3) * 128 + (pc & 7) * 2]);
-    }
+    // shared-memory addresses of this lane's pixel for buffer 0 (buffer 1: + a constant)
+    const uint32_t sa_x = smem_u32(&st.b1h[0][h][(2 * chalf) * kB1Stride + pc * 16]);
+    const uint32_t sa_f1 = smem_u32(&st.b1f[0][h][pc * 16]);
+    const uint32_t sa_f2 = smem_u32(&st.a2f[0][h][(pc >> 3) * 128 + (pc & 7) * 2]);
     constexpr uint32_t DL = offsetof(Stream<C>, b1l) - offsetof(Stream<C>, b1h);     // b1h -> b1l
     constexpr uint32_t BX = HV * (C / 8) * kB1Stride, BF1 = HV * 2 * kB1Stride, BF2 = HV * 2 * kMnK;   // buffer 0 -> 1
-    const int ha = ph[0], hb = ph[NPW - 1];
+    const float* lnw = &sm.lng[16 * chalf];
+    const float* lnb = &sm.lnb[16 * chalf];
     for (int grp = group0; grp < num_groups; grp += gstep) {
-      // per pass slot: row-0 source pointer and column validity; per half (a: slots 0,1; b: slots 2,..): vertical extent
-      const float* base[NPW];
-      bool colok[NPW];
-      int ya = 0, rowsa = 0, yb = 0, rowsb = 0;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int h = hh ? hb : ha;
-        const int unit = grp * HV + h;
-        const bool uok = unit < total_units;
-        const int ws = uok ? unit % nws : 0, t = uok ? unit / nws : 0;
-        const int un = t / nbands, uy0 = (t % nbands) * band_rows, ux0 = ws * kIn;
-        const int uwd = uok ? min(kIn, W - ux0) : 0;
-        const float* rowp = xin + (((long long)un * H + uy0 - 1) * W + ux0 - 1) * C + 4 * cq;   // row it = 0, pixel column 0 (guarded)
-        if (hh == 0) { ya = uy0; rowsa = min(band_rows, H - uy0); } else { yb = uy0; rowsb = min(band_rows, H - uy0); }
-#pragma unroll
-        for (int p = 0; p < NPW; ++p) {
-          if ((p < 2) == (hh == 0)) {
-            const int pc = pg[p] * PPP + lane / LPP, x = ux0 - 1 + pc;
-            colok[p] = uok && pg[p] >= 0 && pc < uwd + 2 && x >= 0 && x < W;
-            base[p] = rowp + (long long)pc * C;
-          }
-        }
-      }
+      const int unit = grp * HV + h;
+      const bool uok = unit < total_units && lane_on;
+      const int ws = uok ? unit % nws : 0, t = uok ? unit / nws : 0;
+      const int un = t / nbands, uy0 = (t % nbands) * band_rows, ux0 = ws * kIn;
+      const int uwd = uok ? min(kIn, W - ux0) : 0, urows = min(band_rows, H - uy0);
+      const int x = ux0 - 1 + pc;
+      const bool colok = uok && pc < uwd + 2 && x >= 0 && x < W;
       const size_t rstride = (size_t)W * C;
-      for (int it = 0; it < iters; ++it, ++gi) {
+      const float* src = xin + (((long long)un * H + uy0 - 1) * W + x) * C + 16 * chalf;   // row it = 0 (guarded)
+      for (int it = 0; it < iters; ++it, ++gi, src += rstride) {
         const uint32_t b = gi & 1;
-        // this row's loads (L2 hits: the row was prefetched two iterations ago), then the prefetch of row it + 2
-        float4 vc[NPW];
-        uint32_t okc = 0;                            // validity bits of the pass slots
-        {
-          const int y_a = ya - 1 + it, y_b = yb - 1 + it;
-          const bool ra = y_a >= 0 && y_a < H && it < rowsa + 2, rb = y_b >= 0 && y_b < H && it < rowsb + 2;
-          const bool pa = y_a + 2 >= 0 && y_a + 2 < H && it < rowsa, pb = y_b + 2 >= 0 && y_b + 2 < H && it < rowsb;
+        const int y = uy0 - 1 + it;
+        const bool ok = colok && y >= 0 && y < H && it < urows + 2;
+        float4 v[4];
 #pragma unroll
-          for (int p = 0; p < NPW; ++p) {
-            vc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (colok[p] && (p < 2 ? ra : rb)) {
-              vc[p] = __ldg(reinterpret_cast<const float4*>(base[p] + it * rstride));
-              okc |= 1u << p;
-            }
-            if (colok[p] && (p < 2 ? pa : pb)) asm volatile("prefetch.global.L2 [%0];" ::"l"(base[p] + (it + 2) * rstride));
-          }
+        for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
         }
+        if (colok && y + 2 < H && it < urows) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * rstride));
+        // LayerNorm over the C channels of the pixel
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        if (LQ == 2) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        const float mean = sum * (1.0f / C);
+        float m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+          m2 = fmaf(v[i].x, v[i].x, m2); m2 = fmaf(v[i].y, v[i].y, m2); m2 = fmaf(v[i].z, v[i].z, m2); m2 = fmaf(v[i].w, v[i].w, m2);
+        }
+        if (LQ == 2) m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+        float rstd;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd) : "f"(fmaf(m2, 1.0f / C, kLnEps)));
         if (gi >= 2) WAIT(&st.empty[b], ((gi - 2) >> 1) & 1);
+        if (lane_on) {
+          const uint32_t msk = ok ? 0xffffffffu : 0u;           // pixels outside the image / segment: exact zeros
+          const uint32_t ax = sa_x + b * BX;
 #pragma unroll
-        for (int p = 0; p < NPW; ++p) {
-          if (HV == 1 || p < 3 || li == 2) {                    // (c = 16: warps 8 / 9 have three pass slots)
-            const bool ok = (okc >> p) & 1;
-            // LayerNorm over the C channels of the pixel = LPP lanes x 4
-            float sum = (vc[p].x + vc[p].y) + (vc[p].z + vc[p].w);
+          for (int c8 = 0; c8 < 2; ++c8) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int o = 1; o < LPP; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float mean = sum * (1.0f / C);
-            const float dx = vc[p].x - mean, dy = vc[p].y - mean, dz = vc[p].z - mean, dw = vc[p].w - mean;
-            float m2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
-#pragma unroll
-            for (int o = 1; o < LPP; o <<= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
-            float rstd;
-            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd) : "f"(fmaf(m2, 1.0f / C, kLnEps)));
-            const float2 t0 = make_float2(fmaf(dx * rstd, g4.x, b4.x), fmaf(dy * rstd, g4.y, b4.y));
-            const float2 t1 = make_float2(fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w));
-            const __half2 h0 = __float22half2_rn(t0), h1 = __float22half2_rn(t1);
-            const float2 k0 = __half22float2(h0), k1 = __half22float2(h1);
-            const __half2 l0 = __float22half2_rn(make_float2(t0.x - k0.x, t0.y - k0.y));
-            const __half2 l1 = __float22half2_rn(make_float2(t1.x - k1.x, t1.y - k1.y));
-            const uint32_t msk = ok ? 0xffffffffu : 0u;         // pixels outside the image / segment: exact zeros
-            const uint32_t ax = sa_x[p] + b * BX;
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ax), "r"(*reinterpret_cast<const uint32_t*>(&h0) & msk),
-                         "r"(*reinterpret_cast<const uint32_t*>(&h1) & msk) : "memory");
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ax + DL), "r"(*reinterpret_cast<const uint32_t*>(&l0) & msk),
-                         "r"(*reinterpret_cast<const uint32_t*>(&l1) & msk) : "memory");
-            if (cq == 0) {
-              const uint32_t f = 0x3C003C00u & msk;                                         // fp16 {1, 1}
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa_f1[p] + b * BF1), "r"(f) : "memory");
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(sa_f2[p] + b * BF2), "h"((unsigned short)f) : "memory");
-              asm volatile("st.shared.b16 [%0], %1;" ::"r"(sa_f2[p] + b * BF2 + 16), "h"((unsigned short)f) : "memory");
+            for (int e = 0; e < 2; ++e) {
+              const float4 g = *reinterpret_cast<const float4*>(lnw + 8 * c8 + 4 * e), bb = *reinterpret_cast<const float4*>(lnb + 8 * c8 + 4 * e);
+              const float4 u = v[2 * c8 + e];
+              const float2 t0 = make_float2(fmaf(u.x * rstd, g.x, bb.x), fmaf(u.y * rstd, g.y, bb.y));
+              const float2 t1 = make_float2(fmaf(u.z * rstd, g.z, bb.z), fmaf(u.w * rstd, g.w, bb.w));
+              const __half2 h0 = __float22half2_rn(t0), h1 = __float22half2_rn(t1);
+              const float2 k0 = __half22float2(h0), k1 = __half22float2(h1);
+              const __half2 l0 = __float22half2_rn(make_float2(t0.x - k0.x, t0.y - k0.y));
+              const __half2 l1 = __float22half2_rn(make_float2(t1.x - k1.x, t1.y - k1.y));
+              hi[2 * e] = *reinterpret_cast<const uint32_t*>(&h0) & msk; hi[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&h1) & msk;
+              lo[2 * e] = *reinterpret_cast<const uint32_t*>(&l0) & msk; lo[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&l1) & msk;
             }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ax + c8 * kB1Stride), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ax + c8 * kB1Stride + DL), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+          }
+          if (chalf == 0) {
+            const uint32_t f = 0x3C003C00u & msk;                                         // fp16 {1, 1}
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa_f1 + b * BF1), "r"(f) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(sa_f2 + b * BF2), "h"((unsigned short)f) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(sa_f2 + b * BF2 + 16), "h"((unsigned short)f) : "memory");
           }
         }
         fence_proxy_async();
@@ -496,10 +477,6 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     }
     if (outw)
       while (o_grp < num_groups) out_step();
-    };
-    if (lw == 8) service(std::integral_constant<int, 0>{});
-    else if (lw == 9) service(std::integral_constant<int, 1>{});
-    else service(std::integral_constant<int, 2>{});
     } else {
     // ---- epilogue warps: lane quarter q, column half ch; thread = one hidden channel (of one half) ---------------------------
     const int q = lw & 3, ch = lw >> 2;
