@@ -54,6 +54,11 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float2& v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
   v = make_float2(__uint_as_float(r0), __uint_as_float(r1));
 }
+// shared-memory stores through 32-bit shared addresses (one STS.128 each; the generic-pointer form was split by the compiler)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -484,11 +489,11 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     const int k = (HV == 2) ? (16 * q + (lane & 15)) : (32 * q + lane);
     const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
     const uint32_t rowoff = (uint32_t)((k >> 3) * kMnK + (k & 7) * 16);
-    unsigned char* const a2h = st.a2h[h] + rowoff;
-    unsigned char* const a2l = st.a2l[h] + rowoff;
+    const uint32_t a2h = smem_u32(st.a2h[h]) + rowoff + 2 * ch * 128;      // this warp's first 8-pixel block of the row
+    const uint32_t a2l = smem_u32(st.a2l[h]) + rowoff + 2 * ch * 128;
     const uint32_t rowoff3 = (uint32_t)((k >> 3) * A3K + h * 512 + (k & 7) * 16);
-    unsigned char* const a3h = st.a3h + rowoff3;
-    unsigned char* const a3l = st.a3l + rowoff3;
+    const uint32_t a3h = smem_u32(st.a3h) + rowoff3 + 2 * ch * 128;
+    const uint32_t a3l = smem_u32(st.a3l) + rowoff3 + 2 * ch * 128;
     float2 wt[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -522,16 +527,16 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
             for (int i = 0; i < 4; ++i) v[i] = gelu_pair(acc[c][i]);
             uint4 hi, lo;
             split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(a2h + (2 * ch + c) * 128) = hi;
-            *reinterpret_cast<uint4*>(a2l + (2 * ch + c) * 128) = lo;
+            sts128(a2h + c * 128, hi);
+            sts128(a2l + c * 128, lo);
           }
           if (ch == 1) {                                  // the two halo-side columns 32, 33
             const float2 v = gelu_pair(ex);
             const __half2 hh = __float22half2_rn(v);
             const float2 back = __half22float2(hh);
             const __half2 ll = __float22half2_rn(make_float2(v.x - back.x, v.y - back.y));
-            *reinterpret_cast<uint32_t*>(a2h + 4 * 128) = *reinterpret_cast<const uint32_t*>(&hh);
-            *reinterpret_cast<uint32_t*>(a2l + 4 * 128) = *reinterpret_cast<const uint32_t*>(&ll);
+            sts32(a2h + 2 * 128, *reinterpret_cast<const uint32_t*>(&hh));       // (ch = 1: block 4 of the row)
+            sts32(a2l + 2 * 128, *reinterpret_cast<const uint32_t*>(&ll));
           }
           signal(&st.ready_a2);
           if (LAG == 0) {
@@ -572,8 +577,8 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
             for (int i = 0; i < 4; ++i) o[i] = gelu_pair(acc[i]);
             uint4 hi, lo;
             split8(o, hi, lo);
-            *reinterpret_cast<uint4*>(a3h + (2 * ch + c) * 128) = hi;
-            *reinterpret_cast<uint4*>(a3l + (2 * ch + c) * 128) = lo;
+            sts128(a3h + c * 128, hi);
+            sts128(a3l + c * 128, lo);
           }
           signal(&st.ready_a3);
         }
