@@ -637,7 +637,14 @@ int lgteun_op_ffn(lgteun_t* c, int prior, int lgb, int block, const float* x, fl
   if (!b) return fail(LGTEUN_EINVAL, "no such block");
   if (x == y) return fail(LGTEUN_EINVAL, "x and y must not alias");
   Workspace ws;
-  int rc = op_shape(c, N * (lgb == 1 ? 4 : 1), H, W, 1, &ws);
+  int rc;
+  if (use_tc_ffn(ch) && ffn_cl()) {
+    // the channels-on-lanes kernel takes any map size (row segments and bands are clipped), and needs no scratch
+    if (N <= 0 || H < 1 || W < 1 || H > 1024 || W > 1024) return fail(LGTEUN_EINVAL, "unsupported operator shape");
+    rc = ensure_ws(c, 1, 4, 4, &ws);
+  } else {
+    rc = op_shape(c, N * (lgb == 1 ? 4 : 1), H, W, 1, &ws);
+  }
   if (rc) return rc;
   CK(run_ffn(*b, ch, x, y, ws.hidden, N, H, W, s));
   return 0;

@@ -133,11 +133,7 @@ __global__ void pack_kernel(const float* __restrict__ w, const float* __restrict
 template <int C, int NS>
 __global__ void __launch_bounds__(NS * kWarpsPerStream * 32, NS == 1 ? 2 : 1)
 ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w, const __half* __restrict__ wpack, int H, int W,
-              int nws, int nbands, int band_rows, int total_units, int num_groups, int wmode) {
-  auto WAIT = [&](uint64_t* bar, uint32_t parity) {
-    if (wmode == 1) mbar_wait_spin(bar, parity);
-    else mbar_wait(bar, parity);
-  };
+              int nws, int nbands, int band_rows, int total_units, int num_groups) {
   constexpr int C4 = 4 * C;
   constexpr int HV = 128 / C4;
   constexpr int NP = (C4 == 64) ? 40 : 48;           // MMA N of GEMM1 / GEMM2 (M = 128 needs a multiple of 16; columns >= 40 alias, unused)
@@ -213,7 +209,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   if (lw == 10) {
     // ---- MMA issuer: the whole warp runs the loop, one elected lane issues (under elect.sync ptxas knows a single thread is
     // active and moves the operands to uniform registers without a divergence loop: ~3 instructions per MMA instead of ~10) ----------
-    WAIT(&sm.wbar, 0);
+    mbar_wait(&sm.wbar, 0);
     // descriptor = base (address >> 4, computed once) + compile-time offsets; the upper word is a per-layout constant
     const uint32_t wb = smem_u32(sm.w) >> 4, sb = smem_u32(&st) >> 4;
     constexpr uint32_t HI = (128u >> 4) | (1u << 14);                     // SBO = 128 B, descriptor version 1
@@ -229,7 +225,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     uint32_t ph_a2 = 0, ph_a3 = 0;
     auto issue_g1 = [&](uint32_t g) {
       const uint32_t b = g & 1;
-      WAIT(&st.ready_b1[b], (g >> 1) & 1);
+      mbar_wait(&st.ready_b1[b], (g >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         constexpr uint32_t id = idesc(C4, NP, 0, 0);
@@ -279,7 +275,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     auto issue_g3 = [&](uint32_t j) {
       const uint32_t b = NB3 == 2 ? (j & 1) : 0;
       if (j >= NB3) {                   // the output warps have read the accumulator this GEMM overwrites
-        WAIT(&st.d3_free[b], NB3 == 2 ? ((j - 2) >> 1) & 1 : (j - 1) & 1);
+        mbar_wait(&st.d3_free[b], NB3 == 2 ? ((j - 2) >> 1) & 1 : (j - 1) & 1);
         tc_fence_after();
       }
       if (elect_one()) {
@@ -306,13 +302,13 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       issue_g1(gi);
       for (int it = 0; it < iters + LAG; ++it) {
         if (it < iters) {
-          WAIT(&st.ready_a2, ph_a2); ph_a2 ^= 1;
+          mbar_wait(&st.ready_a2, ph_a2); ph_a2 ^= 1;
           tc_fence_after();
           issue_g2(gi + it);
           if (it + 1 < iters) issue_g1(gi + it + 1);
         }
         if (it - LAG >= 2) {
-          WAIT(&st.ready_a3, ph_a3); ph_a3 ^= 1;
+          mbar_wait(&st.ready_a3, ph_a3); ph_a3 ^= 1;
           tc_fence_after();
           issue_g3(j3++);
         }
@@ -360,7 +356,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       const float4* src = reinterpret_cast<const float4*>(xin + off);
       float4* dst = reinterpret_cast<float4*>(yout + off);
       float4 ra[C / 16], rb[C / 16];
-      WAIT(&st.g3[ob], NB3 == 2 ? (j3 >> 1) & 1 : j3 & 1);
+      mbar_wait(&st.g3[ob], NB3 == 2 ? (j3 >> 1) & 1 : j3 & 1);
       ++j3;
       tc_fence_after();
       const uint32_t t3 = tmem + D3_COL + ob * D3W + ((uint32_t)(32 * li) << 16);
@@ -444,7 +440,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         if (LQ == 2) m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
         float rstd;
         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd) : "f"(fmaf(m2, 1.0f / C, kLnEps)));
-        if (gi >= 2) WAIT(&st.empty[b], ((gi - 2) >> 1) & 1);
+        if (gi >= 2) mbar_wait(&st.empty[b], ((gi - 2) >> 1) & 1);
         if (lane_on) {
           const uint32_t msk = ok ? 0xffffffffu : 0u;           // pixels outside the image / segment: exact zeros
           const uint32_t ax = sa_x + b * BX;
@@ -513,7 +509,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       for (int it = 0; it < iters + LAG; ++it) {
         if (it < iters) {
           // ---- S_b: GELU(D1) -> A2 -----------------------------------------------------------------------------------------
-          WAIT(&st.g1, ph1); ph1 ^= 1;
+          mbar_wait(&st.g1, ph1); ph1 ^= 1;
           tc_fence_after();
           float2 acc[2][4], ex = make_float2(0.f, 0.f);
           tmem_ld8(d1a, acc[0]);
@@ -540,13 +536,13 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           }
           signal(&st.ready_a2);
           if (LAG == 0) {
-            WAIT(&st.g2, ph2); ph2 ^= 1;
+            mbar_wait(&st.g2, ph2); ph2 ^= 1;
             tc_fence_after();
           }
         }
         if (it - LAG >= 2) {
           // ---- S_c: depthwise 3x3 over hidden rows r-2, r-1, r (r = gi + it - LAG) + bias -> GELU -> A3 ---------------------------
-          if (j3 >= 1) WAIT(&st.g3[NB3 == 2 ? (j3 - 1) & 1 : 0], NB3 == 2 ? ((j3 - 1) >> 1) & 1 : (j3 - 1) & 1);     // GEMM3 of the previous row has read A3
+          if (j3 >= 1) mbar_wait(&st.g3[NB3 == 2 ? (j3 - 1) & 1 : 0], NB3 == 2 ? ((j3 - 1) >> 1) & 1 : (j3 - 1) & 1);     // GEMM3 of the previous row has read A3
           ++j3;
           const uint32_t r2 = gi + it - LAG - 2;
           uint32_t slot[3];
@@ -583,7 +579,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           signal(&st.ready_a3);
         }
         if (LAG == 1 && it < iters) {                     // A2 may be rewritten, hidden row gi + it is in its slot
-          WAIT(&st.g2, ph2); ph2 ^= 1;
+          mbar_wait(&st.g2, ph2); ph2 ^= 1;
           tc_fence_after();
         }
       }
@@ -623,11 +619,10 @@ static cudaError_t launch_t(const BlockW& w, const float* x, float* y, int N, in
   const size_t smem = sizeof(Smem<C, NS>) + 128;
   cudaError_t e = cudaFuncSetAttribute(ffn_cl_kernel<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  static const int wmode = [] { const char* e = getenv("LGTEUN_CL_WAIT"); return e ? atoi(e) : 0; }();
   const int ctas_needed = (groups + NS - 1) / NS, cap = sm_count * (NS == 1 ? 2 : 1);
   const int grid = ctas_needed < cap ? ctas_needed : cap;
   ffn_cl_kernel<C, NS><<<grid, NS * kWarpsPerStream * 32, smem, s>>>(x, y, w, reinterpret_cast<const __half*>(w.ffn_cl_pack), H, W, nws,
-                                                                    nbands, band_rows, units, groups, wmode);
+                                                                    nbands, band_rows, units, groups);
   return cudaGetLastError();
 }
 

@@ -512,7 +512,53 @@ def test_window_msa_variants_match_the_oracle():
         assert diff <= 2e-5, (mode, diff)
 
 
-@pytest.mark.parametrize("env", [{"LGTEUN_FFN": "simt"}, {"LGTEUN_FFT": "stockham"}, {"LGTEUN_MSA": "simt"}, {"LGTEUN_MSA": "hybrid"},
+def test_ffn_variants_match_the_oracle():
+    """The three forms of the conv-FFN (LGTEUN_FFN unset = channels-on-lanes tcgen05 kernel ffn_cl.cu, tc = pixels-on-lanes
+    tcgen05 kernel ffn_tc.cu, simt = CUDA cores) against the oracle at the operator tolerance, in child processes, on
+    shapes that exercise ragged row segments (W not a multiple of 32), short bands and both channel counts."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import os, sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "from conftest import load_weights\n"
+        "from lgteun_b200 import _abi\n"
+        "from oracle import lgteun_oracle as O\n"
+        "worst = 0.0\n"
+        "for bands in (4, 8):\n"
+        "    sd = load_weights(bands)\n"
+        "    h = _abi.Handle(0, bands, 2)\n"
+        "    h.load_weights({k: v.cuda().contiguous() for k, v in sd.items()})\n"
+        "    shapes = ((0, (2, 32, 64)), (1, (3, 16, 16)), (0, (1, 8, 8)), (0, (5, 64, 32)), (1, (1, 128, 128)))\n"
+        "    if not os.environ.get('LGTEUN_FFN'):      # the default kernel clips row segments and bands: any map size\n"
+        "        shapes += ((0, (2, 40, 72)), (0, (1, 1, 1)), (0, (1, 7, 100)), (0, (1, 130, 33)))\n"
+        "        if bands == 4:                        # (the bottleneck of the 8-band model has 64 channels: pwgemm_tc.cu path)\n"
+        "            shapes += ((1, (3, 24, 40)), (1, (1, 130, 33)))\n"
+        "    for lgb, shape in shapes:\n"
+        "        n, H, W = shape\n"
+        "        c = 4 * bands * (2 if lgb == 1 else 1)\n"
+        "        x = torch.randn(n, H, W, c, generator=torch.Generator().manual_seed(5 + lgb))\n"
+        "        y = torch.empty_like(x, device='cuda')\n"
+        "        h.op('ffn', 1, lgb, 0, x.cuda().data_ptr(), y.data_ptr(), n, H, W)\n"
+        "        pre = 'prior_module.1.' + ('encoder_layers.0.0', 'bottleneck')[lgb] + '.blocks.0.1'\n"
+        "        ref = x + O.feed_forward(sd, pre + '.fn.fn', O.layer_norm(sd, pre + '.fn.norm', x))\n"
+        "        worst = max(worst, float((y.cpu() - ref).abs().max()))\n"
+        "print('MAXDIFF', worst)\n"
+    )
+    for mode in ("", "tc", "simt"):
+        env = {**os.environ}
+        env.pop("LGTEUN_FFN", None)
+        if mode:
+            env["LGTEUN_FFN"] = mode
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, (mode, res.stderr[-2000:])
+        diff = float(res.stdout.strip().split("MAXDIFF")[-1])
+        assert diff <= 5e-5, (mode, diff)
+
+
+@pytest.mark.parametrize("env", [{"LGTEUN_FFN": "simt"}, {"LGTEUN_FFN": "tc"}, {"LGTEUN_FFT": "stockham"}, {"LGTEUN_MSA": "simt"}, {"LGTEUN_MSA": "hybrid"},
                                  {"LGTEUN_MSA": "tc"}, {"LGTEUN_DATA_STEP": "split"}])
 def test_ab_switch_paths_stay_correct(env):
     """The A/B switches (CUDA-core FFN, shared-memory Stockham FFT passes) select other kernels of the SAME library for
