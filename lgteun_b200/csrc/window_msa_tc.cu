@@ -158,24 +158,28 @@ window_msa_tc_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW 
   const int pairs = (total_windows + 1) / 2;
 
   if (warp == 8) {
-    // ---- MMA issuer ---------------------------------------------------------------------------------------------------
-    if (lane == 0) {
+    // ---- MMA issuer (whole warp waits, one elected lane issues) -----------------------------------------------------------
+    {
       const uint32_t axh = smem_u32(sm.axh), axl = smem_u32(sm.axl), wqh = smem_u32(sm.wqh), wql = smem_u32(sm.wql);
       uint32_t px = 0, ps = 0, pp[2] = {0, 0};
       auto issue_qkv = [&]() {
         mbar_wait_spin(&sm.ready_x, px); px ^= 1;
         tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc(NQKV);
-        const uint64_t ah = umma_desc(axh, 128 * 16, 128), al = umma_desc(axl, 128 * 16, 128);
-        const uint64_t bh = umma_desc(wqh, NQKV * 16, 128), bl = umma_desc(wql, NQKV * 16, 128);
-        umma_f16(tmem + QKV_COL, ah, bh, idesc, 0);
-        umma_f16(tmem + QKV_COL, ah, bl, idesc, 1);
-        umma_f16(tmem + QKV_COL, al, bh, idesc, 1);
-        umma_commit(&sm.mma_qkv);
+        if (elect_one()) {
+          constexpr uint32_t idesc = umma_idesc(NQKV);
+          const uint64_t ah = umma_desc(axh, 128 * 16, 128), al = umma_desc(axl, 128 * 16, 128);
+          const uint64_t bh = umma_desc(wqh, NQKV * 16, 128), bl = umma_desc(wql, NQKV * 16, 128);
+          umma_f16(tmem + QKV_COL, ah, bh, idesc, 0);
+          umma_f16(tmem + QKV_COL, ah, bl, idesc, 1);
+          umma_f16(tmem + QKV_COL, al, bh, idesc, 1);
+          umma_commit(&sm.mma_qkv);
+        }
+        __syncwarp();
       };
       auto issue_s = [&]() {                  // logits: accumulate onto the pre-loaded positional bias
         mbar_wait_spin(&sm.ready_s, ps); ps ^= 1;
         tc_fence_after();
+        if (elect_one())
 #pragma unroll
         for (int wd = 0; wd < 2; ++wd) {
           constexpr uint32_t idesc = umma_idesc(64);
@@ -187,12 +191,14 @@ window_msa_tc_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW 
           umma_f16(d, al, bh, idesc, 1);
           umma_commit(&sm.mma_s[wd]);
         }
+        __syncwarp();
       };
       auto issue_o = [&](int par) {
 #pragma unroll
         for (int wd = 0; wd < 2; ++wd) {
           mbar_wait_spin(&sm.ready_p[wd], pp[wd]); pp[wd] ^= 1;
           tc_fence_after();
+          if (elect_one()) {
           constexpr uint32_t idesc = umma_idesc(NO);
           const uint32_t aoh = smem_u32(sm.aoh[wd]), aol = smem_u32(sm.aol[wd]);
           const uint32_t boh = smem_u32(sm.boh[par][wd]), bol = smem_u32(sm.bol[par][wd]);
@@ -211,6 +217,8 @@ window_msa_tc_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW 
             }
           }
           umma_commit(&sm.mma_o[wd]);
+          }
+          __syncwarp();
         }
       };
       // pair n: QKV(n) | S(n) | O(n);  issue order QKV(0) S(0) | QKV(n+1) O(n) S(n+1) | ... (mirrors the row warps' phases)
@@ -576,34 +584,36 @@ window_msa_qk_kernel(const float* __restrict__ x, float* __restrict__ y, BlockW 
   const uint32_t tmem = sm.tmem_base;
 
   if (warp == 4) {
-    if (lane == 0) {
-      const uint32_t axh = smem_u32(sm.axh), axl = smem_u32(sm.axl), wqh = smem_u32(sm.wqh), wql = smem_u32(sm.wql);
-      const uint32_t ash = smem_u32(sm.ash), asl = smem_u32(sm.asl), bsh = smem_u32(sm.bsh), bsl = smem_u32(sm.bsl);
-      uint32_t px = 0, ps = 0;
-      for (int widx = blockIdx.x; widx < total_windows; widx += gridDim.x) {
-        mbar_wait(&sm.ready_x, px); px ^= 1;
-        tc_fence_after();
-        {
-          constexpr uint32_t idesc = umma_idesc(NQKV);
-          const uint64_t ah = umma_desc(axh, 128 * 16, 128), al = umma_desc(axl, 128 * 16, 128);
-          const uint64_t bh = umma_desc(wqh, NQKV * 16, 128), bl = umma_desc(wql, NQKV * 16, 128);
-          umma_f16(tmem + QKV_COL, ah, bh, idesc, 0);
-          umma_f16(tmem + QKV_COL, ah, bl, idesc, 1);
-          umma_f16(tmem + QKV_COL, al, bh, idesc, 1);
-          umma_commit(&sm.mma_qkv);
-        }
-        mbar_wait(&sm.ready_s, ps); ps ^= 1;
-        tc_fence_after();
-        {
-          constexpr uint32_t idesc = umma_idesc(64);
-          const uint64_t ah = umma_desc(ash, 128 * 16, 128), al = umma_desc(asl, 128 * 16, 128);
-          const uint64_t bh = umma_desc(bsh, 64 * 16, 128), bl = umma_desc(bsl, 64 * 16, 128);
-          umma_f16(tmem + S_COL, ah, bh, idesc, 1);        // accumulate onto the pre-loaded positional bias
-          umma_f16(tmem + S_COL, ah, bl, idesc, 1);
-          umma_f16(tmem + S_COL, al, bh, idesc, 1);
-          umma_commit(&sm.mma_s);
-        }
+    // MMA issuer: the whole warp waits, one elected lane issues (elect.sync lets ptxas keep the operands in uniform registers
+    // without a divergence loop around every tcgen05.mma)
+    const uint32_t axh = smem_u32(sm.axh), axl = smem_u32(sm.axl), wqh = smem_u32(sm.wqh), wql = smem_u32(sm.wql);
+    const uint32_t ash = smem_u32(sm.ash), asl = smem_u32(sm.asl), bsh = smem_u32(sm.bsh), bsl = smem_u32(sm.bsl);
+    uint32_t px = 0, ps = 0;
+    for (int widx = blockIdx.x; widx < total_windows; widx += gridDim.x) {
+      mbar_wait(&sm.ready_x, px); px ^= 1;
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc(NQKV);
+        const uint64_t ah = umma_desc(axh, 128 * 16, 128), al = umma_desc(axl, 128 * 16, 128);
+        const uint64_t bh = umma_desc(wqh, NQKV * 16, 128), bl = umma_desc(wql, NQKV * 16, 128);
+        umma_f16(tmem + QKV_COL, ah, bh, idesc, 0);
+        umma_f16(tmem + QKV_COL, ah, bl, idesc, 1);
+        umma_f16(tmem + QKV_COL, al, bh, idesc, 1);
+        umma_commit(&sm.mma_qkv);
       }
+      __syncwarp();
+      mbar_wait(&sm.ready_s, ps); ps ^= 1;
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc(64);
+        const uint64_t ah = umma_desc(ash, 128 * 16, 128), al = umma_desc(asl, 128 * 16, 128);
+        const uint64_t bh = umma_desc(bsh, 64 * 16, 128), bl = umma_desc(bsl, 64 * 16, 128);
+        umma_f16(tmem + S_COL, ah, bh, idesc, 1);        // accumulate onto the pre-loaded positional bias
+        umma_f16(tmem + S_COL, ah, bl, idesc, 1);
+        umma_f16(tmem + S_COL, al, bh, idesc, 1);
+        umma_commit(&sm.mma_s);
+      }
+      __syncwarp();
     }
   } else {
     const int row = tid;                       // TMEM lane: (head, query) in the S phase; token (twice) in the QKV phase
