@@ -887,7 +887,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="profiling aid: launch kernels directly instead of the CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
-    ap.add_argument("--e2e-chunk", type=int, default=128, help="pairs per H2D/compute/D2H pipeline chunk of the e2e leg")
+    ap.add_argument("--e2e-chunk", type=int, default=256, help="pairs per H2D/compute/D2H pipeline chunk of the e2e leg")
     ap.add_argument("--other-workloads", action="store_true", default=True)
     ap.add_argument("--no-parity", action="store_true", help="profiling aid: skip the oracle check before timing")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the torch-eager-on-CUDA incumbent baseline (N = 1 only)")

@@ -3,11 +3,28 @@
 The reference's test loop moves a batch to the GPU, runs the forward and copies the result back
 (`set_batch_cuda` -> `get_model_output` -> `torch2np`, models/base/base_model.py:293-305), strictly one after the
 other.  Here the batch is cut into chunks and the three phases run on three CUDA streams, so that the PCIe copies of
-chunk i+1 / i-1 hide under the kernels of chunk i (H2D and D2H are full duplex).  Results are identical to
-`net(ms.cuda(), pan.cuda()).cpu()` — image pairs are independent."""
+chunk i+1 / i-1 hide under the kernels of chunk i (H2D and D2H are full duplex).  Only the upload of the first chunk and
+the download of the last one are exposed, so those two chunks are a quarter of the regular size (`plan_chunks`).
+Results are identical to `net(ms.cuda(), pan.cuda()).cpu()` — image pairs are independent."""
 from __future__ import annotations
 
 import torch
+
+
+def plan_chunks(n: int, chunk: int) -> list:
+    """[(lo, hi)] covering range(n): regular chunks of `chunk` pairs between a short first and a short last chunk
+    (chunk // 4) whose copies cannot hide under another chunk's kernels.  Batches of at most one chunk are not cut."""
+    chunk = max(int(chunk), 1)
+    if n <= chunk:
+        return [(0, n)] if n > 0 else []
+    edge = max(chunk // 4, 1)
+    cuts = [0, edge]
+    while n - cuts[-1] > chunk + edge:
+        cuts.append(cuts[-1] + chunk)
+    if n - cuts[-1] > edge:
+        cuts.append(n - edge)
+    cuts.append(n)
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
 
 class HostPipeline:
@@ -40,8 +57,7 @@ class HostPipeline:
         free = [None, None]                 # event: staging buffer i may be overwritten (its forward has been enqueued and run)
         self.s_in.wait_stream(compute)
         k = 0
-        for lo in range(0, n, self.chunk):
-            hi = min(lo + self.chunk, n)
+        for lo, hi in plan_chunks(n, self.chunk):
             b = k & 1
             with torch.cuda.stream(self.s_in):
                 if free[b] is not None:

@@ -51,3 +51,17 @@ def test_two_rank_gloo_sharded_forward():
         assert p.exitcode == 0
     for rank, ok, t, s in res:
         assert ok and t == 11.0 and s == 5.0
+
+
+@pytest.mark.parametrize("n,chunk", [(512, 128), (512, 64), (100, 64), (64, 64), (65, 64), (1, 4), (0, 4), (130, 128), (7, 1)])
+def test_host_pipeline_chunk_plan(n, chunk):
+    """HostPipeline's chunk plan covers the batch exactly once, never exceeds the staging size, and keeps the two chunks
+    whose copies are exposed (first upload, last download) short."""
+    from lgteun_b200.hostio import plan_chunks
+    plan = plan_chunks(n, chunk)
+    assert sum(hi - lo for lo, hi in plan) == n
+    assert all(0 < hi - lo <= chunk for lo, hi in plan)
+    assert all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+    if n > chunk:
+        edge = max(chunk // 4, 1)
+        assert plan[0] == (0, edge) and plan[-1][1] - plan[-1][0] <= edge
