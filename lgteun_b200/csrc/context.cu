@@ -116,9 +116,11 @@ bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int check_shape(const lgteun_ctx* c, int N, int h, int w) {
   if (N <= 0) return fail(LGTEUN_EINVAL, "batch must be positive");
-  if (h < 4 || w < 4 || !pow2(h) || !pow2(w) || 4 * h > 1024 || 4 * w > 1024)
-    return fail(LGTEUN_EINVAL, "unsupported shape: PAN height/width (4h, 4w) must be powers of two in [16, 1024] "
-                               "(8x8 windows at two U-Net levels, power-of-two FFT passes); got h=" +
+  // what the reference accepts: PAN height / width multiples of 16 (8x8 windows at full and at half resolution, LGT.py:135);
+  // FFT lengths with odd factors take the generic radix stages of fft_mixer.cu
+  if (h < 4 || w < 4 || (h & 3) || (w & 3) || 4 * h > 1024 || 4 * w > 1024)
+    return fail(LGTEUN_EINVAL, "unsupported shape: PAN height/width (4h, 4w) must be multiples of 16 in [16, 1024] "
+                               "(8x8 windows at two U-Net levels); got h=" +
                                    std::to_string(h) + " w=" + std::to_string(w));
   (void)c;
   return 0;
@@ -546,10 +548,11 @@ static const BlockW* pick_block(const lgteun_ctx* c, int prior, int lgb, int blo
   CK(cudaSetDevice(c->device));
 
 static int op_shape(lgteun_ctx* c, int N, int H, int W, int min_side, Workspace* ws) {
-  if (N <= 0 || !pow2(H) || !pow2(W) || H < min_side || W < min_side || H > 1024 || W > 1024)
+  // powers of two (down to min_side) or multiples of 8
+  if (N <= 0 || H < min_side || W < min_side || H > 1024 || W > 1024 || !(pow2(H) || (H & 7) == 0) || !(pow2(W) || (W & 7) == 0))
     return fail(LGTEUN_EINVAL, "unsupported operator shape");
   // a workspace for an (N, H/4, W/4) forward covers every operator at map size H x W (and smaller)
-  int h = H / 4 > 4 ? H / 4 : 4, w = W / 4 > 4 ? W / 4 : 4;
+  int h = (H + 3) / 4 > 4 ? (H + 3) / 4 : 4, w = (W + 3) / 4 > 4 ? (W + 3) / 4 : 4;
   return ensure_ws(c, N, h, w, ws);
 }
 

@@ -42,6 +42,15 @@ cudaError_t fft_init_tables(cudaStream_t s) {
   return fft256_init_tables(s);
 }
 
+// tw[j] = e^{-2 pi i j / L} for the shared-memory passes: from the rounded-from-double table when L divides 1024 (every
+// power of two), else computed in double on the spot (lengths with odd factors: any H, W that are multiples of 8)
+__device__ __forceinline__ float2 tw_entry(int j, int L) {
+  if (kTwN % L == 0) return g_tw[j * (kTwN / L)];
+  double sn, cs;
+  sincospi(-2.0 * (double)j / (double)L, &sn, &cs);
+  return make_float2((float)cs, (float)sn);
+}
+
 size_t spectrum_floats(int N, int H, int W, int c2) { return (size_t)N * H * (W / 2 + 1) * c2 * 2; }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -86,6 +95,42 @@ __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int N
         dst[3 * Ns] = make_float2(d02.x - jd.x, d02.y - jd.y);
       }
       Ns <<= 2;
+    } else if (rem & 1) {
+      // odd factor (lengths that are not powers of two): one generic radix-R stage, R = smallest odd prime factor of rem;
+      // the R-point DFT is evaluated directly (R <= 61 for lengths <= 1024 that are multiples of 16)
+      int R = 3;
+      while (rem % R) R += 2;
+      const int q = L / R;
+      const int tws = L / (Ns * R);                // twiddle stride: w_{R Ns}^{k r} = tw[k r tws]
+      for (int id = tid; id < NF * q; id += nthreads) {
+        const int f = id / q, j = id - f * q;
+        const int k = j % Ns;
+        const float2* src = a + f * LS + j;
+        float2 v[64];
+        for (int r = 0; r < R; ++r) {
+          float2 t = src[r * q];
+          if (k && r) {
+            const float2 w1 = tw[k * r * tws];
+            t = (SIGN < 0) ? cmul(t, w1) : cmul_conj(t, w1);
+          }
+          v[r] = t;
+        }
+        float2* dst = b + f * LS + (j - k) * R + k;
+        for (int o = 0; o < R; ++o) {
+          float2 acc = v[0];
+          int e = 0;                               // (r * o) mod R
+          for (int r = 1; r < R; ++r) {
+            e += o;
+            if (e >= R) e -= R;
+            const float2 wr = tw[e * q];
+            const float2 t = (SIGN < 0) ? cmul(v[r], wr) : cmul_conj(v[r], wr);
+            acc.x += t.x;
+            acc.y += t.y;
+          }
+          dst[o * Ns] = acc;
+        }
+      }
+      Ns *= R;
     } else {
       const int q = L >> 1;
       const int tws = L / (Ns * 2);
@@ -187,7 +232,7 @@ __global__ void __launch_bounds__(NT) fft_rows_fwd_kernel(const float* __restric
   float2* bufB = bufA + NF * LS;
   const int tid = threadIdx.x;
   const size_t row0 = (size_t)blockIdx.x * ROWS;          // n*H + y of the first row
-  for (int j = tid; j < W; j += NT) tw[j] = g_tw[j * (kTwN / W)];
+  for (int j = tid; j < W; j += NT) tw[j] = tw_entry(j, W);
   for (int p = tid; p < ROWS * W; p += NT) {
     const int rl = p / W, px = p - rl * W;
     const float* src = x + ((row0 + rl) * W + px) * CIN;
@@ -222,7 +267,7 @@ __global__ void __launch_bounds__(NT) fft_rows_fwd_kernel(const float* __restric
   for (int id = tid; id < ROWS * Wf * NF1; id += NT) {
     const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
     const int k = rem / NF1, f = rl * NF1 + (rem - k * NF1);
-    float2 z = res[f * LS + k], zm = res[f * LS + ((W - k) & (W - 1))];
+    float2 z = res[f * LS + k], zm = res[f * LS + (k ? W - k : 0)];
     float4 o;
     o.x = 0.5f * (z.x + zm.x);        // Xa = (Z[k] + conj(Z[W-k])) / 2
     o.y = 0.5f * (z.y - zm.y);
@@ -245,7 +290,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
   const int l0 = blockIdx.x * Q;
   const int nl = min(Q, lanes_per_row - l0);
   float2* base = spec + (size_t)blockIdx.y * H * lanes_per_row + l0;
-  for (int j = tid; j < H; j += kFftThreads) tw[j] = g_tw[j * (kTwN / H)];
+  for (int j = tid; j < H; j += kFftThreads) tw[j] = tw_entry(j, H);
 #pragma unroll 4
   for (int id = tid; id < H * Q; id += kFftThreads) {
     const int r = id / Q, l = id - r * Q;
@@ -348,6 +393,52 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_kernel(float2* __restric
   }
 }
 
+// ---- pass 2 for column lengths that are not powers of two: the same three steps with the natural-order Stockham
+// transform (two shared-memory buffers, sequence = one complex lane's column) ------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(kFftThreads) fft_cols_any_kernel(float2* __restrict__ spec, BlockW w, int H, int W, int C2,
+                                                                   int lanes_per_row /* Wf*C2 */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tw = reinterpret_cast<float2*>(smem_raw);       // [H]
+  const int LS = H + kSeqPad;
+  float2* bufA = tw + H;                                  // [Q][LS]
+  float2* bufB = bufA + Q * LS;
+  const int tid = threadIdx.x;
+  const int l0 = blockIdx.x * Q;
+  const int nl = min(Q, lanes_per_row - l0);
+  float2* base = spec + (size_t)blockIdx.y * H * lanes_per_row + l0;
+  for (int j = tid; j < H; j += kFftThreads) tw[j] = tw_entry(j, H);
+  for (int id = tid; id < H * Q; id += kFftThreads) {
+    const int r = id / Q, l = id - r * Q;
+    bufA[l * LS + r] = (l < nl) ? base[(size_t)r * lanes_per_row + l] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  float2* f = stockham<-1>(bufA, bufB, tw, H, Q, tid, kFftThreads);
+  for (int id = tid; id < H * Q; id += kFftThreads) {
+    const int l = id / H, ky = id - l * H;
+    if (l >= nl) continue;
+    const int lane = l0 + l;
+    const int kx = lane / C2, ch = lane - kx * C2;
+    float2 z = f[l * LS + ky];
+    if ((ky == 0 || 2 * ky == H) && (kx == 0 || 2 * kx == W)) z.y = 0.0f;     // exactly-real bins: +0.0 (F7)
+    float amp = sqrtf(fmaf(z.x, z.x, z.y * z.y));
+    float pha = atan2f(z.y, z.x);
+    amp = amp * __ldg(w.amp_w + ch) + __ldg(w.amp_b + ch);
+    pha = pha * __ldg(w.pha_w + ch) + __ldg(w.pha_b + ch);
+    const float sn = __sinf(pha), cs = __cosf(pha);
+    float re = amp * cs + 1e-8f;
+    float im = amp * sn + 1e-8f;
+    re = re + 1e-8f;
+    f[l * LS + ky] = make_float2(re, im);
+  }
+  __syncthreads();
+  float2* g = stockham<+1>(f, f == bufA ? bufB : bufA, tw, H, Q, tid, kFftThreads);
+  for (int id = tid; id < H * Q; id += kFftThreads) {
+    const int r = id / Q, l = id - r * Q;
+    if (l < nl) base[(size_t)r * lanes_per_row + l] = g[l * LS + r];
+  }
+}
+
 // ---- pass 3: rows inverse (+ proj + residual) ------------------------------------------------------------
 template <int C2, bool PROJ, int WCT, int ROWS, int NT = kFftThreads>
 __global__ void __launch_bounds__(NT) fft_rows_inv_kernel(const float2* __restrict__ spec,
@@ -368,7 +459,7 @@ __global__ void __launch_bounds__(NT) fft_rows_inv_kernel(const float2* __restri
   const int tid = threadIdx.x;
   const size_t row0 = (size_t)blockIdx.x * ROWS;
   const int Wf = W / 2 + 1;
-  for (int j = tid; j < W; j += NT) tw[j] = g_tw[j * (kTwN / W)];
+  for (int j = tid; j < W; j += NT) tw[j] = tw_entry(j, W);
   if constexpr (PROJ) {
     for (int i = tid; i < C * C; i += NT) sW[i] = __ldg(w.proj_w + i);
     for (int i = tid; i < C; i += NT) sBias[i] = __ldg(w.proj_b + i);
@@ -438,6 +529,8 @@ __global__ void __launch_bounds__(NT) fft_rows_inv_kernel(const float2* __restri
 
 // ---- launchers ---------------------------------------------------------------------------------------------
 static bool pow2_in_range(int v) { return v >= 8 && v <= kTwN && (v & (v - 1)) == 0; }
+// every length the window partition allows: multiples of 8 (odd factors take the generic radix stages)
+static bool len_ok(int v) { return v >= 8 && v <= kTwN && (v & 7) == 0; }
 
 // rows per CTA on the fast path: 16 complex sequences per CTA (C2=8: 4 rows, C2=16: 2 rows, C2=32: 1 row)
 template <int C2> constexpr int fast_rows() { return (16 / (C2 / 2)) > 0 ? 16 / (C2 / 2) : 1; }
@@ -469,7 +562,7 @@ static bool stockham_only() {                            // LGTEUN_FFT=stockham:
 
 cudaError_t launch_fft_rows_fwd(const BlockW& w, int c, const float* x, float* spec, int pre_ln, int N, int H, int W,
                                 cudaStream_t s) {
-  if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  if (!len_ok(W) || !len_ok(H)) return cudaErrorInvalidValue;
   if (W == 256 && pre_ln && H % 4 == 0 && !stockham_only()) return launch_fft_rows_fwd256(w, c, x, spec, N, H, s);
   if (W == 128 && pre_ln && H % 8 == 0 && !stockham_only()) return launch_fft_rows_fwd128(w, c, x, spec, N, H, s);
   switch (c) {
@@ -492,8 +585,18 @@ static cudaError_t cols_t(const BlockW& w, int c2, float* spec, int N, int H, in
 }
 
 cudaError_t launch_fft_cols(const BlockW& w, int c, float* spec, int N, int H, int W, cudaStream_t s) {
-  if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  if (!len_ok(W) || !len_ok(H)) return cudaErrorInvalidValue;
   const int c2 = c / 2;
+  if (!pow2_in_range(H)) {                                 // column length with odd factors
+    const int lanes = (W / 2 + 1) * c2;
+    constexpr int Q = 8;
+    size_t smem = (size_t)(H + 2 * Q * (H + kSeqPad)) * sizeof(float2);
+    cudaError_t e = cudaFuncSetAttribute(fft_cols_any_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((lanes + Q - 1) / Q, N);
+    fft_cols_any_kernel<Q><<<grid, kFftThreads, smem, s>>>(reinterpret_cast<float2*>(spec), w, H, W, c2, lanes);
+    return cudaGetLastError();
+  }
   if (H == 128 && !stockham_only()) return launch_fft_cols128(w, c2, spec, N, W, s);
   if (H == 128) return cols_t<64, 128>(w, c2, spec, N, H, W, s);
   if (H < 128) return cols_t<64, 0>(w, c2, spec, N, H, W, s);
@@ -532,7 +635,7 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
 
 cudaError_t launch_fft_rows_inv(const BlockW& w, int c, const float* spec, const float* local, const float* xres, float* y,
                                 int proj, int N, int H, int W, cudaStream_t s) {
-  if (!pow2_in_range(W) || !pow2_in_range(H)) return cudaErrorInvalidValue;
+  if (!len_ok(W) || !len_ok(H)) return cudaErrorInvalidValue;
   if (W == 256 && proj && H % 4 == 0 && !stockham_only()) return launch_fft_rows_inv256(w, c, spec, local, xres, y, N, H, s);
   if (W == 128 && proj && H % 8 == 0 && !stockham_only()) return launch_fft_rows_inv128(w, c, spec, local, xres, y, N, H, s);
   switch (c) {

@@ -125,8 +125,18 @@ def local_mixer(sd: SD, p: str, x: Tensor) -> Tensor:
     return out.reshape(b, nh, nw, WINDOW, WINDOW, c2).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c2)
 
 
+# torch.fft.rfft2 returns an exact +0.0 imaginary part in the four purely real bins for power-of-two sizes, but a rounding
+# residue of arbitrary sign at many other lengths (8 x odd, 16 x 5, 16 x 7 ..., in fp32 AND in fp64): where the real part is
+# negative, angle() then flips between +pi and -pi and conv_pha spreads the difference over the whole map.  With
+# this switch on, global_mixer evaluates the same formula with the imaginary part of those bins set to +0.0 (what exact
+# arithmetic gives): the well-defined reference for sizes that are not powers of two (tests only; default = literal restatement).
+EXACT_REAL_BINS = False
+
+
 def global_mixer(sd: SD, p: str, x: Tensor) -> Tensor:
     """FFT amplitude/phase mixer on the global channel half, LGT.py:162-180."""
+    if EXACT_REAL_BINS:
+        return global_mixer_3pass(sd, p, x)
     b, h, w, c2 = x.shape
     x = x.permute(0, 3, 1, 2)
     fre = torch.fft.rfft2(x, norm="backward")                           # LGT.py:166

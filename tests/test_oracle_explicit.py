@@ -53,3 +53,28 @@ def test_real_bins_have_positive_zero_imag():
 def test_gelu_is_erf_form():
     x = torch.linspace(-6, 6, 1001)
     assert torch.equal(O.gelu_erf(x).float(), O.gelu_erf(x)) and (O.gelu_erf(x) - torch.nn.functional.gelu(x)).abs().max() < 1e-6
+
+
+def test_exact_real_bins_switch_is_a_no_op_at_powers_of_two_and_stable_elsewhere():
+    """oracle.EXACT_REAL_BINS (imaginary part of the four purely real rfft2 bins := +0.0): identical to the literal
+    restatement at power-of-two sizes, where torch already returns +0.0; at column lengths such as 72 or 24 the literal
+    fp32 restatement is off by 1e-3 .. 3e-2 from its own fp64 evaluation (arbitrary sign of a rounding residue under
+    angle()) while the exact-bin form agrees between fp32 and fp64 to fp32 rounding."""
+    import torch
+    from conftest import load_weights
+    from oracle import lgteun_oracle as O
+    sd = load_weights(4)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    pre = "prior_module.1.encoder_layers.0.0.blocks.0.0.fn.fn.global_mixer"
+    x = torch.randn(1, 64, 32, 8, generator=torch.Generator().manual_seed(3))
+    lit = O.global_mixer(sd, pre, x)
+    O.EXACT_REAL_BINS = True
+    try:
+        assert (O.global_mixer(sd, pre, x) - lit).abs().max().item() <= 2e-5
+        for H in (72, 24):
+            xs = torch.randn(1, H, 64, 8, generator=torch.Generator().manual_seed(3))
+            a = O.global_mixer(sd, pre, xs).double()
+            b = O.global_mixer(sd64, pre, xs.double())
+            assert (a - b).abs().max().item() <= 1e-4
+    finally:
+        O.EXACT_REAL_BINS = False
