@@ -39,11 +39,21 @@ using namespace tc;
 
 namespace cl {
 
-constexpr int kIn = 32;              // interior pixels of a row segment (output columns per half and iteration)
-constexpr int kNPS = 40;             // stored pixel columns of every operand tile (34 used: interior + 2 halo)
-constexpr int kB1Stride = 736;       // bytes between the 8-channel chunks of the K-major GEMM1 operand (640 + 96: bank spread)
-constexpr int kMnK = (kNPS / 8) * 128;   // bytes between 8-channel blocks of an MN-major tile (5 pixel blocks x 128 B)
 constexpr int kWarpsPerStream = 12;
+
+// Geometry of a row segment.  c = 16: 32 interior pixels (+ 2 halo) in 40 columns, M = 64 MMAs of N = 40.  c = 32: M = 128 MMAs need
+// N = 48 anyway and cost the same ~44 clk for any N <= 64 (tools/tcprobe), so a segment carries 46 interior pixels.
+template <int C>
+struct Geo {
+  static constexpr int KIN = (C == 16) ? 32 : 46;        // interior pixels of a row segment (output columns per half and iteration)
+  static constexpr int NPS = (C == 16) ? 40 : 48;        // pixel columns of every operand tile and of a TMEM slot (= MMA N)
+  static constexpr int CPW = NPS / 16;                   // 8-pixel chunks per epilogue warp and phase (two column halves)
+  static constexpr bool EXTRA = (C == 16);               // columns 32, 33 (the halo side) are a separate 2-column piece
+  static constexpr int B1S = NPS * 16 + 96;              // bytes between the 8-channel chunks of the K-major GEMM1 operand (+96: bank spread)
+  static constexpr int MNK = (NPS / 8) * 128;            // bytes between 8-channel blocks of an MN-major tile
+  static constexpr int A3B = (KIN + 7) / 8;              // 8-pixel blocks of one half in the A3 tile (interior pixels only)
+  static constexpr int NB1 = (C == 16) ? 2 : 1;          // buffers of the GEMM1 operand (c = 32: shared memory is full, see Stream)
+};
 
 __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -82,18 +92,21 @@ struct Pack {
 
 template <int C>
 struct Stream {
+  using G = Geo<C>;
   static constexpr int C4 = 4 * C;
   static constexpr int HV = 128 / C4;                         // row segments sharing the 128 lanes
-  uint64_t g1, g2, g3[2], empty[2], ready_b1[2], ready_a2, ready_a3, d3_free[2];   // c = 32 uses g3[0] / d3_free[0] only
-  alignas(128) unsigned char b1h[2][HV][(C / 8) * kB1Stride];   // GEMM1 B operand, K-major [C/8][40 px][8], per buffer and half
-  unsigned char b1l[2][HV][(C / 8) * kB1Stride];
-  unsigned char b1f[2][HV][2 * kB1Stride];                    // flag K-step: chunk 0 cols 0,1 = valid, chunk 1 = 0
-  unsigned char a2f[2][HV][2 * kMnK];                         // flag K-step of GEMM2, MN-major: rows 0,1 = valid, rest 0
-  unsigned char a2h[HV][C4 / 8 * kMnK], a2l[HV][C4 / 8 * kMnK];   // GELU(D1): GEMM2 B operand, MN-major [C4/8][5][8 ch][8 px]
-  // GELU(dw): GEMM3 A operand (M = pixels), MN-major [C4/8][HV * 4 pixel blocks][8 ch][8 px]: the 32 interior pixels of every half
-  // side by side, so ONE M = 128 MMA covers all halves (rows 0..31 = half 0, 32..63 = half 1; the rest aliases, unused)
-  unsigned char a3h[C4 / 8 * HV * 512], a3l[C4 / 8 * HV * 512];
-  unsigned char tail[1536];                                   // GEMM3 reads 128 pixel rows of a 40-column tile: it runs 1408 B over
+  uint64_t g1, g2, g3[2], empty[2], ready_b1[2], ready_a2, ready_a3, d3_free[2];   // c = 32 uses g3[0] / d3_free[0] / ready_b1[0] only
+  // GEMM1 B operand, K-major [C/8][NPS px][8], per buffer and half.  c = 32 has ONE buffer: the loaders rewrite it as soon as
+  // GEMM1 of the previous row has completed (an iteration before it is needed), which frees 8 KB per stream
+  alignas(128) unsigned char b1h[G::NB1][HV][(C / 8) * G::B1S];
+  unsigned char b1l[G::NB1][HV][(C / 8) * G::B1S];
+  unsigned char b1f[G::NB1][HV][2 * G::B1S];                  // flag K-step: chunk 0 cols 0,1 = valid, chunk 1 = 0
+  unsigned char a2f[2][HV][2 * G::MNK];                       // flag K-step of GEMM2, MN-major: rows 0,1 = valid, rest 0
+  unsigned char a2h[HV][C4 / 8 * G::MNK], a2l[HV][C4 / 8 * G::MNK];   // GELU(D1): GEMM2 B operand, MN-major [C4/8][NPS/8][8 ch][8 px]
+  // GELU(dw): GEMM3 A operand (M = pixels), MN-major [C4/8][HV * A3B pixel blocks][8 ch][8 px]: the interior pixels of every half
+  // side by side, so ONE M = 128 MMA covers all halves (c = 16: rows 0..31 = half 0, 32..63 = half 1; the rest aliases, unused)
+  unsigned char a3h[C4 / 8 * HV * G::A3B * 128], a3l[C4 / 8 * HV * G::A3B * 128];
+  unsigned char tail[1536];                                   // GEMM3 reads 16 pixel blocks per channel block: it runs <= 1280 B over
 };
 
 template <int C, int NS>
@@ -137,9 +150,6 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   constexpr int C4 = 4 * C;
   constexpr int HV = 128 / C4;
   constexpr int NP = (C4 == 64) ? 40 : 48;           // MMA N of GEMM1 / GEMM2 (M = 128 needs a multiple of 16; columns >= 40 alias, unused)
-  constexpr int LPP = C / 4;                         // loader lanes per pixel (16 bytes each)
-  constexpr int PPP = 32 / LPP;                      // pixels per loader pass
-  constexpr int PASSES = (kIn + 2 + PPP - 1) / PPP;  // loader passes per half and row
   // Order of the epilogue phases.  LAG = 0: S_b(row) -> wait GEMM2(row) -> S_c(row).  LAG = 1 (c = 16): S_b(row) -> S_c(row - 1) -> wait
   // GEMM2(row): the latency of GEMM2 / GEMM1 hides under the depthwise stage of the previous row; needs a fourth hidden-row slot.
   constexpr int LAG = (C == 16) ? 1 : 0;
@@ -152,7 +162,9 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
   constexpr bool CONCAT = (C == 32);
   constexpr uint32_t D3W = CONCAT ? 2 * C : C;
   static_assert(D3_COL + NB3 * D3W <= 256, "TMEM columns of one stream");
-  constexpr uint32_t A3K = HV * 512;                 // bytes between 8-channel blocks of the A3 tile
+  using G = Geo<C>;
+  constexpr int kIn = G::KIN, kB1Stride = G::B1S, kMnK = G::MNK, CPW = G::CPW, NB1 = G::NB1;
+  constexpr uint32_t A3K = HV * G::A3B * 128;        // bytes between 8-channel blocks of the A3 tile
   using P = Pack<C>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<C, NS>& sm = *reinterpret_cast<Smem<C, NS>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -174,7 +186,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         mbar_init(&t.g3[b], 1);
         mbar_init(&t.empty[b], 1);
         mbar_init(&t.ready_b1[b], 3);
-        mbar_init(&t.d3_free[b], HV);
+        mbar_init(&t.d3_free[b], 2);
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -224,8 +236,8 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     uint32_t gi = 0, j3 = 0;          // running row index (B1 / flag buffer = gi & 1, hidden slot = gi % 3) and GEMM3 index (D3 buffer = j3 & 1)
     uint32_t ph_a2 = 0, ph_a3 = 0;
     auto issue_g1 = [&](uint32_t g) {
-      const uint32_t b = g & 1;
-      mbar_wait(&st.ready_b1[b], (g >> 1) & 1);
+      const uint32_t b = NB1 == 2 ? (g & 1) : 0;
+      mbar_wait(&st.ready_b1[b], NB1 == 2 ? (g >> 1) & 1 : g & 1);
       tc_fence_after();
       if (elect_one()) {
         constexpr uint32_t id = idesc(C4, NP, 0, 0);
@@ -245,6 +257,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           umma_f16(d, dsc(wb, P::o_w0b * 2, WK), dsc(sbf, o_b1f + h * 2 * kB1Stride, kB1Stride), id, 1);
         }
         umma_commit(&st.g1);
+        if (NB1 == 1) umma_commit(&st.empty[0]);      // single B1 buffer: free again once this GEMM1 (and everything before it) is done
       }
       __syncwarp();
     };
@@ -268,7 +281,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           umma_f16(d, dsc(wb, P::o_w1b * 2, WK), dsc(sbf, o_a2f + h * 2 * kMnK, kMnK), id, 1);
         }
         umma_commit(&st.g2);
-        umma_commit(&st.empty[b]);      // B1 / flag buffers of this row may be rewritten
+        if (NB1 == 2) umma_commit(&st.empty[b]);      // B1 / flag buffers of this row may be rewritten
       }
       __syncwarp();
     };
@@ -328,12 +341,17 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     constexpr int LQ = C / 16;                       // lanes per pixel
     const int chalf = lane % LQ;                     // 16-channel half of this lane
     const int h = (HV == 2) ? (li < 2 ? li : (lane >> 1) & 1) : 0;
-    const int pc = li < 2 ? ((HV == 2) ? lane : li * 16 + lane / LQ) : 32 + ((HV == 2) ? (lane & 1) : lane / LQ);
-    const bool lane_on = li < 2 || lane < 4;
-    const bool outw = li < HV;                       // this warp stores the output rows of half li
+    //   c = 16: warps 8 / 9 = pixel columns 0..31 of half 0 / 1, warp 11 lanes 0..3 = columns 32, 33 of both halves
+    //   c = 32: two lanes per pixel, 48 columns (46 interior + 2 halo): warp 8 = columns 0..15, warp 9 = 16..31, warp 11 = 32..47
+    const int pc = (HV == 2) ? (li < 2 ? lane : 32 + (lane & 1)) : li * 16 + lane / LQ;
+    const bool lane_on = HV == 1 || li < 2 || lane < 4;
+    const bool outw = li < 2;                        // warps 8 / 9 store the output rows: c = 16 of half li, c = 32 pixels 32 li .. 32 li + 31
     uint32_t gi = 0, j3 = 0;
-    // Output cursor (warps 8 / 9): rows are stored 3 + LAG loader iterations after their own: the loaders run at most two rows
-    // ahead of S_b (empty[] gate), so by then the row's GEMM3 has been issued and the wait below is short and cannot deadlock.
+    // Output cursor (warps 8 / 9): rows are stored OUTLAG = NB1 + 1 + LAG loader iterations after their own.  The loaders run at
+    // most NB1 rows ahead of S_b (empty[] gate), so by then the row's GEMM3 has been issued (short wait, no deadlock), and the
+    // lag is small enough that the issuer's wait for a free output accumulator never depends on a loader iteration that
+    // itself needs a later MMA.
+    constexpr int OUTLAG = NB1 + 1 + LAG;
     int o_grp = group0, o_it = 2;
     uint32_t o_gi = 2;                                // running row index of the next output row
     size_t o_off = 0;
@@ -344,9 +362,10 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       const bool uok = unit < total_units && o_grp < num_groups;
       const int ws = uok ? unit % nws : 0, t = uok ? unit / nws : 0;
       const int un = t / nbands, uy0 = (t % nbands) * band_rows, ux0 = ws * kIn;
-      o_col = uok && ux0 + lane < W;
+      const int opx = (HV == 2) ? lane : 32 * (li & 1) + lane;     // interior pixel of the segment = D3 row
+      o_col = uok && opx < min(kIn, W - ux0);
       o_rows = min(band_rows, H - uy0);
-      o_off = (((size_t)un * H + uy0) * W + ux0 + lane) * C;
+      o_off = (((size_t)un * H + uy0) * W + ux0 + opx) * C;
     };
     if (outw) out_geometry();
     auto out_step = [&]() {
@@ -400,7 +419,8 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     const uint32_t sa_f1 = smem_u32(&st.b1f[0][h][pc * 16]);
     const uint32_t sa_f2 = smem_u32(&st.a2f[0][h][(pc >> 3) * 128 + (pc & 7) * 2]);
     constexpr uint32_t DL = offsetof(Stream<C>, b1l) - offsetof(Stream<C>, b1h);     // b1h -> b1l
-    constexpr uint32_t BX = HV * (C / 8) * kB1Stride, BF1 = HV * 2 * kB1Stride, BF2 = HV * 2 * kMnK;   // buffer 0 -> 1
+    constexpr uint32_t BX = NB1 == 2 ? HV * (C / 8) * kB1Stride : 0, BF1 = NB1 == 2 ? HV * 2 * kB1Stride : 0;   // B1 buffer 0 -> 1
+    constexpr uint32_t BF2 = HV * 2 * kMnK;                                                                       // a2f buffer 0 -> 1
     const float* lnw = &sm.lng[16 * chalf];
     const float* lnb = &sm.lnb[16 * chalf];
     for (int grp = group0; grp < num_groups; grp += gstep) {
@@ -440,7 +460,11 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         if (LQ == 2) m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
         float rstd;
         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd) : "f"(fmaf(m2, 1.0f / C, kLnEps)));
-        if (gi >= 2) mbar_wait(&st.empty[b], ((gi - 2) >> 1) & 1);
+        if (NB1 == 2) {
+          if (gi >= 2) mbar_wait(&st.empty[b], ((gi - 2) >> 1) & 1);       // GEMM2 of row gi - 2 issued and done
+        } else {
+          if (gi >= 1) mbar_wait(&st.empty[0], (gi - 1) & 1);              // GEMM1 of row gi - 1 done (hence GEMM2 of row gi - 2 too)
+        }
         if (lane_on) {
           const uint32_t msk = ok ? 0xffffffffu : 0u;           // pixels outside the image / segment: exact zeros
           const uint32_t ax = sa_x + b * BX;
@@ -472,8 +496,8 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&st.ready_b1[b]);
-        if (outw && o_grp < num_groups && o_gi + 3 + LAG <= gi) out_step();
+        if (lane == 0) mbar_arrive(&st.ready_b1[NB1 == 2 ? b : 0]);
+        if (outw && o_grp < num_groups && o_gi + OUTLAG <= gi) out_step();
       }
     }
     if (outw)
@@ -485,11 +509,11 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
     const int k = (HV == 2) ? (16 * q + (lane & 15)) : (32 * q + lane);
     const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
     const uint32_t rowoff = (uint32_t)((k >> 3) * kMnK + (k & 7) * 16);
-    const uint32_t a2h = smem_u32(st.a2h[h]) + rowoff + 2 * ch * 128;      // this warp's first 8-pixel block of the row
-    const uint32_t a2l = smem_u32(st.a2l[h]) + rowoff + 2 * ch * 128;
-    const uint32_t rowoff3 = (uint32_t)((k >> 3) * A3K + h * 512 + (k & 7) * 16);
-    const uint32_t a3h = smem_u32(st.a3h) + rowoff3 + 2 * ch * 128;
-    const uint32_t a3l = smem_u32(st.a3l) + rowoff3 + 2 * ch * 128;
+    const uint32_t a2h = smem_u32(st.a2h[h]) + rowoff + CPW * ch * 128;    // this warp's first 8-pixel block of the row
+    const uint32_t a2l = smem_u32(st.a2l[h]) + rowoff + CPW * ch * 128;
+    const uint32_t rowoff3 = (uint32_t)((k >> 3) * A3K + h * (G::A3B * 128) + (k & 7) * 16);
+    const uint32_t a3h = smem_u32(st.a3h) + rowoff3 + CPW * ch * 128;
+    const uint32_t a3l = smem_u32(st.a3l) + rowoff3 + CPW * ch * 128;
     float2 wt[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -504,20 +528,20 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     };
-    const uint32_t d1a = tl + D1_COL + 16 * ch;            // this warp's 16 columns of D1 / of a hidden-row slot
+    const uint32_t d1a = tl + D1_COL + 8 * CPW * ch;       // this warp's 8 CPW columns of D1 / of a hidden-row slot
     for (int grp = group0; grp < num_groups; grp += gstep) {
       for (int it = 0; it < iters + LAG; ++it) {
         if (it < iters) {
           // ---- S_b: GELU(D1) -> A2 -----------------------------------------------------------------------------------------
           mbar_wait(&st.g1, ph1); ph1 ^= 1;
           tc_fence_after();
-          float2 acc[2][4], ex = make_float2(0.f, 0.f);
-          tmem_ld8(d1a, acc[0]);
-          tmem_ld8(d1a + 8, acc[1]);
-          if (ch == 1) tmem_ld2(d1a + 16, ex);
+          float2 acc[CPW][4], ex = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < CPW; ++c) tmem_ld8(d1a + 8 * c, acc[c]);
+          if (G::EXTRA && ch == 1) tmem_ld2(d1a + 8 * CPW, ex);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < CPW; ++c) {
             float2 v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[i] = gelu_pair(acc[c][i]);
@@ -526,13 +550,13 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
             sts128(a2h + c * 128, hi);
             sts128(a2l + c * 128, lo);
           }
-          if (ch == 1) {                                  // the two halo-side columns 32, 33
+          if (G::EXTRA && ch == 1) {                      // the two halo-side columns 32, 33
             const float2 v = gelu_pair(ex);
             const __half2 hh = __float22half2_rn(v);
             const float2 back = __half22float2(hh);
             const __half2 ll = __float22half2_rn(make_float2(v.x - back.x, v.y - back.y));
-            sts32(a2h + 2 * 128, *reinterpret_cast<const uint32_t*>(&hh));       // (ch = 1: block 4 of the row)
-            sts32(a2l + 2 * 128, *reinterpret_cast<const uint32_t*>(&ll));
+            sts32(a2h + CPW * 128, *reinterpret_cast<const uint32_t*>(&hh));     // (ch = 1: block 4 of the row)
+            sts32(a2l + CPW * 128, *reinterpret_cast<const uint32_t*>(&ll));
           }
           signal(&st.ready_a2);
           if (LAG == 0) {
@@ -549,8 +573,8 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) slot[dy] = d1a + (D2_COL - D1_COL) + ((r2 + dy) % NSLOT) * SLOT;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            // output columns 16 ch + 8 c .. + 7 (pixel columns + 1), inputs .. + 9
+          for (int c = 0; c < CPW; ++c) {
+            // output columns 8 CPW ch + 8 c .. + 7 (pixel columns + 1), inputs .. + 9
             float2 acc[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i] = make_float2(dwb, dwb);
@@ -602,6 +626,7 @@ static cudaError_t launch_t(const BlockW& w, const float* x, float* y, int N, in
   }
   constexpr int HV = 128 / (4 * C);
   const int streams = sm_count * 2;                     // resident streams on the device (2 CTAs x 1 or 1 CTA x 2 per SM)
+  constexpr int kIn = Geo<C>::KIN;
   const int nws = (W + kIn - 1) / kIn;
   int band_rows = 8;
   double best = 0.0;
