@@ -66,7 +66,9 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {     // a * con
 // tw[j] = e^{-2 pi i j / L}.  SIGN = -1 forward, +1 inverse (unnormalised).
 // Returns the buffer holding the result.  All threads of the CTA must call it.
 constexpr int kSeqPad = 2;
-template <int SIGN>
+// ANY = false: L is a power of two (radix-4 / radix-2 stages only; the hot instantiations);  ANY = true: also lengths with odd
+// factors (own kernel instantiations, so the generic stage's local array costs the power-of-two kernels nothing)
+template <int SIGN, bool ANY = false>
 __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int NF, int tid, int nthreads) {
   const int LS = L + kSeqPad;
   for (int Ns = 1; Ns < L;) {
@@ -95,7 +97,7 @@ __device__ float2* stockham(float2* a, float2* b, const float2* tw, int L, int N
         dst[3 * Ns] = make_float2(d02.x - jd.x, d02.y - jd.y);
       }
       Ns <<= 2;
-    } else if (rem & 1) {
+    } else if (ANY && (rem & 1)) {
       // odd factor (lengths that are not powers of two): one generic radix-R stage, R = smallest odd prime factor of rem;
       // the R-point DFT is evaluated directly (R <= 61 for lengths <= 1024 that are multiples of 16)
       int R = 3;
@@ -218,7 +220,7 @@ constexpr int kFftThreads = 256;
 // ---- pass 1: rows forward ----------------------------------------------------------------------------
 // NT threads per CTA: 256 on the compile-time fast paths; long rows (W >= 512) hold one row of 64-128 KB per CTA, i.e.
 // one CTA per SM, and use 512 / 1024 threads so that the SM still has 16 / 32 resident warps
-template <int C2, bool PRE_LN, int WCT, int ROWS, int NT = kFftThreads>
+template <int C2, bool PRE_LN, int WCT, int ROWS, int NT = kFftThreads, bool ANY = false>
 __global__ void __launch_bounds__(NT) fft_rows_fwd_kernel(const float* __restrict__ x, float2* __restrict__ spec,
                                                                    BlockW w, int Wrt) {
   const int W = WCT ? WCT : Wrt;                          // WCT != 0: compile-time row length (fast path)
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(NT) fft_rows_fwd_kernel(const float* __restric
   __syncthreads();
   const float2* res;
   if constexpr (WCT != 0) res = stockham_ct<WCT, NF, -1, NT, 1>(bufA, bufB, tw, tid);
-  else res = stockham<-1>(bufA, bufB, tw, W, NF, tid, NT);
+  else res = stockham<-1, ANY>(bufA, bufB, tw, W, NF, tid, NT);
   // split the packed transform: channel a = 2f (real part), b = 2f+1 (imag part)
   const int Wf = W / 2 + 1;
   float4* out = reinterpret_cast<float4*>(spec + row0 * Wf * C2);      // ROWS rows are contiguous in the spectrum
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_any_kernel(float2* __res
     bufA[l * LS + r] = (l < nl) ? base[(size_t)r * lanes_per_row + l] : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  float2* f = stockham<-1>(bufA, bufB, tw, H, Q, tid, kFftThreads);
+  float2* f = stockham<-1, true>(bufA, bufB, tw, H, Q, tid, kFftThreads);
   for (int id = tid; id < H * Q; id += kFftThreads) {
     const int l = id / H, ky = id - l * H;
     if (l >= nl) continue;
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_any_kernel(float2* __res
     f[l * LS + ky] = make_float2(re, im);
   }
   __syncthreads();
-  float2* g = stockham<+1>(f, f == bufA ? bufB : bufA, tw, H, Q, tid, kFftThreads);
+  float2* g = stockham<+1, true>(f, f == bufA ? bufB : bufA, tw, H, Q, tid, kFftThreads);
   for (int id = tid; id < H * Q; id += kFftThreads) {
     const int r = id / Q, l = id - r * Q;
     if (l < nl) base[(size_t)r * lanes_per_row + l] = g[l * LS + r];
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_any_kernel(float2* __res
 }
 
 // ---- pass 3: rows inverse (+ proj + residual) ------------------------------------------------------------
-template <int C2, bool PROJ, int WCT, int ROWS, int NT = kFftThreads>
+template <int C2, bool PROJ, int WCT, int ROWS, int NT = kFftThreads, bool ANY = false>
 __global__ void __launch_bounds__(NT) fft_rows_inv_kernel(const float2* __restrict__ spec,
                                                                    const float* __restrict__ local,
                                                                    const float* __restrict__ xres, float* __restrict__ y,
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(NT) fft_rows_inv_kernel(const float2* __restri
   __syncthreads();
   const float2* res;
   if constexpr (WCT != 0) res = stockham_ct<WCT, NF, +1, NT, 1>(bufA, bufB, tw, tid);
-  else res = stockham<+1>(bufA, bufB, tw, W, NF, tid, NT);
+  else res = stockham<+1, ANY>(bufA, bufB, tw, W, NF, tid, NT);
   for (int p = tid; p < ROWS * W; p += NT) {
     const int rl = p / W, px = p - rl * W;
     const size_t row = row0 + rl;
@@ -535,16 +537,23 @@ static bool len_ok(int v) { return v >= 8 && v <= kTwN && (v & 7) == 0; }
 // rows per CTA on the fast path: 16 complex sequences per CTA (C2=8: 4 rows, C2=16: 2 rows, C2=32: 1 row)
 template <int C2> constexpr int fast_rows() { return (16 / (C2 / 2)) > 0 ? 16 / (C2 / 2) : 1; }
 
-template <int C2, bool PRE_LN, int WCT, int ROWS, int NT = kFftThreads>
+template <int C2, bool PRE_LN, int WCT, int ROWS, int NT = kFftThreads, bool ANY = false>
 static cudaError_t rows_fwd_launch(const BlockW& w, const float* x, float* spec, int N, int H, int W, cudaStream_t s) {
   size_t smem = (size_t)(W + 2 * ROWS * (C2 / 2) * (W + kSeqPad)) * sizeof(float2);
-  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS, NT, ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS, NT><<<N * H / ROWS, NT, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
+  fft_rows_fwd_kernel<C2, PRE_LN, WCT, ROWS, NT, ANY><<<N * H / ROWS, NT, smem, s>>>(x, reinterpret_cast<float2*>(spec), w, W);
   return cudaGetLastError();
 }
 template <int C2>
 static cudaError_t rows_fwd_t(const BlockW& w, const float* x, float* spec, int pre_ln, int N, int H, int W, cudaStream_t s) {
+  if (W & (W - 1)) {                                       // row length with odd factors: generic radix stages
+    if (pre_ln) {
+      if (W >= 512) return rows_fwd_launch<C2, true, 0, 1, 512, true>(w, x, spec, N, H, W, s);
+      return rows_fwd_launch<C2, true, 0, 1, kFftThreads, true>(w, x, spec, N, H, W, s);
+    }
+    return rows_fwd_launch<C2, false, 0, 1, kFftThreads, true>(w, x, spec, N, H, W, s);
+  }
   if (pre_ln) {
     if (W == 256 && H % fast_rows<C2>() == 0) return rows_fwd_launch<C2, true, 256, fast_rows<C2>()>(w, x, spec, N, H, W, s);
     if (W == 128 && H % fast_rows<C2>() == 0) return rows_fwd_launch<C2, true, 128, fast_rows<C2>()>(w, x, spec, N, H, W, s);
@@ -621,6 +630,11 @@ static cudaError_t rows_inv_t(const BlockW& w, const float* spec, const float* l
     kern<<<N * H / fr, nt, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w, W, scale);
     return cudaGetLastError();
   };
+  if (W & (W - 1)) {                                       // row length with odd factors: generic radix stages
+    if (proj && W >= 512) return go(fft_rows_inv_kernel<C2, true, 0, 1, 512, true>, 512);
+    if (proj) return go(fft_rows_inv_kernel<C2, true, 0, 1, kFftThreads, true>);
+    return go(fft_rows_inv_kernel<C2, false, 0, 1, kFftThreads, true>);
+  }
   if (proj) {
     if (W == 256 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 256, 2>);
     if (W == 128 && fr > 1) return go(fft_rows_inv_kernel<C2, true, 128, 2>);
