@@ -477,12 +477,11 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
               const float4 u = v[2 * c8 + e];
               const float2 t0 = make_float2(fmaf(u.x * rstd, g.x, bb.x), fmaf(u.y * rstd, g.y, bb.y));
               const float2 t1 = make_float2(fmaf(u.z * rstd, g.z, bb.z), fmaf(u.w * rstd, g.w, bb.w));
-              const __half2 h0 = __float22half2_rn(t0), h1 = __float22half2_rn(t1);
-              const float2 k0 = __half22float2(h0), k1 = __half22float2(h1);
-              const __half2 l0 = __float22half2_rn(make_float2(t0.x - k0.x, t0.y - k0.y));
-              const __half2 l1 = __float22half2_rn(make_float2(t1.x - k1.x, t1.y - k1.y));
-              hi[2 * e] = *reinterpret_cast<const uint32_t*>(&h0) & msk; hi[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&h1) & msk;
-              lo[2 * e] = *reinterpret_cast<const uint32_t*>(&l0) & msk; lo[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&l1) & msk;
+              const uint32_t h0 = f2h2_sat(t0), h1 = f2h2_sat(t1);
+              const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+              hi[2 * e] = h0 & msk; hi[2 * e + 1] = h1 & msk;
+              lo[2 * e] = f2h2_sat(make_float2(t0.x - k0.x, t0.y - k0.y)) & msk;
+              lo[2 * e + 1] = f2h2_sat(make_float2(t1.x - k1.x, t1.y - k1.y)) & msk;
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ax + c8 * kB1Stride), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ax + c8 * kB1Stride + DL), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
@@ -552,11 +551,10 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
           }
           if (G::EXTRA && ch == 1) {                      // the two halo-side columns 32, 33
             const float2 v = gelu_pair(ex);
-            const __half2 hh = __float22half2_rn(v);
-            const float2 back = __half22float2(hh);
-            const __half2 ll = __float22half2_rn(make_float2(v.x - back.x, v.y - back.y));
-            sts32(a2h + CPW * 128, *reinterpret_cast<const uint32_t*>(&hh));     // (ch = 1: block 4 of the row)
-            sts32(a2l + CPW * 128, *reinterpret_cast<const uint32_t*>(&ll));
+            const uint32_t hh = f2h2_sat(v);
+            const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+            sts32(a2h + CPW * 128, hh);                                          // (ch = 1: block 4 of the row)
+            sts32(a2l + CPW * 128, f2h2_sat(make_float2(v.x - back.x, v.y - back.y)));
           }
           signal(&st.ready_a2);
           if (LAG == 0) {

@@ -101,15 +101,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ull << 46);
 }
 __host__ __device__ constexpr uint32_t umma_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+// fp32 pair -> packed fp16 pair, round to nearest, SATURATING at +-65504 (one F2FP.SATFINITE): a value beyond the fp16 range
+// degrades to a finite, wrong product instead of the inf - inf = NaN that would poison every pixel the GEMM row touches
+__device__ __forceinline__ uint32_t f2h2_sat(float2 v) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));
+  return r;
+}
 __device__ __forceinline__ void split8(const float2 (&v)[4], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __half2 hh = __float22half2_rn(v[i]);
-    float2 back = __half22float2(hh);
-    __half2 ll = __float22half2_rn(__fadd2_rn(v[i], make_float2(-back.x, -back.y)));
-    h[i] = *reinterpret_cast<uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<uint32_t*>(&ll);
+    h[i] = f2h2_sat(v[i]);
+    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+    l[i] = f2h2_sat(__fadd2_rn(v[i], make_float2(-back.x, -back.y)));
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

@@ -539,6 +539,23 @@ def test_window_msa_variants_match_the_oracle():
         assert diff <= 2e-5, (mode, diff)
 
 
+def test_ffn_split_operands_saturate_instead_of_nan(abi):
+    """The fp16 hi/lo split of the tensor-core operands saturates at +-65504 (F2FP.SATFINITE): hidden activations beyond the
+    fp16 range give a finite (inexact) result, never inf - inf = NaN spread over a GEMM row.  Weights scaled so that the
+    first 1x1 conv of one block produces ~1e6."""
+    sd = {k: v.clone() for k, v in load_weights(4).items()}
+    key = PRIOR + ".encoder_layers.0.0.blocks.0.1.fn.fn.net.0.weight"
+    sd[key] = sd[key] * 2e5                     # |w| up to 5e4: representable in fp16, the products (~2e5) are not
+    h = abi.Handle(0, 4, 2)
+    h.load_weights({k: v.cuda().contiguous() for k, v in sd.items()})
+    x = torch.randn(1, 32, 32, 16, generator=torch.Generator().manual_seed(1)).cuda()
+    y = torch.empty_like(x)
+    h.op("ffn", 1, 0, 0, x.data_ptr(), y.data_ptr(), 1, 32, 32)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    h.close()
+
+
 def test_ffn_variants_match_the_oracle():
     """The three forms of the conv-FFN (LGTEUN_FFN unset = channels-on-lanes tcgen05 kernel ffn_cl.cu, tc = pixels-on-lanes
     tcgen05 kernel ffn_tc.cu, simt = CUDA cores) against the oracle at the operator tolerance, in child processes, on
