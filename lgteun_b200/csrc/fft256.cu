@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
     tc_fence_before();
     if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
-    if ((tid & 127) == 0) {
+    if ((warp & 3) == 0 && elect_one()) {     // one lane of the tile's first warp (elect.sync: no divergence loop around the MMAs)
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc(C);
       const uint32_t ab = smem_u32(a_hi);
