@@ -145,7 +145,7 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {              // (elect.sync: ptxas emits the MMAs back to back, no divergence loop)
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc(kNS);
         const uint32_t d = tmem + ns * kNS;
@@ -208,10 +208,14 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-// ---- depthwise 3x3 (+bias, zero pad) + GELU on an NHWC map, 4 channels per thread (HBM-bound) ---------------------------
+// ---- depthwise 3x3 (+bias, zero pad) + GELU on an NHWC map (HBM-bound) ------------------------------------------------------
+// thread = (4 consecutive pixels of a row, 4 channels): a sliding 3 x 6 window of float4 feeds four outputs, i.e. 4.5 loads per
+// output vector instead of 9 and one set of tap loads per four pixels (the one-pixel-per-thread form was bound by the L1 data
+// pipe: 574 us per 134 M-element map)
+constexpr int kDwPx = 4;
 __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ hid, float* __restrict__ act,
                                                            const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                                                           int H, int W, int C4, long long total_vec) {
+                                                           int H, int W, int C4, long long total_items) {
   extern __shared__ __align__(16) float s_dw[];     // [9][C4] taps then [C4] bias
   for (int i = threadIdx.x; i < C4; i += 256) {
 #pragma unroll
@@ -220,33 +224,49 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
   }
   __syncthreads();
   const long long v = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (v >= total_vec) return;
+  if (v >= total_items) return;
   const int vecs = C4 / 4;
   const int c = (int)(v % vecs) * 4;
-  const long long pix = v / vecs;
-  const int x = (int)(pix % W);
-  const long long t = pix / W;
+  const long long seg = v / vecs;                   // segment of kDwPx pixels
+  const int segs = (W + kDwPx - 1) / kDwPx;
+  const int x0 = (int)(seg % segs) * kDwPx;
+  const long long t = seg / segs;
   const int y = (int)(t % H);
   const long long n = t / H;
-  float4 b = *reinterpret_cast<const float4*>(s_dw + 9 * C4 + c);
-  float2 a0 = make_float2(b.x, b.y), a1 = make_float2(b.z, b.w);
+  const float4 b = *reinterpret_cast<const float4*>(s_dw + 9 * C4 + c);
+  float2 a0[kDwPx], a1[kDwPx];
+#pragma unroll
+  for (int i = 0; i < kDwPx; ++i) { a0[i] = make_float2(b.x, b.y); a1[i] = make_float2(b.z, b.w); }
 #pragma unroll
   for (int dy = -1; dy <= 1; ++dy) {
     const int yy = y + dy;
     if (yy < 0 || yy >= H) continue;
+    const float* rowp = hid + ((n * H + yy) * W) * (long long)C4 + c;
+    float4 wv[3];
 #pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int xx = x + dx;
+    for (int dx = 0; dx < 3; ++dx) wv[dx] = *reinterpret_cast<const float4*>(s_dw + ((dy + 1) * 3 + dx) * C4 + c);
+#pragma unroll
+    for (int j = 0; j < kDwPx + 2; ++j) {           // input column x0 - 1 + j feeds outputs j - 2 .. j
+      const int xx = x0 - 1 + j;
       if (xx < 0 || xx >= W) continue;
-      const float4 hv = __ldg(reinterpret_cast<const float4*>(hid + ((n * H + yy) * W + xx) * C4 + c));
-      const float4 wv = *reinterpret_cast<const float4*>(s_dw + ((dy + 1) * 3 + dx + 1) * C4 + c);
-      a0 = __ffma2_rn(make_float2(wv.x, wv.y), make_float2(hv.x, hv.y), a0);
-      a1 = __ffma2_rn(make_float2(wv.z, wv.w), make_float2(hv.z, hv.w), a1);
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(rowp + (long long)xx * C4));
+      const float2 h0 = make_float2(hv.x, hv.y), h1 = make_float2(hv.z, hv.w);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int o = j - dx;                       // output pixel x0 + o reads column x0 + o - 1 + dx
+        if (o >= 0 && o < kDwPx) {
+          a0[o] = __ffma2_rn(make_float2(wv[dx].x, wv[dx].y), h0, a0[o]);
+          a1[o] = __ffma2_rn(make_float2(wv[dx].z, wv[dx].w), h1, a1[o]);
+        }
+      }
     }
   }
-  a0 = gelu_pair(a0);
-  a1 = gelu_pair(a1);
-  *reinterpret_cast<float4*>(act + pix * C4 + c) = make_float4(a0.x, a0.y, a1.x, a1.y);
+#pragma unroll
+  for (int i = 0; i < kDwPx; ++i) {
+    if (x0 + i >= W) continue;
+    const float2 g0 = gelu_pair(a0[i]), g1 = gelu_pair(a1[i]);
+    *reinterpret_cast<float4*>(act + (((n * H + y) * W) + x0 + i) * (long long)C4 + c) = make_float4(g0.x, g0.y, g1.x, g1.y);
+  }
 }
 
 template <int K, int N, int PRO, int EPI>
@@ -264,7 +284,17 @@ static cudaError_t pwgemm_launch(const float* A, float* Out, const void* wpack, 
   const size_t smem = 16 + (size_t)N * 4 + (size_t)(2 * 128 * K + 2 * NS * K) * 2 + 128;
   cudaError_t e = cudaFuncSetAttribute(pwgemm_tc_kernel<K, N, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int grid = tiles < sm_count ? tiles : sm_count;
+  // persistent grid: as many CTAs per SM as shared memory and the TMEM columns (N rounded up to a power of two, 512 per SM) allow
+  static int per_sm = 0;
+  if (!per_sm) {
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pwgemm_tc_kernel<K, N, PRO, EPI>, kPwThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    constexpr int tcols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+    per_sm = occ < 512 / tcols ? occ : 512 / tcols;
+    if (per_sm > 4) per_sm = 4;
+  }
+  const int cap = sm_count * per_sm;
+  const int grid = tiles < cap ? tiles : cap;
   pwgemm_tc_kernel<K, N, PRO, EPI><<<grid, kPwThreads, smem, s>>>(A, Out, reinterpret_cast<const __half*>(wpack), bias, ln_g,
                                                                   ln_b, resid, total_px, tiles, scale_dev);
   return cudaGetLastError();
@@ -488,7 +518,7 @@ cudaError_t launch_ffn_wide_tc(const BlockW& w, const float* x, float* buf_a, fl
   if (e != cudaSuccess) return e;
   e = pwgemm_launch<C4, C4, PRO_PLAIN, EPI_BIAS>(buf_a, buf_b, pack + 2 * s0, w.f1_b, nullptr, nullptr, nullptr, px, s);
   if (e != cudaSuccess) return e;
-  const long long vec = px * (C4 / 4);
+  const long long vec = (long long)N * H * ((W + kDwPx - 1) / kDwPx) * (C4 / 4);
   dwconv_gelu_kernel<<<(unsigned)((vec + 255) / 256), 256, 10 * C4 * sizeof(float), s>>>(buf_b, buf_a, w.dw_w, w.dw_b, H, W, C4, vec);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
