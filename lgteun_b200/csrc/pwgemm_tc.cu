@@ -48,9 +48,12 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
   float* sbias = reinterpret_cast<float*>(smem_raw + 16);                       // [N]
-  __half* ah = reinterpret_cast<__half*>(smem_raw + 16 + N * 4);                // [KC][128][8]
-  __half* al = ah + 128 * K;
-  __half* wh = al + 128 * K;                                                    // [KC][kNS][8]
+  // A tile: [KC][128 rows][8] with the chunk stride padded by 16 bytes (LBO of the descriptor): the staging below stores 8-byte
+  // pieces of 16 consecutive chunks from one half-warp, and 2048-byte strides would put them all on the same banks
+  constexpr int LBO = 128 * 16 + 16;
+  unsigned char* ah = smem_raw + 16 + N * 4 + ((16 - (N * 4) % 16) % 16);      // [KC][LBO]
+  unsigned char* al = ah + KC * LBO;
+  __half* wh = reinterpret_cast<__half*>(al + KC * LBO);                        // [KC][kNS][8]
   __half* wl = wh + kNS * K;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;                                     // TMEM lane quarter / column half
@@ -74,57 +77,56 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const long long p = (long long)tile * 128 + row;
     const bool live = p < total_px;
-    // ---- prologue: this thread converts channels [half*K/2, (half+1)*K/2) of its pixel ------------------------------
+    // ---- prologue: the tile is ONE contiguous block of 128 x K floats; every warp instruction loads 512 contiguous bytes
+    // (lane = 16-byte piece; the thread-per-pixel form touched 32 rows per instruction and was bound by the L1 data pipe),
+    // converts its four channels to fp16 hi / lo and stores two 8-byte pieces into the K-major core-matrix layout ------------
     {
-      const float* src = A + p * K;
-      float mean = 0.f, rstd = 1.f;
-      if constexpr (PRO == PRO_LN) {
-        float s = 0.f, ss = 0.f;
-        if (live) {
-#pragma unroll 4
-          for (int c = 0; c < K; c += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(src + c));
-            s += (t.x + t.y) + (t.z + t.w);
-          }
-          mean = s * (1.0f / K);
-#pragma unroll 4
-          for (int c = 0; c < K; c += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(src + c));
-            const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
-            ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-          }
-          rstd = 1.0f / sqrtf(ss * (1.0f / K) + kLnEps);
-        }
-      }
-#pragma unroll 2
-      for (int kc = half * (KC / 2); kc < (half + 1) * (KC / 2); ++kc) {
-        float2 v[4];
-        if (live) {
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kc * 8));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kc * 8 + 4));
-          v[0] = make_float2(t0.x, t0.y); v[1] = make_float2(t0.z, t0.w);
-          v[2] = make_float2(t1.x, t1.y); v[3] = make_float2(t1.z, t1.w);
-          if constexpr (PRO == PRO_LN) {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(ln_g + kc * 8)), g1 = __ldg(reinterpret_cast<const float4*>(ln_g + kc * 8 + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ln_b + kc * 8)), b1 = __ldg(reinterpret_cast<const float4*>(ln_b + kc * 8 + 4));
-            v[0] = make_float2((v[0].x - mean) * rstd * g0.x + b0.x, (v[0].y - mean) * rstd * g0.y + b0.y);
-            v[1] = make_float2((v[1].x - mean) * rstd * g0.z + b0.z, (v[1].y - mean) * rstd * g0.w + b0.w);
-            v[2] = make_float2((v[2].x - mean) * rstd * g1.x + b1.x, (v[2].y - mean) * rstd * g1.y + b1.y);
-            v[3] = make_float2((v[3].x - mean) * rstd * g1.z + b1.z, (v[3].y - mean) * rstd * g1.w + b1.w);
-          }
-          if constexpr (PRO == PRO_GELU) {
+      constexpr int F4 = K / 4;                                                  // float4 pieces per pixel row
+      constexpr int PER = 128 * F4 / kPwThreads;                                 // pieces per thread
+      constexpr int UB = PER < 8 ? PER : 8;                                      // loads in flight per batch
+      static_assert(128 * F4 % kPwThreads == 0 && PER % UB == 0, "tile / thread shape");
+      static_assert(PRO != PRO_LN || F4 <= 32, "the LayerNorm prologue reduces over the lanes of one warp");
+      const long long px0 = (long long)tile * 128;
+      const int live_rows = (int)((total_px - px0 < 128) ? (total_px - px0) : 128);
+      const float4* src = reinterpret_cast<const float4*>(A + px0 * K);
+#pragma unroll 1
+      for (int i0 = 0; i0 < PER; i0 += UB) {
+        float4 t[UB];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = gelu_pair(v[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = make_float2(v[i].x * a_scale, v[i].y * a_scale);
-        } else {
-          v[0] = v[1] = v[2] = v[3] = make_float2(0.f, 0.f);
+        for (int u = 0; u < UB; ++u) {
+          const int i = (i0 + u) * kPwThreads + tid;
+          t[u] = (i / F4 < live_rows) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        uint4 hi, lo;
-        split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(ah + (kc * 128 + row) * 8) = hi;
-        *reinterpret_cast<uint4*>(al + (kc * 128 + row) * 8) = lo;
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int i = (i0 + u) * kPwThreads + tid;
+          const int r = i / F4, c = i - r * F4;
+          float2 v0 = make_float2(t[u].x, t[u].y), v1 = make_float2(t[u].z, t[u].w);
+          if constexpr (PRO == PRO_LN) {                                         // the F4 lanes of a pixel are neighbours in the warp
+            float sum = (v0.x + v0.y) + (v1.x + v1.y);
+#pragma unroll
+            for (int o = 1; o < F4; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum * (1.0f / K);
+            const float d0 = v0.x - mean, d1 = v0.y - mean, d2 = v1.x - mean, d3 = v1.y - mean;
+            float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+            for (int o = 1; o < F4; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float rstd = 1.0f / sqrtf(ss * (1.0f / K) + kLnEps);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g) + c), bb = __ldg(reinterpret_cast<const float4*>(ln_b) + c);
+            v0 = make_float2(d0 * rstd * g.x + bb.x, d1 * rstd * g.y + bb.y);
+            v1 = make_float2(d2 * rstd * g.z + bb.z, d3 * rstd * g.w + bb.w);
+            if (r >= live_rows) v0 = v1 = make_float2(0.f, 0.f);
+          }
+          if constexpr (PRO == PRO_GELU) { v0 = gelu_pair(v0); v1 = gelu_pair(v1); }
+          v0 = make_float2(v0.x * a_scale, v0.y * a_scale);
+          v1 = make_float2(v1.x * a_scale, v1.y * a_scale);
+          const uint32_t h0 = f2h2_sat(v0), h1 = f2h2_sat(v1);
+          const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+          const uint32_t l0 = f2h2_sat(make_float2(v0.x - k0.x, v0.y - k0.y)), l1 = f2h2_sat(make_float2(v1.x - k1.x, v1.y - k1.y));
+          const int off = (c >> 1) * LBO + r * 16 + (c & 1) * 8;
+          *reinterpret_cast<uint2*>(ah + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(al + off) = make_uint2(l0, l1);
+        }
       }
     }
     // ---- main loop over weight slices ------------------------------------------------------------------------------------
@@ -151,8 +153,8 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
         const uint32_t d = tmem + ns * kNS;
 #pragma unroll
         for (int ks = 0; ks < K / 16; ++ks) {
-          const uint64_t dah = umma_desc(a_h + ks * 2 * 128 * 16, 128 * 16, 128);
-          const uint64_t dal = umma_desc(a_l + ks * 2 * 128 * 16, 128 * 16, 128);
+          const uint64_t dah = umma_desc(a_h + ks * 2 * LBO, LBO, 128);
+          const uint64_t dal = umma_desc(a_l + ks * 2 * LBO, LBO, 128);
           const uint64_t dbh = umma_desc(w_h + ks * 2 * kNS * 16, kNS * 16, 128);
           const uint64_t dbl = umma_desc(w_l + ks * 2 * kNS * 16, kNS * 16, 128);
           umma_f16(d, dah, dbh, idesc, ks > 0);
@@ -281,7 +283,7 @@ static cudaError_t pwgemm_launch(const float* A, float* Out, const void* wpack, 
   }
   const int tiles = (int)((total_px + 127) / 128);
   constexpr int NS = N < kNS ? N : kNS;
-  const size_t smem = 16 + (size_t)N * 4 + (size_t)(2 * 128 * K + 2 * NS * K) * 2 + 128;
+  const size_t smem = 16 + (size_t)N * 4 + 16 + (size_t)2 * (K / 8) * (128 * 16 + 16) + (size_t)(2 * NS * K) * 2 + 128;
   cudaError_t e = cudaFuncSetAttribute(pwgemm_tc_kernel<K, N, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // one persistent CTA per SM (measured: two co-resident CTAs of the K = 64 variant are 5 % slower, the prologue is bound by the L1 data pipe)
