@@ -16,6 +16,7 @@
 // B (weights, pre-packed hi/lo at load time) is streamed in slices of 64 output channels; every slice issues
 // hi*hi + hi*lo + lo*hi into its 64 TMEM columns (fp32 accumulate).  See ffn_tc.cu for the descriptor formats.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -210,6 +211,260 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+// ---- the same GEMM as a warp-specialised pipeline ---------------------------------------------------------------------------
+// pwgemm_tc_kernel above runs the phases of a tile one after the other (stage A, per slice: stage W, MMAs, wait; epilogue) on one
+// CTA per SM: 7-11 % issue utilisation, 15-28 % of the DRAM peak.  Here the phases overlap:
+//   6 loader warps   stage the A operand (coalesced 16-byte pieces -> fp16 hi / lo, K-major, padded chunk stride) in STAGES of
+//                    KS = K (K <= 128) or K / 2 channels, two stage buffers: the next stage / tile loads under the MMAs
+//   1 producer lane  streams the weight slice of every (K stage, 64 output columns) with cp.async.bulk into two buffers
+//   1 issuer lane    (elect.sync) issues the MMAs of a (K stage, slice) as soon as both operands are there and commits the
+//                    buffers back; the accumulator of a tile is one of TWO TMEM buffers of N columns
+//   4 epilogue warps read the finished accumulator (thread = pixel row), apply bias / GELU / residual / gate and store, under
+//                    the next tile's MMAs
+namespace pipe {
+constexpr int kThreads = 384;
+constexpr int kLoaders = 192;                    // warps 4 .. 9
+constexpr int kLBO = 128 * 16 + 16;              // padded K-chunk stride of the A stages
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+template <int K, int N>
+struct Plan {
+  static constexpr int NSW = N < lg::kNS ? N : lg::kNS;         // output columns per weight slice
+  static constexpr int KS = K > 128 ? K / 2 : K;                // channels per A / W stage
+  static constexpr int NKH = K / KS;
+  static constexpr int A_STAGE = 2 * (KS / 8) * kLBO;           // hi + lo
+  static constexpr int W_STAGE = 2 * (KS / 8) * NSW * 16;       // hi + lo
+  static constexpr int TCOLS = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
+  static constexpr size_t smem = 128 + (size_t)N * 4 + 2 * (size_t)A_STAGE + 2 * (size_t)W_STAGE + 128;
+};
+}  // namespace pipe
+
+template <int K, int N, int PRO, int EPI>
+__global__ void __launch_bounds__(pipe::kThreads, 1)
+pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const __half* __restrict__ wpack,
+                   const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                   const float* __restrict__ resid, long long total_px, int num_tiles, const float* __restrict__ scale_dev) {
+  using namespace pw;
+  using PL = pipe::Plan<K, N>;
+  constexpr int NSW = PL::NSW, KS = PL::KS, NKH = PL::NKH, NSL = N / NSW, LBO = pipe::kLBO;
+  static_assert(K % 16 == 0 && KS % 16 == 0 && N % NSW == 0 && N % 16 == 0 && N <= 256, "tile shape");
+  static_assert(PRO != PRO_LN || (NKH == 1 && K / 4 <= 32), "the LayerNorm prologue needs the whole pixel row in one stage, within one warp");
+  const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base);                          // a_full[2] a_empty[2] w_full[2] w_empty[2] acc_full[2] acc_empty[2]
+  uint64_t *a_full = bars, *a_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *acc_full = bars + 8, *acc_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 96);
+  float* sbias = reinterpret_cast<float*>(base + 128);                         // [N]
+  unsigned char* a_st = base + 128 + N * 4;                                    // two A stages: [hi | lo][KS/8][LBO]
+  unsigned char* w_st = a_st + 2 * PL::A_STAGE;                                // two W stages: [hi | lo][KS/8][NSW][16 B]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a_full[b], pipe::kLoaders / 32);
+      mbar_init(&a_empty[b], 1);
+      mbar_init(&w_full[b], 1);
+      mbar_init(&w_empty[b], 1);
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 2 * PL::TCOLS);
+  for (int i = tid; i < N; i += pipe::kThreads) sbias[i] = bias ? __ldg(bias + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp >= 4 && warp < 10) {
+    // ---- loaders: A stages ---------------------------------------------------------------------------------------------------
+    const int ltid = tid - 128;
+    constexpr int F4 = K / 4;                                                    // float4 pieces per pixel row
+    constexpr int F4S = KS / 4;                                                  // ... of one stage
+    constexpr int TOT = 128 * F4S;                                               // pieces per stage
+    constexpr int UB = 8;
+    uint32_t sa = 0;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const long long px0 = ((long long)blockIdx.x + (long long)lt * gridDim.x) * 128;
+      const int live_rows = (int)((total_px - px0 < 128) ? (total_px - px0) : 128);
+      const float4* src = reinterpret_cast<const float4*>(A + px0 * K);
+      for (int kh = 0; kh < NKH; ++kh, ++sa) {
+        const uint32_t buf = sa & 1;
+        unsigned char* ah = a_st + buf * PL::A_STAGE;
+        unsigned char* al = ah + (KS / 8) * LBO;
+        if (sa >= 2) mbar_wait(&a_empty[buf], ((sa >> 1) - 1) & 1);
+#pragma unroll 1
+        for (int i0 = ltid; i0 < TOT; i0 += UB * pipe::kLoaders) {
+          float4 t[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int i = i0 + u * pipe::kLoaders;
+            const int r = i / F4S, c = i - r * F4S;
+            t[u] = (i < TOT && r < live_rows) ? __ldg(src + r * F4 + kh * F4S + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int i = i0 + u * pipe::kLoaders;
+            if (i - lane >= TOT) continue;                                      // warp-uniform: a warp's 32 pieces are consecutive, TOT is a multiple of 32
+            const int r = i / F4S, c = i - r * F4S;
+            float2 v0 = make_float2(t[u].x, t[u].y), v1 = make_float2(t[u].z, t[u].w);
+            if constexpr (PRO == PRO_LN) {                                       // the F4 lanes of a pixel are neighbours in the warp
+              float sum = (v0.x + v0.y) + (v1.x + v1.y);
+#pragma unroll
+              for (int o = 1; o < F4; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+              const float mean = sum * (1.0f / K);
+              const float d0 = v0.x - mean, d1 = v0.y - mean, d2 = v1.x - mean, d3 = v1.y - mean;
+              float ss = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+              for (int o = 1; o < F4; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+              const float rstd = 1.0f / sqrtf(ss * (1.0f / K) + kLnEps);
+              const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g) + c), bb = __ldg(reinterpret_cast<const float4*>(ln_b) + c);
+              v0 = make_float2(d0 * rstd * g.x + bb.x, d1 * rstd * g.y + bb.y);
+              v1 = make_float2(d2 * rstd * g.z + bb.z, d3 * rstd * g.w + bb.w);
+              if (r >= live_rows) v0 = v1 = make_float2(0.f, 0.f);
+            }
+            if constexpr (PRO == PRO_GELU) { v0 = gelu_pair(v0); v1 = gelu_pair(v1); }
+            v0 = make_float2(v0.x * a_scale, v0.y * a_scale);
+            v1 = make_float2(v1.x * a_scale, v1.y * a_scale);
+            const uint32_t h0 = f2h2_sat(v0), h1 = f2h2_sat(v1);
+            const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+            const uint32_t l0 = f2h2_sat(make_float2(v0.x - k0.x, v0.y - k0.y)), l1 = f2h2_sat(make_float2(v1.x - k1.x, v1.y - k1.y));
+            const int off = (c >> 1) * LBO + r * 16 + (c & 1) * 8;
+            *reinterpret_cast<uint2*>(ah + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(al + off) = make_uint2(l0, l1);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[buf]);
+      }
+    }
+  } else if (warp == 10) {
+    // ---- weight producer: one lane, cp.async.bulk of 1 KB rows (64 output columns x 16 bytes of one K chunk) ------------------
+    if (lane == 0) {
+      uint32_t sw = 0;
+      const unsigned char* gw = reinterpret_cast<const unsigned char*>(wpack);
+      constexpr uint32_t row_bytes = NSW * 16, stage_bytes = 2 * (KS / 8) * row_bytes;
+      for (int lt = 0; lt < my_tiles; ++lt)
+        for (int kh = 0; kh < NKH; ++kh)
+          for (int ns = 0; ns < NSL; ++ns, ++sw) {
+            const uint32_t buf = sw & 1;
+            if (sw >= 2) mbar_wait(&w_empty[buf], ((sw >> 1) - 1) & 1);
+            const uint32_t dst = smem_u32(w_st + buf * PL::W_STAGE);
+            pipe::mbar_expect_tx(&w_full[buf], stage_bytes);
+#pragma unroll 1
+            for (int c = 0; c < KS / 8; ++c) {
+              const size_t goff = ((size_t)(kh * (KS / 8) + c) * N + (size_t)ns * NSW) * 16;
+              pipe::bulk_g2s(dst + c * row_bytes, gw + goff, row_bytes, &w_full[buf]);
+              pipe::bulk_g2s(dst + (KS / 8) * row_bytes + c * row_bytes, gw + (size_t)N * K * 2 + goff, row_bytes, &w_full[buf]);
+            }
+          }
+    }
+  } else if (warp == 11) {
+    // ---- MMA issuer -------------------------------------------------------------------------------------------------------------
+    uint32_t sa = 0, sw = 0;
+    const uint32_t a0 = smem_u32(a_st) >> 4, w0 = smem_u32(w_st) >> 4;
+    constexpr uint32_t HI = (128u >> 4) | (1u << 14);
+    auto dsc = [&](uint32_t base16, uint32_t byte_off, uint32_t lbo) -> uint64_t {
+      return (uint64_t)(base16 + (byte_off >> 4) + ((lbo >> 4) << 16)) | ((uint64_t)HI << 32);
+    };
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const uint32_t ab = lt & 1;
+      if (lt >= 2) {
+        mbar_wait(&acc_empty[ab], ((lt >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      for (int kh = 0; kh < NKH; ++kh, ++sa) {
+        const uint32_t abuf = sa & 1;
+        mbar_wait(&a_full[abuf], (sa >> 1) & 1);
+        for (int ns = 0; ns < NSL; ++ns, ++sw) {
+          const uint32_t wbuf = sw & 1;
+          mbar_wait(&w_full[wbuf], (sw >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc(NSW);
+            const uint32_t d = tmem + ab * PL::TCOLS + ns * NSW;
+            const uint32_t ah = a0 + ((abuf * PL::A_STAGE) >> 4), al = ah + (((KS / 8) * LBO) >> 4);
+            const uint32_t wh = w0 + ((wbuf * PL::W_STAGE) >> 4), wl = wh + (((KS / 8) * NSW * 16) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < KS / 16; ++ks) {
+              const uint64_t dah = dsc(ah, ks * 2 * LBO, LBO), dal = dsc(al, ks * 2 * LBO, LBO);
+              const uint64_t dbh = dsc(wh, ks * 2 * NSW * 16, NSW * 16), dbl = dsc(wl, ks * 2 * NSW * 16, NSW * 16);
+              umma_f16(d, dah, dbh, idesc, (kh > 0 || ks > 0) ? 1u : 0u);
+              umma_f16(d, dah, dbl, idesc, 1);
+              umma_f16(d, dal, dbh, idesc, 1);
+            }
+            umma_commit(&w_empty[wbuf]);
+            if (ns == NSL - 1) {
+              umma_commit(&a_empty[abuf]);
+              if (kh == NKH - 1) umma_commit(&acc_full[ab]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ---- epilogue: thread = pixel row of the finished accumulator --------------------------------------------------------------
+    const int row = warp * 32 + lane;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const uint32_t ab = lt & 1;
+      const long long p = ((long long)blockIdx.x + (long long)lt * gridDim.x) * 128 + row;
+      const bool live = p < total_px;
+      mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem + ab * PL::TCOLS + ((uint32_t)(warp * 32) << 16);
+      float* dst = Out + p * N;
+      const float* res = (EPI == EPI_BIAS_RESID || EPI == EPI_GATE) ? resid + p * N : nullptr;
+#pragma unroll 2
+      for (int c0 = 0; c0 < N; c0 += 8) {
+        float2 v[4];
+        tmem_ld8(lane_addr + c0, v);
+        tmem_ld_wait();
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 4);
+        v[0] = __ffma2_rn(v[0], make_float2(inv_scale, inv_scale), make_float2(b0.x, b0.y));
+        v[1] = __ffma2_rn(v[1], make_float2(inv_scale, inv_scale), make_float2(b0.z, b0.w));
+        v[2] = __ffma2_rn(v[2], make_float2(inv_scale, inv_scale), make_float2(b1.x, b1.y));
+        v[3] = __ffma2_rn(v[3], make_float2(inv_scale, inv_scale), make_float2(b1.z, b1.w));
+        if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = gelu_pair(v[i]);
+        }
+        if (live) {
+          if constexpr (EPI == EPI_BIAS_RESID) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+            v[0] = __fadd2_rn(v[0], make_float2(r0.x, r0.y)); v[1] = __fadd2_rn(v[1], make_float2(r0.z, r0.w));
+            v[2] = __fadd2_rn(v[2], make_float2(r1.x, r1.y)); v[3] = __fadd2_rn(v[3], make_float2(r1.z, r1.w));
+          }
+          if constexpr (EPI == EPI_GATE) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+            v[0] = make_float2(v[0].x * gelu_grad_exact(r0.x), v[0].y * gelu_grad_exact(r0.y));
+            v[1] = make_float2(v[1].x * gelu_grad_exact(r0.z), v[1].y * gelu_grad_exact(r0.w));
+            v[2] = make_float2(v[2].x * gelu_grad_exact(r1.x), v[2].y * gelu_grad_exact(r1.y));
+            v[3] = make_float2(v[3].x * gelu_grad_exact(r1.z), v[3].y * gelu_grad_exact(r1.w));
+          }
+          *reinterpret_cast<float4*>(dst + c0) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+          *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 2 * PL::TCOLS);
+}
+
 // ---- depthwise 3x3 (+bias, zero pad) + GELU on an NHWC map (HBM-bound) ------------------------------------------------------
 // thread = (4 consecutive pixels of a row, 4 channels): a sliding 3 x 6 window of float4 feeds four outputs, i.e. 4.5 loads per
 // output vector instead of 9 and one set of tap loads per four pixels (the one-pixel-per-thread form was bound by the L1 data
@@ -282,6 +537,16 @@ static cudaError_t pwgemm_launch(const float* A, float* Out, const void* wpack, 
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
   const int tiles = (int)((total_px + 127) / 128);
+  static const bool serial = [] { const char* e = getenv("LGTEUN_PWGEMM"); return e && e[0] == 's'; }();   // A/B: the one-phase-at-a-time kernel
+  if (!serial) {
+    using PL = pipe::Plan<K, N>;
+    cudaError_t e = cudaFuncSetAttribute(pwgemm_pipe_kernel<K, N, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::smem);
+    if (e != cudaSuccess) return e;
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    pwgemm_pipe_kernel<K, N, PRO, EPI><<<grid, pipe::kThreads, PL::smem, s>>>(A, Out, reinterpret_cast<const __half*>(wpack), bias, ln_g,
+                                                                         ln_b, resid, total_px, tiles, scale_dev);
+    return cudaGetLastError();
+  }
   constexpr int NS = N < kNS ? N : kNS;
   const size_t smem = 16 + (size_t)N * 4 + 16 + (size_t)2 * (K / 8) * (128 * 16 + 16) + (size_t)(2 * NS * K) * 2 + 128;
   cudaError_t e = cudaFuncSetAttribute(pwgemm_tc_kernel<K, N, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
