@@ -219,11 +219,11 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
 //   1 producer lane  streams the weight slice of every (K stage, 64 output columns) with cp.async.bulk into two buffers
 //   1 issuer lane    (elect.sync) issues the MMAs of a (K stage, slice) as soon as both operands are there and commits the
 //                    buffers back; the accumulator of a tile is one of TWO TMEM buffers of N columns
-//   4 epilogue warps read the finished accumulator (thread = pixel row), apply bias / GELU / residual / gate and store, under
+//   8 epilogue warps read the finished accumulator (thread = pixel row x column half), apply bias / GELU / residual / gate and store, under
 //                    the next tile's MMAs
 namespace pipe {
-constexpr int kThreads = 384;
-constexpr int kLoaders = 192;                    // warps 4 .. 9
+constexpr int kThreads = 512;
+constexpr int kLoaders = 192;                    // warps 8 .. 13
 constexpr int kLBO = 128 * 16 + 16;              // padded K-chunk stride of the A stages
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
@@ -257,7 +257,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
   static_assert(PRO != PRO_LN || (NKH == 1 && K / 4 <= 32), "the LayerNorm prologue needs the whole pixel row in one stage, within one warp");
   const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  unsigned char* const base = smem_raw;          // (no manual re-alignment: through an integer cast the compiler loses the shared address space and emits generic LD / ST)
   uint64_t* bars = reinterpret_cast<uint64_t*>(base);                          // a_full[2] a_empty[2] w_full[2] w_empty[2] acc_full[2] acc_empty[2]
   uint64_t *a_full = bars, *a_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *acc_full = bars + 8, *acc_empty = bars + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 96);
@@ -272,7 +272,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
       mbar_init(&w_full[b], 1);
       mbar_init(&w_empty[b], 1);
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);
+      mbar_init(&acc_empty[b], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -284,37 +284,40 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
   const uint32_t tmem = *tmem_slot;
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 4 && warp < 10) {
+  if (warp >= 8 && warp < 14) {
     // ---- loaders: A stages ---------------------------------------------------------------------------------------------------
-    const int ltid = tid - 128;
+    const int ltid = tid - 256;
     constexpr int F4 = K / 4;                                                    // float4 pieces per pixel row
     constexpr int F4S = KS / 4;                                                  // ... of one stage
-    constexpr int TOT = 128 * F4S;                                               // pieces per stage
-    constexpr int UB = 8;
+    static_assert(pipe::kLoaders % F4S == 0, "a loader step covers whole rows");
+    constexpr int RSTEP = pipe::kLoaders / F4S;                                  // rows per step of all loader threads
+    constexpr int NSTEP = (128 + RSTEP - 1) / RSTEP;                             // steps per stage
+    constexpr int UB = NSTEP < 16 ? NSTEP : 16;                                  // 16-byte loads in flight per thread (48 KB per SM)
+    // a thread keeps its piece column c and walks down the rows r0, r0 + RSTEP, ...: addresses are base + immediates
+    const int r0 = ltid / F4S, c = ltid - r0 * F4S;
+    const int off0 = (c >> 1) * LBO + r0 * 16 + (c & 1) * 8;
     uint32_t sa = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
       const long long px0 = ((long long)blockIdx.x + (long long)lt * gridDim.x) * 128;
       const int live_rows = (int)((total_px - px0 < 128) ? (total_px - px0) : 128);
-      const float4* src = reinterpret_cast<const float4*>(A + px0 * K);
+      const float4* src = reinterpret_cast<const float4*>(A + px0 * K) + r0 * F4 + c;
       for (int kh = 0; kh < NKH; ++kh, ++sa) {
         const uint32_t buf = sa & 1;
-        unsigned char* ah = a_st + buf * PL::A_STAGE;
+        unsigned char* ah = a_st + buf * PL::A_STAGE + off0;
         unsigned char* al = ah + (KS / 8) * LBO;
+        const float4* sk = src + kh * F4S;
         if (sa >= 2) mbar_wait(&a_empty[buf], ((sa >> 1) - 1) & 1);
 #pragma unroll 1
-        for (int i0 = ltid; i0 < TOT; i0 += UB * pipe::kLoaders) {
+        for (int n0 = 0; n0 < NSTEP; n0 += UB) {
           float4 t[UB];
 #pragma unroll
           for (int u = 0; u < UB; ++u) {
-            const int i = i0 + u * pipe::kLoaders;
-            const int r = i / F4S, c = i - r * F4S;
-            t[u] = (i < TOT && r < live_rows) ? __ldg(src + r * F4 + kh * F4S + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r = r0 + (n0 + u) * RSTEP;
+            t[u] = (r < live_rows) ? __ldg(sk + (n0 + u) * RSTEP * F4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int u = 0; u < UB; ++u) {
-            const int i = i0 + u * pipe::kLoaders;
-            if (i - lane >= TOT) continue;                                      // warp-uniform: a warp's 32 pieces are consecutive, TOT is a multiple of 32
-            const int r = i / F4S, c = i - r * F4S;
+            const int r = r0 + (n0 + u) * RSTEP;
             float2 v0 = make_float2(t[u].x, t[u].y), v1 = make_float2(t[u].z, t[u].w);
             if constexpr (PRO == PRO_LN) {                                       // the F4 lanes of a pixel are neighbours in the warp
               float sum = (v0.x + v0.y) + (v1.x + v1.y);
@@ -337,9 +340,10 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
             const uint32_t h0 = f2h2_sat(v0), h1 = f2h2_sat(v1);
             const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
             const uint32_t l0 = f2h2_sat(make_float2(v0.x - k0.x, v0.y - k0.y)), l1 = f2h2_sat(make_float2(v1.x - k1.x, v1.y - k1.y));
-            const int off = (c >> 1) * LBO + r * 16 + (c & 1) * 8;
-            *reinterpret_cast<uint2*>(ah + off) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(al + off) = make_uint2(l0, l1);
+            if (r < 128) {
+              *reinterpret_cast<uint2*>(ah + (n0 + u) * RSTEP * 16) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(al + (n0 + u) * RSTEP * 16) = make_uint2(l0, l1);
+            }
           }
         }
         fence_proxy_async();
@@ -347,7 +351,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
         if (lane == 0) mbar_arrive(&a_full[buf]);
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 14) {
     // ---- weight producer: one lane, cp.async.bulk of 1 KB rows (64 output columns x 16 bytes of one K chunk) ------------------
     if (lane == 0) {
       uint32_t sw = 0;
@@ -368,7 +372,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
             }
           }
     }
-  } else if (warp == 11) {
+  } else if (warp == 15) {
     // ---- MMA issuer -------------------------------------------------------------------------------------------------------------
     uint32_t sa = 0, sw = 0;
     const uint32_t a0 = smem_u32(a_st) >> 4, w0 = smem_u32(w_st) >> 4;
@@ -412,52 +416,64 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
         }
       }
     }
-  } else if (warp < 4) {
-    // ---- epilogue: thread = pixel row of the finished accumulator --------------------------------------------------------------
-    const int row = warp * 32 + lane;
+  } else if (warp < 8) {
+    // ---- epilogue: thread = (pixel row, column half) of the finished accumulator ------------------------------------------------
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    constexpr int NH = N / 2;                      // columns per thread
+    constexpr int CB = NH >= 32 ? 4 : NH / 8;      // 8-column chunks per TMEM batch
     for (int lt = 0; lt < my_tiles; ++lt) {
       const uint32_t ab = lt & 1;
       const long long p = ((long long)blockIdx.x + (long long)lt * gridDim.x) * 128 + row;
       const bool live = p < total_px;
       mbar_wait(&acc_full[ab], (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t lane_addr = tmem + ab * PL::TCOLS + ((uint32_t)(warp * 32) << 16);
-      float* dst = Out + p * N;
-      const float* res = (EPI == EPI_BIAS_RESID || EPI == EPI_GATE) ? resid + p * N : nullptr;
-#pragma unroll 2
-      for (int c0 = 0; c0 < N; c0 += 8) {
-        float2 v[4];
-        tmem_ld8(lane_addr + c0, v);
-        tmem_ld_wait();
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c0), b1 = *reinterpret_cast<const float4*>(sbias + c0 + 4);
-        v[0] = __ffma2_rn(v[0], make_float2(inv_scale, inv_scale), make_float2(b0.x, b0.y));
-        v[1] = __ffma2_rn(v[1], make_float2(inv_scale, inv_scale), make_float2(b0.z, b0.w));
-        v[2] = __ffma2_rn(v[2], make_float2(inv_scale, inv_scale), make_float2(b1.x, b1.y));
-        v[3] = __ffma2_rn(v[3], make_float2(inv_scale, inv_scale), make_float2(b1.z, b1.w));
-        if constexpr (EPI == EPI_BIAS_GELU) {
+      const uint32_t lane_addr = tmem + ab * PL::TCOLS + ((uint32_t)(q * 32) << 16) + half * NH;
+      float* dst = Out + p * N + half * NH;
+      const float* res = (EPI == EPI_BIAS_RESID || EPI == EPI_GATE) ? resid + p * N + half * NH : nullptr;
+      const float* sb = sbias + half * NH;
+#pragma unroll 1
+      for (int cb = 0; cb < NH; cb += 8 * CB) {
+        float2 v[CB][4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = gelu_pair(v[i]);
+        for (int j = 0; j < CB; ++j) tmem_ld8(lane_addr + cb + 8 * j, v[j]);
+        tmem_ld_wait();
+        if (cb + 8 * CB >= NH) {                   // last TMEM read of this accumulator: hand it back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
         }
-        if (live) {
-          if constexpr (EPI == EPI_BIAS_RESID) {
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
-            v[0] = __fadd2_rn(v[0], make_float2(r0.x, r0.y)); v[1] = __fadd2_rn(v[1], make_float2(r0.z, r0.w));
-            v[2] = __fadd2_rn(v[2], make_float2(r1.x, r1.y)); v[3] = __fadd2_rn(v[3], make_float2(r1.z, r1.w));
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          const int c0 = cb + 8 * j;
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + c0), b1 = *reinterpret_cast<const float4*>(sb + c0 + 4);
+          float2* w = v[j];
+          w[0] = __ffma2_rn(w[0], make_float2(inv_scale, inv_scale), make_float2(b0.x, b0.y));
+          w[1] = __ffma2_rn(w[1], make_float2(inv_scale, inv_scale), make_float2(b0.z, b0.w));
+          w[2] = __ffma2_rn(w[2], make_float2(inv_scale, inv_scale), make_float2(b1.x, b1.y));
+          w[3] = __ffma2_rn(w[3], make_float2(inv_scale, inv_scale), make_float2(b1.z, b1.w));
+          if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = gelu_pair(w[i]);
           }
-          if constexpr (EPI == EPI_GATE) {
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
-            v[0] = make_float2(v[0].x * gelu_grad_exact(r0.x), v[0].y * gelu_grad_exact(r0.y));
-            v[1] = make_float2(v[1].x * gelu_grad_exact(r0.z), v[1].y * gelu_grad_exact(r0.w));
-            v[2] = make_float2(v[2].x * gelu_grad_exact(r1.x), v[2].y * gelu_grad_exact(r1.y));
-            v[3] = make_float2(v[3].x * gelu_grad_exact(r1.z), v[3].y * gelu_grad_exact(r1.w));
+          if (live) {
+            if constexpr (EPI == EPI_BIAS_RESID) {
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+              w[0] = __fadd2_rn(w[0], make_float2(r0.x, r0.y)); w[1] = __fadd2_rn(w[1], make_float2(r0.z, r0.w));
+              w[2] = __fadd2_rn(w[2], make_float2(r1.x, r1.y)); w[3] = __fadd2_rn(w[3], make_float2(r1.z, r1.w));
+            }
+            if constexpr (EPI == EPI_GATE) {
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+              w[0] = make_float2(w[0].x * gelu_grad_exact(r0.x), w[0].y * gelu_grad_exact(r0.y));
+              w[1] = make_float2(w[1].x * gelu_grad_exact(r0.z), w[1].y * gelu_grad_exact(r0.w));
+              w[2] = make_float2(w[2].x * gelu_grad_exact(r1.x), w[2].y * gelu_grad_exact(r1.y));
+              w[3] = make_float2(w[3].x * gelu_grad_exact(r1.z), w[3].y * gelu_grad_exact(r1.w));
+            }
+            *reinterpret_cast<float4*>(dst + c0) = make_float4(w[0].x, w[0].y, w[1].x, w[1].y);
+            *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(w[2].x, w[2].y, w[3].x, w[3].y);
           }
-          *reinterpret_cast<float4*>(dst + c0) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
-          *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
     }
   }
   tc_fence_before();
