@@ -214,7 +214,7 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
 // ---- the same GEMM as a warp-specialised pipeline ---------------------------------------------------------------------------
 // pwgemm_tc_kernel above runs the phases of a tile one after the other (stage A, per slice: stage W, MMAs, wait; epilogue) on one
 // CTA per SM: 7-11 % issue utilisation, 15-28 % of the DRAM peak.  Here the phases overlap:
-//   6 loader warps   stage the A operand (coalesced 16-byte pieces -> fp16 hi / lo, K-major, padded chunk stride) in STAGES of
+//   8 loader warps   stage the A operand (coalesced 16-byte pieces -> fp16 hi / lo, K-major, padded chunk stride) in STAGES of
 //                    KS = K (K <= 128) or K / 2 channels, two stage buffers: the next stage / tile loads under the MMAs
 //   1 producer lane  streams the weight slice of every (K stage, 64 output columns) with cp.async.bulk into two buffers
 //   1 issuer lane    (elect.sync) issues the MMAs of a (K stage, slice) as soon as both operands are there and commits the
@@ -222,8 +222,14 @@ pwgemm_tc_kernel(const float* __restrict__ A, float* __restrict__ Out, const __h
 //   8 epilogue warps read the finished accumulator (thread = pixel row x column half), apply bias / GELU / residual / gate and store, under
 //                    the next tile's MMAs
 namespace pipe {
-constexpr int kThreads = 512;
-constexpr int kLoaders = 192;                    // warps 8 .. 13
+// 32-byte global store: a thread's 8 output columns are one full sector (two 16-byte stores are two L2 transactions)
+__device__ __forceinline__ void stg256(float* p, const float2 (&w)[4]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(w[0].x), "f"(w[0].y), "f"(w[1].x), "f"(w[1].y),
+               "f"(w[2].x), "f"(w[2].y), "f"(w[3].x), "f"(w[3].y)
+               : "memory");
+}
+constexpr int kThreads = 576;
+constexpr int kLoaders = 256;                    // warps 8 .. 15
 constexpr int kLBO = 128 * 16 + 16;              // padded K-chunk stride of the A stages
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
@@ -241,7 +247,9 @@ struct Plan {
   static constexpr int A_STAGE = 2 * (KS / 8) * kLBO;           // hi + lo
   static constexpr int W_STAGE = 2 * (KS / 8) * NSW * 16;       // hi + lo
   static constexpr int TCOLS = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128 ? 128 : 256);
-  static constexpr size_t smem = 128 + (size_t)N * 4 + 2 * (size_t)A_STAGE + 2 * (size_t)W_STAGE + 128;
+  // weight ring: as deep as 227 KB allow (the weight stream is what bounds the pipeline: an L2 round trip per stage)
+  static constexpr int NWS = (128 + N * 4 + 2 * A_STAGE + 4 * W_STAGE + 128 <= 232448) ? 4 : (128 + N * 4 + 2 * A_STAGE + 3 * W_STAGE + 128 <= 232448) ? 3 : 2;
+  static constexpr size_t smem = 128 + (size_t)N * 4 + 2 * (size_t)A_STAGE + NWS * (size_t)W_STAGE + 128;
 };
 }  // namespace pipe
 
@@ -258,21 +266,24 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
   const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* const base = smem_raw;          // (no manual re-alignment: through an integer cast the compiler loses the shared address space and emits generic LD / ST)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base);                          // a_full[2] a_empty[2] w_full[2] w_empty[2] acc_full[2] acc_empty[2]
-  uint64_t *a_full = bars, *a_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *acc_full = bars + 8, *acc_empty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 96);
+  constexpr int NWS = PL::NWS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base);                          // a_full[2] a_empty[2] acc_full[2] acc_empty[2] w_full[4] w_empty[4]
+  uint64_t *a_full = bars, *a_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6, *w_full = bars + 8, *w_empty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 128 - 8);
   float* sbias = reinterpret_cast<float*>(base + 128);                         // [N]
   unsigned char* a_st = base + 128 + N * 4;                                    // two A stages: [hi | lo][KS/8][LBO]
-  unsigned char* w_st = a_st + 2 * PL::A_STAGE;                                // two W stages: [hi | lo][KS/8][NSW][16 B]
+  unsigned char* w_st = a_st + 2 * PL::A_STAGE;                                // NWS weight stages: [hi | lo][KS/8][NSW][16 B]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&a_full[b], pipe::kLoaders / 32);
       mbar_init(&a_empty[b], 1);
-      mbar_init(&w_full[b], 1);
-      mbar_init(&w_empty[b], 1);
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], 8);
+    }
+    for (int b = 0; b < NWS; ++b) {
+      mbar_init(&w_full[b], 1);
+      mbar_init(&w_empty[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -284,7 +295,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
   const uint32_t tmem = *tmem_slot;
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 8 && warp < 14) {
+  if (warp >= 8 && warp < 16) {
     // ---- loaders: A stages ---------------------------------------------------------------------------------------------------
     const int ltid = tid - 256;
     constexpr int F4 = K / 4;                                                    // float4 pieces per pixel row
@@ -306,7 +317,6 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
         unsigned char* ah = a_st + buf * PL::A_STAGE + off0;
         unsigned char* al = ah + (KS / 8) * LBO;
         const float4* sk = src + kh * F4S;
-        if (sa >= 2) mbar_wait(&a_empty[buf], ((sa >> 1) - 1) & 1);
 #pragma unroll 1
         for (int n0 = 0; n0 < NSTEP; n0 += UB) {
           float4 t[UB];
@@ -315,6 +325,8 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
             const int r = r0 + (n0 + u) * RSTEP;
             t[u] = (r < live_rows) ? __ldg(sk + (n0 + u) * RSTEP * F4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          // the loads fly while the stage buffer is still being read by the MMAs of two stages ago
+          if (n0 == 0 && sa >= 2) mbar_wait(&a_empty[buf], ((sa >> 1) - 1) & 1);
 #pragma unroll
           for (int u = 0; u < UB; ++u) {
             const int r = r0 + (n0 + u) * RSTEP;
@@ -351,7 +363,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
         if (lane == 0) mbar_arrive(&a_full[buf]);
       }
     }
-  } else if (warp == 14) {
+  } else if (warp == 16) {
     // ---- weight producer: one lane, cp.async.bulk of 1 KB rows (64 output columns x 16 bytes of one K chunk) ------------------
     if (lane == 0) {
       uint32_t sw = 0;
@@ -360,8 +372,8 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
       for (int lt = 0; lt < my_tiles; ++lt)
         for (int kh = 0; kh < NKH; ++kh)
           for (int ns = 0; ns < NSL; ++ns, ++sw) {
-            const uint32_t buf = sw & 1;
-            if (sw >= 2) mbar_wait(&w_empty[buf], ((sw >> 1) - 1) & 1);
+            const uint32_t buf = sw % NWS;
+            if (sw >= NWS) mbar_wait(&w_empty[buf], ((sw / NWS) - 1) & 1);
             const uint32_t dst = smem_u32(w_st + buf * PL::W_STAGE);
             pipe::mbar_expect_tx(&w_full[buf], stage_bytes);
 #pragma unroll 1
@@ -372,7 +384,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
             }
           }
     }
-  } else if (warp == 15) {
+  } else if (warp == 17) {
     // ---- MMA issuer -------------------------------------------------------------------------------------------------------------
     uint32_t sa = 0, sw = 0;
     const uint32_t a0 = smem_u32(a_st) >> 4, w0 = smem_u32(w_st) >> 4;
@@ -390,8 +402,8 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
         const uint32_t abuf = sa & 1;
         mbar_wait(&a_full[abuf], (sa >> 1) & 1);
         for (int ns = 0; ns < NSL; ++ns, ++sw) {
-          const uint32_t wbuf = sw & 1;
-          mbar_wait(&w_full[wbuf], (sw >> 1) & 1);
+          const uint32_t wbuf = sw % NWS;
+          mbar_wait(&w_full[wbuf], (sw / NWS) & 1);
           tc_fence_after();
           if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc(NSW);
@@ -421,6 +433,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
     constexpr int NH = N / 2;                      // columns per thread
+    const bool al32 = (reinterpret_cast<uintptr_t>(Out) & 31) == 0;
     constexpr int CB = NH >= 32 ? 4 : NH / 8;      // 8-column chunks per TMEM batch
     for (int lt = 0; lt < my_tiles; ++lt) {
       const uint32_t ab = lt & 1;
@@ -469,8 +482,12 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
               w[2] = make_float2(w[2].x * gelu_grad_exact(r1.x), w[2].y * gelu_grad_exact(r1.y));
               w[3] = make_float2(w[3].x * gelu_grad_exact(r1.z), w[3].y * gelu_grad_exact(r1.w));
             }
-            *reinterpret_cast<float4*>(dst + c0) = make_float4(w[0].x, w[0].y, w[1].x, w[1].y);
-            *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(w[2].x, w[2].y, w[3].x, w[3].y);
+            if (al32) {
+              pipe::stg256(dst + c0, v[j]);
+            } else {                                 // output base only 16-byte aligned
+              *reinterpret_cast<float4*>(dst + c0) = make_float4(w[0].x, w[0].y, w[1].x, w[1].y);
+              *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(w[2].x, w[2].y, w[3].x, w[3].y);
+            }
           }
         }
       }
