@@ -368,6 +368,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
       o_off = (((size_t)un * H + uy0) * W + ux0 + opx) * C;
     };
     if (outw) out_geometry();
+    const bool out_al32 = (reinterpret_cast<uintptr_t>(yout) & 31) == 0;
     auto out_step = [&]() {
       const uint32_t ob = NB3 == 2 ? (j3 & 1) : 0;
       const bool ok = o_col && o_it - 2 < o_rows;
@@ -401,8 +402,15 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
             float2 v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = CONCAT ? __fadd2_rn(o[0][i][e], o[CONCAT ? 1 : 0][i][e]) : o[0][i][e];
-            dst[2 * (i0 + i)] = make_float4((v[0].x + ba.x) + ra[i].x, (v[0].y + ba.y) + ra[i].y, (v[1].x + ba.z) + ra[i].z, (v[1].y + ba.w) + ra[i].w);
-            dst[2 * (i0 + i) + 1] = make_float4((v[2].x + bb.x) + rb[i].x, (v[2].y + bb.y) + rb[i].y, (v[3].x + bb.z) + rb[i].z, (v[3].y + bb.w) + rb[i].w);
+            const float4 y0 = make_float4((v[0].x + ba.x) + ra[i].x, (v[0].y + ba.y) + ra[i].y, (v[1].x + ba.z) + ra[i].z, (v[1].y + ba.w) + ra[i].w);
+            const float4 y1 = make_float4((v[2].x + bb.x) + rb[i].x, (v[2].y + bb.y) + rb[i].y, (v[3].x + bb.z) + rb[i].z, (v[3].y + bb.w) + rb[i].w);
+            if (out_al32) {                              // one 32-byte store = one full L2 sector per thread
+              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 2 * (i0 + i)), "f"(y0.x), "f"(y0.y), "f"(y0.z),
+                           "f"(y0.w), "f"(y1.x), "f"(y1.y), "f"(y1.z), "f"(y1.w) : "memory");
+            } else {
+              dst[2 * (i0 + i)] = y0;
+              dst[2 * (i0 + i) + 1] = y1;
+            }
           }
         }
       }

@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
     tc_fence_after();
     const float* xr = xres + pix * C;
     float* dst = y + pix * C;
+    const bool al32 = (reinterpret_cast<uintptr_t>(y) & 31) == 0;
 #pragma unroll
     for (int c0 = 0; c0 < C; c0 += 8) {
       float2 acc[4];
@@ -539,10 +540,15 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
       tmem_ld_wait();
       const float4 r0 = __ldg(reinterpret_cast<const float4*>(xr + c0)), r1 = __ldg(reinterpret_cast<const float4*>(xr + c0 + 4));
       const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0), b1 = *reinterpret_cast<const float4*>(sBias + c0 + 4);
-      *reinterpret_cast<float4*>(dst + c0) =
-          make_float4((acc[0].x + b0.x) + r0.x, (acc[0].y + b0.y) + r0.y, (acc[1].x + b0.z) + r0.z, (acc[1].y + b0.w) + r0.w);
-      *reinterpret_cast<float4*>(dst + c0 + 4) =
-          make_float4((acc[2].x + b1.x) + r1.x, (acc[2].y + b1.y) + r1.y, (acc[3].x + b1.z) + r1.z, (acc[3].y + b1.w) + r1.w);
+      const float4 y0 = make_float4((acc[0].x + b0.x) + r0.x, (acc[0].y + b0.y) + r0.y, (acc[1].x + b0.z) + r0.z, (acc[1].y + b0.w) + r0.w);
+      const float4 y1 = make_float4((acc[2].x + b1.x) + r1.x, (acc[2].y + b1.y) + r1.y, (acc[3].x + b1.z) + r1.z, (acc[3].y + b1.w) + r1.w);
+      if (al32) {                                   // one 32-byte store = one full L2 sector per thread and instruction
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c0), "f"(y0.x), "f"(y0.y), "f"(y0.z), "f"(y0.w),
+                     "f"(y1.x), "f"(y1.y), "f"(y1.z), "f"(y1.w) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst + c0) = y0;
+        *reinterpret_cast<float4*>(dst + c0 + 4) = y1;
+      }
     }
     tc_fence_before();
   }
