@@ -24,7 +24,7 @@ using namespace lgtrain;
 namespace lgctx {
 
 struct BlockTape {
-  float *Xin, *A, *qkv, *F, *v, *cat, *Xmid, *A2, *h1, *h2, *h3, *Xout;
+  float *Xin, *A, *qkv, *lse, *ppos, *F, *v, *cat, *Xmid, *A2, *h1, *h2, *h3, *Xout;
 };
 struct PriorTape {
   const float* zin;
@@ -229,23 +229,32 @@ void resize(Run& R, TV x, int Hi, int Wi, TV y, int Ho, int Wo, int C, int N, in
   k_resize<<<blocks((size_t)N * Ho * Wo * C), 256, 0, R.s>>>(x, Hi, Wi, y, Ho, Wo, C, N, (float)Hi / (float)Ho, adjoint);
   R.check();
 }
-void attn_fwd(Run& R, int D, const float* qkv, const float* pos, TV out, int N, int H, int W) {
+// pos -> the two pre-scaled layouts the attention kernels read (k_attn_pos); lse: [NP][2] row statistic for the backward
+void attn_fwd(Run& R, int D, const float* qkv, const float* pos, float* ppos, TV out, float* lse, int N, int H, int W) {
   if (R.dry) return;
-  dim3 grid(N * (H / 8) * (W / 8), 2);
-  if (D == 4) k_attn_fwd<4><<<grid, 64, 0, R.s>>>(qkv, pos, out, N, H, W);
-  else if (D == 8) k_attn_fwd<8><<<grid, 64, 0, R.s>>>(qkv, pos, out, N, H, W);
-  else k_attn_fwd<16><<<grid, 64, 0, R.s>>>(qkv, pos, out, N, H, W);
+  k_attn_pos<<<32, 256, 0, R.s>>>(pos, ppos);
+  const unsigned grid = (unsigned)(N * (H / 8) * (W / 8));
+  if (D == 4) k_attn_fwd<4><<<grid, 64, 0, R.s>>>(qkv, ppos, out, lse, N, H, W);
+  else if (D == 8) k_attn_fwd<8><<<grid, 64, 0, R.s>>>(qkv, ppos, out, lse, N, H, W);
+  else k_attn_fwd<16><<<grid, 64, 0, R.s>>>(qkv, ppos, out, lse, N, H, W);
   R.check();
 }
-void attn_bwd(Run& R, int D, const float* qkv, const float* pos, TV dout, float* dqkv, const float* dpos, int N, int H, int W) {
+template <int D>
+void attn_bwd_launch(Run& R, const float* qkv, const float* ppos, TV dout, TV o, const float* lse, float* dqkv, float* dpos, int N,
+                     int H, int W) {
+  const size_t smem = sizeof(AttnBwdSmem<D>);
+  optin_smem(k_attn_bwd<D>, smem);
+  const int per_sm = (int)std::min<size_t>(8, (227 * 1024) / (smem + 1024));
+  const unsigned grid = (unsigned)std::min(N * (H / 8) * (W / 8), 148 * per_sm);
+  k_attn_bwd<D><<<grid, 64, smem, R.s>>>(qkv, ppos, dout, o, lse, dqkv, dpos, N, H, W);
+}
+void attn_bwd(Run& R, int D, const float* qkv, const float* ppos, TV dout, TV o, const float* lse, float* dqkv, const float* dpos,
+              int N, int H, int W) {
   if (R.dry) return;
-  const int nwin = N * (H / 8) * (W / 8);
-  const unsigned grid = (unsigned)std::min(nwin, 148 * 4);
-  const size_t smem = 2 * (4 * 64 * D + 3 * 64 + 64 * 64) * sizeof(float);
   float* dp = const_cast<float*>(dpos);
-  if (D == 4) { optin_smem(k_attn_bwd<4>, smem); k_attn_bwd<4><<<grid, 128, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
-  else if (D == 8) { optin_smem(k_attn_bwd<8>, smem); k_attn_bwd<8><<<grid, 128, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
-  else { optin_smem(k_attn_bwd<16>, smem); k_attn_bwd<16><<<grid, 128, smem, R.s>>>(qkv, pos, dout, dqkv, dp, N, H, W); }
+  if (D == 4) attn_bwd_launch<4>(R, qkv, ppos, dout, o, lse, dqkv, dp, N, H, W);
+  else if (D == 8) attn_bwd_launch<8>(R, qkv, ppos, dout, o, lse, dqkv, dp, N, H, W);
+  else attn_bwd_launch<16>(R, qkv, ppos, dout, o, lse, dqkv, dp, N, H, W);
   R.check();
 }
 int fft_cpb(int L, int c2) {    // channels of one line per block: at most 8192 complex points (64 KB) of shared memory
@@ -292,7 +301,9 @@ float* fwd_block(Run& R, const Step& S, const BlockW& w, int ch, BlockTape& t, f
   t.qkv = R.take(NP * 3 * c2);
   pw(R, 0, nhwc(t.A, ch), c2, w.qkv_w, c2, 1, w.qkv_b, nhwc(t.qkv, 3 * c2), 3 * c2, NP);
   t.cat = R.take(NP * ch);
-  attn_fwd(R, c2 / 2, t.qkv, w.pos, nhwc(t.cat, ch), N, H, W);
+  t.lse = R.take(NP * 2);
+  t.ppos = R.take(2 * 2 * 64 * 64);
+  attn_fwd(R, c2 / 2, t.qkv, w.pos, t.ppos, nhwc(t.cat, ch), t.lse, N, H, W);
   // global branch: rfft2 -> amplitude / phase mixing -> |irfft2| into cat[:, c2:]
   t.F = R.take(SP);
   fft_rows(R, 0, t.A + c2, ch, nullptr, t.F, nullptr, 0, nullptr, 0, N, H, W, c2, 1.f, 0);
@@ -376,7 +387,7 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
   float* dA = R.take(NP * ch);
   // local branch
   float* dqkv = R.take(NP * 3 * c2);
-  attn_bwd(R, c2 / 2, t.qkv, w.pos, nhwc(dcat, ch), dqkv, g.pos, N, H, W);
+  attn_bwd(R, c2 / 2, t.qkv, t.ppos, nhwc(dcat, ch), nhwc(t.cat, ch), t.lse, dqkv, g.pos, N, H, W);
   pw_wgrad(R, 0, nhwc(t.A, ch), c2, nhwc(dqkv, 3 * c2), 3 * c2, g.qkv_w, c2, 1, g.qkv_b, NP);
   pw(R, 0, nhwc(dqkv, 3 * c2), 3 * c2, w.qkv_w, 1, c2, nullptr, nhwc(dA, ch), c2, NP);
   // global branch: |.| -> C2R rows -> inverse columns -> mixing -> forward columns -> R2C rows, all transposed

@@ -561,136 +561,266 @@ __global__ void __launch_bounds__(256) k_resize_v4(const float4* __restrict__ x,
 }
 
 // ---- window multi-head self-attention (local_mixer, LGT.py:130-146; window merge :207-208) ------------------------------------------
-// qkv [NP, 6D] NHWC (q | k | v thirds, head-major inside a third), D = head dim; one 64-thread block per (window, head),
-// thread = query token i*8+j.
-template <int D>
-__global__ void __launch_bounds__(64) k_attn_fwd(const float* __restrict__ qkv, const float* __restrict__ pos, TV out, int N,
-                                                 int H, int W) {
-  __shared__ float ks[64][D], vs[64][D];
-  const int nwx = W / 8, nwin = (H / 8) * nwx, c2 = 2 * D, ld = 3 * c2;
-  const int head = blockIdx.y, win = blockIdx.x % nwin, n = blockIdx.x / nwin;
-  const int i = threadIdx.x;
-  const size_t gp = ((size_t)n * H + (win / nwx) * 8 + i / 8) * W + (win % nwx) * 8 + i % 8;
-  const float* row = qkv + gp * ld + head * D;
-  float q[D];
-  const float scale = rsqrtf((float)D);
-#pragma unroll
-  for (int d = 0; d < D; ++d) { q[d] = row[d] * scale; ks[i][d] = row[c2 + d]; vs[i][d] = row[2 * c2 + d]; }
-  __syncthreads();
-  const float* pr = pos + ((size_t)head * 64 + i) * 64;
-  float s[64], mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    float a = 0.f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) a = fmaf(q[d], ks[j][d], a);
-    s[j] = a + pr[j];
-    mx = fmaxf(mx, s[j]);
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
-  const float inv = 1.f / sum;
-  float o[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) o[d] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j)
-#pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = fmaf(s[j], vs[j][d], o[d]);
-#pragma unroll
-  for (int d = 0; d < D; ++d) out.p[gp * out.ld + head * D + d] = o[d] * inv;
+// qkv [NP, 6D] NHWC (q | k | v thirds, head-major inside a third), D = head dim, 8x8 windows, two heads.
+// A 64-thread block owns one window, warp = head, lane = tokens {lane, lane + 32} (as queries, and as keys in the backward):
+// every broadcast shared-memory read of a key / value / query row feeds two tokens, which halves the L1 data-pipe traffic that
+// bounded the thread-per-query form (k_attn_fwd 210 -> us, k_attn_bwd 514 -> us at 4 x 256 x 256 x 32 channels).  The window's
+// qkv rows (8 runs of 8 * 6D contiguous floats) move between HBM and shared memory as coalesced 16-byte pieces.  Scores are
+// kept in base 2: q is scaled by D^-1/2 * log2(e) when staged and the positional bias comes pre-multiplied (k_attn_pos).
+// The forward also writes the row statistic L = max + log2(sum) per (pixel, head); the backward needs nothing else from it
+// (delta = sum_j P dP = dO . O, with O read from the tape), so it has no statistics sweep.
+
+// pos [2][64 queries][64 keys] -> ppos[0 .. 8192): log2(e) * [head][key / 4][query][key % 4]  (a query lane fetches four keys with
+// one 16-byte load, a warp reads 512 contiguous bytes);  ppos[8192 .. 16384): log2(e) * pos  (key lanes read consecutive words)
+__global__ void k_attn_pos(const float* __restrict__ pos, float* __restrict__ ppos) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= 2 * 64 * 64) return;
+  const int h = idx >> 12, jq = (idx >> 8) & 15, i = (idx >> 2) & 63, jr = idx & 3;
+  ppos[idx] = pos[(h << 12) + (i << 6) + 4 * jq + jr] * 1.4426950408889634f;
+  ppos[8192 + idx] = pos[idx] * 1.4426950408889634f;
 }
 
-// backward: a 128-thread block handles both heads of a window and loops over windows.  Phase 1 (thread = query token) gets
-// the row statistics (max, 1/sum, delta = sum_j P dP) and dq; phase 2 (thread = key token) recomputes P and dS column-wise
-// for dk, dv and the positional-bias gradient, which accumulates over the block's windows in shared memory and is flushed
-// with one atomicAdd per entry.  dqkv is written exactly once per element.
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <int D>
-__global__ void __launch_bounds__(128) k_attn_bwd(const float* __restrict__ qkv, const float* __restrict__ pos, TV dout,
-                                                  float* __restrict__ dqkv, float* __restrict__ dpos, int N, int H, int W) {
-  extern __shared__ float sm[];
-  const int head = threadIdx.x >> 6, i = threadIdx.x & 63;
-  float* base = sm + head * (4 * 64 * D + 3 * 64 + 64 * 64);
-  float* qs = base;               // [64][D]  scaled q
-  float* ks = qs + 64 * D;
-  float* vs = ks + 64 * D;
-  float* dos = vs + 64 * D;
-  float* st = dos + 64 * D;       // [3][64]  row max, 1 / row sum, delta
-  float* dps = st + 3 * 64;       // [64][64] dpos accumulator, [query][key]
-  const int nwx = W / 8, nwin = (H / 8) * nwx, c2 = 2 * D, ld = 3 * c2;
-  const float scale = rsqrtf((float)D);
-  const float* ph = pos + (size_t)head * 64 * 64;
-  for (int j = 0; j < 64; ++j) dps[j * 64 + i] = 0.f;
+struct AttnGeo {
+  static constexpr int LD = 6 * D;         // floats per pixel of qkv
+  static constexpr int LDP = LD + 4;       // padded shared-memory row: 16-byte aligned, own-token reads hit distinct banks
+  static constexpr int PPX = LD / 4;       // 16-byte pieces per pixel
+  static constexpr int OLD = 2 * D + 4;    // padded row of the dO tile
+  static constexpr int OPX = 2 * D / 4;
+};
+__device__ __forceinline__ size_t attn_pixel(int n, int win, int t, int H, int W) {
+  const int nwx = W / 8;
+  return ((size_t)n * H + (win / nwx) * 8 + (t >> 3)) * W + (win % nwx) * 8 + (t & 7);
+}
+template <int D>
+__device__ __forceinline__ void ld_row(float (&r)[D], const float* src) {
+#pragma unroll
+  for (int d = 0; d < D; d += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + d);
+    r[d] = v.x; r[d + 1] = v.y; r[d + 2] = v.z; r[d + 3] = v.w;
+  }
+}
+template <int D>
+__device__ __forceinline__ void st_row(float* dst, const float (&r)[D], float mul) {
+#pragma unroll
+  for (int d = 0; d < D; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(r[d] * mul, r[d + 1] * mul, r[d + 2] * mul, r[d + 3] * mul);
+}
+template <int D>
+__device__ __forceinline__ float dot_row(const float (&a)[D], const float (&b)[D], float acc) {
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc = fmaf(a[d], b[d], acc);
+  return acc;
+}
+template <int D>
+__device__ __forceinline__ void axpy_row(float (&y)[D], float a, const float (&x)[D]) {
+#pragma unroll
+  for (int d = 0; d < D; ++d) y[d] = fmaf(a, x[d], y[d]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(64) k_attn_fwd(const float* __restrict__ qkv, const float* __restrict__ ppos, TV out,
+                                                 float* __restrict__ lse, int N, int H, int W) {
+  using G = AttnGeo<D>;
+  __shared__ __align__(16) float tile[64 * G::LDP];
+  const int nwin = (H / 8) * (W / 8);
+  const int win = blockIdx.x % nwin, n = blockIdx.x / nwin;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float qs = rsqrtf((float)D) * 1.4426950408889634f;
+  for (int f = threadIdx.x; f < 64 * G::PPX; f += 64) {
+    const int t = f / G::PPX, q = f - t * G::PPX;
+    float4 v = __ldg(reinterpret_cast<const float4*>(qkv + attn_pixel(n, win, t, H, W) * G::LD) + q);
+    if (q < G::PPX / 3) { v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs; }
+    *reinterpret_cast<float4*>(tile + t * G::LDP + 4 * q) = v;
+  }
+  __syncthreads();
+  float q0[D], q1[D], o0[D], o1[D];
+  ld_row<D>(q0, tile + lane * G::LDP + h * D);
+  ld_row<D>(q1, tile + (lane + 32) * G::LDP + h * D);
+#pragma unroll
+  for (int d = 0; d < D; ++d) { o0[d] = 0.f; o1[d] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float4* pp = reinterpret_cast<const float4*>(ppos) + (size_t)h * 1024 + lane;   // [key / 4][query] float4
+  const float* kb = tile + 2 * D + h * D;
+  const float* vb = tile + 4 * D + h * D;
+#pragma unroll 1
+  for (int c = 0; c < 64; c += 8) {                       // 8 keys per softmax rescale
+    float s0[8], s1[8];
+#pragma unroll
+    for (int jq = 0; jq < 2; ++jq) {
+      const float4 b0 = __ldg(pp + (c / 4 + jq) * 64), b1 = __ldg(pp + (c / 4 + jq) * 64 + 32);
+      const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int jr = 0; jr < 4; ++jr) {
+        float k[D];
+        ld_row<D>(k, kb + (c + 4 * jq + jr) * G::LDP);
+        s0[4 * jq + jr] = dot_row<D>(q0, k, bb0[jr]);
+        s1[4 * jq + jr] = dot_row<D>(q1, k, bb1[jr]);
+      }
+    }
+    float c0 = s0[0], c1 = s1[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { c0 = fmaxf(c0, s0[j]); c1 = fmaxf(c1, s1[j]); }
+    const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);
+    const float r0 = ex2f(m0 - n0), r1 = ex2f(m1 - n1);
+    m0 = n0; m1 = n1;
+    l0 *= r0; l1 *= r1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { o0[d] *= r0; o1[d] *= r1; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v[D];
+      ld_row<D>(v, vb + (c + j) * G::LDP);
+      const float e0 = ex2f(s0[j] - m0), e1 = ex2f(s1[j] - m1);
+      l0 += e0; l1 += e1;
+      axpy_row<D>(o0, e0, v);
+      axpy_row<D>(o1, e1, v);
+    }
+  }
+  lse[attn_pixel(n, win, lane, H, W) * 2 + h] = m0 + log2f(l0);
+  lse[attn_pixel(n, win, lane + 32, H, W) * 2 + h] = m1 + log2f(l1);
+  // own q slots (no other lane reads them) carry the output to the coalesced store
+  st_row<D>(tile + lane * G::LDP + h * D, o0, 1.f / l0);
+  st_row<D>(tile + (lane + 32) * G::LDP + h * D, o1, 1.f / l1);
+  __syncthreads();
+  for (int f = threadIdx.x; f < 64 * G::OPX; f += 64) {
+    const int t = f / G::OPX, q = f - t * G::OPX;
+    *reinterpret_cast<float4*>(out.p + attn_pixel(n, win, t, H, W) * out.ld + 4 * q) =
+        *reinterpret_cast<const float4*>(tile + t * G::LDP + 4 * q);
+  }
+}
+
+// backward: persistent 64-thread blocks loop over windows.  Phase 1 (lane = two queries, loop over keys): P from the saved row
+// statistic, dP = dO . v, dS = P (dP - delta), dq.  Phase 2 (lane = two keys, loop over queries): the same P and dS column-wise
+// for dk, dv and the positional-bias gradient, which accumulates over the block's windows in shared memory (each lane owns its
+// two key columns) and is flushed once with 16-byte atomics.  dqkv is written exactly once per element, coalesced.
+template <int D>
+struct AttnBwdSmem {
+  using G = AttnGeo<D>;
+  float dps[2 * 64 * 64];          // [head][query][key]
+  float tile[64 * G::LDP];         // q (scaled) | k | v, later dq | dk | dv
+  float dot[64 * G::OLD];          // dO, both heads
+  float2 st[2 * 64];               // [head][query] (L, delta)
+};
+template <int D>
+__global__ void __launch_bounds__(64) k_attn_bwd(const float* __restrict__ qkv, const float* __restrict__ ppos, TV dout, TV o,
+                                                 const float* __restrict__ lse, float* __restrict__ dqkv,
+                                                 float* __restrict__ dpos, int N, int H, int W) {
+  using G = AttnGeo<D>;
+  extern __shared__ __align__(16) unsigned char attn_smem_raw[];
+  AttnBwdSmem<D>& S = *reinterpret_cast<AttnBwdSmem<D>*>(attn_smem_raw);
+  const int nwin = (H / 8) * (W / 8);
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float scale = rsqrtf((float)D), qs = scale * 1.4426950408889634f;
+  for (int f = threadIdx.x; f < 2 * 64 * 64 / 4; f += 64) reinterpret_cast<float4*>(S.dps)[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* dps = S.dps + h * 4096 + lane;
+  const float4* pp = reinterpret_cast<const float4*>(ppos) + (size_t)h * 1024 + lane;
+  const float* pk = ppos + 8192 + h * 4096 + lane;         // log2(e) * pos[head][query][key]
   for (int g = blockIdx.x; g < N * nwin; g += gridDim.x) {
     const int win = g % nwin, n = g / nwin;
-    const size_t gp = ((size_t)n * H + (win / nwx) * 8 + i / 8) * W + (win % nwx) * 8 + i % 8;
-    const float* row = qkv + gp * ld + head * D;
-    float q[D], kk[D], vv[D], dO[D];
-    __syncthreads();              // the previous window's phase 2 is done with the shared tiles
+    __syncthreads();                                        // the previous window's store has read the tile
+    for (int f = threadIdx.x; f < 64 * G::PPX; f += 64) {
+      const int t = f / G::PPX, q = f - t * G::PPX;
+      float4 v = __ldg(reinterpret_cast<const float4*>(qkv + attn_pixel(n, win, t, H, W) * G::LD) + q);
+      if (q < G::PPX / 3) { v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs; }
+      *reinterpret_cast<float4*>(S.tile + t * G::LDP + 4 * q) = v;
+    }
+    for (int f = threadIdx.x; f < 64 * G::OPX; f += 64) {  // dO tile and delta = dO . O (D / 4 neighbouring lanes per head)
+      const int t = f / G::OPX, q = f - t * G::OPX;
+      const size_t gp = attn_pixel(n, win, t, H, W);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(dout.p + gp * dout.ld) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(o.p + gp * o.ld) + q);
+      *reinterpret_cast<float4*>(S.dot + t * G::OLD + 4 * q) = a;
+      float dl = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      q[d] = row[d] * scale;
-      kk[d] = row[c2 + d];
-      vv[d] = row[2 * c2 + d];
-      dO[d] = dout.p[gp * dout.ld + head * D + d];
-      qs[i * D + d] = q[d];
-      ks[i * D + d] = kk[d];
-      vs[i * D + d] = vv[d];
-      dos[i * D + d] = dO[d];
+      for (int w = 1; w < D / 4; w *= 2) dl += __shfl_xor_sync(0xffffffffu, dl, w);
+      if (q % (D / 4) == 0) {
+        const int hh = q / (D / 4);
+        S.st[hh * 64 + t] = make_float2(__ldg(lse + gp * 2 + hh), dl);
+      }
     }
     __syncthreads();
-    // phase 1: query row i — online softmax statistics, then a second sweep for dq (scores are recomputed, not stored)
-    float mx = -INFINITY, sum = 0.f, dsum = 0.f;
-    const float* pr = ph + i * 64;
-#pragma unroll 4
-    for (int j = 0; j < 64; ++j) {
-      float a = pr[j], dp = 0.f;
+    float ga[D], gb[D];                                    // dq of the two queries
+    // ---- phase 1 ---------------------------------------------------------------------------------------------------------------
+    {
+      float q0[D], q1[D], d0[D], d1[D];
+      ld_row<D>(q0, S.tile + lane * G::LDP + h * D);
+      ld_row<D>(q1, S.tile + (lane + 32) * G::LDP + h * D);
+      ld_row<D>(d0, S.dot + lane * G::OLD + h * D);
+      ld_row<D>(d1, S.dot + (lane + 32) * G::OLD + h * D);
+      const float2 st0 = S.st[h * 64 + lane], st1 = S.st[h * 64 + lane + 32];
 #pragma unroll
-      for (int d = 0; d < D; ++d) { a = fmaf(q[d], ks[j * D + d], a); dp = fmaf(dO[d], vs[j * D + d], dp); }
-      const float mn = fmaxf(mx, a), r = __expf(mx - mn), e = __expf(a - mn);
-      sum = fmaf(sum, r, e);
-      dsum = fmaf(dsum, r, e * dp);
-      mx = mn;
+      for (int d = 0; d < D; ++d) { ga[d] = 0.f; gb[d] = 0.f; }
+      const float* kb = S.tile + 2 * D + h * D;
+      const float* vb = S.tile + 4 * D + h * D;
+#pragma unroll 2
+      for (int jq = 0; jq < 16; ++jq) {
+        const float4 b0 = __ldg(pp + jq * 64), b1 = __ldg(pp + jq * 64 + 32);
+        const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int jr = 0; jr < 4; ++jr) {
+          float k[D], v[D];
+          ld_row<D>(k, kb + (4 * jq + jr) * G::LDP);
+          ld_row<D>(v, vb + (4 * jq + jr) * G::LDP);
+          const float p0 = ex2f(dot_row<D>(q0, k, bb0[jr]) - st0.x), p1 = ex2f(dot_row<D>(q1, k, bb1[jr]) - st1.x);
+          const float s0 = p0 * (dot_row<D>(d0, v, 0.f) - st0.y), s1 = p1 * (dot_row<D>(d1, v, 0.f) - st1.y);
+          axpy_row<D>(ga, s0, k);
+          axpy_row<D>(gb, s1, k);
+        }
+      }
     }
-    const float inv = 1.f / sum, delta = dsum * inv;
-    float dq[D];
+    // ---- phase 2 ---------------------------------------------------------------------------------------------------------------
+    float dk0[D], dk1[D], dv0[D], dv1[D];
+    {
+      float ra[D], rb[D], v0[D], v1[D];                    // k, v of the two keys
+      ld_row<D>(ra, S.tile + lane * G::LDP + 2 * D + h * D);
+      ld_row<D>(rb, S.tile + (lane + 32) * G::LDP + 2 * D + h * D);
+      ld_row<D>(v0, S.tile + lane * G::LDP + 4 * D + h * D);
+      ld_row<D>(v1, S.tile + (lane + 32) * G::LDP + 4 * D + h * D);
 #pragma unroll
-    for (int d = 0; d < D; ++d) dq[d] = 0.f;
+      for (int d = 0; d < D; ++d) { dk0[d] = 0.f; dk1[d] = 0.f; dv0[d] = 0.f; dv1[d] = 0.f; }
+      const float* qb = S.tile + h * D;
+      const float* ob = S.dot + h * D;
 #pragma unroll 4
-    for (int j = 0; j < 64; ++j) {
-      float a = pr[j], dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) { a = fmaf(q[d], ks[j * D + d], a); dp = fmaf(dO[d], vs[j * D + d], dp); }
-      const float ds = __expf(a - mx) * inv * (dp - delta);
-#pragma unroll
-      for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, ks[j * D + d], dq[d]);
+      for (int r = 0; r < 64; ++r) {
+        float q[D], dO[D];
+        ld_row<D>(q, qb + r * G::LDP);
+        ld_row<D>(dO, ob + r * G::OLD);
+        const float2 st = S.st[h * 64 + r];
+        const float p0 = ex2f(dot_row<D>(q, ra, __ldg(pk + r * 64)) - st.x), p1 = ex2f(dot_row<D>(q, rb, __ldg(pk + r * 64 + 32)) - st.x);
+        const float s0 = p0 * (dot_row<D>(dO, v0, 0.f) - st.y), s1 = p1 * (dot_row<D>(dO, v1, 0.f) - st.y);
+        dps[r * 64] += s0;
+        dps[r * 64 + 32] += s1;
+        axpy_row<D>(dk0, s0, q);
+        axpy_row<D>(dk1, s1, q);
+        axpy_row<D>(dv0, p0, dO);
+        axpy_row<D>(dv1, p1, dO);
+      }
     }
-    st[i] = mx;
-    st[64 + i] = inv;
-    st[128 + i] = delta;
+    __syncwarp();                                           // this head's slices of the tile are read by this warp only
+    st_row<D>(S.tile + lane * G::LDP + h * D, ga, scale);
+    st_row<D>(S.tile + (lane + 32) * G::LDP + h * D, gb, scale);
+    st_row<D>(S.tile + lane * G::LDP + 2 * D + h * D, dk0, 0.6931471805599453f);      // q was staged with log2(e) folded in
+    st_row<D>(S.tile + (lane + 32) * G::LDP + 2 * D + h * D, dk1, 0.6931471805599453f);
+    st_row<D>(S.tile + lane * G::LDP + 4 * D + h * D, dv0, 1.f);
+    st_row<D>(S.tile + (lane + 32) * G::LDP + 4 * D + h * D, dv1, 1.f);
     __syncthreads();
-    // phase 2: key column i
-    float dk[D], dv[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
-#pragma unroll 4
-    for (int r = 0; r < 64; ++r) {
-      float a = ph[r * 64 + i], dp = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) { a = fmaf(qs[r * D + d], kk[d], a); dp = fmaf(dos[r * D + d], vv[d], dp); }
-      const float p = __expf(a - st[r]) * st[64 + r];
-      const float ds = p * (dp - st[128 + r]);
-      dps[r * 64 + i] += ds;
-#pragma unroll
-      for (int d = 0; d < D; ++d) { dk[d] = fmaf(ds, qs[r * D + d], dk[d]); dv[d] = fmaf(p, dos[r * D + d], dv[d]); }
+    for (int f = threadIdx.x; f < 64 * G::PPX; f += 64) {
+      const int t = f / G::PPX, q = f - t * G::PPX;
+      *(reinterpret_cast<float4*>(dqkv + attn_pixel(n, win, t, H, W) * G::LD) + q) =
+          *reinterpret_cast<const float4*>(S.tile + t * G::LDP + 4 * q);
     }
-    float* orow = dqkv + gp * ld + head * D;
-#pragma unroll
-    for (int d = 0; d < D; ++d) { orow[d] = dq[d] * scale; orow[c2 + d] = dk[d]; orow[2 * c2 + d] = dv[d]; }
   }
-  float* dph = dpos + (size_t)head * 64 * 64;
-  for (int r = 0; r < 64; ++r) atomicAdd(dph + r * 64 + i, dps[r * 64 + i]);
+  __syncthreads();
+  if ((reinterpret_cast<uintptr_t>(dpos) & 15) == 0) {
+    for (int f = threadIdx.x; f < 2 * 64 * 64 / 4; f += 64) atomicAdd(reinterpret_cast<float4*>(dpos) + f, reinterpret_cast<const float4*>(S.dps)[f]);
+  } else {
+    for (int f = threadIdx.x; f < 2 * 64 * 64; f += 64) atomicAdd(dpos + f, S.dps[f]);
+  }
 }
 
 // ---- FFT passes of the global mixer (LGT.py:162-180) and their adjoints ---------------------------------------------------------
