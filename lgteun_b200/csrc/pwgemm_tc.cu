@@ -642,13 +642,17 @@ cudaError_t launch_pack_umma_f16_strided(const float* w, int wso, int wsi, void*
 // >= Cout stay zero) and B = f(X)^T [ci][pixel] are K-major; every tile adds 8 x (hi*hi + hi*lo + lo*hi) MMAs into the same
 // [128 x NCI] fp32 TMEM accumulator, which is read once at the end and added to dW with atomics (the CTAs split the pixels).
 // dY is a gradient (~1e-7): it is multiplied by the step's power-of-two scale before the fp16 split, dW divided by it.
+// Staging: 16 warps; a thread issues the loads of up to four items (32 values) before it converts any of them, so that a tile's
+// 40 - 190 KB are in flight together (the one-item-at-a-time form was latency-bound: 24k clocks per tile at 8 warps).
+constexpr int kGradThreads = 512;
 template <int NCI, int ACT>
-__global__ void __launch_bounds__(kPwThreads, 1)
+__global__ void __launch_bounds__(kGradThreads, 1)
 pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy, int Cout, float* __restrict__ dW,
                  int wso, int wsi, float* __restrict__ db, long long total_px, int num_tiles, const float* __restrict__ scale_dev) {
   using namespace pw;
   static_assert(NCI % 16 == 0 && NCI <= 256, "tile shape");
   constexpr int KC = 16;                                                        // 128 pixels per tile = 16 K-chunks of 8
+  constexpr int UB = 4;                                                         // items whose loads are issued together
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
@@ -657,9 +661,10 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
   __half* bh = al + 128 * 128;                                                  // [KC][NCI][8]
   __half* bl = bh + NCI * 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, part = warp >> 2;
   const int co0 = blockIdx.y * 128;
   const int mrows = Cout - co0 < 128 ? Cout - co0 : 128;                        // a power of two >= 16
+  const int lm = __ffs(mrows) - 1;
   constexpr uint32_t TCOLS = (NCI <= 32) ? 32 : (NCI <= 64) ? 64 : (NCI <= 128 ? 128 : 256);
   const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
 
@@ -668,7 +673,7 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  for (int i = tid; i < 128 * 128 * 2 / 8; i += kPwThreads) reinterpret_cast<uint4*>(ah)[i] = make_uint4(0, 0, 0, 0);   // ah and al
+  for (int i = tid; i < 128 * 128 * 2 / 8; i += kGradThreads) reinterpret_cast<uint4*>(ah)[i] = make_uint4(0, 0, 0, 0);   // ah and al
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -677,49 +682,68 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
   uint32_t phase = 0;
   float bsum = 0.f;
   bool first = true;
+  const int n_dy = KC * mrows;
 
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * 128;
-    for (int item = tid; item < KC * mrows; item += kPwThreads) {              // 256 % mrows == 0: a thread keeps its channel
-      const int co = item & (mrows - 1), g = item / mrows;
-      float2 v[4];
-      float t[8];
+    const bool full = p0 + 128 <= total_px;
+    for (int base = tid; base < n_dy; base += UB * kGradThreads) {             // kGradThreads % mrows == 0: a thread keeps its channel
+      float t[UB][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const long long p = p0 + g * 8 + j;
-        t[j] = p < total_px ? __ldg(dY + p * ldy + co0 + co) : 0.f;
-        bsum += t[j];
+      for (int u = 0; u < UB; ++u) {
+        const int item = base + u * kGradThreads, co = item & (mrows - 1), g = item >> lm;
+        const float* src = dY + (p0 + g * 8) * ldy + co0 + co;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[u][j] = (item < n_dy && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldy) : 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = make_float2(t[2 * j] * a_scale, t[2 * j + 1] * a_scale);
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(ah + (g * 128 + co) * 8) = hi;
-      *reinterpret_cast<uint4*>(al + (g * 128 + co) * 8) = lo;
+      for (int u = 0; u < UB; ++u) {
+        const int item = base + u * kGradThreads, co = item & (mrows - 1), g = item >> lm;
+        if (item < n_dy) {
+          float2 v[4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bsum += t[u][j];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = make_float2(t[u][2 * j] * a_scale, t[u][2 * j + 1] * a_scale);
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(ah + (g * 128 + co) * 8) = hi;
+          *reinterpret_cast<uint4*>(al + (g * 128 + co) * 8) = lo;
+        }
+      }
     }
-    for (int item = tid; item < KC * NCI; item += kPwThreads) {
-      const int ci = item % NCI, g = item / NCI;
-      float2 v[4];
-      float t[8];
+    constexpr int NX = KC * NCI;
+#pragma unroll 1
+    for (int base = tid; base < NX; base += UB * kGradThreads) {
+      float t[UB][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const long long p = p0 + g * 8 + j;
-        t[j] = p < total_px ? __ldg(X + p * ldx + ci) : 0.f;
+      for (int u = 0; u < UB; ++u) {
+        const int item = base + u * kGradThreads, ci = item % NCI, g = item / NCI;
+        const float* src = X + (p0 + g * 8) * ldx + ci;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[u][j] = (item < NX && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldx) : 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j] = make_float2(t[2 * j], t[2 * j + 1]);
-        if constexpr (ACT == 1) v[j] = gelu_pair(v[j]);
+      for (int u = 0; u < UB; ++u) {
+        const int item = base + u * kGradThreads, ci = item % NCI, g = item / NCI;
+        if (item < NX) {
+          float2 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = make_float2(t[u][2 * j], t[u][2 * j + 1]);
+            if constexpr (ACT == 1) v[j] = gelu_pair(v[j]);
+          }
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(bh + (g * NCI + ci) * 8) = hi;
+          *reinterpret_cast<uint4*>(bl + (g * NCI + ci) * 8) = lo;
+        }
       }
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      *reinterpret_cast<uint4*>(bh + (g * NCI + ci) * 8) = hi;
-      *reinterpret_cast<uint4*>(bl + (g * NCI + ci) * 8) = lo;
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc(NCI);
 #pragma unroll
@@ -743,7 +767,7 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
     const int row = q * 32 + lane;                 // output channel co0 + row
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = half * (NCI / 2); c0 < (half + 1) * (NCI / 2); c0 += 8) {
+    for (int c0 = part * 8; c0 < NCI; c0 += 32) {
       float2 v[4];
       tmem_ld8(lane_addr + c0, v);
       tmem_ld_wait();
@@ -756,7 +780,7 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
         }
       }
     }
-    if (db && tid < KC * mrows) atomicAdd(db + co0 + (tid & (mrows - 1)), bsum);
+    if (db && tid < n_dy) atomicAdd(db + co0 + (tid & (mrows - 1)), bsum);
   }
   tc_fence_before();
   __syncthreads();
@@ -773,11 +797,11 @@ static cudaError_t pwgrad_launch(int act, const float* X, int ldx, const float* 
   if (act) {
     e = cudaFuncSetAttribute(pwgrad_tc_kernel<NCI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pwgrad_tc_kernel<NCI, 1><<<grid, kPwThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, tiles, scale_dev);
+    pwgrad_tc_kernel<NCI, 1><<<grid, kGradThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, tiles, scale_dev);
   } else {
     e = cudaFuncSetAttribute(pwgrad_tc_kernel<NCI, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pwgrad_tc_kernel<NCI, 0><<<grid, kPwThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, tiles, scale_dev);
+    pwgrad_tc_kernel<NCI, 0><<<grid, kGradThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, px, tiles, scale_dev);
   }
   return cudaGetLastError();
 }
