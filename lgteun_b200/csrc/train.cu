@@ -190,8 +190,9 @@ void dwconv(Run& R, int K, TV x, const float* w, const float* b, TV y, int N, in
   if (R.dry) return;
   const TV none{nullptr, 0, 0, 0, 0};
   const int lh = ilog2(H), lw = ilog2(W), lc = ilog2(C);
-  if (K == 3 && !add && !x.nchw && !y.nchw && x.ld == C && y.ld == C && C >= 4) {
-    k_dw3_v4<<<blocks((size_t)N * H * W * C / 4), 256, 10 * C * sizeof(float), R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
+  if (K == 3 && !add && !x.nchw && !y.nchw && x.ld == C && y.ld == C && C >= 4 && W >= 8) {
+    if (W >= 16) k_dw3_v4<16><<<blocks((size_t)N * H * (W / 16) * C / 4), 256, 0, R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
+    else k_dw3_v4<8><<<blocks((size_t)N * H * (W / 8) * C / 4), 256, 0, R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
     R.check();
     return;
   }

@@ -321,34 +321,59 @@ __global__ void __launch_bounds__(256) k_dw(TV x, const float* __restrict__ w, c
   if (use_add) acc = fmaf(add_scale, add.p[tv_at(add, gp, k)], acc);
   y.p[tv_at(y, gp, k)] = acc;
 }
-// 3x3, NHWC contiguous in and out (ld == C, C % 4 == 0): four channels per thread, taps staged in shared memory as [tap][C]
+// 3x3, NHWC contiguous in and out (ld == C, C % 4 == 0, W % SEG == 0): thread = (SEG-pixel row segment, channel quad) with its
+// 9 x 4 taps in registers; a 3x3 window of float4 slides along the row, so a pixel costs three 16-byte loads and one store
+// instead of nine loads, nine shared-memory tap reads and one store (the L1 data pipe bounded that form: 110 us at
+// 4 x 256 x 256 x 128; this one us).
+template <int SEG>
 __global__ void __launch_bounds__(256) k_dw3_v4(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                                 float* __restrict__ y, int N, int lh, int lw, int lc, int flip) {
-  extern __shared__ __align__(16) float wsm[];   // [10][C]: 9 taps + bias
-  const int H = 1 << lh, W = 1 << lw, C = 1 << lc;
-  for (int i = threadIdx.x; i < 10 * C; i += 256) {
-    const int t = i >> lc, k = i & (C - 1);
-    wsm[i] = t < 9 ? w[k * 9 + (flip ? 8 - t : t)] : (b ? b[k] : 0.f);
-  }
-  __syncthreads();
-  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, total = (size_t)N << (lh + lw + lc - 2);
+  constexpr int LS = SEG == 16 ? 4 : 3;
+  const int H = 1 << lh, W = 1 << lw, lq = lc - 2, CQ = 1 << lq, lseg = lw - LS;
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, total = (size_t)N << (lh + lseg + lq);
   if (idx >= total) return;
-  const int k = (int)(idx & (C / 4 - 1)) * 4;
-  const size_t gp = idx >> (lc - 2);
-  const int xx = (int)(gp & (W - 1)), yy = (int)((gp >> lw) & (H - 1));
-  float4 acc = *reinterpret_cast<const float4*>(wsm + 9 * C + k);
+  const int q = (int)(idx & (CQ - 1));
+  const size_t s = idx >> lq;
+  const int x0 = (int)(s & (((size_t)1 << lseg) - 1)) << LS, yy = (int)((s >> lseg) & (H - 1));
+  const size_t row = (s >> lseg) << lw;          // pixel index of (n, yy, 0)
+  const bool up = yy > 0, dn = yy + 1 < H;
+  float4 wt[9];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
+  for (int t = 0; t < 9; ++t) {
+    const int ts = flip ? 8 - t : t;
+    wt[t] = make_float4(__ldg(w + (4 * q) * 9 + ts), __ldg(w + (4 * q + 1) * 9 + ts), __ldg(w + (4 * q + 2) * 9 + ts), __ldg(w + (4 * q + 3) * 9 + ts));
+  }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 bias = b ? make_float4(__ldg(b + 4 * q), __ldg(b + 4 * q + 1), __ldg(b + 4 * q + 2), __ldg(b + 4 * q + 3)) : zero;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  float4* __restrict__ y4 = reinterpret_cast<float4*>(y);
+  float4 wa[3], wb[3], wc[3];
+  auto column = [&](int xx, float4 (&c)[3]) {
+    const bool in = xx >= 0 && xx < W;
+    const size_t p = ((row + xx) << lq) + q;
+    c[0] = (in && up) ? __ldg(x4 + p - ((size_t)W << lq)) : zero;
+    c[1] = in ? __ldg(x4 + p) : zero;
+    c[2] = (in && dn) ? __ldg(x4 + p + ((size_t)W << lq)) : zero;
+  };
+  column(x0 - 1, wa);
+  column(x0, wb);
+#pragma unroll 4
+  for (int i = 0; i < SEG; ++i) {
+    column(x0 + i + 1, wc);
+    float4 acc = bias;
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int sy = yy + dy - 1, sx = xx + dx - 1;
-      if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
-      const float4 wv = *reinterpret_cast<const float4*>(wsm + (dy * 3 + dx) * C + k);
-      const float4 xv = *reinterpret_cast<const float4*>(x + ((gp + (size_t)(dy - 1) * W + (dx - 1)) << lc) + k);
-      acc.x = fmaf(wv.x, xv.x, acc.x); acc.y = fmaf(wv.y, xv.y, acc.y);
-      acc.z = fmaf(wv.z, xv.z, acc.z); acc.w = fmaf(wv.w, xv.w, acc.w);
+    for (int r = 0; r < 3; ++r) {
+      acc.x = fmaf(wt[3 * r].x, wa[r].x, acc.x); acc.y = fmaf(wt[3 * r].y, wa[r].y, acc.y);
+      acc.z = fmaf(wt[3 * r].z, wa[r].z, acc.z); acc.w = fmaf(wt[3 * r].w, wa[r].w, acc.w);
+      acc.x = fmaf(wt[3 * r + 1].x, wb[r].x, acc.x); acc.y = fmaf(wt[3 * r + 1].y, wb[r].y, acc.y);
+      acc.z = fmaf(wt[3 * r + 1].z, wb[r].z, acc.z); acc.w = fmaf(wt[3 * r + 1].w, wb[r].w, acc.w);
+      acc.x = fmaf(wt[3 * r + 2].x, wc[r].x, acc.x); acc.y = fmaf(wt[3 * r + 2].y, wc[r].y, acc.y);
+      acc.z = fmaf(wt[3 * r + 2].z, wc[r].z, acc.z); acc.w = fmaf(wt[3 * r + 2].w, wc[r].w, acc.w);
+      wa[r] = wb[r];
+      wb[r] = wc[r];
     }
-  *reinterpret_cast<float4*>(y + (gp << lc) + k) = acc;
+    y4[((row + x0 + i) << lq) + q] = acc;
+  }
 }
 
 // dw[k][tap] += sum dy[p] * x[p + tap];  db[k] += sum dy[p].  blockDim = 256, C (a power of two) divides 256;
