@@ -635,16 +635,22 @@ __device__ __forceinline__ void st_row(float* dst, const float (&r)[D], float mu
 #pragma unroll
   for (int d = 0; d < D; d += 4) *reinterpret_cast<float4*>(dst + d) = make_float4(r[d] * mul, r[d + 1] * mul, r[d + 2] * mul, r[d + 3] * mul);
 }
+// packed fp32 (FFMA2): a dot product keeps an even and an odd partial sum, which also lets two additive terms ride along
 template <int D>
-__device__ __forceinline__ float dot_row(const float (&a)[D], const float (&b)[D], float acc) {
+__device__ __forceinline__ float dot_row(const float (&a)[D], const float (&b)[D], float init_even, float init_odd) {
+  float2 s = make_float2(init_even, init_odd);
 #pragma unroll
-  for (int d = 0; d < D; ++d) acc = fmaf(a[d], b[d], acc);
-  return acc;
+  for (int d = 0; d < D; d += 2) s = __ffma2_rn(make_float2(a[d], a[d + 1]), make_float2(b[d], b[d + 1]), s);
+  return s.x + s.y;
 }
 template <int D>
 __device__ __forceinline__ void axpy_row(float (&y)[D], float a, const float (&x)[D]) {
+  const float2 aa = make_float2(a, a);
 #pragma unroll
-  for (int d = 0; d < D; ++d) y[d] = fmaf(a, x[d], y[d]);
+  for (int d = 0; d < D; d += 2) {
+    const float2 r = __ffma2_rn(aa, make_float2(x[d], x[d + 1]), make_float2(y[d], y[d + 1]));
+    y[d] = r.x; y[d + 1] = r.y;
+  }
 }
 
 template <int D>
@@ -683,8 +689,8 @@ __global__ void __launch_bounds__(64) k_attn_fwd(const float* __restrict__ qkv, 
       for (int jr = 0; jr < 4; ++jr) {
         float k[D];
         ld_row<D>(k, kb + (c + 4 * jq + jr) * G::LDP);
-        s0[4 * jq + jr] = dot_row<D>(q0, k, bb0[jr]);
-        s1[4 * jq + jr] = dot_row<D>(q1, k, bb1[jr]);
+        s0[4 * jq + jr] = dot_row<D>(q0, k, bb0[jr], 0.f);
+        s1[4 * jq + jr] = dot_row<D>(q1, k, bb1[jr], 0.f);
       }
     }
     float c0 = s0[0], c1 = s1[0];
@@ -791,8 +797,8 @@ __global__ void __launch_bounds__(64) k_attn_bwd(const float* __restrict__ qkv, 
           float k[D], v[D];
           ld_row<D>(k, kb + (4 * jq + jr) * G::LDP);
           ld_row<D>(v, vb + (4 * jq + jr) * G::LDP);
-          const float p0 = ex2f(dot_row<D>(q0, k, bb0[jr]) - st0.x), p1 = ex2f(dot_row<D>(q1, k, bb1[jr]) - st1.x);
-          const float s0 = p0 * (dot_row<D>(d0, v, 0.f) - st0.y), s1 = p1 * (dot_row<D>(d1, v, 0.f) - st1.y);
+          const float p0 = ex2f(dot_row<D>(q0, k, bb0[jr], -st0.x)), p1 = ex2f(dot_row<D>(q1, k, bb1[jr], -st1.x));
+          const float s0 = p0 * dot_row<D>(d0, v, -st0.y, 0.f), s1 = p1 * dot_row<D>(d1, v, -st1.y, 0.f);
           axpy_row<D>(ga, s0, k);
           axpy_row<D>(gb, s1, k);
         }
@@ -816,8 +822,8 @@ __global__ void __launch_bounds__(64) k_attn_bwd(const float* __restrict__ qkv, 
         ld_row<D>(q, qb + r * G::LDP);
         ld_row<D>(dO, ob + r * G::OLD);
         const float2 st = S.st[h * 64 + r];
-        const float p0 = ex2f(dot_row<D>(q, ra, __ldg(pk + r * 64)) - st.x), p1 = ex2f(dot_row<D>(q, rb, __ldg(pk + r * 64 + 32)) - st.x);
-        const float s0 = p0 * (dot_row<D>(dO, v0, 0.f) - st.y), s1 = p1 * (dot_row<D>(dO, v1, 0.f) - st.y);
+        const float p0 = ex2f(dot_row<D>(q, ra, __ldg(pk + r * 64), -st.x)), p1 = ex2f(dot_row<D>(q, rb, __ldg(pk + r * 64 + 32), -st.x));
+        const float s0 = p0 * dot_row<D>(dO, v0, -st.y, 0.f), s1 = p1 * dot_row<D>(dO, v1, -st.y, 0.f);
         dps[r * 64] += s0;
         dps[r * 64 + 32] += s1;
         axpy_row<D>(dk0, s0, q);

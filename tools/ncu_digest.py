@@ -1,5 +1,5 @@
 """Digest of one ncu report (first kernel): headline metrics, stall reasons, dynamic instruction mix and the
-instruction segments between synchronisation points.  Usage: python tools/ncu_digest.py REPORT.ncu-rep [--segments] [--hot N]"""
+instruction segments between synchronisation points.  Usage: python tools/ncu_digest.py REPORT.ncu-rep [--kernel REGEX] [--segments] [--hot N]"""
 import collections
 import csv
 import io
@@ -8,6 +8,8 @@ import sys
 
 
 def page(rep, name, extra=()):
+    if "--kernel" in sys.argv:                   # first launch whose name matches
+        extra = (*extra, "-k", "regex:" + sys.argv[sys.argv.index("--kernel") + 1], "-c", "1")
     out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv", *extra], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
