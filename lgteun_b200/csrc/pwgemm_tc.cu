@@ -642,8 +642,12 @@ cudaError_t launch_pack_umma_f16_strided(const float* w, int wso, int wsi, void*
 // >= Cout stay zero) and B = f(X)^T [ci][pixel] are K-major; every tile adds 8 x (hi*hi + hi*lo + lo*hi) MMAs into the same
 // [128 x NCI] fp32 TMEM accumulator, which is read once at the end and added to dW with atomics (the CTAs split the pixels).
 // dY is a gradient (~1e-7): it is multiplied by the step's power-of-two scale before the fp16 split, dW divided by it.
-// Staging: 16 warps; a thread issues the loads of up to four items (32 values) before it converts any of them, so that a tile's
-// 40 - 190 KB are in flight together (the one-item-at-a-time form was latency-bound: 24k clocks per tile at 8 warps).
+// Two groups of 8 warps work on alternate 64-pixel tiles, each with its own operand buffers, mbarrier and TMEM accumulator: one
+// group's loads are in flight while the other converts or waits for its MMAs (a single group spent most of a tile waiting:
+// 24k clocks per 128 pixels at 8 warps, 13k with batched loads, now ).  A thread issues every load of its share of a tile
+// (up to 8 items = 64 values) before it converts any of them.  A is stored with only the live rows (K-group stride =
+// mrows * 16 bytes): the M = 128 MMA then reads rows >= mrows out of the following K-groups / buffers, which only fills
+// accumulator rows nobody reads.
 constexpr int kGradThreads = 512;
 template <int NCI, int ACT>
 __global__ void __launch_bounds__(kGradThreads, 1)
@@ -651,86 +655,87 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
                  int wso, int wsi, float* __restrict__ db, long long total_px, int num_tiles, const float* __restrict__ scale_dev) {
   using namespace pw;
   static_assert(NCI % 16 == 0 && NCI <= 256, "tile shape");
-  constexpr int KC = 16;                                                        // 128 pixels per tile = 16 K-chunks of 8
-  constexpr int UB = 4;                                                         // items whose loads are issued together
+  constexpr int KC = 8, TP = 64;                                                // 64 pixels per tile = 8 K-chunks of 8
+  constexpr int UB = 4, GT = 256;                                               // items per load batch, threads per group
+  constexpr int NX = KC * NCI, XB = (NX + UB * GT - 1) / (UB * GT);             // X items per tile, batches per thread
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
-  __half* ah = reinterpret_cast<__half*>(smem_raw + 16);                        // [KC][128][8]
-  __half* al = ah + 128 * 128;
-  __half* bh = al + 128 * 128;                                                  // [KC][NCI][8]
-  __half* bl = bh + NCI * 128;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, part = warp >> 2;
+  const int grp = warp >> 3, gtid = tid & (GT - 1);
   const int co0 = blockIdx.y * 128;
   const int mrows = Cout - co0 < 128 ? Cout - co0 : 128;                        // a power of two >= 16
   const int lm = __ffs(mrows) - 1;
-  constexpr uint32_t TCOLS = (NCI <= 32) ? 32 : (NCI <= 64) ? 64 : (NCI <= 128 ? 128 : 256);
+  const uint32_t a_bytes = 2u * KC * mrows * 16, b_bytes = 2u * KC * NCI * 16;  // hi + lo of one group
+  __half* ah = reinterpret_cast<__half*>(smem_raw + 128 + grp * a_bytes);       // [KC][mrows][8]
+  __half* al = ah + KC * mrows * 8;
+  __half* bh = reinterpret_cast<__half*>(smem_raw + 128 + 2 * a_bytes + grp * b_bytes);   // [KC][NCI][8]
+  __half* bl = bh + KC * NCI * 8;
+  constexpr uint32_t TCOLS = (NCI <= 16) ? 32 : (NCI <= 32) ? 64 : (NCI <= 64) ? 128 : (NCI <= 128 ? 256 : 512);
   const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
 
   if (tid == 0) {
-    mbar_init(mbar, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  for (int i = tid; i < 128 * 128 * 2 / 8; i += kGradThreads) reinterpret_cast<uint4*>(ah)[i] = make_uint4(0, 0, 0, 0);   // ah and al
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = *tmem_slot, acc = tmem + grp * NCI;
   const uint32_t a_h = smem_u32(ah), a_l = smem_u32(al), b_h = smem_u32(bh), b_l = smem_u32(bl);
+  const uint32_t lbo_a = (uint32_t)mrows * 16;
   uint32_t phase = 0;
   float bsum = 0.f;
   bool first = true;
-  const int n_dy = KC * mrows;
+  const int n_dy = KC * mrows;                                                  // <= UB * GT: one batch
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const long long p0 = (long long)tile * 128;
-    const bool full = p0 + 128 <= total_px;
-    for (int base = tid; base < n_dy; base += UB * kGradThreads) {             // kGradThreads % mrows == 0: a thread keeps its channel
-      float t[UB][8];
+  for (int tile = blockIdx.x * 2 + grp; tile < num_tiles; tile += 2 * gridDim.x) {
+    const long long p0 = (long long)tile * TP;
+    const bool full = p0 + TP <= total_px;
+    float td[UB][8], tx[XB][UB][8];
 #pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int item = base + u * kGradThreads, co = item & (mrows - 1), g = item >> lm;
-        const float* src = dY + (p0 + g * 8) * ldy + co0 + co;
+    for (int u = 0; u < UB; ++u) {                                              // GT % mrows == 0: a thread keeps its channel
+      const int item = gtid + u * GT, co = item & (mrows - 1), g = item >> lm;
+      const float* src = dY + (p0 + g * 8) * ldy + co0 + co;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[u][j] = (item < n_dy && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldy) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int item = base + u * kGradThreads, co = item & (mrows - 1), g = item >> lm;
-        if (item < n_dy) {
-          float2 v[4];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bsum += t[u][j];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = make_float2(t[u][2 * j] * a_scale, t[u][2 * j + 1] * a_scale);
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          *reinterpret_cast<uint4*>(ah + (g * 128 + co) * 8) = hi;
-          *reinterpret_cast<uint4*>(al + (g * 128 + co) * 8) = lo;
-        }
-      }
+      for (int j = 0; j < 8; ++j) td[u][j] = (item < n_dy && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldy) : 0.f;
     }
-    constexpr int NX = KC * NCI;
-#pragma unroll 1
-    for (int base = tid; base < NX; base += UB * kGradThreads) {
-      float t[UB][8];
+#pragma unroll
+    for (int xb = 0; xb < XB; ++xb)
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
-        const int item = base + u * kGradThreads, ci = item % NCI, g = item / NCI;
+        const int item = gtid + (xb * UB + u) * GT, ci = item % NCI, g = item / NCI;
         const float* src = X + (p0 + g * 8) * ldx + ci;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[u][j] = (item < NX && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldx) : 0.f;
+        for (int j = 0; j < 8; ++j) tx[xb][u][j] = (item < NX && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldx) : 0.f;
       }
 #pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int item = gtid + u * GT, co = item & (mrows - 1), g = item >> lm;
+      if (item < n_dy) {
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bsum += td[u][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = make_float2(td[u][2 * j] * a_scale, td[u][2 * j + 1] * a_scale);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(ah + ((g << lm) + co) * 8) = hi;
+        *reinterpret_cast<uint4*>(al + ((g << lm) + co) * 8) = lo;
+      }
+    }
+#pragma unroll
+    for (int xb = 0; xb < XB; ++xb)
+#pragma unroll
       for (int u = 0; u < UB; ++u) {
-        const int item = base + u * kGradThreads, ci = item % NCI, g = item / NCI;
+        const int item = gtid + (xb * UB + u) * GT, ci = item % NCI, g = item / NCI;
         if (item < NX) {
           float2 v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            v[j] = make_float2(t[u][2 * j], t[u][2 * j + 1]);
+            v[j] = make_float2(tx[xb][u][2 * j], tx[xb][u][2 * j + 1]);
             if constexpr (ACT == 1) v[j] = gelu_pair(v[j]);
           }
           uint4 hi, lo;
@@ -739,48 +744,52 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
           *reinterpret_cast<uint4*>(bl + (g * NCI + ci) * 8) = lo;
         }
       }
-    }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    if (warp == 0 && elect_one()) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory");
+    if ((warp & 7) == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc(NCI);
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t dah = umma_desc(a_h + ks * 2 * 128 * 16, 128 * 16, 128);
-        const uint64_t dal = umma_desc(a_l + ks * 2 * 128 * 16, 128 * 16, 128);
+      for (int ks = 0; ks < KC / 2; ++ks) {
+        const uint64_t dah = umma_desc(a_h + ks * 2 * lbo_a, lbo_a, 128);
+        const uint64_t dal = umma_desc(a_l + ks * 2 * lbo_a, lbo_a, 128);
         const uint64_t dbh = umma_desc(b_h + ks * 2 * NCI * 16, NCI * 16, 128);
         const uint64_t dbl = umma_desc(b_l + ks * 2 * NCI * 16, NCI * 16, 128);
-        umma_f16(tmem, dah, dbh, idesc, !(first && ks == 0));
-        umma_f16(tmem, dah, dbl, idesc, 1);
-        umma_f16(tmem, dal, dbh, idesc, 1);
+        umma_f16(acc, dah, dbh, idesc, !(first && ks == 0));
+        umma_f16(acc, dah, dbl, idesc, 1);
+        umma_f16(acc, dal, dbh, idesc, 1);
       }
-      umma_commit(mbar);
+      umma_commit(&mbar[grp]);
     }
     first = false;
-    mbar_wait(mbar, phase);                        // the operand tiles may be overwritten
+    mbar_wait(&mbar[grp], phase);                  // this group's operand tiles may be overwritten
     phase ^= 1;
   }
+  tc_fence_before();
+  __syncthreads();
   tc_fence_after();
-  if (!first) {
+  {
+    const int q = warp & 3, part = warp >> 2;      // lane quarter, column slice
     const int row = q * 32 + lane;                 // output channel co0 + row
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const bool used0 = blockIdx.x * 2 < num_tiles, used1 = blockIdx.x * 2 + 1 < num_tiles;
 #pragma unroll 1
-    for (int c0 = part * 8; c0 < NCI; c0 += 32) {
-      float2 v[4];
+    for (int c0 = part * 8; c0 < NCI && used0; c0 += 32) {
+      float2 v[4], u[4];
       tmem_ld8(lane_addr + c0, v);
+      if (used1) tmem_ld8(lane_addr + NCI + c0, u);
       tmem_ld_wait();
       if (row < mrows) {
         float* dst = dW + (size_t)(co0 + row) * wso;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          atomicAdd(dst + (size_t)(c0 + 2 * j) * wsi, v[j].x * inv_scale);
-          atomicAdd(dst + (size_t)(c0 + 2 * j + 1) * wsi, v[j].y * inv_scale);
+          atomicAdd(dst + (size_t)(c0 + 2 * j) * wsi, (used1 ? v[j].x + u[j].x : v[j].x) * inv_scale);
+          atomicAdd(dst + (size_t)(c0 + 2 * j + 1) * wsi, (used1 ? v[j].y + u[j].y : v[j].y) * inv_scale);
         }
       }
     }
-    if (db && tid < n_dy) atomicAdd(db + co0 + (tid & (mrows - 1)), bsum);
+    if (db && !first && gtid < n_dy) atomicAdd(db + co0 + (gtid & (mrows - 1)), bsum);
   }
   tc_fence_before();
   __syncthreads();
@@ -790,9 +799,11 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
 template <int NCI>
 static cudaError_t pwgrad_launch(int act, const float* X, int ldx, const float* dY, int ldy, int Cout, float* dW, int wso, int wsi,
                                  float* db, long long px, const float* scale_dev, cudaStream_t s) {
-  const int tiles = (int)((px + 127) / 128);
-  const size_t smem = 16 + (size_t)(2 * 128 * 128 + 2 * NCI * 128) * 2 + 128;
-  const dim3 grid(tiles < 148 ? tiles : 148, (Cout + 127) / 128);
+  const int tiles = (int)((px + 63) / 64);
+  const int mrows = Cout < 128 ? Cout : 128;
+  // two groups x (A hi|lo [8][mrows][8] + B hi|lo [8][NCI][8]) + slack for the M = 128 read past the last live row
+  const size_t smem = 128 + 2 * (size_t)(2 * 8 * mrows * 16 + 2 * 8 * NCI * 16) + 128 * 16;
+  const dim3 grid(tiles < 2 * 148 ? (tiles + 1) / 2 : 148, (Cout + 127) / 128);
   cudaError_t e;
   if (act) {
     e = cudaFuncSetAttribute(pwgrad_tc_kernel<NCI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
