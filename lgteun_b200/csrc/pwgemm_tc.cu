@@ -656,15 +656,18 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
   using namespace pw;
   static_assert(NCI % 16 == 0 && NCI <= 256, "tile shape");
   constexpr int KC = 8, TP = 64;                                                // 64 pixels per tile = 8 K-chunks of 8
-  constexpr int UB = 4, GT = 256;                                               // items per load batch, threads per group
-  constexpr int NX = KC * NCI, XB = (NX + UB * GT - 1) / (UB * GT);             // X items per tile, batches per thread
+  constexpr int GT = 256;                                                       // threads per group
+  constexpr int NX = KC * NCI, XI = (NX + GT - 1) / GT;                         // X items per tile, per thread
+  constexpr int DI = 4;                                                         // dY items per thread (KC * 128 / GT)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);                       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = warp >> 3, gtid = tid & (GT - 1);
   const int co0 = blockIdx.y * 128;
-  const int mrows = Cout - co0 < 128 ? Cout - co0 : 128;                        // a power of two >= 16
+  const int live = Cout - co0 < 128 ? Cout - co0 : 128;                         // output channels of this CTA
+  int mrows = 16;                                                               // rows of A: the next power of two
+  while (mrows < live) mrows *= 2;
   const int lm = __ffs(mrows) - 1;
   const uint32_t a_bytes = 2u * KC * mrows * 16, b_bytes = 2u * KC * NCI * 16;  // hi + lo of one group
   __half* ah = reinterpret_cast<__half*>(smem_raw + 128 + grp * a_bytes);       // [KC][mrows][8]
@@ -689,32 +692,40 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
   uint32_t phase = 0;
   float bsum = 0.f;
   bool first = true;
-  const int n_dy = KC * mrows;                                                  // <= UB * GT: one batch
+  const int n_dy = KC * mrows;                                                  // <= DI * GT
+  // tile-invariant part of every item: source offset (floats, relative to the tile's first pixel), destination, validity.
+  // GT % mrows == 0: a thread keeps its channel co.
+  const int co = gtid & (mrows - 1);
+  int dyo[DI], dyd[DI];
+#pragma unroll
+  for (int u = 0; u < DI; ++u) {
+    const int item = gtid + u * GT, g = item >> lm;
+    dyo[u] = (item < n_dy && co < live) ? g * 8 * ldy + co0 + co : -1;          // rows in [live, mrows) are staged as zeros
+    dyd[u] = item < n_dy ? ((g << lm) + co) * 8 : -1;
+  }
+  int xo[XI];
+#pragma unroll
+  for (int u = 0; u < XI; ++u) {
+    const int item = gtid + u * GT, ci = item % NCI, g = item / NCI;
+    xo[u] = item < NX ? g * 8 * ldx + ci : -1;
+  }
 
-  for (int tile = blockIdx.x * 2 + grp; tile < num_tiles; tile += 2 * gridDim.x) {
-    const long long p0 = (long long)tile * TP;
-    const bool full = p0 + TP <= total_px;
-    float td[UB][8], tx[XB][UB][8];
+  for (int tile = blockIdx.x * 2 + grp; tile < num_tiles; tile += 2 * gridDim.x) {   // total_px % 64 == 0 (launch check)
+    const float* __restrict__ dyt = dY + (long long)tile * TP * ldy;
+    const float* __restrict__ xt = X + (long long)tile * TP * ldx;
+    constexpr int XB = XI < 4 ? XI : 4;                                         // X items whose loads are issued together
+    float td[DI][8], tx[XB][8];
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {                                              // GT % mrows == 0: a thread keeps its channel
-      const int item = gtid + u * GT, co = item & (mrows - 1), g = item >> lm;
-      const float* src = dY + (p0 + g * 8) * ldy + co0 + co;
+    for (int u = 0; u < DI; ++u)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) td[u][j] = (item < n_dy && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldy) : 0.f;
-    }
+      for (int j = 0; j < 8; ++j) td[u][j] = dyo[u] >= 0 ? __ldg(dyt + (dyo[u] + j * ldy)) : 0.f;
 #pragma unroll
-    for (int xb = 0; xb < XB; ++xb)
+    for (int u = 0; u < XB; ++u)
 #pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int item = gtid + (xb * UB + u) * GT, ci = item % NCI, g = item / NCI;
-        const float* src = X + (p0 + g * 8) * ldx + ci;
+      for (int j = 0; j < 8; ++j) tx[u][j] = xo[u] >= 0 ? __ldg(xt + (xo[u] + j * ldx)) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tx[xb][u][j] = (item < NX && (full || p0 + g * 8 + j < total_px)) ? __ldg(src + (size_t)j * ldx) : 0.f;
-      }
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const int item = gtid + u * GT, co = item & (mrows - 1), g = item >> lm;
-      if (item < n_dy) {
+    for (int u = 0; u < DI; ++u) {
+      if (dyd[u] >= 0) {
         float2 v[4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bsum += td[u][j];
@@ -722,28 +733,35 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
         for (int j = 0; j < 4; ++j) v[j] = make_float2(td[u][2 * j] * a_scale, td[u][2 * j + 1] * a_scale);
         uint4 hi, lo;
         split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(ah + ((g << lm) + co) * 8) = hi;
-        *reinterpret_cast<uint4*>(al + ((g << lm) + co) * 8) = lo;
+        *reinterpret_cast<uint4*>(ah + dyd[u]) = hi;
+        *reinterpret_cast<uint4*>(al + dyd[u]) = lo;
       }
     }
 #pragma unroll
-    for (int xb = 0; xb < XB; ++xb)
+    for (int xb = 0; xb < XI; xb += XB) {
+      if (xb > 0) {
 #pragma unroll
-      for (int u = 0; u < UB; ++u) {
-        const int item = gtid + (xb * UB + u) * GT, ci = item % NCI, g = item / NCI;
-        if (item < NX) {
+        for (int u = 0; u < XB; ++u)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tx[u][j] = xo[xb + u] >= 0 ? __ldg(xt + (xo[xb + u] + j * ldx)) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < XB; ++u) {
+        if (xo[xb + u] >= 0) {
+          const int item = gtid + (xb + u) * GT;                                // destination [g][ci][8] = item * 8
           float2 v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            v[j] = make_float2(tx[xb][u][2 * j], tx[xb][u][2 * j + 1]);
+            v[j] = make_float2(tx[u][2 * j], tx[u][2 * j + 1]);
             if constexpr (ACT == 1) v[j] = gelu_pair(v[j]);
           }
           uint4 hi, lo;
           split8(v, hi, lo);
-          *reinterpret_cast<uint4*>(bh + (g * NCI + ci) * 8) = hi;
-          *reinterpret_cast<uint4*>(bl + (g * NCI + ci) * 8) = lo;
+          *reinterpret_cast<uint4*>(bh + item * 8) = hi;
+          *reinterpret_cast<uint4*>(bl + item * 8) = lo;
         }
       }
+    }
     fence_proxy_async();
     tc_fence_before();
     asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory");
@@ -780,7 +798,7 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
       tmem_ld8(lane_addr + c0, v);
       if (used1) tmem_ld8(lane_addr + NCI + c0, u);
       tmem_ld_wait();
-      if (row < mrows) {
+      if (row < live) {
         float* dst = dW + (size_t)(co0 + row) * wso;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -789,7 +807,7 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
         }
       }
     }
-    if (db && !first && gtid < n_dy) atomicAdd(db + co0 + (gtid & (mrows - 1)), bsum);
+    if (db && !first && gtid < n_dy && co < live) atomicAdd(db + co0 + co, bsum);
   }
   tc_fence_before();
   __syncthreads();
@@ -799,8 +817,10 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
 template <int NCI>
 static cudaError_t pwgrad_launch(int act, const float* X, int ldx, const float* dY, int ldy, int Cout, float* dW, int wso, int wsi,
                                  float* db, long long px, const float* scale_dev, cudaStream_t s) {
-  const int tiles = (int)((px + 63) / 64);
-  const int mrows = Cout < 128 ? Cout : 128;
+  if (px % 64) return cudaErrorInvalidValue;
+  const int tiles = (int)(px / 64);
+  int mrows = 16;
+  while (mrows < Cout && mrows < 128) mrows *= 2;
   // two groups x (A hi|lo [8][mrows][8] + B hi|lo [8][NCI][8]) + slack for the M = 128 read past the last live row
   const size_t smem = 128 + 2 * (size_t)(2 * 8 * mrows * 16 + 2 * 8 * NCI * 16) + 128 * 16;
   const dim3 grid(tiles < 2 * 148 ? (tiles + 1) / 2 : 148, (Cout + 127) / 128);
@@ -816,9 +836,9 @@ static cudaError_t pwgrad_launch(int act, const float* X, int ldx, const float* 
   }
   return cudaGetLastError();
 }
-bool train_pwgrad_supported(int Cin, int Cout) {
+bool train_pwgrad_supported(int Cin, int Cout) {     // Cout: any count up to 256 (rows up to the next power of two are zeros)
   auto p2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
-  return p2(Cin) && Cin >= 16 && Cin <= 256 && p2(Cout) && Cout >= 16 && Cout <= 256;
+  return p2(Cin) && Cin >= 16 && Cin <= 256 && Cout >= 1 && Cout <= 256;
 }
 cudaError_t launch_train_pwgrad(int Cin, int Cout, int act, const float* X, int ldx, const float* dY, int ldy, float* dW, int wso,
                                 int wsi, float* db, long long px, const float* scale_dev, cudaStream_t s) {

@@ -126,7 +126,7 @@ bool use_tc_wgrad(int Cin, int Cout) {
 void pw_wgrad(Run& R, int act, TV x, int Cin, TV dy, int Cout, const float* dW, int wso, int wsi, const float* db, size_t NP,
               const float* gscale = nullptr) {
   if (R.dry) return;
-  if (gscale && !x.nchw && !dy.nchw && use_tc_wgrad(Cin, Cout)) {
+  if (gscale && !x.nchw && !dy.nchw && NP % 64 == 0 && use_tc_wgrad(Cin, Cout)) {
     cudaError_t e = launch_train_pwgrad(Cin, Cout, act, x.p, x.ld, dy.p, dy.ld, const_cast<float*>(dW), wso, wsi,
                                         const_cast<float*>(db), (long long)NP, gscale, R.s);
     ++R.launches;
@@ -389,7 +389,7 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
   // local branch
   float* dqkv = R.take(NP * 3 * c2);
   attn_bwd(R, c2 / 2, t.qkv, t.ppos, nhwc(dcat, ch), nhwc(t.cat, ch), t.lse, dqkv, g.pos, N, H, W);
-  pw_wgrad(R, 0, nhwc(t.A, ch), c2, nhwc(dqkv, 3 * c2), 3 * c2, g.qkv_w, c2, 1, g.qkv_b, NP);
+  pw_wgrad(R, 0, nhwc(t.A, ch), c2, nhwc(dqkv, 3 * c2), 3 * c2, g.qkv_w, c2, 1, g.qkv_b, NP, S.T->gscale);
   pw(R, 0, nhwc(dqkv, 3 * c2), 3 * c2, w.qkv_w, 1, c2, nullptr, nhwc(dA, ch), c2, NP);
   // global branch: |.| -> C2R rows -> inverse columns -> mixing -> forward columns -> R2C rows, all transposed
   float* dG = R.take(SP);

@@ -8,8 +8,9 @@ import sys
 
 
 def page(rep, name, extra=()):
-    if "--kernel" in sys.argv:                   # first launch whose name matches
-        extra = (*extra, "-k", "regex:" + sys.argv[sys.argv.index("--kernel") + 1], "-c", "1")
+    extra = (*extra, "-c", "1")                  # first launch (whose name matches --kernel)
+    if "--kernel" in sys.argv:
+        extra = (*extra, "-k", "regex:" + sys.argv[sys.argv.index("--kernel") + 1])
     out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv", *extra], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
@@ -37,6 +38,10 @@ def main():
             print(f"  {k:75s} {d[k][1]:>16s} {d[k][0]}")
     src = page(rep, "source", ["--print-source", "sass"])
     hdr, data = src[1], src[2:]
+    for k, r in enumerate(data):                 # a report with several launches repeats the header per launch: keep the first
+        if len(r) < 10:
+            data = data[:k]
+            break
     iS, iE, iSm = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     st = [(i, n) for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
     tot = sum(int(r[iE]) for r in data)
