@@ -605,13 +605,15 @@ static cudaError_t train_pw_dispatch(int pro, int epi, const float* X, float* Y,
 }
 bool train_pwgemm_supported(int K, int N) {
   const int c = K < N ? K : N, c4 = K < N ? N : K;
-  return (c == 16 || c == 32 || c == 64) && (c4 == 4 * c || (K == N && (K == 64 || K == 128 || K == 256)));
+  return ((c == 16 || c == 32 || c == 64) && (c4 == 4 * c || (K == N && (K == 64 || K == 128 || K == 256)))) ||
+         (K == N && (K == 16 || K == 32));       // the mixer's projection
 }
 cudaError_t launch_train_pwgemm(int K, int N, int pro, int epi, const float* X, float* Y, const void* wpack, const float* bias,
                                 const float* aux, long long px, const float* scale_dev, cudaStream_t s) {
 #define LG_TPW(KK, NN) if (K == KK && N == NN) return train_pw_dispatch<KK, NN>(pro, epi, X, Y, wpack, bias, aux, px, scale_dev, s)
   LG_TPW(16, 64); LG_TPW(32, 128); LG_TPW(64, 256);      // c -> 4c
   LG_TPW(64, 64); LG_TPW(128, 128); LG_TPW(256, 256);    // 4c -> 4c
+  LG_TPW(16, 16); LG_TPW(32, 32);                        // c -> c
   LG_TPW(64, 16); LG_TPW(128, 32); LG_TPW(256, 64);      // 4c -> c
 #undef LG_TPW
   return cudaErrorInvalidValue;

@@ -319,7 +319,8 @@ float* fwd_block(Run& R, const Step& S, const BlockW& w, int ch, BlockTape& t, f
   t.v = R.take(NP * c2);
   fft_rows(R, 1, nullptr, 0, nullptr, G, t.v, c2, t.cat + c2, ch, N, H, W, c2, 1.f / ((float)H * (float)W), 1);
   float* pr = R.take(NP * ch);
-  pw(R, 0, nhwc(t.cat, ch), ch, w.proj_w, ch, 1, w.proj_b, nhwc(pr, ch), ch, NP);
+  if (use_tc_gemm(ch, ch)) tc_pw(R, ch, ch, 0, 0, t.cat, pr, w.proj_w, ch, 1, w.proj_b, nullptr, NP, nullptr);
+  else pw(R, 0, nhwc(t.cat, ch), ch, w.proj_w, ch, 1, w.proj_b, nhwc(pr, ch), ch, NP);
   t.Xmid = R.take(NP * ch);
   if (!R.dry) {
     k_dropout<<<blocks(NP * ch), 256, 0, R.s>>>(Xin, pr, t.Xmid, NP * ch, S.T->seed, layer, S.T->p_drop, 0,
@@ -384,7 +385,8 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
   }
   pw_wgrad(R, 0, nhwc(t.cat, ch), ch, nhwc(dpr, ch), ch, g.proj_w, ch, 1, g.proj_b, NP, S.T->gscale);
   float* dcat = R.take(NP * ch);
-  pw(R, 0, nhwc(dpr, ch), ch, w.proj_w, 1, ch, nullptr, nhwc(dcat, ch), ch, NP);
+  if (use_tc_gemm(ch, ch)) tc_pw(R, ch, ch, 0, 0, dpr, dcat, w.proj_w, 1, ch, nullptr, nullptr, NP, S.T->gscale);
+  else pw(R, 0, nhwc(dpr, ch), ch, w.proj_w, 1, ch, nullptr, nhwc(dcat, ch), ch, NP);
   float* dA = R.take(NP * ch);
   // local branch
   float* dqkv = R.take(NP * 3 * c2);
