@@ -95,7 +95,13 @@ cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int 
 cudaError_t launch_fft_cols128(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s);   // H = 128
 cudaError_t launch_fft_rows_fwd256(const BlockW& w, int c, const float* x, float* spec, int N, int H, cudaStream_t s);
 // plain register-resident passes (no LayerNorm / mixing / projection) for the companion operator of companion_ops.cu
-cudaError_t launch_fft_cols_plain(int H, int c2, float* spec, int N, int W, int dir, cudaStream_t s);                 // H in {128, 256}
+cudaError_t launch_fft_cols_plain(int H, int c2, float* spec, int N, int W, int dir, cudaStream_t s, int fixreal = 1);                 // H in {128, 256}
+// plain row transforms of the training step at W in {128, 256}, c2 in {8, 16, 32} (fft256.cu)
+bool fft_rows_plain_supported(int W, int c2, int ldx, const void* p0, const void* p1, const void* p2);
+cudaError_t launch_fft_rows_r2c(int W, int c2, const float* x, int ldx, const float* sgn, float* spec, size_t rows, float scale,
+                                float wint, cudaStream_t s);
+cudaError_t launch_fft_rows_c2r(int W, int c2, const float* spec, float* xout, int ldo, float* xabs, int ldabs, size_t rows,
+                                float scale, float wint, cudaStream_t s);
 // forward columns + amp/pha fusion + inverse columns of Freprocess in one launch; cudaErrorNotSupported if (H, C) is not built.
 // fuse_w = {amp_fuse.0.weight, .0.bias, amp_fuse.2.weight, .2.bias, pha_fuse.0.weight, .0.bias, pha_fuse.2.weight, .2.bias}
 cudaError_t launch_fre_cols_fused(int H, int C, const float* S, float* G, const float* const* fuse_w, int N, int W, cudaStream_t s);

@@ -112,7 +112,8 @@ __device__ __forceinline__ void fft_m(float2* v) {
 // exchange, pass B an M-point FFT over n2 for each k1 (16/M of them per thread), leaving X[k1 + 16 k2] in registers.
 // The inverse consumes exactly that distribution (m = m2 + 16 m1 with m2 = k1, m1 = k2): M-point over m1, twiddle,
 // exchange, 16-point over m2, so no reordering is needed between the two transforms.
-// MODE 0: forward + mixing + inverse (the global mixer).  MODE 1: forward only, MODE 2: unnormalised inverse only — the plain
+// MODE 0: forward + mixing + inverse (the global mixer).  MODE 1: forward only (MODE 3: the same without the real-bin rule,
+// the adjoint of the inverse in the training backward), MODE 2: unnormalised inverse only — the plain
 // column transforms of the companion operator SFIIN.Freprocess (companion_ops.cu), which mixes channels between the two.
 template <int Q, int M, int MODE = 0>
 __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restric
     fft_m<M, -1>(v + kk * M);                             // v[kk*M + k2] = X[ky = (lo + M kk) + 16 k2]
   }
   }
-  if constexpr (MODE == 1) {
-    const bool real_col = ((l0 + l) / C2 == 0 || (l0 + l) / C2 == W / 2);
+  if constexpr (MODE == 1 || MODE == 3) {
+    const bool real_col = MODE == 1 && ((l0 + l) / C2 == 0 || (l0 + l) / C2 == W / 2);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int kk = i / M, k2 = i % M;
@@ -242,7 +243,8 @@ template <int M> __device__ __forceinline__ int padded_m(int i) { return i + i /
 // register passes, splits the packed transforms and writes spec rows [row0, row0 + RW).  Starts with the barrier that
 // publishes X.
 template <int C2, int M>
-__device__ __forceinline__ void rows_fwd_transform(float2* X, const float2* tw, float2* __restrict__ spec, size_t row0) {
+__device__ __forceinline__ void rows_fwd_transform(float2* X, const float2* tw, float2* __restrict__ spec, size_t row0,
+                                                   float scale = 0.5f, float wint = 1.f) {   // scale includes the 1/2 of the split
   using namespace f256;
   constexpr int W = 16 * M, Wf = W / 2 + 1, RP = 16 * (M + 1), KPT = 16 / M, TS = 16 / M;
   constexpr int NF1 = C2 / 2, RW = (256 / M) / NF1;
@@ -281,11 +283,12 @@ __device__ __forceinline__ void rows_fwd_transform(float2* X, const float2* tw, 
     const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
     const int k = rem / NF1, s = rl * NF1 + (rem - k * NF1);
     const float2 z = X[s * RP + k], zm = X[s * RP + ((W - k) & (W - 1))];
+    const float f = (k > 0 && k < W / 2) ? scale * wint : scale;
     float4 o;
-    o.x = 0.5f * (z.x + zm.x);        // Xa = (Z[k] + conj(Z[W-k])) / 2
-    o.y = 0.5f * (z.y - zm.y);
-    o.z = 0.5f * (z.y + zm.y);        // Xb = (Z[k] - conj(Z[W-k])) / (2i)
-    o.w = 0.5f * (zm.x - z.x);
+    o.x = f * (z.x + zm.x);           // Xa = (Z[k] + conj(Z[W-k])) / 2
+    o.y = f * (z.y - zm.y);
+    o.z = f * (z.y + zm.y);           // Xb = (Z[k] - conj(Z[W-k])) / (2i)
+    o.w = f * (zm.x - z.x);
     out[id] = o;
   }
 }
@@ -593,9 +596,9 @@ static cudaError_t cols_plain_t(int c2, float* spec, int N, int W, cudaStream_t 
 }
 // in-place column FFT of spec[n][H][W/2+1][c2] for H in {128, 256}: dir < 0 forward (the four real bins get +0.0 imaginary
 // parts), dir > 0 unnormalised inverse
-cudaError_t launch_fft_cols_plain(int H, int c2, float* spec, int N, int W, int dir, cudaStream_t s) {
-  if (H == 256) return dir < 0 ? cols_plain_t<16, 1>(c2, spec, N, W, s) : cols_plain_t<16, 2>(c2, spec, N, W, s);
-  if (H == 128) return dir < 0 ? cols_plain_t<8, 1>(c2, spec, N, W, s) : cols_plain_t<8, 2>(c2, spec, N, W, s);
+cudaError_t launch_fft_cols_plain(int H, int c2, float* spec, int N, int W, int dir, cudaStream_t s, int fixreal) {
+  if (H == 256) return dir > 0 ? cols_plain_t<16, 2>(c2, spec, N, W, s) : fixreal ? cols_plain_t<16, 1>(c2, spec, N, W, s) : cols_plain_t<16, 3>(c2, spec, N, W, s);
+  if (H == 128) return dir > 0 ? cols_plain_t<8, 2>(c2, spec, N, W, s) : fixreal ? cols_plain_t<8, 1>(c2, spec, N, W, s) : cols_plain_t<8, 3>(c2, spec, N, W, s);
   return cudaErrorInvalidValue;
 }
 // The whole column stage of Freprocess in one kernel (models/SFIIN.py:223-234 between the row transforms): forward FFT
@@ -902,6 +905,165 @@ cudaError_t launch_fft_rows_inv_post(int W, int C, const float* spec, const floa
     if (C == 8) return rows_inv_post_t<8, 8>(spec, post_w, post_b, y_nchw, N, H, s);
     if (C == 16) return rows_inv_post_t<16, 8>(spec, post_w, post_b, y_nchw, N, H, s);
   }
+  return cudaErrorInvalidValue;
+}
+
+// ---- plain row passes of the training step (train.cu; the adjoints are the same two transforms with other weights) -------------
+// R2C: real rows x[pixel * ldx + c] (optionally times sign(sgn[pixel * C2 + c]): the backward of |.|) -> spec[row][k <= W/2][C2],
+// times scale, interior bins (0 < k < W/2) also times wint.  wint = 2 makes it the adjoint of the C2R below.
+template <int C2, int M>
+__global__ void __launch_bounds__(256) fft_rows_r2c_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ sgn,
+                                                            float2* __restrict__ spec, float scale, float wint) {
+  using namespace f256;
+  constexpr int W = 16 * M, RP = 16 * (M + 1), NF1 = C2 / 2, RW = (256 / M) / NF1;
+  static_assert(RW >= 1, "a CTA holds at least one image row");
+  __shared__ float2 tw[256];
+  extern __shared__ __align__(16) float2 smf[];
+  float2* X = smf;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * RW;
+  tw[tid] = g_tw256[tid];
+#pragma unroll
+  for (int i = 0; i < RW * W / 256; ++i) {
+    const int p = tid + 256 * i, rl = p / W, px = p % W;
+    const size_t pix = (row0 + rl) * W + px;
+    float g[C2];
+    load_vec<C2>(g, x + pix * ldx);
+    if (sgn) {
+      float t[C2];
+      load_vec<C2>(t, sgn + pix * C2);
+#pragma unroll
+      for (int c = 0; c < C2; ++c) g[c] = t[c] > 0.f ? g[c] : (t[c] < 0.f ? -g[c] : 0.f);
+    }
+#pragma unroll
+    for (int f = 0; f < NF1; ++f) X[(rl * NF1 + f) * RP + padded_m<M>(px)] = make_float2(g[2 * f], g[2 * f + 1]);
+  }
+  rows_fwd_transform<C2, M>(X, tw, spec, row0, 0.5f * scale, wint);
+}
+// C2R: spec[row][k <= W/2][C2] (interior bins times wint; the imaginary parts of bins 0 and W/2 drop out) -> real rows times
+// scale -> xout[pixel * ldo + c], and |.| of it -> xabs[pixel * ldabs + c].  wint = 1: irfft's C2R; wint = 1/2: the real part
+// of the inverse transform of the zero-padded half spectrum (the adjoint of the plain R2C).
+template <int C2, int M>
+__global__ void __launch_bounds__(256) fft_rows_c2r_kernel(const float2* __restrict__ spec, float* __restrict__ xout, int ldo,
+                                                            float* __restrict__ xabs, int ldabs, float scale, float wint) {
+  using namespace f256;
+  constexpr int W = 16 * M, Wf = W / 2 + 1, RP = 16 * (M + 1), NSEQ = 256 / M, KPT = 16 / M, TS = 16 / M;
+  constexpr int NF1 = C2 / 2, RW = NSEQ / NF1;
+  static_assert(RW >= 1, "a CTA holds at least one image row");
+  __shared__ float2 tw[256];
+  extern __shared__ __align__(16) float2 smf[];
+  float2* X = smf;                                        // [NSEQ][RP]
+  float2* E = smf;
+  const int tid = threadIdx.x;
+  const size_t row0 = (size_t)blockIdx.x * RW;
+  tw[tid] = g_tw256[tid];
+  const float4* in = reinterpret_cast<const float4*>(spec + row0 * Wf * C2);
+  {
+    constexpr int TOTAL = RW * Wf * NF1, ITERS = (TOTAL + 255) / 256;
+    float4 vb[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int id = tid + 256 * i;
+      vb[i] = (id < TOTAL) ? __ldg(in + id) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int id = tid + 256 * i;
+      if (id >= TOTAL) break;
+      const int rl = id / (Wf * NF1), rem = id - rl * (Wf * NF1);
+      const int k = rem / NF1, sq = rl * NF1 + (rem - k * NF1);
+      float4 v = vb[i];                                   // (Xa.re, Xa.im, Xb.re, Xb.im)
+      if (k == 0 || k == W / 2) {
+        X[sq * RP + padded_m<M>(k)] = make_float2(v.x, v.z);
+      } else {
+        v.x *= wint; v.y *= wint; v.z *= wint; v.w *= wint;
+        X[sq * RP + padded_m<M>(k)] = make_float2(v.x - v.w, v.y + v.z);          // Xa + i Xb
+        X[sq * RP + padded_m<M>(W - k)] = make_float2(v.x + v.w, v.z - v.y);      // conj(Xa) + i conj(Xb)
+      }
+    }
+  }
+  __syncthreads();
+  const int seq = tid / M, lo = tid % M;
+  float2 v[16];
+#pragma unroll
+  for (int m1 = 0; m1 < 16; ++m1) v[m1] = X[seq * RP + (M + 1) * m1 + lo];
+  fft16<+1>(v);
+#pragma unroll
+  for (int j1 = 1; j1 < 16; ++j1) v[j1] = ctw<+1>(v[j1], tw[TS * lo * j1]);
+  __syncwarp();
+#pragma unroll
+  for (int j1 = 0; j1 < 16; ++j1) E[seq * RP + j1 * (M + 1) + lo] = v[j1];
+  __syncwarp();
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk) {
+#pragma unroll
+    for (int m2 = 0; m2 < M; ++m2) v[kk * M + m2] = E[seq * RP + (lo + M * kk) * (M + 1) + m2];
+    fft_m<M, +1>(v + kk * M);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+    for (int j2 = 0; j2 < M; ++j2)
+      X[seq * RP + (lo + M * kk) + 16 * j2] = make_float2(v[kk * M + j2].x * scale, v[kk * M + j2].y * scale);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RW * W / 256; ++i) {                // thread = pixel
+    const int p = tid + 256 * i, rl = p / W, px = p % W;
+    const size_t pix = (row0 + rl) * W + px;
+    float g[C2];
+#pragma unroll
+    for (int f = 0; f < NF1; ++f) {
+      const float2 t = X[(rl * NF1 + f) * RP + px];
+      g[2 * f] = t.x;
+      g[2 * f + 1] = t.y;
+    }
+    store_vec<C2>(xout + pix * ldo, g);
+    if (xabs) {
+#pragma unroll
+      for (int c = 0; c < C2; ++c) g[c] = fabsf(g[c]);
+      store_vec<C2>(xabs + pix * ldabs, g);
+    }
+  }
+}
+template <int C2, int M>
+static cudaError_t rows_r2c_t(const float* x, int ldx, const float* sgn, float* spec, size_t rows, float scale, float wint, cudaStream_t s) {
+  constexpr int RW = (256 / M) / (C2 / 2);
+  if (rows % RW) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(256 / M) * 16 * (M + 1) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_r2c_kernel<C2, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_rows_r2c_kernel<C2, M><<<(unsigned)(rows / RW), 256, smem, s>>>(x, ldx, sgn, reinterpret_cast<float2*>(spec), scale, wint);
+  return cudaGetLastError();
+}
+template <int C2, int M>
+static cudaError_t rows_c2r_t(const float* spec, float* xout, int ldo, float* xabs, int ldabs, size_t rows, float scale, float wint,
+                              cudaStream_t s) {
+  constexpr int RW = (256 / M) / (C2 / 2);
+  if (rows % RW) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(256 / M) * 16 * (M + 1) * sizeof(float2);
+  cudaError_t e = cudaFuncSetAttribute(fft_rows_c2r_kernel<C2, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fft_rows_c2r_kernel<C2, M><<<(unsigned)(rows / RW), 256, smem, s>>>(reinterpret_cast<const float2*>(spec), xout, ldo, xabs, ldabs,
+                                                                       scale, wint);
+  return cudaGetLastError();
+}
+bool fft_rows_plain_supported(int W, int c2, int ldx, const void* p0, const void* p1, const void* p2) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (W == 128 || W == 256) && (c2 == 8 || c2 == 16 || c2 == 32) && ldx % 4 == 0 && al(p0) && al(p1) && al(p2);
+}
+cudaError_t launch_fft_rows_r2c(int W, int c2, const float* x, int ldx, const float* sgn, float* spec, size_t rows, float scale,
+                                float wint, cudaStream_t s) {
+#define LG_R2C(CC, MM) if (c2 == CC && W == 16 * MM) return rows_r2c_t<CC, MM>(x, ldx, sgn, spec, rows, scale, wint, s)
+  LG_R2C(8, 16); LG_R2C(16, 16); LG_R2C(32, 16); LG_R2C(8, 8); LG_R2C(16, 8); LG_R2C(32, 8);
+#undef LG_R2C
+  return cudaErrorInvalidValue;
+}
+cudaError_t launch_fft_rows_c2r(int W, int c2, const float* spec, float* xout, int ldo, float* xabs, int ldabs, size_t rows,
+                                float scale, float wint, cudaStream_t s) {
+#define LG_C2R(CC, MM) if (c2 == CC && W == 16 * MM) return rows_c2r_t<CC, MM>(spec, xout, ldo, xabs, ldabs, rows, scale, wint, s)
+  LG_C2R(8, 16); LG_C2R(16, 16); LG_C2R(32, 16); LG_C2R(8, 8); LG_C2R(16, 8); LG_C2R(32, 8);
+#undef LG_C2R
   return cudaErrorInvalidValue;
 }
 

@@ -266,6 +266,18 @@ int fft_cpb(int L, int c2) {    // channels of one line per block: at most 8192 
 void fft_rows(Run& R, int mode, const float* xin, int ldx, const float* sgn, float* spec, float* xout, int ldo, float* xabs,
               int ldabs, int N, int H, int W, int c2, float scale, int weight2) {
   if (R.dry) return;
+  // W in {128, 256}: the register-resident row transforms of the inference path (two real channels per complex FFT, fft256.cu)
+  static const bool smem_fft = [] { const char* e = getenv("LGTEUN_TRAIN_FFT"); return e && std::string(e) == "smem"; }();
+  const size_t rows = (size_t)N * H;
+  if (!smem_fft && rows % 4 == 0) {
+    cudaError_t e = cudaErrorInvalidValue;
+    if (mode == 0 && lg::fft_rows_plain_supported(W, c2, ldx, xin, sgn, spec))
+      e = lg::launch_fft_rows_r2c(W, c2, xin, ldx, sgn, spec, rows, scale, weight2 ? 2.f : 1.f, R.s);
+    else if (mode == 1 && (!xabs || ldabs % 4 == 0) && lg::fft_rows_plain_supported(W, c2, ldo, spec, xout, xabs))
+      e = lg::launch_fft_rows_c2r(W, c2, spec, xout, ldo, xabs, ldabs, rows, scale, weight2 ? 1.f : 0.5f, R.s);
+    if (e == cudaSuccess) { ++R.launches; return; }
+    (void)cudaGetLastError();
+  }
   const int cpb = fft_cpb(W, c2);
   const size_t smem = (W / 2 + (size_t)cpb * (W + 1)) * sizeof(float2);
   optin_smem(k_fft_rows, smem);
@@ -275,6 +287,13 @@ void fft_rows(Run& R, int mode, const float* xin, int ldx, const float* sgn, flo
 }
 void fft_cols(Run& R, float* spec, int N, int H, int W, int c2, int dir, int fixreal) {
   if (R.dry) return;
+  static const bool smem_fft = [] { const char* e = getenv("LGTEUN_TRAIN_FFT"); return e && std::string(e) == "smem"; }();
+  if (!smem_fft && (H == 128 || H == 256)) {   // the register-resident two-pass column transform of the inference path (fft256.cu)
+    cudaError_t e = lg::launch_fft_cols_plain(H, c2, spec, N, W, dir, R.s, fixreal);
+    ++R.launches;
+    if (R.err == cudaSuccess) R.err = e;
+    return;
+  }
   const int cpb = fft_cpb(H, c2);
   const size_t smem = (H / 2 + (size_t)cpb * (H + 1)) * sizeof(float2);
   optin_smem(k_fft_cols, smem);
