@@ -160,10 +160,18 @@ void tc_pw(Run& R, int K, int N, int pro, int epi, const float* X, float* Y, con
 bool ln_fast(TV a, TV b, int C, size_t NP) {
   return !a.nchw && !b.nchw && a.ld == C && b.ld == C && (C == 16 || C == 32 || C == 64) && NP % 2 == 0;
 }
+bool ln_v4(const void* a, const void* b, const void* c, const void* d, size_t NP) {   // 16-byte accesses, 8 pixels per warp at most
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al(a) && al(b) && al(c) && al(d) && NP % 8 == 0;
+}
 void ln_fwd(Run& R, TV x, int C, const float* g, const float* b, TV y, size_t NP) {
   if (R.dry) return;
   const unsigned gw = (unsigned)std::min<size_t>(148 * 8, (NP + 63) / 64);
-  if (ln_fast(x, y, C, NP)) {
+  if (ln_fast(x, y, C, NP) && ln_v4(x.p, y.p, g, b, NP)) {
+    if (C == 16) k_ln_v4<16, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
+    else if (C == 32) k_ln_v4<32, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
+    else k_ln_v4<64, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
+  } else if (ln_fast(x, y, C, NP)) {
     if (C == 16) k_ln_warp<16, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
     else if (C == 32) k_ln_warp<32, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
     else k_ln_warp<64, 0><<<gw, 256, 0, R.s>>>(x.p, g, b, nullptr, y.p, 0, nullptr, nullptr, NP);
@@ -176,7 +184,11 @@ void ln_bwd(Run& R, TV x, int C, const float* g, TV dy, TV dx, int accumulate, c
   if (R.dry) return;
   float *pg = const_cast<float*>(dg), *pb = const_cast<float*>(db);
   const unsigned gw = (unsigned)std::min<size_t>(148 * 8, (NP + 63) / 64);
-  if (ln_fast(x, dy, C, NP) && !dx.nchw && dx.ld == C) {
+  if (ln_fast(x, dy, C, NP) && !dx.nchw && dx.ld == C && ln_v4(x.p, dy.p, dx.p, g, NP)) {
+    if (C == 16) k_ln_v4<16, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
+    else if (C == 32) k_ln_v4<32, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
+    else k_ln_v4<64, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
+  } else if (ln_fast(x, dy, C, NP) && !dx.nchw && dx.ld == C) {
     if (C == 16) k_ln_warp<16, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
     else if (C == 32) k_ln_warp<32, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);
     else k_ln_warp<64, 1><<<gw, 256, 0, R.s>>>(x.p, g, nullptr, dy.p, dx.p, accumulate, pg, pb, NP);

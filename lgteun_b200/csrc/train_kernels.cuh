@@ -295,6 +295,71 @@ __global__ void __launch_bounds__(256) k_ln_warp(const float* __restrict__ x, co
   }
 }
 
+// The same with four channels per lane (C / 4 lanes per pixel, 128 / C pixels per warp and iteration): 16-byte accesses and
+// log2(C / 4) shuffle steps per reduction instead of log2(min(C, 32)) on scalars — the scalar form spent its time in SHFL
+// (20 per pixel in the backward).  NP % (128 / C) == 0.
+template <int C, int BWD>
+__global__ void __launch_bounds__(256) k_ln_v4(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                               const float* __restrict__ dy, float* __restrict__ out, int accumulate,
+                                               float* __restrict__ dgamma, float* __restrict__ dbeta, size_t NP) {
+  constexpr int GROUP = C / 4, PPW = 32 / GROUP;
+  __shared__ float red[2 * C];
+  if (BWD) {
+    for (int i = threadIdx.x; i < 2 * C; i += 256) red[i] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, cl = lane % GROUP, sub = lane / GROUP;
+  const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * 8;
+  const float4 gam = *reinterpret_cast<const float4*>(g + 4 * cl);
+  const float4 bet = BWD ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b + 4 * cl);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* d4 = reinterpret_cast<const float4*>(dy);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  for (size_t gp = warp * PPW + sub; gp < NP; gp += nwarps * PPW) {
+    const size_t o = gp * GROUP + cl;
+    float4 v = __ldg(x4 + o), d = make_float4(0.f, 0.f, 0.f, 0.f), acc = d;
+    if (BWD) {
+      d = __ldg(d4 + o);
+      if (accumulate) acc = o4[o];
+    }
+    float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int w = GROUP / 2; w > 0; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+    const float mean = s * (1.f / C);
+    v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+    float var = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+    for (int w = GROUP / 2; w > 0; w >>= 1) var += __shfl_xor_sync(0xffffffffu, var, w);
+    const float rstd = 1.f / sqrtf(var * (1.f / C) + 1e-5f);
+    v.x *= rstd; v.y *= rstd; v.z *= rstd; v.w *= rstd;
+    if (!BWD) {
+      o4[o] = make_float4(fmaf(v.x, gam.x, bet.x), fmaf(v.y, gam.y, bet.y), fmaf(v.z, gam.z, bet.z), fmaf(v.w, gam.w, bet.w));
+    } else {
+      const float4 gg = make_float4(d.x * gam.x, d.y * gam.y, d.z * gam.z, d.w * gam.w);
+      float m1 = (gg.x + gg.y) + (gg.z + gg.w);
+      float m2 = fmaf(gg.x, v.x, fmaf(gg.y, v.y, fmaf(gg.z, v.z, gg.w * v.w)));
+      ag.x = fmaf(d.x, v.x, ag.x); ag.y = fmaf(d.y, v.y, ag.y); ag.z = fmaf(d.z, v.z, ag.z); ag.w = fmaf(d.w, v.w, ag.w);
+      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+#pragma unroll
+      for (int w = GROUP / 2; w > 0; w >>= 1) {
+        m1 += __shfl_xor_sync(0xffffffffu, m1, w);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, w);
+      }
+      m1 *= (1.f / C);
+      m2 *= (1.f / C);
+      o4[o] = make_float4(fmaf(rstd, gg.x - m1 - v.x * m2, acc.x), fmaf(rstd, gg.y - m1 - v.y * m2, acc.y),
+                          fmaf(rstd, gg.z - m1 - v.z * m2, acc.z), fmaf(rstd, gg.w - m1 - v.w * m2, acc.w));
+    }
+  }
+  if (BWD) {
+    atomicAdd(red + 4 * cl, ag.x); atomicAdd(red + 4 * cl + 1, ag.y); atomicAdd(red + 4 * cl + 2, ag.z); atomicAdd(red + 4 * cl + 3, ag.w);
+    atomicAdd(red + C + 4 * cl, ab.x); atomicAdd(red + C + 4 * cl + 1, ab.y); atomicAdd(red + C + 4 * cl + 2, ab.z); atomicAdd(red + C + 4 * cl + 3, ab.w);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(dgamma + i, red[i]); atomicAdd(dbeta + i, red[C + i]); }
+  }
+}
+
 // ---- depthwise KxK convolution with zero padding (bmu.dep_conv, basic_module_unformer_v2.py:17-18), K in {1, 3} ---------------
 // flip = 1 uses the point-reflected taps: the data gradient of the same conv.  H, W, C are powers of two (lh, lw, lc).
 template <int K>
