@@ -322,6 +322,19 @@ struct Step {                   // everything one pass needs
   int N;
 };
 
+// y = a + drop(b) (mode 0) or drop(b) (mode 1); 16-byte form when the pointers allow it
+void dropout(Run& R, const float* a, const float* b, float* y, size_t n, const Step& S, int layer, int mode) {
+  if (R.dry) return;
+  const float* ext = S.T->use_ext ? S.T->ext_mask[layer] : nullptr;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (n % 4 == 0 && al(a) && al(b) && al(y) && al(ext))
+    k_dropout_v4<<<blocks(n / 4), 256, 0, R.s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                reinterpret_cast<float4*>(y), n / 4, S.T->seed, layer, S.T->p_drop, mode,
+                                                reinterpret_cast<const float4*>(ext));
+  else k_dropout<<<blocks(n), 256, 0, R.s>>>(a, b, y, n, S.T->seed, layer, S.T->p_drop, mode, ext);
+  R.check();
+}
+
 // ---- one LGB block (LGT.py:231-247): x + drop(proj(cat(local, global)(LN x))), then x + FFN(LN x) -----------------------------
 float* fwd_block(Run& R, const Step& S, const BlockW& w, int ch, BlockTape& t, float* Xin, int H, int W, int layer) {
   const int N = S.N, c2 = ch / 2, c4 = 4 * ch, Wh = W / 2 + 1;
@@ -353,11 +366,7 @@ float* fwd_block(Run& R, const Step& S, const BlockW& w, int ch, BlockTape& t, f
   if (use_tc_gemm(ch, ch)) tc_pw(R, ch, ch, 0, 0, t.cat, pr, w.proj_w, ch, 1, w.proj_b, nullptr, NP, nullptr);
   else pw(R, 0, nhwc(t.cat, ch), ch, w.proj_w, ch, 1, w.proj_b, nhwc(pr, ch), ch, NP);
   t.Xmid = R.take(NP * ch);
-  if (!R.dry) {
-    k_dropout<<<blocks(NP * ch), 256, 0, R.s>>>(Xin, pr, t.Xmid, NP * ch, S.T->seed, layer, S.T->p_drop, 0,
-                                                S.T->use_ext ? S.T->ext_mask[layer] : nullptr);
-    R.check();
-  }
+  dropout(R, Xin, pr, t.Xmid, NP * ch, S, layer, 0);
   // conv-FFN (LGT.py:95-109); the GELUs are applied while staging the next conv's input
   t.A2 = R.take(NP * ch);
   ln_fwd(R, nhwc(t.Xmid, ch), ch, w.ln2_w, w.ln2_b, nhwc(t.A2, ch), NP);
@@ -408,11 +417,7 @@ void bwd_block(Run& R, const Step& S, const BlockW& w, const BlockW& g, int ch, 
   float* dpr = gX;
   if (S.T->p_drop > 0.f || S.T->use_ext) {
     dpr = R.take(NP * ch);
-    if (!R.dry) {
-      k_dropout<<<blocks(NP * ch), 256, 0, R.s>>>(nullptr, gX, dpr, NP * ch, S.T->seed, layer, S.T->p_drop, 1,
-                                                  S.T->use_ext ? S.T->ext_mask[layer] : nullptr);
-      R.check();
-    }
+    dropout(R, nullptr, gX, dpr, NP * ch, S, layer, 1);
   }
   pw_wgrad(R, 0, nhwc(t.cat, ch), ch, nhwc(dpr, ch), ch, g.proj_w, ch, 1, g.proj_b, NP, S.T->gscale);
   float* dcat = R.take(NP * ch);

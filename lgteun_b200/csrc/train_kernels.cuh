@@ -1124,6 +1124,26 @@ __global__ void __launch_bounds__(256) k_dropout(const float* __restrict__ a, co
   y[i] = mode == 0 ? a[i] + m * b[i] : mode == 1 ? m * b[i] : m;
 }
 
+// four elements per thread (n % 4 == 0, 16-byte aligned pointers): the same mask, element by element
+__global__ void __launch_bounds__(256) k_dropout_v4(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y,
+                                                    size_t n4, uint64_t seed, int layer, float p, int mode,
+                                                    const float4* __restrict__ ext) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 m;
+  if (ext) m = __ldg(ext + i);
+  else if (p > 0.f) m = make_float4(drop_scale(seed, layer, 4 * i, p), drop_scale(seed, layer, 4 * i + 1, p),
+                                    drop_scale(seed, layer, 4 * i + 2, p), drop_scale(seed, layer, 4 * i + 3, p));
+  else m = make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 bv = __ldg(b + i);
+  float4 r = make_float4(m.x * bv.x, m.y * bv.y, m.z * bv.z, m.w * bv.w);
+  if (mode == 0) {
+    const float4 av = __ldg(a + i);
+    r.x += av.x; r.y += av.y; r.z += av.z; r.w += av.w;
+  }
+  y[i] = r;
+}
+
 // ---- data module (models/unlg_former.py:29-40,58-61), NCHW ------------------------------------------------------------------------
 // r = R(Z) - pan
 __global__ void __launch_bounds__(256) k_data_r(const float* __restrict__ Z, const float* __restrict__ pan,
