@@ -193,6 +193,12 @@ int lgteun_dropout_mask(lgteun_t* ctx, uint64_t seed, int layer, float p, float*
  * 1/(1-p)) used by the following train_forward / train_backward pairs instead of the generated masks; NULL switches back. */
 int lgteun_train_set_masks(lgteun_t* ctx, const float* const* masks);
 
+/* CUDA-graph support of the training step: with seed_dev != NULL the dropout kernels of the following train_forward /
+ * train_backward calls read their seed from *seed_dev (one uint64 in device memory) when they execute, instead of the by-value
+ * seed of lgteun_train_forward, so a captured fwd + loss + bwd can be replayed with the seed of each step (the reference
+ * draws a fresh nn.Dropout mask per iteration, LGT.py:198,216).  NULL switches back. */
+int lgteun_train_set_seed_ptr(lgteun_t* ctx, const uint64_t* seed_dev);
+
 /* ---- companion operators -----------------------------------------------------------------------
  * SFIIN.Freprocess.forward(msf, panf) (models/SFIIN.py:210-236), the FFT amplitude / phase fusion of a network the
  * reference repository ships beside LGTEUN: rfft2 of the two pre-convolved maps, amp_fuse / pha_fuse perceptrons per

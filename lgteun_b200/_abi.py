@@ -53,6 +53,7 @@ SIGNATURES = {
                                  ctypes.c_float, c_int, ctypes.c_float, c_void_p]),
     "lgteun_dropout_mask": (c_int, [c_void_p, ctypes.c_uint64, c_int, ctypes.c_float, _F, c_int64, c_void_p]),
     "lgteun_train_set_masks": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "lgteun_train_set_seed_ptr": (c_int, [c_void_p, c_void_p]),
     # companion operators
     "lgteun_op_freprocess_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "lgteun_op_freprocess": (c_int, [c_int, _F, _F, _F, c_int, c_int, c_int, c_int, POINTER(c_void_p), _F, c_int64, c_void_p]),
@@ -179,7 +180,11 @@ class Handle:
     def dropout_mask(self, seed, layer, p, out_ptr, n, stream=0):
         check(lib().lgteun_dropout_mask(self._p, seed, layer, p, out_ptr, n, c_void_p(stream)))
 
+    def train_set_seed_ptr(self, seed_dev_ptr):
+        check(lib().lgteun_train_set_seed_ptr(self._p, c_void_p(seed_dev_ptr) if seed_dev_ptr else None))
+
     def set_masks(self, ptrs):
+        self.ext_masks = ptrs is not None
         if ptrs is None:
             check(lib().lgteun_train_set_masks(self._p, None))
         else:

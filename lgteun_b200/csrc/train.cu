@@ -45,6 +45,7 @@ struct TrainState {
   int N = 0, h = 0, w = 0;
   float p_drop = 0.f;
   uint64_t seed = 0;
+  const uint64_t* seed_dev = nullptr;   // when set (lgteun_train_set_seed_ptr) the dropout kernels read the seed from device memory
   size_t fwd_end = 0;           // arena offset where the backward's scratch starts
   const float* flat_param = nullptr;
   const float *ms = nullptr, *pan = nullptr;
@@ -330,8 +331,8 @@ void dropout(Run& R, const float* a, const float* b, float* y, size_t n, const S
   if (n % 4 == 0 && al(a) && al(b) && al(y) && al(ext))
     k_dropout_v4<<<blocks(n / 4), 256, 0, R.s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
                                                 reinterpret_cast<float4*>(y), n / 4, S.T->seed, layer, S.T->p_drop, mode,
-                                                reinterpret_cast<const float4*>(ext));
-  else k_dropout<<<blocks(n), 256, 0, R.s>>>(a, b, y, n, S.T->seed, layer, S.T->p_drop, mode, ext);
+                                                reinterpret_cast<const float4*>(ext), S.T->seed_dev);
+  else k_dropout<<<blocks(n), 256, 0, R.s>>>(a, b, y, n, S.T->seed, layer, S.T->p_drop, mode, ext, S.T->seed_dev);
   R.check();
 }
 
@@ -762,6 +763,15 @@ int lgteun_train_set_masks(lgteun_t* c, const float* const* masks) {
     if (masks && !masks[i]) return fail(LGTEUN_EINVAL, "five mask pointers are required");
     c->train->ext_mask[i] = masks ? masks[i] : nullptr;
   }
+  return 0;
+}
+
+// seed_dev != NULL: the dropout kernels of the following forwards / backwards read their seed from *seed_dev (device memory) when
+// they run, so a CUDA graph of the step can be replayed with a new seed; NULL restores the by-value seed of lgteun_train_forward.
+int lgteun_train_set_seed_ptr(lgteun_t* c, const uint64_t* seed_dev) {
+  if (!c) return fail(LGTEUN_EINVAL, "NULL handle");
+  if (!c->train) c->train = new TrainState();
+  c->train->seed_dev = seed_dev;
   return 0;
 }
 

@@ -1117,9 +1117,10 @@ __device__ __forceinline__ float drop_scale(uint64_t seed, int layer, size_t idx
 // (values 0 or 1/(1-p)) replaces the generated one.
 __global__ void __launch_bounds__(256) k_dropout(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
                                                  size_t n, uint64_t seed, int layer, float p, int mode,
-                                                 const float* __restrict__ ext) {
+                                                 const float* __restrict__ ext, const uint64_t* __restrict__ seed_dev = nullptr) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
+  if (seed_dev) seed = *seed_dev;                      // a captured step reads the seed of the replay, not of the capture
   const float m = ext ? ext[i] : (p > 0.f ? drop_scale(seed, layer, i, p) : 1.f);
   y[i] = mode == 0 ? a[i] + m * b[i] : mode == 1 ? m * b[i] : m;
 }
@@ -1127,9 +1128,10 @@ __global__ void __launch_bounds__(256) k_dropout(const float* __restrict__ a, co
 // four elements per thread (n % 4 == 0, 16-byte aligned pointers): the same mask, element by element
 __global__ void __launch_bounds__(256) k_dropout_v4(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y,
                                                     size_t n4, uint64_t seed, int layer, float p, int mode,
-                                                    const float4* __restrict__ ext) {
+                                                    const float4* __restrict__ ext, const uint64_t* __restrict__ seed_dev) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
+  if (seed_dev) seed = *seed_dev;
   float4 m;
   if (ext) m = __ldg(ext + i);
   else if (p > 0.f) m = make_float4(drop_scale(seed, layer, 4 * i, p), drop_scale(seed, layer, 4 * i + 1, p),

@@ -14,6 +14,8 @@ all hand-written kernels behind ``include/lgteun.h``; torch provides memory, str
 There is no CPU path: everything raises without the CUDA library / a CUDA device."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -87,7 +89,7 @@ class Trainer:
 
     def __init__(self, module: Pansharpening, lr: float = 1.5e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  loss_weight: float = 1.0, dropout_p: float = 0.1, seed: int = 19971118, step_size: int = 0,
-                 gamma: float = 0.85, process_group=None):
+                 gamma: float = 0.85, process_group=None, cuda_graph: bool = True):
         # ONE flat buffer per module: the drop-in module's own train-mode forward (module._flat_parameters) must see the
         # buffer this trainer updates, otherwise a later module(ms, pan) would re-flatten into a new buffer and the
         # trainer would keep stepping the orphaned one
@@ -107,6 +109,11 @@ class Trainer:
         self.world = dist.get_world_size(process_group) if ddp else 1
         self.rank = dist.get_rank(process_group) if ddp else 0
         self._buf = {}
+        # forward + loss + backward (~330 launches) replayed as ONE CUDA graph per input shape: static input buffers, the
+        # dropout seed read from device memory (lgteun_train_set_seed_ptr).  The all-reduce and Adam stay outside the graph.
+        self.cuda_graph = bool(cuda_graph) and os.environ.get("LGTEUN_TRAIN_GRAPH", "1") != "0"
+        self._graphs = {}
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.allreduce_events = None      # set to [] to collect a CUDA-event pair around every step's all-reduce
         if self.world > 1:
             self.broadcast_state()
@@ -160,6 +167,8 @@ class Trainer:
                 raise RuntimeError("Trainer needs float32 tensors on the module's CUDA device")
         ms, pan, gt = ms.contiguous(), pan.contiguous(), gt.contiguous()
         self._check_alias()
+        if self.cuda_graph and not getattr(self.handle, "ext_masks", False) and not torch.cuda.is_current_stream_capturing():
+            return self._graphed_forward_backward(ms, pan, gt)
         with torch.cuda.device(self.flat.device):
             stream = torch.cuda.current_stream().cuda_stream
             out, dout = self._buffers(tuple(gt.shape))
@@ -168,6 +177,51 @@ class Trainer:
             self.handle.l1_loss(out.data_ptr(), gt.data_ptr(), out.numel(), self.loss_weight, self.loss.data_ptr(),
                                 dout.data_ptr(), stream)
             self.handle.train_backward(dout.data_ptr(), self.flat.grad.data_ptr(), stream)
+        return out, self.loss
+
+    def _graphed_forward_backward(self, ms, pan, gt):
+        """The same three native calls, captured once per shape and replayed.  The first call of a shape runs eagerly (it sizes
+        the tape), the second captures; inputs are copied into the graph's static buffers, the seed into device memory."""
+        key = tuple(ms.shape)
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            out, dout = self._buffers(tuple(gt.shape))
+            entry = self._graphs.get(key)
+            if entry is None:                               # eager warm-up: allocations, function attributes, the tape
+                self._graphs = {key: "warm"}                # (one shape at a time, like _buffers)
+                stream = torch.cuda.current_stream().cuda_stream
+                n, b, h, w = ms.shape
+                self.handle.train_forward(self.flat.param.data_ptr(), ms.data_ptr(), pan.data_ptr(), out.data_ptr(), n, h, w,
+                                          self.dropout_p, self.dropout_seed(), stream)
+                self.handle.l1_loss(out.data_ptr(), gt.data_ptr(), out.numel(), self.loss_weight, self.loss.data_ptr(),
+                                    dout.data_ptr(), stream)
+                self.handle.train_backward(dout.data_ptr(), self.flat.grad.data_ptr(), stream)
+                return out, self.loss
+            if entry == "warm":
+                n, b, h, w = ms.shape
+                sms, span, sgt = torch.empty_like(ms), torch.empty_like(pan), torch.empty_like(gt)
+                graph = torch.cuda.CUDAGraph()
+                self.handle.train_set_seed_ptr(self._seed_dev.data_ptr())
+                try:
+                    torch.cuda.synchronize(dev)
+                    with torch.cuda.graph(graph):
+                        stream = torch.cuda.current_stream().cuda_stream
+                        self.handle.train_forward(self.flat.param.data_ptr(), sms.data_ptr(), span.data_ptr(), out.data_ptr(),
+                                                  n, h, w, self.dropout_p, 0, stream)
+                        self.handle.l1_loss(out.data_ptr(), sgt.data_ptr(), out.numel(), self.loss_weight,
+                                            self.loss.data_ptr(), dout.data_ptr(), stream)
+                        self.handle.train_backward(dout.data_ptr(), self.flat.grad.data_ptr(), stream)
+                finally:
+                    self.handle.train_set_seed_ptr(0)
+                entry = self._graphs[key] = (graph, sms, span, sgt, self.flat.param.data_ptr(), self.flat.grad.data_ptr())
+            graph, sms, span, sgt, p_ptr, g_ptr = entry
+            if p_ptr != self.flat.param.data_ptr() or g_ptr != self.flat.grad.data_ptr():
+                raise RuntimeError("the flat parameter / gradient buffers moved after the step was captured; build a new Trainer")
+            sms.copy_(ms)
+            span.copy_(pan)
+            sgt.copy_(gt)
+            self._seed_dev.fill_(self.dropout_seed())
+            graph.replay()
         return out, self.loss
 
     def step(self, ms: torch.Tensor, pan: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:

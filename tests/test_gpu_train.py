@@ -202,6 +202,32 @@ def test_module_train_iter_and_trainer(abi, O):
             assert ((v.cpu() - after[k]).abs()[ok] <= 2e-5).all(), k
 
 
+def test_graphed_step_matches_the_eager_step(abi):
+    """Trainer.step replays forward + loss + backward as one CUDA graph from the third step of a shape on (the first runs
+    eagerly, the second captures).  With dropout ON the replayed steps must draw the masks of THEIR step (the seed is read from
+    device memory, lgteun_train_set_seed_ptr) on the batches of THEIR step (static input buffers): five steps on five
+    different batches give the same losses and the same weights as the launch-by-launch path."""
+    import lgteun_b200
+    from oracle.ref_import import Config
+    gen = torch.Generator().manual_seed(11)
+    batches = [(torch.rand(2, 4, 8, 8, generator=gen).cuda(), torch.rand(2, 1, 32, 32, generator=gen).cuda(),
+                torch.rand(2, 4, 32, 32, generator=gen).cuda()) for _ in range(5)]
+    runs = []
+    for graph in (True, False):
+        torch.manual_seed(19971118)
+        net = lgteun_b200.Pansharpening(Config(ms_chans=4), None, stage=2).cuda().train()
+        tr = lgteun_b200.Trainer(net, lr=1.5e-3, dropout_p=0.1, seed=77, cuda_graph=graph)
+        losses = [tr.step(*b).item() for b in batches]
+        assert bool(tr._graphs) == graph
+        runs.append((losses, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}))
+    (lg_, wg), (le, we) = runs
+    assert len(set(le)) == 5                                              # different batches / masks: different losses
+    for a, b in zip(lg_, le):
+        assert abs(a - b) <= 2e-6 * max(1.0, abs(b)), (lg_, le)
+    for k in we:      # atomics reorder the gradient sums, and Adam's m / sqrt(v) amplifies that where the gradient is ~0:
+        assert (wg[k] - we[k]).abs().max().item() <= 3e-4, k              # far below the 5 x lr = 7.5e-3 a wrong mask would move
+
+
 def test_trainer_and_module_share_one_flat_buffer(abi):
     """Trainer first, module call second: the module's own train-mode forward must not re-flatten the
     parameters into a new buffer; moving the module after Trainer creation raises instead of training an orphan."""
