@@ -204,7 +204,8 @@ class Trainer:
                 self.handle.train_set_seed_ptr(self._seed_dev.data_ptr())
                 try:
                     torch.cuda.synchronize(dev)
-                    with torch.cuda.graph(graph):
+                    # thread_local: the NCCL watchdog thread of a data-parallel job keeps polling events during the capture
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                         stream = torch.cuda.current_stream().cuda_stream
                         self.handle.train_forward(self.flat.param.data_ptr(), sms.data_ptr(), span.data_ptr(), out.data_ptr(),
                                                   n, h, w, self.dropout_p, 0, stream)
