@@ -17,6 +17,8 @@
 // hi*hi + hi*lo + lo*hi into its 64 TMEM columns (fp32 accumulate).  See ffn_tc.cu for the descriptor formats.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -816,17 +818,222 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+// ---- the same weight gradient as a bulk-copy pipeline (default) ---------------------------------------------------------------
+// The direct kernel above spends its issue slots on 40 - 64 scalar global loads per thread and tile with 64-bit address
+// arithmetic and then waits for them (long-scoreboard stalls 35 %).  Here a producer warp moves the raw fp32 pixel rows of a tile
+// into shared memory with cp.async.bulk (dense operands: one 8 - 32 KB copy per tile and operand — per-row copies of 128 -
+// 512 bytes were 2.5x slower than the direct kernel —, completion counted on an mbarrier), eight converter
+// warps read them with immediate-offset LDS, apply the GELU / scale, split to fp16 hi | lo and write the K-major operand
+// tiles, and one elected thread issues the MMAs; raw tiles and operand tiles are both double-buffered, so the copy of tile
+// t + 2, the conversion of tile t + 1 and the MMAs of tile t overlap.  One TMEM accumulator for the CTA's whole pixel share.
+namespace gradb {
+constexpr int kConv = 256;                       // warps 0 .. 7
+constexpr int kThreads = kConv + 64;             // warp 8: producer, warp 9: MMA issuer
+}
+template <int NCI, int ACT>
+__global__ void __launch_bounds__(gradb::kThreads, 1)
+pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy, int Cout, float* __restrict__ dW,
+                   int wso, int wsi, float* __restrict__ db, int num_tiles, int tp, const float* __restrict__ scale_dev) {
+  using namespace pw;
+  static_assert(NCI % 16 == 0 && NCI <= 256, "tile shape");
+  constexpr int GT = gradb::kConv;
+  constexpr int XI = (8 * NCI + GT - 1) / GT;                                   // X items per thread at tp = 64
+  constexpr int DI = 4;                                                         // dY items per thread at tp = 64, 128 rows
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t *raw_full = bars, *raw_empty = bars + 2, *op_full = bars + 4, *op_empty = bars + 6, *done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 120);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kc = tp >> 3;                                                       // K-chunks of 8 pixels per tile (4 or 8)
+  const int co0 = blockIdx.y * 128;
+  const int live = Cout - co0 < 128 ? Cout - co0 : 128;                         // output channels of this CTA (a multiple of 4)
+  int mrows = 16;                                                               // rows of A: the next power of two
+  while (mrows < live) mrows *= 2;
+  const int lm = __ffs(mrows) - 1;
+  const uint32_t raw_bytes = (uint32_t)tp * (NCI + mrows) * 4;                  // X rows, then dY rows (live floats each)
+  const uint32_t a_half = (uint32_t)kc * mrows * 16, b_half = (uint32_t)kc * NCI * 16;
+  const uint32_t op_bytes = 2 * a_half + 2 * b_half;                            // A hi | A lo | B hi | B lo
+  unsigned char* raw0 = smem_raw + 128;
+  unsigned char* op0 = raw0 + 2 * raw_bytes;
+  constexpr uint32_t TCOLS = (NCI <= 32) ? 32 : (NCI <= 64) ? 64 : (NCI <= 128 ? 128 : 256);
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&raw_full[b], 1);
+      mbar_init(&raw_empty[b], GT / 32);
+      mbar_init(&op_full[b], GT / 32);
+      mbar_init(&op_empty[b], 1);
+    }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ---- producer ----------------------------------------------------------------------------------------------------------------
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t & 1;
+      if (t >= 2) mbar_wait(&raw_empty[s], ((t >> 1) - 1) & 1);
+      const long long p0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * tp;
+      if (lane == 0) pipe::mbar_expect_tx(&raw_full[s], (uint32_t)tp * (NCI + live) * 4);
+      __syncwarp();
+      const uint32_t xdst = smem_u32(raw0 + s * raw_bytes), ydst = xdst + (uint32_t)tp * NCI * 4;
+      if (lane == 0) {                             // dense operands (launch check): a tile is one contiguous block of each
+        pipe::bulk_g2s(xdst, X + p0 * NCI, (uint32_t)tp * NCI * 4, &raw_full[s]);
+        pipe::bulk_g2s(ydst, dY + p0 * live, (uint32_t)tp * live * 4, &raw_full[s]);
+      }
+    }
+  } else if (warp == 9) {
+    // ---- MMA issuer ---------------------------------------------------------------------------------------------------------------
+    const uint32_t lbo_a = (uint32_t)mrows * 16;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t & 1;
+      mbar_wait(&op_full[s], (t >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc(NCI);
+        const uint32_t a_h = smem_u32(op0 + s * op_bytes), a_l = a_h + a_half, b_h = a_l + a_half, b_l = b_h + b_half;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (2 * ks < kc) {
+            const uint64_t dah = umma_desc(a_h + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t dal = umma_desc(a_l + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t dbh = umma_desc(b_h + ks * 2 * NCI * 16, NCI * 16, 128);
+            const uint64_t dbl = umma_desc(b_l + ks * 2 * NCI * 16, NCI * 16, 128);
+            umma_f16(tmem, dah, dbh, idesc, !(t == 0 && ks == 0));
+            umma_f16(tmem, dah, dbl, idesc, 1);
+            umma_f16(tmem, dal, dbh, idesc, 1);
+          }
+        }
+        umma_commit(&op_empty[s]);
+        if (t == my_tiles - 1) umma_commit(done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- converters ---------------------------------------------------------------------------------------------------------------
+    const float a_scale = scale_dev ? __ldg(scale_dev) : 1.f, inv_scale = 1.f / a_scale;
+    const int co = tid & (mrows - 1);                                           // GT % mrows == 0: a thread keeps its channel
+    const int n_dy = kc * mrows, n_x = kc * NCI;
+    float bsum = 0.f;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int s = t & 1;
+      const float* xr = reinterpret_cast<const float*>(raw0 + s * raw_bytes);
+      const float* yr = xr + tp * NCI;
+      __half* ah = reinterpret_cast<__half*>(op0 + s * op_bytes);
+      __half* al = ah + kc * mrows * 8;
+      __half* bh = al + kc * mrows * 8;
+      __half* bl = bh + kc * NCI * 8;
+      mbar_wait(&raw_full[s], (t >> 1) & 1);
+      if (t >= 2) mbar_wait(&op_empty[s], ((t >> 1) - 1) & 1);
+#pragma unroll
+      for (int u = 0; u < DI; ++u) {
+        const int item = tid + u * GT;
+        if (item < n_dy && co < live) {                                         // rows in [live, mrows) only feed accumulator rows nobody reads
+          const int g = item >> lm;
+          const float* src = yr + g * 8 * live + co;
+          float2 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float e0 = src[(2 * j) * live], e1 = src[(2 * j + 1) * live];
+            bsum += e0 + e1;
+            v[j] = make_float2(e0 * a_scale, e1 * a_scale);
+          }
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(ah + ((g << lm) + co) * 8) = hi;
+          *reinterpret_cast<uint4*>(al + ((g << lm) + co) * 8) = lo;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < XI; ++u) {
+        const int item = tid + u * GT;
+        if (item < n_x) {
+          const int ci = item % NCI, g = item / NCI;
+          const float* src = xr + g * 8 * NCI + ci;
+          float2 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = make_float2(src[(2 * j) * NCI], src[(2 * j + 1) * NCI]);
+            if constexpr (ACT == 1) v[j] = gelu_pair(v[j]);
+          }
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          *reinterpret_cast<uint4*>(bh + item * 8) = hi;                        // [g][ci][8] = item * 8
+          *reinterpret_cast<uint4*>(bl + item * 8) = lo;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&op_full[s]);
+        mbar_arrive(&raw_empty[s]);
+      }
+    }
+    // ---- epilogue: accumulator -> dW (atomics: the CTAs split the pixels) ---------------------------------------------------------
+    if (my_tiles > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int q = warp & 3, part = warp >> 2;    // lane quarter, column slice
+      const int row = q * 32 + lane;               // output channel co0 + row
+      const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = part * 8; c0 < NCI; c0 += 16) {
+        float2 v[4];
+        tmem_ld8(lane_addr + c0, v);
+        tmem_ld_wait();
+        if (row < live) {
+          float* dst = dW + (size_t)(co0 + row) * wso;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            atomicAdd(dst + (size_t)(c0 + 2 * j) * wsi, v[j].x * inv_scale);
+            atomicAdd(dst + (size_t)(c0 + 2 * j + 1) * wsi, v[j].y * inv_scale);
+          }
+        }
+      }
+      if (db && tid < n_dy && co < live) atomicAdd(db + co0 + co, bsum);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
 template <int NCI>
 static cudaError_t pwgrad_launch(int act, const float* X, int ldx, const float* dY, int ldy, int Cout, float* dW, int wso, int wsi,
                                  float* db, long long px, const float* scale_dev, cudaStream_t s) {
   if (px % 64) return cudaErrorInvalidValue;
-  const int tiles = (int)(px / 64);
   int mrows = 16;
   while (mrows < Cout && mrows < 128) mrows *= 2;
+  static const bool direct = [] { const char* e = getenv("LGTEUN_PWGRAD"); return e && std::string(e) == "direct"; }();
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  cudaError_t e;
+  if (!direct && al16(X) && al16(dY) && ldx == NCI && ldy == Cout && Cout <= 128 && Cout % 4 == 0) {
+    // bulk-copy pipeline: two raw fp32 stages + two operand stages = 16 bytes per pixel and channel
+    const int tp = (NCI + mrows) <= 192 ? 64 : 32;
+    const int tiles = (int)(px / tp);
+    const size_t smem = 128 + (size_t)16 * tp * (NCI + mrows) + 128 * 16;
+    const dim3 grid(tiles < 148 ? tiles : 148, (Cout + 127) / 128);
+    if (act) {
+      e = cudaFuncSetAttribute(pwgrad_bulk_kernel<NCI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      pwgrad_bulk_kernel<NCI, 1><<<grid, gradb::kThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, tiles, tp, scale_dev);
+    } else {
+      e = cudaFuncSetAttribute(pwgrad_bulk_kernel<NCI, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      pwgrad_bulk_kernel<NCI, 0><<<grid, gradb::kThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, tiles, tp, scale_dev);
+    }
+    return cudaGetLastError();
+  }
+  const int tiles = (int)(px / 64);
   // two groups x (A hi|lo [8][mrows][8] + B hi|lo [8][NCI][8]) + slack for the M = 128 read past the last live row
   const size_t smem = 128 + 2 * (size_t)(2 * 8 * mrows * 16 + 2 * 8 * NCI * 16) + 128 * 16;
   const dim3 grid(tiles < 2 * 148 ? (tiles + 1) / 2 : 148, (Cout + 127) / 128);
-  cudaError_t e;
   if (act) {
     e = cudaFuncSetAttribute(pwgrad_tc_kernel<NCI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
