@@ -827,21 +827,21 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
 // tiles, and one elected thread issues the MMAs; raw tiles and operand tiles are both double-buffered, so the copy of tile
 // t + 2, the conversion of tile t + 1 and the MMAs of tile t overlap.  One TMEM accumulator for the CTA's whole pixel share.
 namespace gradb {
-constexpr int kConv = 256;                       // warps 0 .. 7
-constexpr int kThreads = kConv + 64;             // warp 8: producer, warp 9: MMA issuer
+constexpr int kConv = 512;                       // warps 0 .. 15 (8 warps left the SM's issue slots half idle: dependent LDS -> GELU -> split chains)
+constexpr int kThreads = kConv + 64;             // then the producer warp and the MMA issuer warp
 }
 template <int NCI, int ACT>
 __global__ void __launch_bounds__(gradb::kThreads, 1)
 pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy, int Cout, float* __restrict__ dW,
-                   int wso, int wsi, float* __restrict__ db, int num_tiles, int tp, const float* __restrict__ scale_dev) {
+                   int wso, int wsi, float* __restrict__ db, int num_tiles, int tp, int nraw, const float* __restrict__ scale_dev) {
   using namespace pw;
   static_assert(NCI % 16 == 0 && NCI <= 256, "tile shape");
   constexpr int GT = gradb::kConv;
   constexpr int XI = (8 * NCI + GT - 1) / GT;                                   // X items per thread at tp = 64
-  constexpr int DI = 4;                                                         // dY items per thread at tp = 64, 128 rows
+  constexpr int DI = 8 * 128 / GT;                                              // dY items per thread at tp = 64, 128 rows
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t *raw_full = bars, *raw_empty = bars + 2, *op_full = bars + 4, *op_empty = bars + 6, *done = bars + 8;
+  uint64_t *raw_full = bars, *raw_empty = bars + 4, *op_full = bars + 8, *op_empty = bars + 10, *done = bars + 12;   // raw: up to 4 stages
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 120);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kc = tp >> 3;                                                       // K-chunks of 8 pixels per tile (4 or 8)
@@ -854,14 +854,16 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
   const uint32_t a_half = (uint32_t)kc * mrows * 16, b_half = (uint32_t)kc * NCI * 16;
   const uint32_t op_bytes = 2 * a_half + 2 * b_half;                            // A hi | A lo | B hi | B lo
   unsigned char* raw0 = smem_raw + 128;
-  unsigned char* op0 = raw0 + 2 * raw_bytes;
+  unsigned char* op0 = raw0 + nraw * raw_bytes;
   constexpr uint32_t TCOLS = (NCI <= 32) ? 32 : (NCI <= 64) ? 64 : (NCI <= 128 ? 128 : 256);
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(&raw_full[b], 1);
       mbar_init(&raw_empty[b], GT / 32);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(&op_full[b], GT / 32);
       mbar_init(&op_empty[b], 1);
     }
@@ -874,11 +876,11 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == GT / 32) {
     // ---- producer ----------------------------------------------------------------------------------------------------------------
     for (int t = 0; t < my_tiles; ++t) {
-      const int s = t & 1;
-      if (t >= 2) mbar_wait(&raw_empty[s], ((t >> 1) - 1) & 1);
+      const int s = t % nraw, use = t / nraw;
+      if (use >= 1) mbar_wait(&raw_empty[s], (use - 1) & 1);
       const long long p0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * tp;
       if (lane == 0) pipe::mbar_expect_tx(&raw_full[s], (uint32_t)tp * (NCI + live) * 4);
       __syncwarp();
@@ -888,7 +890,7 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
         pipe::bulk_g2s(ydst, dY + p0 * live, (uint32_t)tp * live * 4, &raw_full[s]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == GT / 32 + 1) {
     // ---- MMA issuer ---------------------------------------------------------------------------------------------------------------
     const uint32_t lbo_a = (uint32_t)mrows * 16;
     for (int t = 0; t < my_tiles; ++t) {
@@ -922,14 +924,14 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
     const int n_dy = kc * mrows, n_x = kc * NCI;
     float bsum = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
-      const int s = t & 1;
-      const float* xr = reinterpret_cast<const float*>(raw0 + s * raw_bytes);
+      const int s = t & 1, sr = t % nraw;
+      const float* xr = reinterpret_cast<const float*>(raw0 + sr * raw_bytes);
       const float* yr = xr + tp * NCI;
       __half* ah = reinterpret_cast<__half*>(op0 + s * op_bytes);
       __half* al = ah + kc * mrows * 8;
       __half* bh = al + kc * mrows * 8;
       __half* bl = bh + kc * NCI * 8;
-      mbar_wait(&raw_full[s], (t >> 1) & 1);
+      mbar_wait(&raw_full[sr], (t / nraw) & 1);
       if (t >= 2) mbar_wait(&op_empty[s], ((t >> 1) - 1) & 1);
 #pragma unroll
       for (int u = 0; u < DI; ++u) {
@@ -972,7 +974,7 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&op_full[s]);
-        mbar_arrive(&raw_empty[s]);
+        mbar_arrive(&raw_empty[sr]);
       }
     }
     // ---- epilogue: accumulator -> dW (atomics: the CTAs split the pixels) ---------------------------------------------------------
@@ -983,7 +985,7 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
       const int row = q * 32 + lane;               // output channel co0 + row
       const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = part * 8; c0 < NCI; c0 += 16) {
+      for (int c0 = part * 8; c0 < NCI; c0 += 8 * (GT / 128)) {
         float2 v[4];
         tmem_ld8(lane_addr + c0, v);
         tmem_ld_wait();
@@ -1017,16 +1019,19 @@ static cudaError_t pwgrad_launch(int act, const float* X, int ldx, const float* 
     // bulk-copy pipeline: two raw fp32 stages + two operand stages = 16 bytes per pixel and channel
     const int tp = (NCI + mrows) <= 192 ? 64 : 32;
     const int tiles = (int)(px / tp);
-    const size_t smem = 128 + (size_t)16 * tp * (NCI + mrows) + 128 * 16;
+    const size_t per_stage = (size_t)4 * tp * (NCI + mrows);                     // one raw stage; an operand stage is the same size
+    int nraw = 4;                                                              // as many raw stages in flight as 227 KB allow
+    while (nraw > 2 && 128 + (nraw + 2) * per_stage + 128 * 16 > 232448) --nraw;
+    const size_t smem = 128 + (nraw + 2) * per_stage + 128 * 16;
     const dim3 grid(tiles < 148 ? tiles : 148, (Cout + 127) / 128);
     if (act) {
       e = cudaFuncSetAttribute(pwgrad_bulk_kernel<NCI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      pwgrad_bulk_kernel<NCI, 1><<<grid, gradb::kThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, tiles, tp, scale_dev);
+      pwgrad_bulk_kernel<NCI, 1><<<grid, gradb::kThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, tiles, tp, nraw, scale_dev);
     } else {
       e = cudaFuncSetAttribute(pwgrad_bulk_kernel<NCI, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      pwgrad_bulk_kernel<NCI, 0><<<grid, gradb::kThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, tiles, tp, scale_dev);
+      pwgrad_bulk_kernel<NCI, 0><<<grid, gradb::kThreads, smem, s>>>(X, ldx, dY, ldy, Cout, dW, wso, wsi, db, tiles, tp, nraw, scale_dev);
     }
     return cudaGetLastError();
   }
