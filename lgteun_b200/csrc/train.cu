@@ -204,7 +204,9 @@ void dwconv(Run& R, int K, TV x, const float* w, const float* b, TV y, int N, in
   const TV none{nullptr, 0, 0, 0, 0};
   const int lh = ilog2(H), lw = ilog2(W), lc = ilog2(C);
   if (K == 3 && !add && !x.nchw && !y.nchw && x.ld == C && y.ld == C && C >= 4 && W >= 8) {
-    if (W >= 16) k_dw3_v4<16><<<blocks((size_t)N * H * (W / 16) * C / 4), 256, 0, R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
+    static const bool v4 = [] { const char* e = getenv("LGTEUN_DW3"); return e && std::string(e) == "v4"; }();
+    if (W >= 16 && !v4) k_dw3_v2<16><<<blocks((size_t)N * H * (W / 16) * C / 2), 256, 0, R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
+    else if (W >= 16) k_dw3_v4<16><<<blocks((size_t)N * H * (W / 16) * C / 4), 256, 0, R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
     else k_dw3_v4<8><<<blocks((size_t)N * H * (W / 8) * C / 4), 256, 0, R.s>>>(x.p, w, b, y.p, N, lh, lw, lc, flip);
     R.check();
     return;
@@ -218,10 +220,17 @@ void dw_wgrad(Run& R, int K, TV x, TV dy, const float* dw, const float* db, int 
   if (R.dry) return;
   const size_t NP = (size_t)N * H * W;
   const int lh = ilog2(H), lw = ilog2(W), lc = ilog2(C);
-  if (K == 3 && !x.nchw && !dy.nchw && x.ld == C && dy.ld == C && C >= 4 && C <= 1024 && W >= 8) {
+  if (K == 3 && !x.nchw && !dy.nchw && x.ld == C && dy.ld == C && C >= 4 && C <= 512 && W >= 8) {
     const size_t per_block = (size_t)(1024 / C) * 8;   // pixels one block visits per sweep
     const unsigned gv = (unsigned)std::min<size_t>(148 * 8, (NP + per_block - 1) / per_block);
-    k_dw3_wgrad_v4<<<gv, 256, C * 10 * sizeof(float), R.s>>>(x.p, dy.p, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
+    static const bool v4 = [] { const char* e = getenv("LGTEUN_DW3"); return e && std::string(e) == "v4"; }();
+    if (v4) {
+      k_dw3_wgrad_v4<<<gv, 256, C * 10 * sizeof(float), R.s>>>(x.p, dy.p, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
+    } else {
+      const size_t per_block2 = (size_t)(512 / C) * 8;
+      const unsigned g2 = (unsigned)std::min<size_t>(148 * 8, (NP + per_block2 - 1) / per_block2);
+      k_dw3_wgrad_v2<<<g2, 256, C * 10 * sizeof(float), R.s>>>(x.p, dy.p, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
+    }
     R.check();
     return;
   }

@@ -441,6 +441,55 @@ __global__ void __launch_bounds__(256) k_dw3_v4(const float* __restrict__ x, con
   }
 }
 
+// two channels per thread: half the registers of k_dw3_v4, twice the resident warps (the float4 form is latency-bound at 16 warps/SM)
+template <int SEG>
+__global__ void __launch_bounds__(256, 4) k_dw3_v2(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                float* __restrict__ y, int N, int lh, int lw, int lc, int flip) {
+  constexpr int LS = SEG == 16 ? 4 : 3;
+  const int H = 1 << lh, W = 1 << lw, lq = lc - 1, CQ = 1 << lq, lseg = lw - LS;
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, total = (size_t)N << (lh + lseg + lq);
+  if (idx >= total) return;
+  const int q = (int)(idx & (CQ - 1));
+  const size_t s = idx >> lq;
+  const int x0 = (int)(s & (((size_t)1 << lseg) - 1)) << LS, yy = (int)((s >> lseg) & (H - 1));
+  const size_t row = (s >> lseg) << lw;          // pixel index of (n, yy, 0)
+  const bool up = yy > 0, dn = yy + 1 < H;
+  float2 wt[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int ts = flip ? 8 - t : t;
+    wt[t] = make_float2(__ldg(w + (2 * q) * 9 + ts), __ldg(w + (2 * q + 1) * 9 + ts));
+  }
+  const float2 zero = make_float2(0.f, 0.f);
+  const float2 bias = b ? make_float2(__ldg(b + 2 * q), __ldg(b + 2 * q + 1)) : zero;
+  const float2* __restrict__ x4 = reinterpret_cast<const float2*>(x);
+  float2* __restrict__ y4 = reinterpret_cast<float2*>(y);
+  float2 wa[3], wb[3], wc[3];
+  auto column = [&](int xx, float2 (&c)[3]) {
+    const bool in = xx >= 0 && xx < W;
+    const size_t p = ((row + xx) << lq) + q;
+    c[0] = (in && up) ? __ldg(x4 + p - ((size_t)W << lq)) : zero;
+    c[1] = in ? __ldg(x4 + p) : zero;
+    c[2] = (in && dn) ? __ldg(x4 + p + ((size_t)W << lq)) : zero;
+  };
+  column(x0 - 1, wa);
+  column(x0, wb);
+#pragma unroll 4
+  for (int i = 0; i < SEG; ++i) {
+    column(x0 + i + 1, wc);
+    float2 acc = bias;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      acc.x = fmaf(wt[3 * r].x, wa[r].x, acc.x); acc.y = fmaf(wt[3 * r].y, wa[r].y, acc.y);
+      acc.x = fmaf(wt[3 * r + 1].x, wb[r].x, acc.x); acc.y = fmaf(wt[3 * r + 1].y, wb[r].y, acc.y);
+      acc.x = fmaf(wt[3 * r + 2].x, wc[r].x, acc.x); acc.y = fmaf(wt[3 * r + 2].y, wc[r].y, acc.y);
+      wa[r] = wb[r];
+      wb[r] = wc[r];
+    }
+    y4[((row + x0 + i) << lq) + q] = acc;
+  }
+}
+
 // dw[k][tap] += sum dy[p] * x[p + tap];  db[k] += sum dy[p].  blockDim = 256, C (a power of two) divides 256;
 // thread = (pixel slot, channel).
 template <int K>
@@ -537,6 +586,67 @@ __global__ void __launch_bounds__(256) k_dw3_wgrad_v4(const float* __restrict__ 
     atomicAdd(mine + 20 + i, acc[i].z); atomicAdd(mine + 30 + i, acc[i].w);
   }
   atomicAdd(mine + 9, bacc.x); atomicAdd(mine + 19, bacc.y); atomicAdd(mine + 29, bacc.z); atomicAdd(mine + 39, bacc.w);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 10; i += 256) {
+    const int kk = i / 10, t = i % 10;
+    if (t < 9) atomicAdd(dw + kk * 9 + t, sm[i]);
+    else if (db) atomicAdd(db + kk, sm[i]);
+  }
+}
+
+__device__ __forceinline__ void fma2v(float2& a, const float2 g, const float2 v) { a.x = fmaf(g.x, v.x, a.x); a.y = fmaf(g.y, v.y, a.y); }
+// two channels per thread: half the registers, twice the resident warps (as k_dw3_v2)
+__global__ void __launch_bounds__(256, 3) k_dw3_wgrad_v2(const float* __restrict__ x, const float* __restrict__ dy,
+                                                      float* __restrict__ dw, float* __restrict__ db, int N, int lh, int lw,
+                                                      int lc) {
+  extern __shared__ float sm[];   // [C][10]
+  const int H = 1 << lh, W = 1 << lw, C = 1 << lc, lq = lc - 1, CQ = 1 << lq;
+  for (int i = threadIdx.x; i < C * 10; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const int q = threadIdx.x & (CQ - 1), slot = threadIdx.x >> lq, slots = 256 >> lq, lseg = lw - 3;
+  const size_t nseg = (size_t)N << (lh + lseg);
+  const float2* __restrict__ x4 = reinterpret_cast<const float2*>(x);
+  const float2* __restrict__ g4 = reinterpret_cast<const float2*>(dy);
+  const float2 zero = make_float2(0.f, 0.f);
+  float2 acc[9], bacc = zero;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = zero;
+  for (size_t s = (size_t)blockIdx.x * slots + slot; s < nseg; s += (size_t)gridDim.x * slots) {
+    const int x0 = (int)(s & (((size_t)1 << lseg) - 1)) << 3, yy = (int)((s >> lseg) & (H - 1));
+    const size_t row = (s >> lseg) << lw;        // pixel index of (n, yy, 0)
+    const bool up = yy > 0, dn = yy + 1 < H;
+    float2 wa[3], wb[3], wc[3];
+    auto column = [&](int xx, float2 (&c)[3]) {
+      const bool in = xx >= 0 && xx < W;
+      const size_t p = ((row + xx) << lq) + q;
+      c[0] = (in && up) ? __ldg(x4 + p - ((size_t)W << lq)) : zero;
+      c[1] = in ? __ldg(x4 + p) : zero;
+      c[2] = (in && dn) ? __ldg(x4 + p + ((size_t)W << lq)) : zero;
+    };
+    column(x0 - 1, wa);
+    column(x0, wb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int xx = x0 + i;
+      column(xx + 1, wc);
+      const float2 g = __ldg(g4 + ((row + xx) << lq) + q);
+      bacc.x += g.x; bacc.y += g.y;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        fma2v(acc[r * 3 + 0], g, wa[r]);
+        fma2v(acc[r * 3 + 1], g, wb[r]);
+        fma2v(acc[r * 3 + 2], g, wc[r]);
+        wa[r] = wb[r];
+        wb[r] = wc[r];
+      }
+    }
+  }
+  float* mine = sm + (q << 1) * 10;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    atomicAdd(mine + i, acc[i].x); atomicAdd(mine + 10 + i, acc[i].y);
+  }
+  atomicAdd(mine + 9, bacc.x); atomicAdd(mine + 19, bacc.y);
   __syncthreads();
   for (int i = threadIdx.x; i < C * 10; i += 256) {
     const int kk = i / 10, t = i % 10;
