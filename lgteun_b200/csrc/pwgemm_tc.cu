@@ -804,10 +804,18 @@ pwgrad_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
       tmem_ld_wait();
       if (row < live) {
         float* dst = dW + (size_t)(co0 + row) * wso;
+        float r[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          atomicAdd(dst + (size_t)(c0 + 2 * j) * wsi, (used1 ? v[j].x + u[j].x : v[j].x) * inv_scale);
-          atomicAdd(dst + (size_t)(c0 + 2 * j + 1) * wsi, (used1 ? v[j].y + u[j].y : v[j].y) * inv_scale);
+          r[2 * j] = (used1 ? v[j].x + u[j].x : v[j].x) * inv_scale;
+          r[2 * j + 1] = (used1 ? v[j].y + u[j].y : v[j].y) * inv_scale;
+        }
+        if (wsi == 1 && wso % 4 == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0) {   // 16-byte atomics (see pwgrad_bulk_kernel)
+          atomicAdd(reinterpret_cast<float4*>(dst + c0), make_float4(r[0], r[1], r[2], r[3]));
+          atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4), make_float4(r[4], r[5], r[6], r[7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(dst + (size_t)(c0 + j) * wsi, r[j]);
         }
       }
     }
@@ -984,6 +992,7 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
       const int q = warp & 3, part = warp >> 2;    // lane quarter, column slice
       const int row = q * 32 + lane;               // output channel co0 + row
       const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+      const bool vec = wsi == 1 && wso % 4 == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0;
 #pragma unroll 1
       for (int c0 = part * 8; c0 < NCI; c0 += 8 * (GT / 128)) {
         float2 v[4];
@@ -991,10 +1000,15 @@ pwgrad_bulk_kernel(const float* __restrict__ X, int ldx, const float* __restrict
         tmem_ld_wait();
         if (row < live) {
           float* dst = dW + (size_t)(co0 + row) * wso;
+          if (vec) {                               // 16-byte atomics: 148 CTAs add into the same few thousand words
+            atomicAdd(reinterpret_cast<float4*>(dst + c0), make_float4(v[0].x * inv_scale, v[0].y * inv_scale, v[1].x * inv_scale, v[1].y * inv_scale));
+            atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4), make_float4(v[2].x * inv_scale, v[2].y * inv_scale, v[3].x * inv_scale, v[3].y * inv_scale));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            atomicAdd(dst + (size_t)(c0 + 2 * j) * wsi, v[j].x * inv_scale);
-            atomicAdd(dst + (size_t)(c0 + 2 * j + 1) * wsi, v[j].y * inv_scale);
+            for (int j = 0; j < 4; ++j) {
+              atomicAdd(dst + (size_t)(c0 + 2 * j) * wsi, v[j].x * inv_scale);
+              atomicAdd(dst + (size_t)(c0 + 2 * j + 1) * wsi, v[j].y * inv_scale);
+            }
           }
         }
       }

@@ -228,7 +228,7 @@ void dw_wgrad(Run& R, int K, TV x, TV dy, const float* dw, const float* db, int 
       k_dw3_wgrad_v4<<<gv, 256, C * 10 * sizeof(float), R.s>>>(x.p, dy.p, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
     } else {
       const size_t per_block2 = (size_t)(512 / C) * 8;
-      const unsigned g2 = (unsigned)std::min<size_t>(148 * 8, (NP + per_block2 - 1) / per_block2);
+      const unsigned g2 = (unsigned)std::min<size_t>(148 * 3, (NP + per_block2 - 1) / per_block2);   // resident CTAs only: every CTA ends with C * 10 atomics
       k_dw3_wgrad_v2<<<g2, 256, C * 10 * sizeof(float), R.s>>>(x.p, dy.p, const_cast<float*>(dw), const_cast<float*>(db), N, lh, lw, lc);
     }
     R.check();
