@@ -10,6 +10,10 @@
 // (k2 = register index) — exactly the "fixed low index, stride-16" distribution the inverse transform consumes, so no
 // reordering is needed between the two.
 #include <math.h>
+#include <stdlib.h>
+
+#include <string>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_pre_kernel(const float* __re
 template <int C2, int M>
 __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __restrict__ spec, const float* __restrict__ local,
                                                                const float* __restrict__ xres, float* __restrict__ y,
-                                                               BlockW w, float scale) {
+                                                               BlockW w, float scale, int staged) {
   using namespace f256;
   using namespace tc;
   constexpr int W = 16 * M, Wf = W / 2 + 1, RP = 16 * (M + 1), NSEQ = 256 / M, KPT = 16 / M, TS = 16 / M;
@@ -533,24 +537,65 @@ __global__ void __launch_bounds__(256) fft_rows_inv256_kernel(const float2* __re
     mbar_wait(&mbar[t], phase);
     phase ^= 1;
     tc_fence_after();
-    const float* xr = xres + pix * C;
-    float* dst = y + pix * C;
-    const bool al32 = (reinterpret_cast<uintptr_t>(y) & 31) == 0;
+    // Epilogue through shared memory: a TMEM lane is a pixel, so adding the residual and storing from here would make every
+    // lane touch its own 64 - 256-byte row (16 - 32 L1 wavefronts per instruction; the L1 data pipe bounded the c = 32 form).
+    // The accumulator + bias goes into the tile's own A-operand buffer (free once its MMAs have completed, and exactly
+    // 128 x C floats), 16-byte pieces XOR-swizzled by the row so that the row-wise writes and the linear reads are both
+    // conflict-free; the residual read and the store then run over the tile's contiguous 128 x C floats, lane = piece.
+    if (!staged) {                                          // direct form: the TMEM lane's thread adds the residual and stores its own row
+      const float* xr = xres + pix * C;
+      float* dst = y + pix * C;
+      const bool al32 = (reinterpret_cast<uintptr_t>(y) & 31) == 0;
 #pragma unroll
-    for (int c0 = 0; c0 < C; c0 += 8) {
-      float2 acc[4];
-      tmem_ld8(lane_addr + c0, acc);
-      tmem_ld_wait();
-      const float4 r0 = __ldg(reinterpret_cast<const float4*>(xr + c0)), r1 = __ldg(reinterpret_cast<const float4*>(xr + c0 + 4));
-      const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0), b1 = *reinterpret_cast<const float4*>(sBias + c0 + 4);
-      const float4 y0 = make_float4((acc[0].x + b0.x) + r0.x, (acc[0].y + b0.y) + r0.y, (acc[1].x + b0.z) + r0.z, (acc[1].y + b0.w) + r0.w);
-      const float4 y1 = make_float4((acc[2].x + b1.x) + r1.x, (acc[2].y + b1.y) + r1.y, (acc[3].x + b1.z) + r1.z, (acc[3].y + b1.w) + r1.w);
-      if (al32) {                                   // one 32-byte store = one full L2 sector per thread and instruction
-        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c0), "f"(y0.x), "f"(y0.y), "f"(y0.z), "f"(y0.w),
-                     "f"(y1.x), "f"(y1.y), "f"(y1.z), "f"(y1.w) : "memory");
-      } else {
-        *reinterpret_cast<float4*>(dst + c0) = y0;
-        *reinterpret_cast<float4*>(dst + c0 + 4) = y1;
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        float2 acc[4];
+        tmem_ld8(lane_addr + c0, acc);
+        tmem_ld_wait();
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(xr + c0)), r1 = __ldg(reinterpret_cast<const float4*>(xr + c0 + 4));
+        const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0), b1 = *reinterpret_cast<const float4*>(sBias + c0 + 4);
+        const float4 y0 = make_float4((acc[0].x + b0.x) + r0.x, (acc[0].y + b0.y) + r0.y, (acc[1].x + b0.z) + r0.z, (acc[1].y + b0.w) + r0.w);
+        const float4 y1 = make_float4((acc[2].x + b1.x) + r1.x, (acc[2].y + b1.y) + r1.y, (acc[3].x + b1.z) + r1.z, (acc[3].y + b1.w) + r1.w);
+        if (al32) {                                 // one 32-byte store = one full L2 sector per thread and instruction
+          asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c0), "f"(y0.x), "f"(y0.y), "f"(y0.z), "f"(y0.w),
+                       "f"(y1.x), "f"(y1.y), "f"(y1.z), "f"(y1.w) : "memory");
+        } else {
+          *reinterpret_cast<float4*>(dst + c0) = y0;
+          *reinterpret_cast<float4*>(dst + c0 + 4) = y1;
+        }
+      }
+    } else
+    {
+      float* stage = reinterpret_cast<float*>(a_hi);
+      const int swz = (C == 16) ? ((trow >> 1) & 3) : (trow & 7);
+#pragma unroll
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        float2 acc[4];
+        tmem_ld8(lane_addr + c0, acc);
+        tmem_ld_wait();
+        const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0), b1 = *reinterpret_cast<const float4*>(sBias + c0 + 4);
+        *reinterpret_cast<float4*>(stage + trow * C + (((c0 >> 2) ^ swz) << 2)) =
+            make_float4(acc[0].x + b0.x, acc[0].y + b0.y, acc[1].x + b0.z, acc[1].y + b0.w);
+        *reinterpret_cast<float4*>(stage + trow * C + ((((c0 >> 2) + 1) ^ swz) << 2)) =
+            make_float4(acc[2].x + b1.x, acc[2].y + b1.y, acc[3].x + b1.z, acc[3].y + b1.w);
+      }
+      tc_fence_before();
+      if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      const size_t pix0 = (row0 + (size_t)((round * 2 + t) * 128) / W) * W + ((round * 2 + t) * 128) % W;   // the tile's first pixel
+      const float4* xr4 = reinterpret_cast<const float4*>(xres + pix0 * C);
+      float4* y4 = reinterpret_cast<float4*>(y + pix0 * C);
+      constexpr int PPR = C / 4;                            // 16-byte pieces per pixel row
+#pragma unroll
+      for (int i = 0; i < PPR; ++i) {
+        const int idx = i * 128 + trow, r = idx / PPR, pc = idx % PPR;
+        const int sw = (C == 16) ? ((r >> 1) & 3) : (r & 7);
+        const float4 a = *reinterpret_cast<const float4*>(stage + r * C + ((pc ^ sw) << 2));
+        const float4 x4 = __ldg(xr4 + idx);
+        y4[idx] = make_float4(a.x + x4.x, a.y + x4.y, a.z + x4.z, a.w + x4.w);
+      }
+      if (round + 1 < TILES / 2) {                          // the next round's A operand overwrites the staging tile
+        if (t == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
     }
     tc_fence_before();
@@ -577,8 +622,12 @@ static cudaError_t rows256_inv_t(const BlockW& w, const float* spec, const float
   const size_t smem = (size_t)(256 / M) * 16 * (M + 1) * sizeof(float2) + (size_t)(2 * C * C + 2 * 2 * 128 * C) * 2 + (size_t)C * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(fft_rows_inv256_kernel<C2, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  // staged epilogue (coalesced residual read + store through the tile's A buffer) by default: forward 13.67 -> 13.49 ms (GF-2, 64 pairs),
+  // 18.46 -> 17.69 ms (WV-3, 32 pairs); LGTEUN_ROWS_INV_EPI=direct keeps the lane-per-pixel form for A/B runs
+  static const int epi = [] { const char* e = getenv("LGTEUN_ROWS_INV_EPI"); return !e ? -1 : (std::string(e) == "staged" ? 1 : 0); }();
+  const int staged = epi >= 0 ? epi : 1;
   fft_rows_inv256_kernel<C2, M><<<N * H / RW, 256, smem, s>>>(reinterpret_cast<const float2*>(spec), local, xres, y, w,
-                                                              1.0f / ((float)H * (float)(16 * M)));
+                                                              1.0f / ((float)H * (float)(16 * M)), staged);
   return cudaGetLastError();
 }
 
