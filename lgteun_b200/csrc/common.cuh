@@ -213,9 +213,23 @@ __device__ __forceinline__ void layer_norm_inplace(float (&v)[C], const float* _
   for (int i = 0; i < C; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
 }
 
+// A thread reading its own pixel row: 32-byte loads (LDG.256) when the row allows it — with a lane stride of 64 - 256 bytes every
+// load instruction costs one L1 wavefront per lane whatever its width, so halving the instruction count halves the L1 data-pipe
+// traffic that bounds the thread-per-pixel prologues (LayerNorm of the FFT row pass, window MSA).
 template <int C>
 __device__ __forceinline__ void load_vec(float (&v)[C], const float* __restrict__ p) {
   static_assert(C % 4 == 0, "channel vectors are multiples of 4");
+  if constexpr (C % 8 == 0) {
+    if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < C / 8; ++i)
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[8 * i]), "=f"(v[8 * i + 1]), "=f"(v[8 * i + 2]), "=f"(v[8 * i + 3]), "=f"(v[8 * i + 4]), "=f"(v[8 * i + 5]),
+                       "=f"(v[8 * i + 6]), "=f"(v[8 * i + 7])
+                     : "l"(p + 8 * i));
+      return;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < C / 4; ++i) {
     float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
