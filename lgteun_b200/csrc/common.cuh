@@ -236,6 +236,12 @@ __device__ __forceinline__ void load_vec(float (&v)[C], const float* __restrict_
     v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
   }
 }
+// two adjacent float4 with one 32-byte load (p 32-byte aligned, read-only data)
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+}
 template <int C>
 __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[C]) {
 #pragma unroll

@@ -149,6 +149,7 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
               int nws, int nbands, int band_rows, int total_units, int num_groups) {
   constexpr int C4 = 4 * C;
   constexpr int HV = 128 / C4;
+  const bool in_al32 = (reinterpret_cast<uintptr_t>(xin) & 31) == 0;   // 32-byte loads of a pixel row (LDG.256)
   constexpr int NP = (C4 == 64) ? 40 : 48;           // MMA N of GEMM1 / GEMM2 (M = 128 needs a multiple of 16; columns >= 40 alias, unused)
   // Order of the epilogue phases.  LAG = 0: S_b(row) -> wait GEMM2(row) -> S_c(row).  LAG = 1 (c = 16): S_b(row) -> S_c(row - 1) -> wait
   // GEMM2(row): the latency of GEMM2 / GEMM1 hides under the depthwise stage of the previous row; needs a fourth hidden-row slot.
@@ -385,7 +386,10 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
         float2 o[CONCAT ? 2 : 1][C / 16][4];
 #pragma unroll
         for (int i = 0; i < C / 16; ++i) {
-          if (ok) { ra[i] = __ldg(src + 2 * (i0 + i)); rb[i] = __ldg(src + 2 * (i0 + i) + 1); }
+          if (ok) {
+            if (in_al32) lg::ldg256(src + 2 * (i0 + i), ra[i], rb[i]);
+            else { ra[i] = __ldg(src + 2 * (i0 + i)); rb[i] = __ldg(src + 2 * (i0 + i) + 1); }
+          }
           tmem_ld8(t3 + 8 * (i0 + i), o[0][i]);
           if (CONCAT) tmem_ld8(t3 + C + 8 * (i0 + i), o[CONCAT ? 1 : 0][i]);
         }
@@ -449,8 +453,13 @@ ffn_cl_kernel(const float* __restrict__ xin, float* __restrict__ yout, BlockW w,
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) {
+          if (in_al32) {
+            lg::ldg256(reinterpret_cast<const float4*>(src), v[0], v[1]);
+            lg::ldg256(reinterpret_cast<const float4*>(src) + 2, v[2], v[3]);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+          }
         }
         if (colok && y + 2 < H && it < urows) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * rstride));
         // LayerNorm over the C channels of the pixel
