@@ -244,6 +244,16 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
 }
 template <int C>
 __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[C]) {
+  if constexpr (C % 8 == 0) {
+    if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {      // 32-byte stores: one full L2 sector per thread and instruction
+#pragma unroll
+      for (int i = 0; i < C / 8; ++i)
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
+                     "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
+                     : "memory");
+      return;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < C / 4; ++i)
     *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
