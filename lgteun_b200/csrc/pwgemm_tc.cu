@@ -447,6 +447,7 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
       float* dst = Out + p * N + half * NH;
       const float* res = (EPI == EPI_BIAS_RESID || EPI == EPI_GATE) ? resid + p * N + half * NH : nullptr;
       const float* sb = sbias + half * NH;
+      const bool ral32 = (reinterpret_cast<uintptr_t>(resid) & 31) == 0;   // residual / gate rows with 32-byte loads
 #pragma unroll 1
       for (int cb = 0; cb < NH; cb += 8 * CB) {
         float2 v[CB][4];
@@ -473,12 +474,16 @@ pwgemm_pipe_kernel(const float* __restrict__ A, float* __restrict__ Out, const _
           }
           if (live) {
             if constexpr (EPI == EPI_BIAS_RESID) {
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+              float4 r0, r1;
+              if (ral32) ldg256(reinterpret_cast<const float4*>(res + c0), r0, r1);
+              else { r0 = __ldg(reinterpret_cast<const float4*>(res + c0)); r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4)); }
               w[0] = __fadd2_rn(w[0], make_float2(r0.x, r0.y)); w[1] = __fadd2_rn(w[1], make_float2(r0.z, r0.w));
               w[2] = __fadd2_rn(w[2], make_float2(r1.x, r1.y)); w[3] = __fadd2_rn(w[3], make_float2(r1.z, r1.w));
             }
             if constexpr (EPI == EPI_GATE) {
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(res + c0)), r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4));
+              float4 r0, r1;
+              if (ral32) ldg256(reinterpret_cast<const float4*>(res + c0), r0, r1);
+              else { r0 = __ldg(reinterpret_cast<const float4*>(res + c0)); r1 = __ldg(reinterpret_cast<const float4*>(res + c0 + 4)); }
               w[0] = make_float2(w[0].x * gelu_grad_exact(r0.x), w[0].y * gelu_grad_exact(r0.y));
               w[1] = make_float2(w[1].x * gelu_grad_exact(r0.z), w[1].y * gelu_grad_exact(r0.w));
               w[2] = make_float2(w[2].x * gelu_grad_exact(r1.x), w[2].y * gelu_grad_exact(r1.y));
