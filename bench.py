@@ -646,6 +646,18 @@ def run_train(args):
         "gpu_launches": int(launches * args.steps), "clocks": clocks,
         "loss_after": float(trainer.loss.item()), "train_tape_bytes": int(trainer.handle.train_workspace_bytes(batch, h, h)),
     }
+    # whole-step roofline (no single kernel dominates): 3 x the forward FLOPs of the live path per pair, as in train_leg
+    peaks = load_peaks()
+    fwd_flops = FLOPS_PER_PAIR["wv3" if bands == 8 else "gf2"] * 0.5008 * (H * H) / (256 * 256)
+    achieved = 3 * fwd_flops * batch * world / (ms_total / args.steps * 1e-3) / 1e12
+    line["roofline"] = {"bound": "tensor", "kernel": "whole training step (~330 launches replayed as one CUDA graph; pixel-GEMMs and weight "
+                        "gradients on tcgen05, attention / FFT / depthwise / resize on CUDA cores; per-kernel table: tools/train_prof.py)",
+                        "achieved": achieved, "peak": peaks["bf16_tflops_sustained"] * world, "unit": "TFLOP/s",
+                        "frac": achieved / (peaks["bf16_tflops_sustained"] * world), "traffic": None,
+                        "work": "3 x forward FLOPs of the live path (data steps + last prior) per pair",
+                        "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_train_baseline(bands, h, batch)
     if rank == 0:
         emit(line)
     if world > 1:
