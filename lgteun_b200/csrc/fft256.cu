@@ -110,6 +110,35 @@ __device__ __forceinline__ void fft_m(float2* v) {
 }
 }  // namespace f256
 
+// atan2 without branches: octant reduction, t = min / max in [0, 1], atan(t) = t P(t^2) with a degree-8 P fitted on Chebyshev nodes
+// (max |error| 1.1e-7 rad in fp32 evaluation, the level of atan2f's 2 ulp near pi/4), sign handling on the sign BITS so that
+// (+0, x < 0) -> +pi, (-0, x < 0) -> -pi and (+0, -0) -> +pi as IEEE atan2 / torch.angle have it (the F7 rule feeds +0.0 here).
+// atan2f's slow paths cost ~35 instructions and three divergent branches per bin; this is ~24 straight-line.
+__device__ __forceinline__ float atan2_poly(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+  const float s = t * t;
+  float p = 0.0028340641874819994f;
+  p = fmaf(p, s, -0.016005029901862144f);
+  p = fmaf(p, s, 0.042587608098983765f);
+  p = fmaf(p, s, -0.07495445758104324f);
+  p = fmaf(p, s, 0.10636754333972931f);
+  p = fmaf(p, s, -0.14202570915222168f);
+  p = fmaf(p, s, 0.19992484152317047f);
+  p = fmaf(p, s, -0.3333306610584259f);
+  p = fmaf(p, s, 1.0f);
+  float r = p * t;
+  r = ay > ax ? 1.5707963267948966f - r : r;
+  r = (__float_as_uint(x) >> 31) ? 3.14159265358979323846f - r : r;
+  return copysignf(r, y);
+}
+__device__ __forceinline__ float sqrt_fast(float v) {    // one MUFU, <= 1 ulp; no denormal / special-case branch
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // ---- column pass at H = 16 M (M = 16: 256, M = 8: 128) --------------------------------------------------------------------
 // CTA = Q adjacent complex lanes (kx*C2 + ch) of one image; thread = (lane, low index); M * Q threads.
 // H = 16 M is split as n = M n1 + n2: pass A is a 16-point FFT over n1 (one per thread, n2 = thread), twiddle W_H^{n2 k1},
@@ -121,7 +150,7 @@ __device__ __forceinline__ void fft_m(float2* v) {
 // column transforms of the companion operator SFIIN.Freprocess (companion_ops.cu), which mixes channels between the two.
 template <int Q, int M, int MODE = 0>
 __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restrict__ spec, BlockW w, int W, int C2,
-                                                                int lanes_per_row) {
+                                                                int lanes_per_row, int exact_math = 0) {
   using namespace f256;
   constexpr int H = 16 * M, KPT = 16 / M, TS = 16 / M;    // k1 values per thread in pass B; twiddle-table stride
   __shared__ float2 tw[256];
@@ -180,8 +209,8 @@ __global__ void __launch_bounds__(M * Q, 3) fft_cols256_kernel(float2* __restric
       float2 z = v[i];
       // ky in {0, H/2} <=> k1 = 0 and k2 in {0, M/2}: exactly-real bins get +0.0 (F7)
       if (real_col && lo == 0 && kk == 0 && (k2 == 0 || k2 == M / 2)) z.y = 0.0f;
-      float amp = sqrtf(fmaf(z.x, z.x, z.y * z.y));
-      float pha = atan2f(z.y, z.x);
+      float amp = exact_math ? sqrtf(fmaf(z.x, z.x, z.y * z.y)) : sqrt_fast(fmaf(z.x, z.x, z.y * z.y));
+      float pha = exact_math ? atan2f(z.y, z.x) : atan2_poly(z.y, z.x);
       amp = amp * aw + ab;
       pha = pha * pw + pb;
       const float sn = __sinf(pha), cs = __cosf(pha);
@@ -222,7 +251,8 @@ static cudaError_t cols_reg_t(const BlockW& w, int c2, float* spec, int N, int W
   cudaError_t e = cudaFuncSetAttribute(fft_cols256_kernel<Q, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((lanes + Q - 1) / Q, N);
-  fft_cols256_kernel<Q, M><<<grid, M * Q, smem, s>>>(reinterpret_cast<float2*>(spec), w, W, c2, lanes);
+  static const int exact = [] { const char* e = getenv("LGTEUN_SPEC_MATH"); return (e && std::string(e) == "libm") ? 1 : 0; }();   // A/B: atan2f / sqrtf
+  fft_cols256_kernel<Q, M><<<grid, M * Q, smem, s>>>(reinterpret_cast<float2*>(spec), w, W, c2, lanes, exact);
   return cudaGetLastError();
 }
 cudaError_t launch_fft_cols256(const BlockW& w, int c2, float* spec, int N, int W, cudaStream_t s) {
