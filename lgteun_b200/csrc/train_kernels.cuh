@@ -710,6 +710,50 @@ __global__ void __launch_bounds__(256) k_resize(TV x, int Hi, int Wi, TV y, int 
   }
 }
 
+// NCHW planes in and out (the data module): thread = output pixel of one image, looping over the C planes — the tap coefficients and
+// the 16 clamped source indices are computed once instead of once per channel (they were ~100 of the ~150 instructions per output).
+__global__ void __launch_bounds__(256) k_resize_nchw(const float* __restrict__ x, int Hi, int Wi, float* __restrict__ y, int Ho, int Wo,
+                                                     int C, int N, float rscale, int adjoint) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, Po = (size_t)Ho * Wo, Pi = (size_t)Hi * Wi;
+  if (idx >= (size_t)N * Po) return;
+  const size_t n = idx / Po, pix = idx - n * Po;
+  const int ox = (int)(pix % Wo), oy = (int)(pix / Wo);
+  const float sy = (oy + 0.5f) * rscale - 0.5f, sx = (ox + 0.5f) * rscale - 0.5f;
+  const float fy = floorf(sy), fx = floorf(sx);
+  float cy[4], cx[4];
+  cubic_coef(sy - fy, cy);
+  cubic_coef(sx - fx, cx);
+  const int iy = (int)fy, ix = (int)fx;
+  int ro[4], co[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    ro[a] = min(max(iy - 1 + a, 0), Hi - 1) * Wi;
+    co[a] = min(max(ix - 1 + a, 0), Wi - 1);
+  }
+  const float* xp = x + n * C * Pi;
+  float* yp = y + n * C * Po + pix;
+  for (int k = 0; k < C; ++k, xp += Pi, yp += Po) {
+    if (!adjoint) {
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float row = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) row = fmaf(cx[b], __ldg(xp + ro[a] + co[b]), row);
+        acc = fmaf(cy[a], row, acc);
+      }
+      *yp = acc;
+    } else {
+      const float g = *yp;
+      float* xo = const_cast<float*>(xp);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) atomicAdd(xo + ro[a] + co[b], cy[a] * cx[b] * g);
+    }
+  }
+}
+
 // NHWC maps with ld == C, C % 4 == 0: thread = (output pixel, channel quad), 128-bit taps; the adjoint scatters with the
 // 128-bit vector atomics of sm_90+.
 __global__ void __launch_bounds__(256) k_resize_v4(const float4* __restrict__ x, int Hi, int Wi, float4* __restrict__ y, int Ho, int Wo,
