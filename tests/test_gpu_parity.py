@@ -603,7 +603,8 @@ def test_ffn_variants_match_the_oracle():
 
 
 @pytest.mark.parametrize("env", [{"LGTEUN_FFN": "simt"}, {"LGTEUN_FFN": "tc"}, {"LGTEUN_FFT": "stockham"}, {"LGTEUN_MSA": "simt"}, {"LGTEUN_MSA": "hybrid"},
-                                 {"LGTEUN_MSA": "tc"}, {"LGTEUN_DATA_STEP": "split"}])
+                                 {"LGTEUN_MSA": "tc"}, {"LGTEUN_MSA": "q4"}, {"LGTEUN_DATA_STEP": "split"}, {"LGTEUN_ROWS_INV_EPI": "direct"},
+                                 {"LGTEUN_SPEC_MATH": "libm"}])
 def test_ab_switch_paths_stay_correct(env):
     """The A/B switches (CUDA-core FFN, shared-memory Stockham FFT passes) select other kernels of the SAME library for
     measurement; they are read once per process, so they are exercised in a child process against the golden output."""
