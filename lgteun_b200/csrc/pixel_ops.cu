@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) low_conv2_kernel(const float* __restrict_
   }
 }
 
-constexpr int UFH = 16, UFW = 32;                 // output tile (rows x cols) = 128 blocks of 2x2 pixels
+constexpr int UFH = 8, UFW = 32;                  // output tile (rows x cols) = 64 blocks of 2x2 pixels
 constexpr int UFPH = UFH / 2 + 4, UFPW = UFW / 2 + 4;   // low-res patch 12 x 20
 
 // Work item = (2x2 output block, 4-channel quad): the low-res patch, the skip tile and the transposed skip half of the
